@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- observations/s and ms per Gauss-Newton iteration of the B200 hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A step is one full Gauss-Newton iteration (the body of the reference's while loop,
+main.m:412-494: BuildAwG, normal equations, Schur elimination of the points, (bordered) solve,
+update, sumabs) over one synthetic network.  Workload at N=1 is BASELINE.json configs[3], the
+configuration the metric is quoted on ("10M-observation synthetic network": 2,000 images,
+1M points, ~10M observations, inner constraints, IOP + distortion estimated); it fits one GPU.
+At N>1 the same network is sharded by object point (strong scaling) with one all-reduce of the
+reduced camera system per iteration.
+
+Output: ONE JSON line on rank 0 (see the keys below).  ``value`` is device-resident throughput
+(inputs in HBM, CUDA events); ``e2e`` goes through the host-buffer C-ABI calls per step
+(xhat H2D from pinned memory, iterate, xhat + deltasum D2H).  ``cpu_baseline`` / ``--impl
+reference`` time the CPU restatement of the reference algorithm (oracle/) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (baseline_config index, description)
+    "config4": (3, "BASELINE.json configs[3]: synthetic free network 2,000 images / 1M points / ~10M obs"),
+    "config3": (2, "BASELINE.json configs[2]: synthetic free network 500 images / 200k points / ~5M obs"),
+    "config2": (1, "BASELINE.json configs[1]: EOP-only, 50 images / 20k control points / ~500k obs"),
+    "config5block": (4, "one block of BASELINE.json configs[4]: 200 images / 20k points / ~200k obs"),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(smax)) if smax else None,
+                "power_w_max": float(max(power)) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- workload math
+
+def algorithmic_counts(prob):
+    """algorithmic bytes / flops of one iteration (per kernel)."""
+    s = prob.settings
+    n_obs, nImg, nCam, nPts, nTie = prob.n_obs, prob.numImg, prob.numCam, prob.numPts, prob.numtie
+    NC = 3 + s.NK + 2
+    u_c = prob.u_c
+    b = s.u_perimage + s.u_percam + (3 if nTie else 0)
+    B_asm = 24 * n_obs + 8 * (6 * nImg + NC * nCam + 3 * nPts) + 8 * (u_c * (u_c + 1) // 2 + u_c) + 8 * 12 * nTie
+    F_asm = n_obs * (300 + 4 * (b * (b + 1) // 2 + b))
+    m = np.bincount(prob.obs_pt, minlength=nPts)
+    m_tie = m[prob.pt_tie >= 0] if nTie else np.zeros(0)
+    F_schur = float(np.sum(3.0 * (s.u_perimage * m_tie + s.u_percam) ** 2))
+    F_chol = u_c ** 3 / 3.0
+    B_rsd = 64 * n_obs
+    return dict(B_asm=float(B_asm), F_asm=float(F_asm), F_schur=F_schur, F_chol=float(F_chol), B_rsd=float(B_rsd))
+
+
+def make_workload(name: str, scale: float):
+    import feba_b200 as fb
+    idx, desc = WORKLOADS[name]
+    prob = fb.synth.baseline_config(idx, scale=scale)
+    return prob, desc
+
+
+# --------------------------------------------------------------------------- CPU baseline
+
+def cpu_iteration_seconds(prob, sample_points: int, seed: int = 0):
+    """Time of ONE Gauss-Newton iteration of the CPU restatement (oracle/sparse.py: block normal
+    equations, Schur complement, LAPACK Cholesky + border, back-substitution) for ``prob``,
+    measured on a bounded sample: assembly + point elimination + back-substitution on the first
+    ``sample_points`` object points with all their observations (cost linear in observations,
+    scaled up), the dense reduced solve at the FULL reduced size u_c.  Returns (seconds, parts)."""
+    import copy
+    from oracle import sparse
+    import feba_b200 as fb
+    nP = prob.numPts
+    k = min(sample_points, nP)
+    if k < nP:
+        keep_pt = np.zeros(nP, dtype=bool)
+        keep_pt[:k] = True
+        rows = np.nonzero(keep_pt[prob.obs_pt])[0]
+        sub = copy.copy(prob)
+        sub.obs_x, sub.obs_y = prob.obs_x[rows], prob.obs_y[rows]
+        sub.obs_img, sub.obs_pt = prob.obs_img[rows], prob.obs_pt[rows]
+        sub.xyz0 = prob.xyz0[:k]
+        pt_tie = prob.pt_tie[:k].copy()
+        sel = pt_tie >= 0
+        pt_tie[sel] = np.arange(int(sel.sum()), dtype=np.int32)
+        sub.pt_tie = pt_tie
+        sub.tie_pt = np.nonzero(sel)[0].astype(np.int32)
+        sub.point_ids = None
+    else:
+        sub = prob
+    err, x0, _ = fb.Buildxhat(sub)
+    t0 = time.perf_counter()
+    nb = sparse.normal_blocks(sub, x0)
+    S, g, Vinv = sparse.reduce(sub, nb)
+    t1 = time.perf_counter()
+    # thinning the points can leave the sampled S rank deficient beyond the datum: the timing of
+    # the factorisation does not depend on the values, so factor a safely definite matrix.
+    S[np.diag_indices_from(S)] += 1e-3 * np.abs(np.diag(S)).max()
+    d_c = sparse.solve_reduced(sub, S, g, nb.get("Gc"))
+    t2 = time.perf_counter()
+    sparse.back_substitute(sub, nb, Vinv, d_c)
+    t3 = time.perf_counter()
+    ratio = prob.n_obs / max(sub.n_obs, 1)
+    t_lin = (t1 - t0) + (t3 - t2)
+    total = t_lin * ratio + (t2 - t1)
+    return total, dict(sample_obs=int(sub.n_obs), sample_points=int(k), assemble_schur_s=t1 - t0,
+                       solve_s=t2 - t1, backsub_s=t3 - t2, scale=ratio)
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU restatement of the reference algorithm on the host cores."""
+    if rank != 0:
+        return
+    prob, desc = make_workload(args.workload, args.scale)
+    cores = os.cpu_count() or 1
+    times = []
+    parts = None
+    for i in range(args.warmup + args.steps):
+        t, parts = cpu_iteration_seconds(prob, args.cpu_sample_points)
+        if i >= args.warmup:
+            times.append(t)
+    sec = float(np.mean(times))
+    val = prob.n_obs / sec
+    sample = (f"assembly+Schur+back-substitution timed on {parts['sample_points']} of {prob.numPts} points "
+              f"({parts['sample_obs']} obs, scaled x{parts['scale']:.1f}); dense reduced solve timed at full "
+              f"u_c={prob.u_c} (LAPACK dpotrf, all BLAS threads)")
+    line = {"impl": "reference", "metric": "observations/sec per Gauss-Newton iteration", "value": val,
+            "unit": "obs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "desc": desc, "n_obs": prob.n_obs, "n_img": prob.numImg,
+                       "n_pts": prob.numPts, "u": prob.u, "u_c": prob.u_c},
+            "cpu_baseline": {"value": val, "unit": "obs/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "obs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+
+def fp64_tensor_peak(torch):
+    """cuBLAS DGEMM 8192^3 on this box (FP64 peaks are not in MEASURED_PEAKS.json)."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    best = 0.0
+    for i in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        if i:
+            best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    del a, b
+    torch.cuda.empty_cache()
+    return best
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import feba_b200 as fb
+    from feba_b200 import shard as sh
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    prob, desc = make_workload(args.workload, args.scale)
+    counts = algorithmic_counts(prob)
+    shard = sh.shard_problem(prob, rank, world)
+    err, x0 = fb.Buildxhat(shard.prob)[:2]
+    assert err == 0
+    h = fb.Handle(shard.prob)
+    stream = torch.cuda.current_stream()
+    h.set_stream(stream.cuda_stream)            # torch events then see the library's kernels
+    adj = sh.ShardedAdjustment(h, shard)
+    h.set_xhat(x0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: inputs already in HBM, nothing read back inside the region
+    for _ in range(max(args.warmup, 3)):
+        adj.iterate_async()
+    deltasum_warm = h.sync()
+    sampler = ClockSampler(local_rank)
+    launches0 = h.launch_count()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    phase_ms = np.zeros(6)
+    e0.record()
+    for _ in range(args.steps):
+        adj.iterate_async()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = h.launch_count() - launches0
+    h.sync()
+    t = h.last_timing()
+    phase_ms = np.array([t["prep_ms"], t["assemble_ms"], t["factor_ms"], t["solve_ms"], t["update_ms"], t["total_ms"]])
+    ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+        pm = torch.tensor(phase_ms, device="cuda")
+        dist.all_reduce(pm, op=dist.ReduceOp.MAX)
+        phase_ms = pm.cpu().numpy()
+    ms_step = float(ms_total.item()) / args.steps
+    value = prob.n_obs / (ms_step * 1e-3)
+
+    # ---- end to end through the host-buffer ABI: per step xhat H2D (pinned), iterate, xhat + deltasum D2H
+    u_loc = h.u
+    pin_in = torch.empty(u_loc, dtype=torch.float64).pin_memory()
+    pin_out = torch.empty(u_loc, dtype=torch.float64).pin_memory()
+    pin_in.numpy()[:] = h.get_xhat()
+    xin, xout = pin_in.numpy(), pin_out.numpy()
+
+    def e2e_step():
+        h.set_xhat(xin)
+        ds = adj.iterate()
+        h.get_xhat(xout)
+        xin[:] = xout
+        return ds
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t_e2e.item()) * 1e3 / args.steps
+    e2e_val = prob.n_obs / (e2e_ms * 1e-3)
+
+    # ---- residual stage (main.m:569-602), once, device time + D2H of v and RSD
+    t0 = time.perf_counter()
+    res = h.residuals()
+    rsd_ms = (time.perf_counter() - t0) * 1e3
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm_peak, peak_src = measured_peaks()
+    dgemm_peak = fp64_tensor_peak(torch)
+    kernels = {
+        "assemble_schur": {"ms": float(phase_ms[1]), "GBps": counts["B_asm"] / world / (phase_ms[1] * 1e-3) / 1e9,
+                           "TFLOPs": (counts["F_asm"] + counts["F_schur"]) / world / (phase_ms[1] * 1e-3) / 1e12},
+        "cholesky": {"ms": float(phase_ms[2]), "TFLOPs": counts["F_chol"] / (phase_ms[2] * 1e-3) / 1e12},
+        "prep_clear": {"ms": float(phase_ms[0])}, "triangular_solve": {"ms": float(phase_ms[3])},
+        "update_backsub": {"ms": float(phase_ms[4])},
+    }
+    if phase_ms[2] >= phase_ms[1]:
+        roof = {"kernel": "k_gemm_nt (DMMA trailing updates of the blocked Cholesky)", "bound": "tensor",
+                "achieved": kernels["cholesky"]["TFLOPs"], "peak": dgemm_peak, "unit": "TFLOP/s",
+                "frac": kernels["cholesky"]["TFLOPs"] / dgemm_peak if dgemm_peak else None, "traffic": None,
+                "peak_source": "cuBLAS DGEMM 8192^3 measured live (FP64 tensor peak is not in MEASURED_PEAKS.json)"}
+    else:
+        roof = {"kernel": "k_assemble (fused BuildAwG + normal blocks + Schur)", "bound": "hbm",
+                "achieved": kernels["assemble_schur"]["GBps"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": kernels["assemble_schur"]["GBps"] / hbm_peak, "traffic": None, "peak_source": peak_src}
+    # CPU baseline: bounded sample on the host cores (rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        sec, parts = cpu_iteration_seconds(prob, args.cpu_sample_points)
+        cpu = {"value": prob.n_obs / sec, "unit": "obs/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "ms_per_step": sec * 1e3,
+               "sample": (f"assembly+Schur+back-substitution on {parts['sample_points']} of {prob.numPts} points "
+                          f"({parts['sample_obs']} obs, scaled x{parts['scale']:.1f}); dense reduced solve at full "
+                          f"u_c={prob.u_c} (LAPACK, all BLAS threads)")}
+    line = {
+        "metric": "observations/sec per Gauss-Newton iteration", "value": value, "unit": "obs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": desc, "n_obs": prob.n_obs, "n_img": prob.numImg,
+                   "n_pts": prob.numPts, "u": prob.u, "u_c": prob.u_c, "inner_constraints": prob.settings.Inner_Constraints,
+                   "type": prob.settings.type, "parallelism": f"point-sharded x{world}" if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2 (observations + reduced system > 126 MB); no flush needed"},
+        "e2e": {"value": e2e_val, "unit": "obs/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(8 * u_loc),
+                "d2h_bytes_per_step": int(8 * u_loc + 16)},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels,
+        "fp64_dgemm_peak_tflops": dgemm_peak, "residual_stage_ms": rsd_ms,
+        "sigma02": float(res["sigma02"]), "deltasum_after_warmup": deltasum_warm,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config4", choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (tests only)")
+    ap.add_argument("--cpu-sample-points", type=int, default=20000)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

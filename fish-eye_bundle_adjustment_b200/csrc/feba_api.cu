@@ -1,0 +1,562 @@
+// C ABI of the Gauss-Newton hot path (include/feba.h): handle, uploads, iteration driver.
+//
+// Replaces the body of the reference's while loop (main.m:412-494) and the residual stage
+// (main.m:569-602).  Host work here is limited to argument checks, the one-off ordering of the
+// observations by object point (feba_create) and launching kernels; there is no CPU compute path:
+// every call fails with FEBA_ERR_CUDA when no CUDA device is usable.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/feba.h"
+#include "feba_dev.h"
+#include "feba_kernels.h"
+#include "feba_model.cuh"
+
+using namespace feba;
+
+static thread_local std::string g_create_error;
+
+struct feba_handle {
+    DevProblem P{};
+    feba_settings cfg{};
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<void*> allocs;
+    // device state
+    double *eop = nullptr, *iop = nullptr, *cam_box = nullptr, *img_tab = nullptr, *cam_tab = nullptr;
+    double *xhat = nullptr, *sol = nullptr, *dcam = nullptr, *dcam_unscaled = nullptr, *work = nullptr;
+    double *scal = nullptr;       // [0] sumabs camera part, [1] sumabs points, [2] sum vx^2, [3] sum vy^2
+    double *v_out = nullptr, *rsd_out = nullptr, *delta_out = nullptr;
+    int *opt = nullptr, *tie_pt = nullptr, *info = nullptr;
+    double* scal_host = nullptr;  // pinned mirror of scal
+    int* info_host = nullptr;
+    size_t S_count = 0;
+    int64_t u = 0;
+    int n_partial = 0;
+    int64_t launches = 0;
+    int iterations = 0;           // completed iterations since the last set_xhat
+    int phase = 0;                // 0 idle, 1 assembled (waiting for solve)
+    double timing[6] = {0, 0, 0, 0, 0, 0};
+    bool timing_valid = false;
+    std::string err;
+};
+
+namespace {
+
+int fail(feba_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CU(h, call)                                                                                  \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(h, FEBA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                                   \
+    } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(feba_handle* h, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, (count ? count : 1) * sizeof(T));
+    if (e == cudaSuccess) {
+        h->allocs.push_back(q);
+        *p = static_cast<T*>(q);
+    }
+    return e;
+}
+
+template <typename T>
+cudaError_t upload(feba_handle* h, T** p, const T* src, size_t count) {
+    cudaError_t e = dev_alloc(h, p, count);
+    if (e != cudaSuccess) return e;
+    if (count) e = cudaMemcpyAsync(*p, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream);
+    return e;
+}
+
+int check_settings(const feba_problem* pr) {
+    const feba_settings& s = pr->settings;
+    if (s.type < 0 || s.type > 4)
+        return fail(nullptr, FEBA_ERR_INVALID, "BuildAwG, invalid type in data.settings.type (typeint %d)", s.type);
+    if (s.num_radial < 1 || s.num_radial > FEBA_MAX_NK)
+        return fail(nullptr, FEBA_ERR_INVALID, "Num_Radial_Distortions must be 1..%d (got %d)", FEBA_MAX_NK,
+                    s.num_radial);
+    int ui = 0;
+    for (int q = 0; q < 6; ++q) ui += s.estimate_eop[q] ? 1 : 0;
+    if (s.inner_constraints && ui != 6)
+        return fail(nullptr, FEBA_ERR_INVALID,
+                    "Inner_Constraints needs all six EOPs estimated (Gblock is 6 rows, BuildAwG.m:516-525)");
+    if (!(s.sigma_x > 0.0) || !(s.sigma_y > 0.0))
+        return fail(nullptr, FEBA_ERR_INVALID, "Meas_std / Meas_std_y must be positive");
+    if (pr->n_obs < 0 || pr->n_obs > 2000000000LL || pr->n_img < 1 || pr->n_cam < 1 || pr->n_pts < 0 ||
+        pr->n_tie < 0)
+        return fail(nullptr, FEBA_ERR_INVALID, "bad problem sizes");
+    if (pr->n_cam != 1)
+        return fail(nullptr, FEBA_ERR_INVALID, "this build supports one camera per adjustment (n_cam = %d)",
+                    pr->n_cam);
+    return FEBA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* feba_last_error(const feba_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+void feba_destroy(feba_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->scal_host) cudaFreeHost(h->scal_host);
+    if (h->info_host) cudaFreeHost(h->info_host);
+    for (auto& e : h->ev)
+        if (e) cudaEventDestroy(e);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int feba_create(const feba_problem* pr, feba_handle** out) {
+    if (!pr || !out) return fail(nullptr, FEBA_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int rc = check_settings(pr);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, FEBA_ERR_CUDA, "no CUDA device: the hot path has no CPU fallback");
+    feba_handle* h = new (std::nothrow) feba_handle();
+    if (!h) return fail(nullptr, FEBA_ERR_INVALID, "out of host memory");
+    struct Guard {
+        feba_handle* h;
+        bool keep = false;
+        ~Guard() {
+            if (!keep) {
+                g_create_error = h->err;
+                feba_destroy(h);
+            }
+        }
+    } guard{h};
+    CU(h, cudaGetDevice(&h->device));
+    CU(h, cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device));
+    CU(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+    for (auto& e : h->ev) CU(h, cudaEventCreate(&e));
+    h->cfg = pr->settings;
+    const feba_settings& s = pr->settings;
+
+    DevProblem& P = h->P;
+    P.n_obs = pr->n_obs;
+    P.n_img = pr->n_img;
+    P.n_cam = pr->n_cam;
+    P.n_pts = pr->n_pts;
+    P.n_tie = pr->n_tie;
+    P.type = s.type;
+    P.NK = s.num_radial;
+    P.NC = P.NK + 5;
+    P.inner = s.inner_constraints ? 1 : 0;
+    P.px = 1.0 / (s.sigma_x * s.sigma_x);      // main.m:396-405
+    P.py = 1.0 / (s.sigma_y * s.sigma_y);
+    // slots of the estimated parameters (BuildAwG.m:24-25, :52-93, :110-155)
+    int k = 0;
+    for (int q = 0; q < 6; ++q) P.ecol[q] = s.estimate_eop[q] ? k++ : -1;
+    P.ui = k;
+    k = 0;
+    for (int q = 0; q < 16; ++q) P.ccol[q] = -1;
+    P.ccol[0] = s.estimate_xp ? k++ : -1;
+    P.ccol[1] = s.estimate_yp ? k++ : -1;
+    P.ccol[2] = s.estimate_c ? k++ : -1;
+    for (int j = 0; j < P.NK; ++j) P.ccol[3 + j] = s.estimate_radial ? k++ : -1;
+    for (int j = 0; j < 2; ++j) P.ccol[3 + P.NK + j] = s.estimate_decent ? k++ : -1;
+    P.uc = k;
+    P.off_cam = P.ui * P.n_img;
+    P.n_red = P.off_cam + P.uc * P.n_cam;
+    if (P.n_red < 1) return fail(h, FEBA_ERR_INVALID, "no EOP/IOP unknowns: nothing to adjust");
+    P.n_pad = (P.n_red + kBlk - 1) / kBlk * kBlk;
+    P.ld = P.n_pad + kBlk;
+    h->u = (int64_t)P.n_red + 3 * (int64_t)P.n_tie;
+
+    // ---- order the observations by object point (stable counting sort, PHO order inside a point)
+    const int64_t n = pr->n_obs;
+    std::vector<int> start((size_t)pr->n_pts + 1, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        const int p = pr->obs_pt[i], im = pr->obs_img[i];
+        if (p < 0 || p >= pr->n_pts) return fail(h, FEBA_ERR_INVALID, "obs_pt[%lld] out of range", (long long)i);
+        if (im < 0 || im >= pr->n_img) return fail(h, FEBA_ERR_INVALID, "obs_img[%lld] out of range", (long long)i);
+        ++start[(size_t)p + 1];
+    }
+    std::vector<int> seg_start, seg_pt;
+    seg_start.reserve((size_t)pr->n_pts + 1);
+    seg_pt.reserve((size_t)pr->n_pts);
+    for (int p = 0; p < pr->n_pts; ++p) {
+        if (start[(size_t)p + 1] > 0) {
+            seg_start.push_back(start[p]);
+            seg_pt.push_back(p);
+        }
+        start[(size_t)p + 1] += start[p];
+    }
+    seg_start.push_back((int)n);
+    P.n_seg = (int)seg_pt.size();
+    std::vector<int> perm((size_t)n), simg((size_t)n), spt((size_t)n);
+    std::vector<double> sx((size_t)n), sy((size_t)n);
+    {
+        std::vector<int> cur(start.begin(), start.end() - 1);
+        for (int64_t i = 0; i < n; ++i) {
+            const int p = pr->obs_pt[i];
+            const int d = cur[p]++;
+            perm[d] = (int)i;
+            simg[d] = pr->obs_img[i];
+            spt[d] = p;
+            sx[d] = pr->obs_x[i];
+            sy[d] = pr->obs_y[i];
+        }
+    }
+    // tie index <-> CNT row (main.m:362-375, Buildxhat.m:108-135)
+    std::vector<int> tie_pt((size_t)pr->n_tie, -1);
+    for (int p = 0; p < pr->n_pts; ++p) {
+        const int t = pr->pt_tie[p];
+        if (t < -1 || t >= pr->n_tie) return fail(h, FEBA_ERR_INVALID, "pt_tie[%d] out of range", p);
+        if (t >= 0) {
+            if (tie_pt[t] >= 0) return fail(h, FEBA_ERR_INVALID, "tie index %d used by two points", t);
+            tie_pt[t] = p;
+        }
+    }
+    for (int j = 0; j < pr->n_img; ++j)
+        if (pr->img_cam[j] < 0 || pr->img_cam[j] >= pr->n_cam)
+            return fail(h, FEBA_ERR_INVALID, "img_cam[%d] out of range", j);
+    for (int c = 0; c < pr->n_cam; ++c)
+        if (std::fabs(pr->cam_box[5 * c]) != 1.0)
+            return fail(h, FEBA_ERR_INVALID, "y_dir should be +-1 only (main.m:334-337)");
+
+    // ---- uploads
+    double *ox, *oy, *xyz, *xyz_prev;
+    int *oimg, *operm, *dseg_start, *dseg_pt, *dimg_cam, *dpt_tie;
+    CU(h, upload(h, &ox, sx.data(), (size_t)n));
+    CU(h, upload(h, &oy, sy.data(), (size_t)n));
+    CU(h, upload(h, &oimg, simg.data(), (size_t)n));
+    CU(h, upload(h, &operm, perm.data(), (size_t)n));
+    CU(h, upload(h, &h->opt, spt.data(), (size_t)n));
+    CU(h, upload(h, &dseg_start, seg_start.data(), seg_start.size()));
+    CU(h, upload(h, &dseg_pt, seg_pt.data(), seg_pt.size()));
+    CU(h, upload(h, &dimg_cam, pr->img_cam, (size_t)pr->n_img));
+    CU(h, upload(h, &dpt_tie, pr->pt_tie, (size_t)pr->n_pts));
+    CU(h, upload(h, &h->tie_pt, tie_pt.data(), tie_pt.size()));
+    CU(h, upload(h, &h->eop, pr->eop0, (size_t)pr->n_img * 6));
+    CU(h, upload(h, &h->iop, pr->iop0, (size_t)pr->n_cam * P.NC));
+    CU(h, upload(h, &h->cam_box, pr->cam_box, (size_t)pr->n_cam * 5));
+    CU(h, upload(h, &xyz, pr->xyz0, (size_t)pr->n_pts * 3));
+    CU(h, upload(h, &xyz_prev, pr->xyz0, (size_t)pr->n_pts * 3));
+    CU(h, dev_alloc(h, &h->img_tab, (size_t)pr->n_img * kImgStride));
+    CU(h, dev_alloc(h, &h->cam_tab, (size_t)pr->n_cam * kCamStride));
+    h->S_count = (size_t)P.ld * (size_t)P.ld;
+    CU(h, dev_alloc(h, &P.S, h->S_count));
+    CU(h, dev_alloc(h, &h->xhat, (size_t)h->u));
+    CU(h, dev_alloc(h, &h->sol, (size_t)P.n_pad));
+    CU(h, dev_alloc(h, &h->dcam, (size_t)P.n_pad));
+    CU(h, dev_alloc(h, &h->dcam_unscaled, (size_t)P.n_pad));
+    CU(h, dev_alloc(h, &P.dpts, (size_t)pr->n_tie * 3));
+    CU(h, dev_alloc(h, &h->work, 64));
+    CU(h, dev_alloc(h, &h->scal, 8));
+    CU(h, dev_alloc(h, &h->info, 1));
+    CU(h, cudaMallocHost((void**)&h->scal_host, 8 * sizeof(double)));
+    CU(h, cudaMallocHost((void**)&h->info_host, sizeof(int)));
+    if (pr->n_tie > 0) CU(h, cudaMemsetAsync(P.dpts, 0, (size_t)pr->n_tie * 3 * sizeof(double), h->stream));
+    CU(h, cudaMemsetAsync(h->dcam, 0, (size_t)P.n_pad * sizeof(double), h->stream));
+    CU(h, cudaMemsetAsync(h->dcam_unscaled, 0, (size_t)P.n_pad * sizeof(double), h->stream));
+    P.ox = ox;
+    P.oy = oy;
+    P.oimg = oimg;
+    P.operm = operm;
+    P.seg_start = dseg_start;
+    P.seg_pt = dseg_pt;
+    P.img_cam = dimg_cam;
+    P.pt_tie = dpt_tie;
+    P.img_tab = h->img_tab;
+    P.cam_tab = h->cam_tab;
+    P.xyz = xyz;
+    P.xyz_prev = xyz_prev;
+    P.dcam = h->dcam;
+    P.dcam_unscaled = h->dcam_unscaled;
+    {
+        const int a = backsub_warps(P, h->sm_count), b = 2 * residual_blocks(P, h->sm_count);
+        h->n_partial = a > b ? a : b;
+    }
+    CU(h, dev_alloc(h, &P.partial, (size_t)h->n_partial));
+    // xhat = Buildxhat of the uploaded tables (Buildxhat.m:22-135)
+    CU(h, cudaMemsetAsync(h->xhat, 0, (size_t)h->u * sizeof(double), h->stream));
+    CU(h, launch_xhat_gather(P, h->sm_count, h->xhat, h->eop, h->iop, h->tie_pt, h->stream));
+    ++h->launches;
+    CU(h, cudaStreamSynchronize(h->stream));   // host staging vectors go out of scope
+    guard.keep = true;
+    *out = h;
+    return FEBA_OK;
+}
+
+int feba_set_stream(feba_handle* h, void* stream) {
+    if (!h) return FEBA_ERR_INVALID;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    h->stream = static_cast<cudaStream_t>(stream);
+    h->own_stream = false;
+    return FEBA_OK;
+}
+
+int feba_num_unknowns(const feba_handle* h, int64_t* u, int64_t* u_c) {
+    if (!h) return FEBA_ERR_INVALID;
+    if (u) *u = h->u;
+    if (u_c) *u_c = h->P.n_red;
+    return FEBA_OK;
+}
+
+int feba_set_xhat(feba_handle* h, const double* xhat, size_t u) {
+    if (!h || !xhat) return FEBA_ERR_INVALID;
+    if ((int64_t)u != h->u) return fail(h, FEBA_ERR_INVALID, "xhat has %zu entries, expected %lld", u, (long long)h->u);
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaMemcpyAsync(h->xhat, xhat, u * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(h, launch_xhat_scatter(h->P, h->sm_count, h->xhat, h->eop, h->iop, h->tie_pt, h->stream));
+    ++h->launches;
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->iterations = 0;
+    h->phase = 0;
+    return FEBA_OK;
+}
+
+int feba_get_xhat(feba_handle* h, double* xhat, size_t u) {
+    if (!h || !xhat) return FEBA_ERR_INVALID;
+    if ((int64_t)u != h->u) return fail(h, FEBA_ERR_INVALID, "xhat has %zu entries, expected %lld", u, (long long)h->u);
+    CU(h, cudaSetDevice(h->device));
+    CU(h, launch_xhat_gather(h->P, h->sm_count, h->xhat, h->eop, h->iop, h->tie_pt, h->stream));
+    ++h->launches;
+    CU(h, cudaMemcpyAsync(xhat, h->xhat, u * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return FEBA_OK;
+}
+
+int feba_get_delta(feba_handle* h, double* delta, size_t u) {
+    if (!h || !delta) return FEBA_ERR_INVALID;
+    if ((int64_t)u != h->u) return fail(h, FEBA_ERR_INVALID, "delta has %zu entries, expected %lld", u, (long long)h->u);
+    if (h->iterations < 1) return fail(h, FEBA_ERR_STATE, "feba_get_delta before any iteration");
+    CU(h, cudaSetDevice(h->device));
+    if (!h->delta_out) CU(h, dev_alloc(h, &h->delta_out, (size_t)h->u));
+    CU(h, launch_delta_gather(h->P, h->sm_count, h->delta_out, h->stream));
+    ++h->launches;
+    CU(h, cudaMemcpyAsync(delta, h->delta_out, u * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return FEBA_OK;
+}
+
+// ---- one Gauss-Newton step, first half: tables, zero S, fused BuildAwG + normal blocks + Schur.
+int feba_iterate_assemble(feba_handle* h) {
+    if (!h) return FEBA_ERR_INVALID;
+    CU(h, cudaSetDevice(h->device));
+    DevProblem& P = h->P;
+    CU(h, cudaEventRecord(h->ev[0], h->stream));
+    CU(h, launch_tables(P, h->eop, h->iop, h->cam_box, h->img_tab, h->cam_tab, h->stream));
+    CU(h, cudaMemsetAsync(P.S, 0, h->S_count * sizeof(double), h->stream));
+    CU(h, cudaMemsetAsync(h->info, 0, sizeof(int), h->stream));
+    CU(h, cudaEventRecord(h->ev[1], h->stream));
+    CU(h, launch_assemble(P, h->sm_count, h->stream));
+    h->launches += 2;
+    CU(h, cudaEventRecord(h->ev[2], h->stream));
+    h->phase = 1;
+    return FEBA_OK;
+}
+
+int feba_reduced_dev(feba_handle* h, double** dev_ptr, size_t* count) {
+    if (!h || !dev_ptr || !count) return FEBA_ERR_INVALID;
+    *dev_ptr = h->P.S;
+    *count = h->S_count;
+    return FEBA_OK;
+}
+
+// ---- second half: inner-constraint border, factorisation, solve, update, back-substitution.
+static int solve_async(feba_handle* h) {
+    DevProblem& P = h->P;
+    if (h->phase != 1) return fail(h, FEBA_ERR_STATE, "feba_iterate_solve without feba_iterate_assemble");
+    if (P.inner) {
+        CU(h, launch_constraints(P, h->eop, h->stream));
+        h->launches += 2;
+    }
+    CU(h, launch_pad_diag(P, h->stream));
+    if (P.n_pad > P.n_red) ++h->launches;
+    const int nb = P.n_pad / kBlk;
+    CU(h, chol_augmented(P.S, P.ld, nb, h->info, h->stream, &h->launches));
+    CU(h, cudaEventRecord(h->ev[3], h->stream));
+    CU(h, border_and_backsolve(P.S, P.ld, nb, P.inner, h->work, h->sol, h->info, h->stream, &h->launches));
+    CU(h, cudaEventRecord(h->ev[4], h->stream));
+    CU(h, launch_update_cam(P, h->sol, h->dcam, h->dcam_unscaled, h->eop, h->iop, h->scal, h->stream));
+    ++h->launches;
+    if (P.n_tie > 0 && P.n_seg > 0) {
+        CU(h, launch_backsub(P, h->sm_count, h->stream));
+        CU(h, launch_sum_partials(P.partial, backsub_warps(P, h->sm_count), 1, 0, h->scal + 1, h->stream));
+        h->launches += 2;
+    } else {
+        CU(h, cudaMemsetAsync(h->scal + 1, 0, sizeof(double), h->stream));
+    }
+    CU(h, cudaEventRecord(h->ev[5], h->stream));
+    h->phase = 0;
+    ++h->iterations;
+    return FEBA_OK;
+}
+
+static int finish_iteration(feba_handle* h, double* dcam_sum, double* dpts_sum) {
+    CU(h, cudaMemcpyAsync(h->scal_host, h->scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(h->info_host, h->info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    bool ok = true;
+    double tot = 0.0;
+    for (int i = 0; i < 5 && ok; ++i) {
+        float ms = 0.f;
+        ok = cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]) == cudaSuccess;
+        h->timing[i] = ms;
+        tot += ms;
+    }
+    if (ok) h->timing[5] = tot;
+    h->timing_valid = ok;
+    if (dcam_sum) *dcam_sum = h->scal_host[0];
+    if (dpts_sum) *dpts_sum = h->scal_host[1];
+    if (*h->info_host == 1)
+        return fail(h, FEBA_ERR_NUMERIC, "reduced normal matrix is not positive definite");
+    if (*h->info_host == 2) return fail(h, FEBA_ERR_NUMERIC, "inner-constraint border system is singular");
+    if (!std::isfinite(h->scal_host[0]) || !std::isfinite(h->scal_host[1]))
+        return fail(h, FEBA_ERR_NUMERIC, "non-finite increment (R = 0 on the optical axis? BuildAwG.m:186)");
+    return FEBA_OK;
+}
+
+int feba_iterate_solve(feba_handle* h, double* deltasum_cam, double* deltasum_pts) {
+    if (!h) return FEBA_ERR_INVALID;
+    CU(h, cudaSetDevice(h->device));
+    int rc = solve_async(h);
+    if (rc) return rc;
+    return finish_iteration(h, deltasum_cam, deltasum_pts);
+}
+
+int feba_iterate_solve_async(feba_handle* h) {
+    if (!h) return FEBA_ERR_INVALID;
+    CU(h, cudaSetDevice(h->device));
+    return solve_async(h);
+}
+
+int feba_iterate_async(feba_handle* h) {
+    int rc = feba_iterate_assemble(h);
+    if (rc) return rc;
+    return solve_async(h);
+}
+
+int feba_sync(feba_handle* h, double* deltasum_out) {
+    if (!h) return FEBA_ERR_INVALID;
+    CU(h, cudaSetDevice(h->device));
+    double a = 0, b = 0;
+    int rc = finish_iteration(h, &a, &b);
+    if (deltasum_out) *deltasum_out = a + b;      // main.m:487
+    return rc;
+}
+
+int feba_iterate(feba_handle* h, double* deltasum_out) {
+    int rc = feba_iterate_async(h);
+    if (rc) return rc;
+    return feba_sync(h, deltasum_out);
+}
+
+int feba_solve(feba_handle* h, int32_t* iterations_out, double* trace_out, size_t trace_cap) {
+    if (!h) return FEBA_ERR_INVALID;
+    // main.m:407-494: deltasum = 100; while deltasum > threshold; ...; if count >= cap, break
+    double deltasum = 100.0;
+    int count = 0;
+    while (deltasum > h->cfg.threshold) {
+        ++count;
+        int rc = feba_iterate(h, &deltasum);
+        if (rc) {
+            if (iterations_out) *iterations_out = count;
+            return rc;
+        }
+        if (trace_out && (size_t)(count - 1) < trace_cap) trace_out[count - 1] = deltasum;
+        if (count >= h->cfg.iteration_cap) break;
+    }
+    if (iterations_out) *iterations_out = count;
+    return FEBA_OK;
+}
+
+int feba_residuals(feba_handle* h, double* v, double* rsd, double stats[6]) {
+    if (!h) return FEBA_ERR_INVALID;
+    if (h->iterations < 1) return fail(h, FEBA_ERR_STATE, "feba_residuals before any iteration (main.m:569 uses the last A, w, delta)");
+    CU(h, cudaSetDevice(h->device));
+    DevProblem& P = h->P;
+    const size_t n = (size_t)P.n_obs;
+    if (v && !h->v_out) CU(h, dev_alloc(h, &h->v_out, 2 * n));
+    if (rsd && !h->rsd_out) CU(h, dev_alloc(h, &h->rsd_out, 5 * n));
+    CU(h, launch_residuals(P, h->sm_count, h->opt, P.xyz_prev, h->iop, v ? h->v_out : nullptr,
+                           rsd ? h->rsd_out : nullptr, h->stream));
+    const int nblk = residual_blocks(P, h->sm_count);
+    CU(h, launch_sum_partials(P.partial, nblk, 2, 0, h->scal + 2, h->stream));
+    CU(h, launch_sum_partials(P.partial, nblk, 2, 1, h->scal + 3, h->stream));
+    h->launches += 3;
+    if (v) CU(h, cudaMemcpyAsync(v, h->v_out, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (rsd) CU(h, cudaMemcpyAsync(rsd, h->rsd_out, 5 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(h->scal_host + 2, h->scal + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (stats) {
+        const double sxx = h->scal_host[2], syy = h->scal_host[3];
+        const double nn = (double)P.n_obs;
+        const double rmsx = std::sqrt(sxx / nn), rmsy = std::sqrt(syy / nn);     // main.m:594-597, :998-1002
+        stats[0] = rmsx;
+        stats[1] = rmsy;
+        stats[2] = std::sqrt(rmsx * rmsx + rmsy * rmsy);                         // main.m:598
+        stats[3] = (sxx * P.px + syy * P.py) / (2.0 * nn - (double)h->u);         // main.m:601 (n - u)
+        stats[4] = sxx;
+        stats[5] = syy;
+    }
+    return FEBA_OK;
+}
+
+int feba_last_timing(const feba_handle* h, double ms[6]) {
+    if (!h || !ms) return FEBA_ERR_INVALID;
+    if (!h->timing_valid) return FEBA_ERR_STATE;
+    for (int i = 0; i < 6; ++i) ms[i] = h->timing[i];
+    return FEBA_OK;
+}
+
+int feba_debug_oob(void) { return debug_oob_count(); }
+
+int64_t feba_launch_count(const feba_handle* h) { return h ? h->launches : 0; }
+
+// Diagnostic: the reduced camera system as assembled by the last feba_iterate_assemble (before the
+// inner-constraint border is added): S_out n_red x n_red column-major, full symmetric; g_out n_red.
+int feba_debug_reduced(feba_handle* h, double* S_out, double* g_out) {
+    if (!h) return FEBA_ERR_INVALID;
+    if (h->phase != 1) return fail(h, FEBA_ERR_STATE, "feba_debug_reduced needs a pending feba_iterate_assemble");
+    CU(h, cudaSetDevice(h->device));
+    const DevProblem& P = h->P;
+    const size_t nr = (size_t)P.n_red;
+    std::vector<double> col((size_t)P.ld);
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (size_t c = 0; c < nr; ++c) {
+        CU(h, cudaMemcpy(col.data(), P.S + (size_t)P.ld * c, (size_t)P.ld * sizeof(double), cudaMemcpyDeviceToHost));
+        if (S_out)
+            for (size_t r = c; r < nr; ++r) {
+                S_out[r + nr * c] = col[r];
+                S_out[c + nr * r] = col[r];
+            }
+        if (g_out) g_out[c] = col[(size_t)P.n_pad];
+    }
+    return FEBA_OK;
+}
+
+}  // extern "C"

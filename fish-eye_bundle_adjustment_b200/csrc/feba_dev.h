@@ -1,0 +1,49 @@
+// Device-side problem description shared by the kernel translation units (internal header).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace feba {
+
+constexpr int kBlk = 64;          // dense linear-algebra tile; reduced system is padded to it
+constexpr int kAugRows = 8;       // rows of the augmented block in use: [g ; G(:,1..7)]
+
+// Everything a kernel needs, passed by value (lives in the constant bank).
+struct DevProblem {
+    int64_t n_obs;
+    int n_img, n_cam, n_pts, n_tie, n_seg;
+    int type, NK, NC;             // NC = NK + 5 camera columns (xp yp c k1..kNK p1 p2)
+    int ui, uc;                   // estimated unknowns per image / per camera (BuildAwG.m:24-25)
+    int n_red;                    // u_c = ui*n_img + uc*n_cam  (size of the reduced system)
+    int n_pad;                    // n_red rounded up to kBlk
+    int ld;                       // leading dimension of S  (= n_pad + kBlk: augmented rows)
+    int off_cam;                  // ui*n_img
+    int inner;                    // Inner_Constraints
+    int ecol[6];                  // slot of EOP q inside the image block or -1
+    int ccol[16];                 // slot of camera parameter q inside the camera block or -1
+    double px, py;                // 1/sigma_x^2, 1/sigma_y^2                     (main.m:396-405)
+
+    // observations, sorted by point (segment s = observations [seg_start[s], seg_start[s+1]))
+    const double* ox;
+    const double* oy;
+    const int* oimg;
+    const int* operm;             // sorted position -> PHO row
+    const int* seg_start;
+    const int* seg_pt;            // CNT row of segment s
+    const int* img_cam;
+    const int* pt_tie;
+
+    // parameters at the linearisation point of the current / last iteration
+    const double* img_tab;        // n_img x kImgStride
+    const double* cam_tab;        // n_cam x kCamStride
+    double* xyz;                  // n_pts x 3, current object coordinates (updated in place)
+    double* xyz_prev;             // coordinates at the linearisation point of the last iteration
+
+    double* S;                    // (n_pad + kBlk) x ld, column-major, lower triangle
+    const double* dcam;           // scaled increment of the camera part (length n_pad)
+    const double* dcam_unscaled;  // un-scaled increment (main.m:458-482)
+    double* dpts;                 // increment of the tie points, n_tie x 3
+    double* partial;              // per-warp partial sums (deterministic final reduction)
+};
+
+}  // namespace feba

@@ -1,0 +1,883 @@
+// Gauss-Newton hot-path kernels (sm_100a): parameter tables, fused BuildAwG + normal-equation
+// blocks + Schur elimination of the object points, camera-parameter update, point
+// back-substitution, residual / RSD reduction.
+//
+// Reference path replaced: functions/BuildAwG.m:46-528 (A, w, G), main.m:424-425 (u=A'Pw,
+// N=A'PA), the point part of main.m:428-444, main.m:458-488 (un-scaling, update, sumabs),
+// main.m:569 (v=A*delta+w), functions/BuildRSD.m:9-42, main.m:594-601.
+// The design matrix A and the full normal matrix N are never formed.
+#include "feba_dev.h"
+#include "feba_kernels.h"
+#include "feba_model.cuh"
+
+namespace feba {
+
+// Accumulation into the reduced system.  A -DFEBA_CHECK build range-checks every target address
+// (compute-sanitizer is not available on the GPU pool) and counts violations instead of writing.
+#ifdef FEBA_CHECK
+__device__ int g_feba_oob = 0;
+#define RED_ADD(ptr, v)                                                                   \
+    do {                                                                                  \
+        double* p_ = (ptr);                                                               \
+        if (p_ < P.S || p_ >= P.S + (size_t)P.ld * (size_t)P.ld) atomicAdd(&g_feba_oob, 1); \
+        else atomicAdd(p_, (v));                                                          \
+    } while (0)
+#else
+#define RED_ADD(ptr, v) atomicAdd((ptr), (v))
+#endif
+
+// ------------------------------------------------------------------------------------------
+// K0: per-image and per-camera tables from the current parameters.
+// M = R3(kappa) R2(phi) R1(omega) as written in BuildAwG.m:163-165.
+__global__ void k_tables(int n_img, int n_cam, int NK, const double* __restrict__ eop,
+                         const double* __restrict__ iop, const double* __restrict__ cam_box,
+                         double* __restrict__ img_tab, double* __restrict__ cam_tab) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_img) {
+        const double* e = eop + 6 * i;
+        double sw, cw, sp, cp, sk, ck;
+        sincos(e[3], &sw, &cw);
+        sincos(e[4], &sp, &cp);
+        sincos(e[5], &sk, &ck);
+        double* t = img_tab + kImgStride * i;
+        t[0] = e[0]; t[1] = e[1]; t[2] = e[2];
+        t[3] = ck * cp;  t[4] = cw * sk + ck * sp * sw;  t[5] = sk * sw - ck * cw * sp;
+        t[6] = -cp * sk; t[7] = ck * cw - sk * sp * sw;  t[8] = ck * sw + cw * sk * sp;
+        t[9] = sp;       t[10] = -cp * sw;               t[11] = cp * cw;
+        t[12] = ck; t[13] = sk; t[14] = 0.0; t[15] = 0.0;
+    }
+    if (i < n_cam) {
+        const int NC = NK + 5;
+        const double* p = iop + NC * i;
+        const double* b = cam_box + 5 * i;
+        double* t = cam_tab + kCamStride * i;
+        for (int k = 0; k < kCamStride; ++k) t[k] = 0.0;
+        t[0] = p[0]; t[1] = p[1]; t[2] = p[2]; t[3] = b[0];
+        t[4] = p[3 + NK]; t[5] = p[4 + NK];
+        for (int j = 0; j < NK; ++j) t[6 + j] = p[3 + j];
+        const double hx = (b[3] - b[1]) * 0.5, hy = (b[4] - b[2]) * 0.5;
+        const double rmax2 = hx * hx + hy * hy;          // r_max^2  (BuildAwG.m:422)
+        double s = 1.0;
+        for (int j = 0; j < NK; ++j) {
+            s *= rmax2;                                  // r_max^(2j) (BuildAwG.m:424-426)
+            t[16 + j] = 1.0 / s;
+            t[24 + j] = s;
+        }
+    }
+}
+
+// Inner-constraint rows per image from the CURRENT EOPs (BuildAwG.m:514-527), written as the
+// augmented rows 1..7 of S (row r of the augmented block holds column r-1 of G).
+__global__ void k_G_rows(DevProblem P, const double* __restrict__ eop) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_img) return;
+    const double* e = eop + 6 * i;
+    const double Xc = e[0], Yc = e[1], Zc = e[2];
+    double sw, cw;
+    sincos(e[3], &sw, &cw);
+    const double tp = tan(e[4]), secp = 1.0 / cos(e[4]);
+    double G[6][7] = {{1, 0, 0, 0, -Zc, Yc, Xc},
+                      {0, 1, 0, Zc, 0, -Xc, Yc},
+                      {0, 0, 1, -Yc, Xc, 0, Zc},
+                      {0, 0, 0, -1, -sw * tp, cw * tp, 0},
+                      {0, 0, 0, 0, -cw, -sw, 0},
+                      {0, 0, 0, 0, sw * secp, -cw * secp, 0}};
+    for (int q = 0; q < 6; ++q)
+        for (int c = 0; c < 7; ++c)
+            P.S[(size_t)(P.n_pad + 1 + c) + (size_t)P.ld * (6 * i + q)] = G[q][c];
+}
+
+// M = S + Gc Gc'  on the lower triangle of the EOP part: Gc is non-zero only
+// in EOP rows, so the border stays in the camera block.  G is read from the augmented rows.
+__global__ void k_add_GGt(DevProblem P) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y * blockDim.y + threadIdx.y;
+    const int ne = P.off_cam;
+    if (r >= ne || c >= ne || r < c) return;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+        acc += P.S[(size_t)(P.n_pad + 1 + k) + (size_t)P.ld * r] *
+               P.S[(size_t)(P.n_pad + 1 + k) + (size_t)P.ld * c];
+    P.S[(size_t)r + (size_t)P.ld * c] += acc;
+}
+
+// Unit diagonal on the padding rows so the padded matrix stays positive definite.
+__global__ void k_pad_diag(DevProblem P) {
+    const int i = P.n_red + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.n_pad) P.S[(size_t)i + (size_t)P.ld * i] = 1.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// xhat <-> parameter tables.  Layout of xhat: Buildxhat.m:22-135 (per image the estimated EOPs,
+// per camera the estimated xp yp c k1..kNK p1 p2, per TIE entry X Y Z); the gather of
+// BuildAwG.m:52-155 (estimated -> from xhat, else the file value) is done once per set, not per
+// observation.  scatter: xhat -> tables (both coordinate buffers), gather: tables -> xhat.
+__global__ void k_xhat_scatter(DevProblem P, const double* __restrict__ xhat, double* __restrict__ eop,
+                               double* __restrict__ iop, const int* __restrict__ tie_pt) {
+    const int64_t n_e = (int64_t)P.n_img * 6, n_c = (int64_t)P.n_cam * P.NC, n_t = (int64_t)P.n_tie * 3;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_e + n_c + n_t;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < n_e) {
+            const int im = (int)(i / 6), q = (int)(i - 6 * (int64_t)im);
+            if (P.ecol[q] >= 0) eop[i] = xhat[(int64_t)P.ui * im + P.ecol[q]];
+        } else if (i < n_e + n_c) {
+            const int64_t r = i - n_e;
+            const int cam = (int)(r / P.NC), q = (int)(r - (int64_t)cam * P.NC);
+            if (P.ccol[q] >= 0) iop[r] = xhat[(int64_t)P.off_cam + (int64_t)P.uc * cam + P.ccol[q]];
+        } else {
+            const int64_t r = i - n_e - n_c;
+            const int t = (int)(r / 3), k = (int)(r - 3 * (int64_t)t);
+            const int pt = tie_pt[t];
+            if (pt >= 0) {
+                const double val = xhat[(int64_t)P.n_red + r];
+                P.xyz[3 * (int64_t)pt + k] = val;
+                P.xyz_prev[3 * (int64_t)pt + k] = val;
+            }
+        }
+    }
+}
+
+__global__ void k_xhat_gather(DevProblem P, double* __restrict__ xhat, const double* __restrict__ eop,
+                              const double* __restrict__ iop, const int* __restrict__ tie_pt) {
+    const int64_t n_e = (int64_t)P.n_img * 6, n_c = (int64_t)P.n_cam * P.NC, n_t = (int64_t)P.n_tie * 3;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_e + n_c + n_t;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < n_e) {
+            const int im = (int)(i / 6), q = (int)(i - 6 * (int64_t)im);
+            if (P.ecol[q] >= 0) xhat[(int64_t)P.ui * im + P.ecol[q]] = eop[i];
+        } else if (i < n_e + n_c) {
+            const int64_t r = i - n_e;
+            const int cam = (int)(r / P.NC), q = (int)(r - (int64_t)cam * P.NC);
+            if (P.ccol[q] >= 0) xhat[(int64_t)P.off_cam + (int64_t)P.uc * cam + P.ccol[q]] = iop[r];
+        } else {
+            const int64_t r = i - n_e - n_c;
+            const int t = (int)(r / 3), k = (int)(r - 3 * (int64_t)t);
+            const int pt = tie_pt[t];
+            if (pt >= 0) xhat[(int64_t)P.n_red + r] = P.xyz[3 * (int64_t)pt + k];
+        }
+    }
+}
+
+// delta in xhat layout (un-scaled, main.m:458-482): camera part from dcam_unscaled, ties from dpts.
+__global__ void k_delta_gather(DevProblem P, double* __restrict__ delta) {
+    const int64_t n = (int64_t)P.n_red + 3 * (int64_t)P.n_tie;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        delta[i] = i < P.n_red ? P.dcam_unscaled[i] : P.dpts[i - P.n_red];
+}
+
+// ------------------------------------------------------------------------------------------
+// 3x3 symmetric inverse through a Cholesky factor.  v = [v00 v10 v11 v20 v21 v22].
+__device__ __forceinline__ void sym3_inverse(const double* v, double* inv) {
+    const double l00 = sqrt(v[0]);
+    const double l10 = v[1] / l00;
+    const double l20 = v[3] / l00;
+    const double l11 = sqrt(v[2] - l10 * l10);
+    const double l21 = (v[4] - l20 * l10) / l11;
+    const double l22 = sqrt(v[5] - l20 * l20 - l21 * l21);
+    // inverse of L (lower)
+    const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
+    const double i10 = -l10 * i00 * i11;
+    const double i21 = -l21 * i11 * i22;
+    const double i20 = -(l20 * i00 + l21 * i10) * i22;
+    // V^-1 = L^-T L^-1
+    inv[0] = i00 * i00 + i10 * i10 + i20 * i20;
+    inv[1] = i10 * i11 + i20 * i21;
+    inv[2] = i11 * i11 + i21 * i21;
+    inv[3] = i20 * i22;
+    inv[4] = i21 * i22;
+    inv[5] = i22 * i22;
+}
+
+__device__ __forceinline__ double sym3(const double* m, int i, int j) {
+    // element (i,j) of a packed symmetric 3x3 [00 10 11 20 21 22]
+    const int a = i > j ? i : j, b = i > j ? j : i;
+    return m[a * (a + 1) / 2 + b];
+}
+
+// ------------------------------------------------------------------------------------------
+// K1+K2: fused assembly of the block normal equations and Schur elimination of the points.
+// One warp per object point, lanes over its observations (chunks of 32).
+//
+// For a tie point p with observations a = 1..m (image i_a), per-observation blocks
+//   We_a = Je_a' P Jt_a (u_img x 3), Wc = sum_a Jc_a' P Jt_a (u_cam x 3), V = sum_a Jt_a' P Jt_a,
+// the contribution to the reduced system S = N_cc - W V^-1 W' (never forming N) is
+//   S[i_a,i_b] += delta_ab Je_a'PJe_a - (We_a V^-1) We_b'
+//   S[cam,i_a] += Jc_a'PJe_a - Wc V^-1 We_a'
+//   S[cam,cam] += sum_a Jc_a'PJc_a - Wc V^-1 Wc'
+//   g[i_a]     += Je_a'P w_a - We_a V^-1 u_p,   g[cam] += sum_a Jc_a'P w_a - Wc V^-1 u_p.
+// Control points contribute only the direct terms.  Only the lower triangle is written.
+// Single camera per problem in this kernel (n_cam == 1); camera block sums are kept in
+// lane-owned registers across the warp's points and flushed once.
+template <int NK>
+struct AsmSmem {
+    static constexpr int NC = NK + 5;
+    double rowJc[32][2][NC];
+    double rowJt[32][2][3];
+    double roww[32][2];
+    double We[32][18];
+    double Wc[NC][3];
+    double Yc[NC][3];
+    double V[6];
+    double up[3];
+    int img[32];
+};
+
+template <int NK, bool HAS_CAM>
+__global__ void __launch_bounds__(128) k_assemble(DevProblem P) {
+    constexpr int NC = NK + 5;
+    constexpr int ND = NC * (NC + 1) / 2;          // packed camera-camera block
+    constexpr int DPL = (ND + 31) / 32;            // entries of D per lane
+    constexpr int WPL = (NC * 3 + 31) / 32;        // entries of Wc per lane
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    AsmSmem<NK>* sm_all = reinterpret_cast<AsmSmem<NK>*>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    AsmSmem<NK>& sm = sm_all[wib];
+    const int nwarp = gridDim.x * (blockDim.x >> 5);
+    const int gw = blockIdx.x * (blockDim.x >> 5) + wib;
+    const double pw[2] = {P.px, P.py};
+    const int type = P.type;
+
+    // static ownership of camera-block entries
+    int dI[DPL], dJ[DPL];
+    double dacc[DPL];
+#pragma unroll
+    for (int t = 0; t < DPL; ++t) {
+        const int e = lane + 32 * t;
+        int i = 0;
+        while ((i + 1) * (i + 2) / 2 <= e) ++i;    // row of packed lower-triangular index e
+        dI[t] = i;
+        dJ[t] = e - i * (i + 1) / 2;
+        dacc[t] = 0.0;
+    }
+    double gcacc = 0.0;
+
+    for (int seg = gw; seg < P.n_seg; seg += nwarp) {
+        const int beg = P.seg_start[seg], end = P.seg_start[seg + 1];
+        const int pt = P.seg_pt[seg];
+        const bool is_tie = P.pt_tie[pt] >= 0;
+        const double X = P.xyz[3 * pt], Y = P.xyz[3 * pt + 1], Z = P.xyz[3 * pt + 2];
+        const bool single = (end - beg) <= 32;
+        ObsJac<NK> J;
+        int img = -1;
+        bool act = false;
+
+        // ---------------- pass 1: V, u_p, Wc, and the direct camera-camera sums
+        double vacc = 0.0;                          // lanes 0..5: V entries, 6..8: u_p
+        double wcacc[WPL];
+#pragma unroll
+        for (int t = 0; t < WPL; ++t) wcacc[t] = 0.0;
+        if (is_tie || HAS_CAM) {
+            for (int c0 = beg; c0 < end; c0 += 32) {
+                const int o = c0 + lane;
+                act = o < end;
+                if (act) {
+                    img = P.oimg[o];
+                    observation<NK, HAS_CAM>(type, P.ox[o], P.oy[o], P.img_tab + kImgStride * img,
+                                             P.cam_tab, X, Y, Z, J);
+                }
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    if (HAS_CAM) {
+#pragma unroll
+                        for (int j = 0; j < NC; ++j) sm.rowJc[lane][r][j] = act ? J.Jc[r][j] : 0.0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) sm.rowJt[lane][r][k] = act ? J.Jt[r][k] : 0.0;
+                    sm.roww[lane][r] = act ? J.w[r] : 0.0;
+                }
+                __syncwarp();
+                const int nrow = min(32, end - c0);
+                if (HAS_CAM) {
+#pragma unroll
+                    for (int t = 0; t < DPL; ++t) {
+                        if (lane + 32 * t < ND) {
+                            double a = 0.0;
+                            for (int l = 0; l < nrow; ++l)
+                                a += sm.rowJc[l][0][dI[t]] * pw[0] * sm.rowJc[l][0][dJ[t]] +
+                                     sm.rowJc[l][1][dI[t]] * pw[1] * sm.rowJc[l][1][dJ[t]];
+                            dacc[t] += a;
+                        }
+                    }
+                    if (lane < NC) {
+                        double a = 0.0;
+                        for (int l = 0; l < nrow; ++l)
+                            a += sm.rowJc[l][0][lane] * pw[0] * sm.roww[l][0] +
+                                 sm.rowJc[l][1][lane] * pw[1] * sm.roww[l][1];
+                        gcacc += a;
+                    }
+                    if (is_tie) {
+#pragma unroll
+                        for (int t = 0; t < WPL; ++t) {
+                            const int e = lane + 32 * t;
+                            if (e < NC * 3) {
+                                const int i = e / 3, k = e - 3 * i;
+                                double a = 0.0;
+                                for (int l = 0; l < nrow; ++l)
+                                    a += sm.rowJc[l][0][i] * pw[0] * sm.rowJt[l][0][k] +
+                                         sm.rowJc[l][1][i] * pw[1] * sm.rowJt[l][1][k];
+                                wcacc[t] += a;
+                            }
+                        }
+                    }
+                }
+                if (is_tie && lane < 9) {
+                    double a = 0.0;
+                    if (lane < 6) {
+                        const int i = lane < 1 ? 0 : (lane < 3 ? 1 : 2);
+                        const int k = lane - i * (i + 1) / 2;
+                        for (int l = 0; l < nrow; ++l)
+                            a += sm.rowJt[l][0][i] * pw[0] * sm.rowJt[l][0][k] +
+                                 sm.rowJt[l][1][i] * pw[1] * sm.rowJt[l][1][k];
+                    } else {
+                        const int k = lane - 6;
+                        for (int l = 0; l < nrow; ++l)
+                            a += sm.rowJt[l][0][k] * pw[0] * sm.roww[l][0] +
+                                 sm.rowJt[l][1][k] * pw[1] * sm.roww[l][1];
+                    }
+                    vacc += a;
+                }
+                __syncwarp();
+            }
+        }
+        double Vinv[6] = {0, 0, 0, 0, 0, 0};
+        double up[3] = {0, 0, 0};
+        if (is_tie) {
+            if (lane < 6) sm.V[lane] = vacc;
+            else if (lane < 9) sm.up[lane - 6] = vacc;
+            if (HAS_CAM) {
+#pragma unroll
+                for (int t = 0; t < WPL; ++t) {
+                    const int e = lane + 32 * t;
+                    if (e < NC * 3) (&sm.Wc[0][0])[e] = wcacc[t];
+                }
+            }
+            __syncwarp();
+            double Vp[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) Vp[k] = sm.V[k];
+            sym3_inverse(Vp, Vinv);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) up[k] = sm.up[k];
+            if (HAS_CAM) {
+                if (lane < NC) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        sm.Yc[lane][k] = sm.Wc[lane][0] * sym3(Vinv, 0, k) +
+                                         sm.Wc[lane][1] * sym3(Vinv, 1, k) +
+                                         sm.Wc[lane][2] * sym3(Vinv, 2, k);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < DPL; ++t) {
+                    if (lane + 32 * t < ND)
+                        dacc[t] -= sm.Yc[dI[t]][0] * sm.Wc[dJ[t]][0] + sm.Yc[dI[t]][1] * sm.Wc[dJ[t]][1] +
+                                   sm.Yc[dI[t]][2] * sm.Wc[dJ[t]][2];
+                }
+                if (lane < NC)
+                    gcacc -= sm.Yc[lane][0] * up[0] + sm.Yc[lane][1] * up[1] + sm.Yc[lane][2] * up[2];
+            }
+        }
+
+        // ---------------- pass 2: image-keyed blocks
+        for (int a0 = beg; a0 < end; a0 += 32) {
+            const int oa = a0 + lane;
+            const bool acta = oa < end;
+            if (!single || !(is_tie || HAS_CAM)) {
+                act = acta;
+                if (acta) {
+                    img = P.oimg[oa];
+                    observation<NK, HAS_CAM>(type, P.ox[oa], P.oy[oa], P.img_tab + kImgStride * img,
+                                             P.cam_tab, X, Y, Z, J);
+                }
+            }
+            const int img_a = acta ? img : -1;
+            double We[6][3], Ye[6][3];
+            if (acta) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        We[i][k] = J.Je[0][i] * pw[0] * J.Jt[0][k] + J.Je[1][i] * pw[1] * J.Jt[1][k];
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        Ye[i][k] = is_tie ? We[i][0] * sym3(Vinv, 0, k) + We[i][1] * sym3(Vinv, 1, k) +
+                                                We[i][2] * sym3(Vinv, 2, k)
+                                          : 0.0;
+                const size_t col0 = (size_t)P.ui * img_a;
+                // right-hand side of the image block -> augmented row 0
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    if (P.ecol[i] >= 0) {
+                        double gval = J.Je[0][i] * pw[0] * J.w[0] + J.Je[1][i] * pw[1] * J.w[1] -
+                                      (Ye[i][0] * up[0] + Ye[i][1] * up[1] + Ye[i][2] * up[2]);
+                        RED_ADD(&P.S[(size_t)P.n_pad + (size_t)P.ld * (col0 + P.ecol[i])], gval);
+                    }
+                }
+                // direct diagonal block Je'PJe (lower)
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) {
+                        if (P.ecol[i] >= 0 && P.ecol[j] >= 0) {
+                            const double val = J.Je[0][i] * pw[0] * J.Je[0][j] + J.Je[1][i] * pw[1] * J.Je[1][j];
+                            RED_ADD(&P.S[(col0 + P.ecol[i]) + (size_t)P.ld * (col0 + P.ecol[j])], val);
+                        }
+                    }
+                if (HAS_CAM) {
+                    // camera x image block: Jc'PJe - Wc V^-1 We' = Jc'PJe - Wc Ye'
+#pragma unroll
+                    for (int j = 0; j < NC; ++j) {
+                        if (P.ccol[j] >= 0) {
+                            const size_t row = (size_t)P.off_cam + P.ccol[j];
+                            double wc0 = 0, wc1 = 0, wc2 = 0;
+                            if (is_tie) { wc0 = sm.Wc[j][0]; wc1 = sm.Wc[j][1]; wc2 = sm.Wc[j][2]; }
+#pragma unroll
+                            for (int i = 0; i < 6; ++i) {
+                                if (P.ecol[i] >= 0) {
+                                    const double val = J.Jc[0][j] * pw[0] * J.Je[0][i] +
+                                                       J.Jc[1][j] * pw[1] * J.Je[1][i] -
+                                                       (wc0 * Ye[i][0] + wc1 * Ye[i][1] + wc2 * Ye[i][2]);
+                                    RED_ADD(&P.S[row + (size_t)P.ld * (col0 + P.ecol[i])], val);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (is_tie) {
+                for (int b0 = beg; b0 < end; b0 += 32) {
+                    __syncwarp();
+                    if (b0 == a0) {
+                        sm.img[lane] = img_a;
+                        if (acta) {
+#pragma unroll
+                            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                                for (int k = 0; k < 3; ++k) sm.We[lane][3 * i + k] = We[i][k];
+                        }
+                    } else {
+                        const int ob = b0 + lane;
+                        sm.img[lane] = -1;
+                        if (ob < end) {
+                            ObsJac<NK> Jb;
+                            const int ib = P.oimg[ob];
+                            observation<NK, false>(type, P.ox[ob], P.oy[ob], P.img_tab + kImgStride * ib,
+                                                   P.cam_tab, X, Y, Z, Jb);
+                            sm.img[lane] = ib;
+#pragma unroll
+                            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                                for (int k = 0; k < 3; ++k)
+                                    sm.We[lane][3 * i + k] =
+                                        Jb.Je[0][i] * pw[0] * Jb.Jt[0][k] + Jb.Je[1][i] * pw[1] * Jb.Jt[1][k];
+                        }
+                    }
+                    __syncwarp();
+                    const int nb = min(32, end - b0);
+                    if (acta) {
+                        const size_t rowa = (size_t)P.ui * img_a;
+                        for (int b = 0; b < nb; ++b) {
+                            const int ib = sm.img[b];
+                            if (ib > img_a) continue;
+                            const bool diag = (ib == img_a);
+                            const size_t colb = (size_t)P.ui * ib;
+                            double wb[18];
+#pragma unroll
+                            for (int q = 0; q < 18; ++q) wb[q] = sm.We[b][q];
+#pragma unroll
+                            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                                for (int j = 0; j < 6; ++j) {
+                                    if (P.ecol[i] >= 0 && P.ecol[j] >= 0 && (!diag || j <= i)) {
+                                        const double val = -(Ye[i][0] * wb[3 * j] + Ye[i][1] * wb[3 * j + 1] +
+                                                             Ye[i][2] * wb[3 * j + 2]);
+                                        RED_ADD(&P.S[(rowa + P.ecol[i]) + (size_t)P.ld * (colb + P.ecol[j])], val);
+                                    }
+                                }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // flush the camera block (one camera)
+    if (HAS_CAM) {
+#pragma unroll
+        for (int t = 0; t < DPL; ++t) {
+            if (lane + 32 * t < ND && P.ccol[dI[t]] >= 0 && P.ccol[dJ[t]] >= 0) {
+                // packed index (i >= j) in parameter order; slots are monotone so row >= col
+                const size_t row = (size_t)P.off_cam + P.ccol[dI[t]];
+                const size_t col = (size_t)P.off_cam + P.ccol[dJ[t]];
+                RED_ADD(&P.S[row + (size_t)P.ld * col], dacc[t]);
+            }
+        }
+        if (lane < NC && P.ccol[lane] >= 0)
+            RED_ADD(&P.S[(size_t)P.n_pad + (size_t)P.ld * ((size_t)P.off_cam + P.ccol[lane])], gcacc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Camera-part update (main.m:458-488 for the EOP/IOP unknowns): delta_c = -sol, un-scale the
+// distortion increments by r_max^(2j) / r_max^2, add to the parameter tables, partial sumabs.
+__global__ void k_update_cam(DevProblem P, const double* __restrict__ sol, double* __restrict__ dcam,
+                             double* __restrict__ dcam_unscaled, double* __restrict__ eop,
+                             double* __restrict__ iop, double* __restrict__ out_sumabs) {
+    __shared__ double red[1024];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < P.n_pad; i += blockDim.x) {
+        double d = 0.0, du = 0.0;
+        if (i < P.n_red) {
+            d = -sol[i];
+            du = d;
+            if (i < P.off_cam) {
+                const int im = i / P.ui, slot = i - im * P.ui;
+                int q = 0;
+                for (int k = 0; k < 6; ++k) if (P.ecol[k] == slot) q = k;
+                eop[6 * im + q] += du;
+            } else {
+                const int r = i - P.off_cam;
+                const int cam = r / P.uc, slot = r - cam * P.uc;
+                int q = 0;
+                for (int k = 0; k < P.NC; ++k) if (P.ccol[k] == slot) q = k;
+                const double* ct = P.cam_tab + kCamStride * cam;
+                if (q >= 3 && q < 3 + P.NK) du = d / ct[24 + (q - 3)];      // main.m:467
+                else if (q >= 3 + P.NK) du = d / ct[24];                     // main.m:476,479
+                iop[P.NC * cam + q] += du;
+            }
+            acc += fabs(du);
+        }
+        dcam[i] = d;
+        dcam_unscaled[i] = du;
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out_sumabs[0] = red[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: back-substitution of the tie points, d_p = -V_p^-1 (u_p + W_p' d_c), X += d_p, sumabs.
+// Recomputes the Jacobians at the linearisation point (W_p is never stored):
+//   W_p' d_c = sum_a Jt_a' P (Je_a d_e(i_a) + Jc_a d_cam).
+template <int NK, bool HAS_CAM>
+__global__ void __launch_bounds__(128) k_backsub(DevProblem P) {
+    constexpr int NC = NK + 5;
+    const int lane = threadIdx.x & 31;
+    const int nwarp = gridDim.x * (blockDim.x >> 5);
+    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const double pw[2] = {P.px, P.py};
+    double dsum = 0.0;
+    for (int seg = gw; seg < P.n_seg; seg += nwarp) {
+        const int pt = P.seg_pt[seg];
+        const int tie = P.pt_tie[pt];
+        if (tie < 0) continue;
+        const int beg = P.seg_start[seg], end = P.seg_start[seg + 1];
+        const double X = P.xyz[3 * pt], Y = P.xyz[3 * pt + 1], Z = P.xyz[3 * pt + 2];
+        double acc[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc[k] = 0.0;
+        for (int o = beg + lane; o < end; o += 32) {
+            ObsJac<NK> J;
+            const int img = P.oimg[o];
+            observation<NK, HAS_CAM>(P.type, P.ox[o], P.oy[o], P.img_tab + kImgStride * img, P.cam_tab,
+                                     X, Y, Z, J);
+            double q[2] = {0.0, 0.0};
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                if (P.ecol[i] >= 0) {
+                    const double d = P.dcam[P.ui * img + P.ecol[i]];
+                    q[0] += J.Je[0][i] * d;
+                    q[1] += J.Je[1][i] * d;
+                }
+            }
+            if (HAS_CAM) {
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    if (P.ccol[j] >= 0) {
+                        const double d = P.dcam[P.off_cam + P.ccol[j]];
+                        q[0] += J.Jc[0][j] * d;
+                        q[1] += J.Jc[1][j] * d;
+                    }
+                }
+            }
+            int e = 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int k = 0; k <= i; ++k)
+                    acc[e++] += J.Jt[0][i] * pw[0] * J.Jt[0][k] + J.Jt[1][i] * pw[1] * J.Jt[1][k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                acc[6 + k] += J.Jt[0][k] * pw[0] * J.w[0] + J.Jt[1][k] * pw[1] * J.w[1];
+                acc[9 + k] += J.Jt[0][k] * pw[0] * q[0] + J.Jt[1][k] * pw[1] * q[1];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 12; ++k)
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], s);
+        double Vinv[6];
+        sym3_inverse(acc, Vinv);
+        double t[3] = {acc[6] + acc[9], acc[7] + acc[10], acc[8] + acc[11]};
+        double d[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            d[k] = -(sym3(Vinv, k, 0) * t[0] + sym3(Vinv, k, 1) * t[1] + sym3(Vinv, k, 2) * t[2]);
+        if (lane < 3) {
+            const double dv = lane == 0 ? d[0] : (lane == 1 ? d[1] : d[2]);
+            const double xv = lane == 0 ? X : (lane == 1 ? Y : Z);
+            // each point belongs to exactly one warp and was read above: in-place update is safe
+            P.xyz_prev[3 * pt + lane] = xv;
+            P.xyz[3 * pt + lane] = xv + dv;                      // main.m:484
+            P.dpts[3 * tie + lane] = dv;
+        }
+        dsum += fabs(d[0]) + fabs(d[1]) + fabs(d[2]);            // main.m:487 (sumabs)
+    }
+    if (lane == 0) P.partial[gw] = dsum;
+}
+
+// Fixed-order sum of per-warp / per-block partials (deterministic).
+__global__ void k_sum_partials(const double* __restrict__ partial, int n, int stride, int offset,
+                               double* __restrict__ out) {
+    __shared__ double red[1024];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[(size_t)i * stride + offset];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = red[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: residuals v = A*delta + w with A, w of the LAST iteration (linearisation point before the
+// last update) and the UN-scaled delta against the SCALED distortion columns (main.m:569 after
+// main.m:458-482 -- reproduced as coded), BuildRSD columns r vx vy vr vt with xp, yp from the
+// post-update parameters (BuildRSD.m:14-27), and sum vx^2, sum vy^2 for main.m:594-601.
+template <int NK, bool HAS_CAM>
+__global__ void __launch_bounds__(256) k_residuals(DevProblem P, const int* __restrict__ opt,
+                                                   const double* __restrict__ xyz_prev,
+                                                   const double* __restrict__ iop_new,
+                                                   double* __restrict__ v_out, double* __restrict__ rsd_out) {
+    constexpr int NC = NK + 5;
+    __shared__ double red[2][256];
+    double sx = 0.0, sy = 0.0;
+    for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < P.n_obs;
+         o += (int64_t)gridDim.x * blockDim.x) {
+        const int img = P.oimg[o], pt = opt[o];
+        const int tie = P.pt_tie[pt];
+        ObsJac<NK> J;
+        const double x = P.ox[o], y = P.oy[o];
+        observation<NK, HAS_CAM>(P.type, x, y, P.img_tab + kImgStride * img, P.cam_tab, xyz_prev[3 * pt],
+                                 xyz_prev[3 * pt + 1], xyz_prev[3 * pt + 2], J);
+        double v[2] = {J.w[0], J.w[1]};
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            if (P.ecol[i] >= 0) {
+                const double d = P.dcam_unscaled[P.ui * img + P.ecol[i]];
+                v[0] += J.Je[0][i] * d;
+                v[1] += J.Je[1][i] * d;
+            }
+        }
+        if (HAS_CAM) {
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                if (P.ccol[j] >= 0) {
+                    const double d = P.dcam_unscaled[P.off_cam + P.ccol[j]];
+                    v[0] += J.Jc[0][j] * d;
+                    v[1] += J.Jc[1][j] * d;
+                }
+            }
+        }
+        if (tie >= 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double d = P.dpts[3 * tie + k];
+                v[0] += J.Jt[0][k] * d;
+                v[1] += J.Jt[1][k] * d;
+            }
+        }
+        sx += v[0] * v[0];
+        sy += v[1] * v[1];
+        const int row = P.operm[o];
+        if (v_out) {
+            v_out[2 * (size_t)row] = v[0];
+            v_out[2 * (size_t)row + 1] = v[1];
+        }
+        if (rsd_out) {
+            const int cam = P.img_cam[img];
+            const double xb = x - iop_new[P.NC * cam], yb = y - iop_new[P.NC * cam + 1];
+            const double theta = atan2(yb, xb), Phi = atan2(v[1], v[0]);
+            const double vd = sqrt(v[0] * v[0] + v[1] * v[1]);
+            double* r = rsd_out + 5 * (size_t)row;
+            r[0] = sqrt(xb * xb + yb * yb);
+            r[1] = v[0];
+            r[2] = v[1];
+            r[3] = vd * cos(theta - Phi);
+            r[4] = vd * sin(theta - Phi);
+        }
+    }
+    red[0][threadIdx.x] = sx;
+    red[1][threadIdx.x] = sy;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            red[0][threadIdx.x] += red[0][threadIdx.x + s];
+            red[1][threadIdx.x] += red[1][threadIdx.x + s];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        P.partial[2 * blockIdx.x] = red[0][0];
+        P.partial[2 * blockIdx.x + 1] = red[1][0];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host launchers (dispatch on NK and on whether any camera parameter is estimated)
+
+#define FEBA_NK_DISPATCH(NKV, HASCAM, CALL)                                  \
+    switch (NKV) {                                                           \
+        case 1: { constexpr int NK_ = 1; if (HASCAM) { constexpr bool HC_ = true; CALL; } else { constexpr bool HC_ = false; CALL; } } break; \
+        case 2: { constexpr int NK_ = 2; if (HASCAM) { constexpr bool HC_ = true; CALL; } else { constexpr bool HC_ = false; CALL; } } break; \
+        case 3: { constexpr int NK_ = 3; if (HASCAM) { constexpr bool HC_ = true; CALL; } else { constexpr bool HC_ = false; CALL; } } break; \
+        case 4: { constexpr int NK_ = 4; if (HASCAM) { constexpr bool HC_ = true; CALL; } else { constexpr bool HC_ = false; CALL; } } break; \
+        case 5: { constexpr int NK_ = 5; if (HASCAM) { constexpr bool HC_ = true; CALL; } else { constexpr bool HC_ = false; CALL; } } break; \
+        case 6: { constexpr int NK_ = 6; if (HASCAM) { constexpr bool HC_ = true; CALL; } else { constexpr bool HC_ = false; CALL; } } break; \
+        case 7: { constexpr int NK_ = 7; if (HASCAM) { constexpr bool HC_ = true; CALL; } else { constexpr bool HC_ = false; CALL; } } break; \
+        case 8: { constexpr int NK_ = 8; if (HASCAM) { constexpr bool HC_ = true; CALL; } else { constexpr bool HC_ = false; CALL; } } break; \
+        default: return cudaErrorInvalidValue;                               \
+    }
+
+cudaError_t launch_tables(const DevProblem& P, const double* eop, const double* iop, const double* cam_box,
+                          double* img_tab, double* cam_tab, cudaStream_t st) {
+    const int n = P.n_img > P.n_cam ? P.n_img : P.n_cam;
+    k_tables<<<(n + 127) / 128, 128, 0, st>>>(P.n_img, P.n_cam, P.NK, eop, iop, cam_box, img_tab, cam_tab);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_constraints(const DevProblem& P, const double* eop, cudaStream_t st) {
+    k_G_rows<<<(P.n_img + 127) / 128, 128, 0, st>>>(P, eop);
+    dim3 blk(32, 8), grd((P.off_cam + 31) / 32, (P.off_cam + 7) / 8);
+    k_add_GGt<<<grd, blk, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pad_diag(const DevProblem& P, cudaStream_t st) {
+    if (P.n_pad > P.n_red) k_pad_diag<<<1, 64, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+template <int NK, bool HC>
+static cudaError_t launch_assemble_t(const DevProblem& P, int sm_count, cudaStream_t st) {
+    const size_t smem = 4 * sizeof(AsmSmem<NK>);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_assemble<NK, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    int grid = (P.n_seg + 3) / 4;
+    const int cap = sm_count * 4;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    k_assemble<NK, HC><<<grid, 128, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_assemble(const DevProblem& P, int sm_count, cudaStream_t st) {
+    const bool hc = P.uc > 0;
+    FEBA_NK_DISPATCH(P.NK, hc, return (launch_assemble_t<NK_, HC_>(P, sm_count, st)));
+    return cudaSuccess;
+}
+
+int backsub_warps(const DevProblem& P, int sm_count) {
+    int grid = (P.n_seg + 3) / 4;
+    const int cap = sm_count * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    return grid * 4;
+}
+
+cudaError_t launch_backsub(const DevProblem& P, int sm_count, cudaStream_t st) {
+    const bool hc = P.uc > 0;
+    const int grid = backsub_warps(P, sm_count) / 4;
+    FEBA_NK_DISPATCH(P.NK, hc, (k_backsub<NK_, HC_><<<grid, 128, 0, st>>>(P)));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_update_cam(const DevProblem& P, const double* sol, double* dcam, double* dcam_unscaled,
+                              double* eop, double* iop, double* out_sumabs, cudaStream_t st) {
+    k_update_cam<<<1, 1024, 0, st>>>(P, sol, dcam, dcam_unscaled, eop, iop, out_sumabs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sum_partials(const double* partial, int n, int stride, int offset, double* out,
+                                cudaStream_t st) {
+    k_sum_partials<<<1, 1024, 0, st>>>(partial, n, stride, offset, out);
+    return cudaGetLastError();
+}
+
+static int stream_grid(int64_t n, int sm_count) {
+    int64_t grid = (n + 255) / 256;
+    if (grid > (int64_t)sm_count * 8) grid = (int64_t)sm_count * 8;
+    return grid < 1 ? 1 : (int)grid;
+}
+
+cudaError_t launch_xhat_scatter(const DevProblem& P, int sm_count, const double* xhat, double* eop, double* iop,
+                                const int* tie_pt, cudaStream_t st) {
+    const int64_t n = (int64_t)P.n_img * 6 + (int64_t)P.n_cam * P.NC + (int64_t)P.n_tie * 3;
+    k_xhat_scatter<<<stream_grid(n, sm_count), 256, 0, st>>>(P, xhat, eop, iop, tie_pt);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_xhat_gather(const DevProblem& P, int sm_count, double* xhat, const double* eop,
+                               const double* iop, const int* tie_pt, cudaStream_t st) {
+    const int64_t n = (int64_t)P.n_img * 6 + (int64_t)P.n_cam * P.NC + (int64_t)P.n_tie * 3;
+    k_xhat_gather<<<stream_grid(n, sm_count), 256, 0, st>>>(P, xhat, eop, iop, tie_pt);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_delta_gather(const DevProblem& P, int sm_count, double* delta, cudaStream_t st) {
+    k_delta_gather<<<stream_grid((int64_t)P.n_red + 3 * (int64_t)P.n_tie, sm_count), 256, 0, st>>>(P, delta);
+    return cudaGetLastError();
+}
+
+int debug_oob_count() {
+#ifdef FEBA_CHECK
+    int v = 0;
+    cudaMemcpyFromSymbol(&v, g_feba_oob, sizeof(int));
+    return v;
+#else
+    return -1;
+#endif
+}
+
+int residual_blocks(const DevProblem& P, int sm_count) {
+    int64_t grid = (P.n_obs + 255) / 256;
+    const int cap = sm_count * 8;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    return (int)grid;
+}
+
+cudaError_t launch_residuals(const DevProblem& P, int sm_count, const int* opt, const double* xyz_prev,
+                             const double* iop_new, double* v_out, double* rsd_out, cudaStream_t st) {
+    const bool hc = P.uc > 0;
+    const int grid = residual_blocks(P, sm_count);
+    FEBA_NK_DISPATCH(P.NK, hc, (k_residuals<NK_, HC_><<<grid, 256, 0, st>>>(P, opt, xyz_prev, iop_new, v_out, rsd_out)));
+    return cudaGetLastError();
+}
+
+}  // namespace feba

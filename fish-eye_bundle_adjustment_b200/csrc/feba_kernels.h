@@ -1,0 +1,42 @@
+// Host-callable launchers of the kernel translation units (internal header).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "feba_dev.h"
+
+namespace feba {
+
+// feba_kernels.cu
+cudaError_t launch_tables(const DevProblem& P, const double* eop, const double* iop, const double* cam_box,
+                          double* img_tab, double* cam_tab, cudaStream_t st);
+cudaError_t launch_xhat_scatter(const DevProblem& P, int sm_count, const double* xhat, double* eop, double* iop,
+                                const int* tie_pt, cudaStream_t st);
+cudaError_t launch_xhat_gather(const DevProblem& P, int sm_count, double* xhat, const double* eop,
+                               const double* iop, const int* tie_pt, cudaStream_t st);
+cudaError_t launch_delta_gather(const DevProblem& P, int sm_count, double* delta, cudaStream_t st);
+cudaError_t launch_constraints(const DevProblem& P, const double* eop, cudaStream_t st);
+cudaError_t launch_pad_diag(const DevProblem& P, cudaStream_t st);
+cudaError_t launch_assemble(const DevProblem& P, int sm_count, cudaStream_t st);
+int backsub_warps(const DevProblem& P, int sm_count);
+cudaError_t launch_backsub(const DevProblem& P, int sm_count, cudaStream_t st);
+cudaError_t launch_update_cam(const DevProblem& P, const double* sol, double* dcam, double* dcam_unscaled,
+                              double* eop, double* iop, double* out_sumabs, cudaStream_t st);
+cudaError_t launch_sum_partials(const double* partial, int n, int stride, int offset, double* out,
+                                cudaStream_t st);
+int debug_oob_count();   // -1 unless built with -DFEBA_CHECK
+int residual_blocks(const DevProblem& P, int sm_count);
+cudaError_t launch_residuals(const DevProblem& P, int sm_count, const int* opt, const double* xyz_prev,
+                             const double* iop_new, double* v_out, double* rsd_out, cudaStream_t st);
+
+// feba_chol.cu -- dense factorisation of the reduced camera system.
+// A: (nb+1)*kBlk square, column-major, leading dimension ld, lower triangle; the last block row is
+// the augmented block (right-hand side g in row 0, G columns in rows 1..7) and is not factorised:
+// on return A = [L 0; Y' T] with Y' = B' L^-T and T = -B' M^-1 B (Schur complement).
+// info (device int) is set non-zero when a pivot is not positive.
+cudaError_t chol_augmented(double* A, int ld, int nb, int* info, cudaStream_t st, int64_t* launches);
+// y (n_pad) := combination of the augmented rows: y = Y'(0,:) + sum_k kvec[k] Y'(1+k,:) where kvec
+// solves the 7x7 border system (inner != 0), else y = Y'(0,:).  Then sol := L^-T y.
+cudaError_t border_and_backsolve(double* A, int ld, int nb, int inner, double* work, double* sol, int* info,
+                                 cudaStream_t st, int64_t* launches);
+
+}  // namespace feba

@@ -1,0 +1,135 @@
+"""Host-side mirror of the reference's entry points over the C ABI.
+
+``main(folder, plot)``  -- main.m:10-32 (same arguments, returns ``main_error`` 0/1);
+``BatchRun(folders)``    -- BatchRun.m:42-65 with the GUI folder pick replaced by an argument and
+                            ``findfiles`` (BatchRun.m:68-150) kept as the recursive discovery;
+``adjust(prob)``         -- the part between "files are read" and "report is written":
+                            Buildxhat (main.m:388), the Gauss-Newton loop (main.m:412-494) and the
+                            residual stage (main.m:569-602), all on the GPU through ``lib.Handle``.
+
+The loop body is one ``feba_iterate`` per pass -- the MEX gateway a MATLAB user would call makes
+exactly these calls.  Console lines follow main.m (``Iteration k:``, the echoed
+``deltasum =``, ``Elapsed time is ...``, ``sigma02 =``).  Report formatting (.out) is out of scope;
+the numeric tables .rsd / .par inputs are returned and the .rsd table is written
+(main.m:957, BuildRSD.m:6,40).
+"""
+from __future__ import annotations
+
+import os
+import time
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import formats
+from .lib import FebaError, Handle
+from .problem import Buildxhat, Problem, load_problem
+
+
+def adjust(prob: Problem, xhat0: Optional[np.ndarray] = None, verbose: bool = True,
+           handle: Optional[Handle] = None) -> dict:
+    """main.m:386-602 for an already built ``data``.  Returns xhat, iterations, deltasum trace,
+    v, RSD (n_obs x 5: r vx vy vr vt), RMSx, RMSy, RMS, sigma02, elapsed seconds."""
+    prob.validate()
+    t0 = time.perf_counter()                                              # main.m:386 tic
+    if xhat0 is None:
+        err, xhat0, _ = Buildxhat(prob)                                   # main.m:388
+        if err:
+            raise FebaError(1, "Error building xhat")                     # main.m:389-393
+    own = handle is None
+    h = Handle(prob) if own else handle
+    try:
+        h.set_xhat(xhat0)
+        s = prob.settings
+        deltasum, count, trace = 100.0, 0, []                             # main.m:407-408
+        while deltasum > s.threshold:                                     # main.m:412
+            count += 1
+            if verbose:
+                print(f"Iteration {count}:")                              # main.m:414
+            deltasum = h.iterate()                                        # main.m:416-487
+            trace.append(deltasum)
+            if verbose:
+                print(f"deltasum = {deltasum:.6g}")                       # main.m:487 (echo)
+            if count >= s.Iteration_Cap:                                  # main.m:490-493
+                if verbose:
+                    print("Iteration Cap reached. This can be changed in the .cfg file")
+                break
+        xhat = h.get_xhat()
+        elapsed = time.perf_counter() - t0                                # main.m:496 toc
+        if verbose:
+            print(f"Elapsed time is {elapsed:.6f} seconds.")              # main.m:497
+        res = h.residuals()                                               # main.m:569-601
+        if verbose:
+            print(f"sigma02 = {res['sigma02']:.6g}")                      # main.m:601 (echo)
+        res.update(xhat=xhat, iterations=count, deltasum=trace, elapsed=elapsed,
+                   delta=h.get_delta(), timing=h.last_timing(), launches=h.launch_count())
+        return res
+    finally:
+        if own:
+            h.close()
+
+
+def write_rsd(path: str, prob: Problem, RSD: np.ndarray) -> None:
+    """``writecell(RSD, name.rsd, 'Delimiter','tab')`` (main.m:957): targetID imageID x y r vx vy vr vt."""
+    with open(path, "w") as fh:
+        for i in range(prob.n_obs):
+            row = [prob.point_name(int(prob.obs_pt[i])), prob.image_name(int(prob.obs_img[i])),
+                   repr(float(prob.obs_x[i])), repr(float(prob.obs_y[i]))]
+            row += [repr(float(val)) for val in RSD[i]]
+            fh.write("\t".join(row) + "\n")
+
+
+def main(folder: Optional[str] = None, plot: bool = True, cfg_folder: Optional[str] = None,
+         write_files: bool = True, verbose: bool = True):
+    """``main_error = main(folder, plot)`` (main.m:10).  ``folder`` None = current directory
+    (non-batch mode, main.m:24-31).  Returns 0/1; the results of the last run are in
+    ``main.last`` (MATLAB keeps them in the workspace / output files)."""
+    main.last = None
+    data_dir = os.getcwd() if folder is None else folder
+    try:
+        prob = load_problem(data_dir, cfg_folder=cfg_folder)               # main.m:60-384
+    except (OSError, IndexError, ValueError) as exc:
+        print(f"Error reading files ({exc})")
+        return 1
+    if prob is None:
+        return 1
+    try:
+        out = adjust(prob, verbose=verbose)
+    except (FebaError, ValueError) as exc:
+        print("Error building A and w")                                    # main.m:417-421
+        print(str(exc))
+        return 1
+    if write_files:
+        name = os.path.splitext(os.path.basename(prob.settings.Output_Filename))[0]
+        write_rsd(os.path.join(data_dir, name + ".rsd"), prob, out["RSD"])
+    if verbose:
+        print("Done!")
+    out["problem"] = prob
+    main.last = out
+    return 0
+
+
+main.last = None
+
+
+def findfiles(root: str, exts: Sequence[str] = (".pho", ".ext", ".cnt", ".int")) -> List[str]:
+    """BatchRun.m:68-150: folders (recursively) that hold exactly one file of each extension."""
+    found = []
+    for cur, dirs, files in os.walk(root):
+        dirs.sort()
+        if all(sum(f.endswith(e) for f in files) == 1 for e in exts):
+            found.append(cur)
+    return found
+
+
+def BatchRun(selpath: Sequence[str], cfg_folder: Optional[str] = None, verbose: bool = False) -> int:
+    """BatchRun.m:42-65: run ``main(folder, false)`` over every data folder; stop at the first
+    error.  The reference runs them one at a time on the host; each adjustment here runs on the
+    current CUDA device (the multi-GPU sweep shards folders over ranks, see ``bench.py``)."""
+    allfolders: List[str] = []
+    for p in selpath:
+        allfolders += findfiles(p)
+    for folder in allfolders:
+        if main(folder, False, cfg_folder=cfg_folder, verbose=verbose) == 1:
+            return 1
+    return 0

@@ -1,0 +1,165 @@
+/*
+ * feba.h -- C ABI of the B200-native Gauss-Newton hot path of the equidistant fish-eye
+ * bundle adjustment (drop-in for the loop body of the reference's main.m).
+ *
+ * The reference (MATLAB) has no FFI for this path; its seams are the function calls
+ *   main.m:388  [xhaterror,xhat,xhatnames] = Buildxhat(data,EXT,INT,TIE,CNT)
+ *   main.m:416  [Awerror,A,w,G,dist_scaling] = BuildAwG(data,xhat)
+ *   main.m:424-493  u=A'Pw, N=A'PA, (bordered) inverse, delta, un-scaling, update, sumabs
+ *   main.m:569  v = A*delta + w
+ *   main.m:571  RSD = BuildRSD(v,data,xhat)
+ *   main.m:594-602  RMSx, RMSy, RMS, sigma02
+ * Because A (n x u) and N (u x u) are never materialised on the device, the seam sits one level
+ * above BuildAwG: feba_iterate() is one pass of the while-body of main.m:412-494.  The MEX
+ * gateway (fish-eye_bundle_adjustment_b200/mex/feba_mex.c) and INTEGRATION.md show the
+ * MATLAB-side binding.
+ *
+ * Conventions: every function returns an int status, 0 = ok, non-zero = error (the reference's
+ * 0/1 `error` flags, BuildAwG.m:16, Buildxhat.m:3, main.m:23); feba_last_error() gives the text.
+ * All pointers are HOST pointers owned by the caller unless a name says `dev`.  Indices are
+ * 0-based (reference value minus one).  Calls are synchronous.  One handle must not be used
+ * from two host threads at once; different handles are independent.  There is no CPU fallback:
+ * without a CUDA device feba_create() fails.
+ */
+#ifndef FEBA_H
+#define FEBA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FEBA_VERSION 100
+#define FEBA_MAX_NK 8 /* largest Num_Radial_Distortions supported by the kernels */
+
+enum feba_status {
+    FEBA_OK = 0,
+    FEBA_ERR_INVALID = 1,    /* bad argument / unsupported settings combination        */
+    FEBA_ERR_CUDA = 2,       /* CUDA runtime failure (text in feba_last_error)         */
+    FEBA_ERR_NUMERIC = 3,    /* reduced normal matrix not positive definite, NaN, ...  */
+    FEBA_ERR_STATE = 4       /* call order (e.g. residuals before any iterate)         */
+};
+
+/* data.settings (main.m:112-177) -- the subset the hot path depends on. */
+typedef struct feba_settings {
+    int32_t estimate_eop[6];    /* Estimate_Xc Yc Zc Omega Phi Kappa   (main.m:158-163)  */
+    int32_t estimate_xp;        /* main.m:166 */
+    int32_t estimate_yp;        /* main.m:167 */
+    int32_t estimate_c;         /* main.m:165 */
+    int32_t estimate_radial;    /* Estimate_Radial_Distortions          (main.m:169)     */
+    int32_t num_radial;         /* Num_Radial_Distortions, clamped to >=1 (BuildAwG.m:18) */
+    int32_t estimate_decent;    /* Estimate_Decentering_Distortions     (main.m:171)     */
+    int32_t inner_constraints;  /* Inner_Constraints                    (main.m:156)     */
+    int32_t type;               /* typeint 0..4: fisheye pinhole equisolid orthographic
+                                   stereographic                        (BuildAwG.m:184-208) */
+    int32_t iteration_cap;      /* Iteration_Cap   (main.m:153, used by feba_solve only) */
+    int32_t reserved;
+    double sigma_x;             /* Meas_std                             (main.m:123)     */
+    double sigma_y;             /* Meas_std_y, = sigma_x when absent    (main.m:397-402) */
+    double threshold;           /* Threshold_Value (main.m:154, used by feba_solve only) */
+} feba_settings;
+
+/* The reference's `data` struct (main.m:277-384) as numeric structure-of-arrays. */
+typedef struct feba_problem {
+    int64_t n_obs;              /* data.n / 2                           (main.m:381)      */
+    int32_t n_img;              /* data.numImg                          (main.m:379)      */
+    int32_t n_cam;              /* data.numCam                          (main.m:380)      */
+    int32_t n_pts;              /* rows of CNT                                           */
+    int32_t n_tie;              /* data.numtie = rows of TIE            (main.m:383)      */
+    const double *obs_x;        /* [n_obs] data.points(i).x             (main.m:282)      */
+    const double *obs_y;        /* [n_obs] data.points(i).y             (main.m:283)      */
+    const int32_t *obs_img;     /* [n_obs] ext_index - 1                (main.m:298)      */
+    const int32_t *obs_pt;      /* [n_obs] cnt_index - 1                (main.m:358)      */
+    const int32_t *img_cam;     /* [n_img] cam_num - 1 of the image     (main.m:322)      */
+    const double *eop0;         /* [n_img*6] Xc Yc Zc w p k (rad), row-major (main.m:301-307) */
+    const double *iop0;         /* [n_cam*(3+NK+2)] xp yp c k1..kNK p1 p2 (main.m:324-330) */
+    const double *cam_box;      /* [n_cam*5] y_dir xmin ymin xmax ymax  (main.m:331-343)  */
+    const double *xyz0;         /* [n_pts*3] X Y Z                      (main.m:359-361)  */
+    const int32_t *pt_tie;      /* [n_pts] tieIndex - 1, or -1          (main.m:362-375)  */
+    feba_settings settings;
+} feba_problem;
+
+typedef struct feba_handle feba_handle;
+
+/* Multi-GPU runs: one handle per rank on its own device.  Each rank passes the full
+ * image / camera tables and ONLY ITS OWN object points (xyz0, pt_tie, n_tie local) and their
+ * observations; partial reduced systems are summed between feba_iterate_assemble() and
+ * feba_iterate_solve() through feba_reduced_dev(). */
+
+/* Upload the problem to the current CUDA device, sort/segment observations by point, allocate
+ * block storage.  Replaces the per-iteration allocations of BuildAwG.m:29-42. */
+int feba_create(const feba_problem *problem, feba_handle **out);
+/* Run this handle's kernels and copies on a caller-owned CUDA stream (a cudaStream_t passed as
+ * void*; e.g. the stream the caller's NCCL all-reduce is enqueued on).  Default: a private
+ * non-blocking stream. */
+int feba_set_stream(feba_handle *h, void *cuda_stream);
+void feba_destroy(feba_handle *h);
+const char *feba_last_error(const feba_handle *h); /* h may be NULL: last create error */
+
+/* Number of unknowns u, and the split u_c (EOP+IOP part) / 3*n_tie (Buildxhat.m:5-15). */
+int feba_num_unknowns(const feba_handle *h, int64_t *u, int64_t *u_c);
+
+/* xhat in the layout of Buildxhat.m:22-135 (length u). */
+int feba_set_xhat(feba_handle *h, const double *xhat, size_t u);
+int feba_get_xhat(feba_handle *h, double *xhat, size_t u);
+
+/* One Gauss-Newton step = body of the while loop main.m:412-494:
+ * BuildAwG + normal equations + (bordered) solve + un-scaling + xhat += delta.
+ * deltasum_out = sumabs(delta) (main.m:487).  */
+int feba_iterate(feba_handle *h, double *deltasum_out);
+
+/* The same step in two halves, for multi-GPU runs: _assemble forms this rank's
+ * partial reduced camera system (point blocks eliminated) on the device; the caller sums
+ * feba_reduced_dev() across ranks (ncclAllReduce / torch.distributed.all_reduce, sum, f64);
+ * _solve adds the inner-constraint border, factorises, updates the EOP/IOP part (identical on
+ * every rank), back-substitutes THIS rank's points.  deltasum_cam = sum|delta| over the EOP/IOP
+ * part, deltasum_pts = over this rank's tie points: sumabs(delta) of main.m:487 is
+ * deltasum_cam + sum over ranks of deltasum_pts. */
+int feba_iterate_assemble(feba_handle *h);
+int feba_reduced_dev(feba_handle *h, double **dev_ptr, size_t *count);
+int feba_iterate_solve(feba_handle *h, double *deltasum_cam, double *deltasum_pts);
+
+/* Last increment delta (un-scaled, main.m:458-482), length u. */
+int feba_get_delta(feba_handle *h, double *delta, size_t u);
+
+/* After the loop: v = A*delta + w of the LAST iteration (main.m:569), BuildRSD columns
+ * r vx vy vr vt (BuildRSD.m:29-40) in PHO row order, and stats = {RMSx, RMSy, RMS, sigma02,
+ * sum vx^2, sum vy^2} (main.m:594-601).  v: [2*n_obs] interleaved x,y; rsd: [n_obs*5] row-major.
+ * Either output pointer may be NULL.  sigma02 uses this handle's own n and u (main.m:601, n - u);
+ * multi-GPU callers recombine it from stats[4], stats[5] of every rank.  */
+int feba_residuals(feba_handle *h, double *v, double *rsd, double stats[6]);
+
+/* Whole loop main.m:412-494 on the device: iterate until deltasum <= threshold or the cap.
+ * iterations_out, trace_out[<=cap] (deltasum per iteration, may be NULL). */
+int feba_solve(feba_handle *h, int32_t *iterations_out, double *trace_out, size_t trace_cap);
+
+/* Timing of the last completed iteration in milliseconds (CUDA events on the handle's stream):
+ * ms[0] parameter tables + clearing S, ms[1] fused BuildAwG/normal-blocks/Schur kernel,
+ * ms[2] border + Cholesky (includes the caller's all-reduce in a multi-GPU run), ms[3] border
+ * solve + backward substitution, ms[4] update + point back-substitution, ms[5] total. */
+int feba_last_timing(const feba_handle *h, double ms[6]);
+
+/* Kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
+int64_t feba_launch_count(const feba_handle *h);
+
+/* Diagnostic for parity tests: the point-eliminated camera system left by a pending
+ * feba_iterate_assemble() (S = N_cc - W V^-1 W', g = u_c - W V^-1 u_p; main.m:424-425 reduced),
+ * S_out [u_c*u_c] column-major full symmetric, g_out [u_c]; either may be NULL. */
+int feba_debug_reduced(feba_handle *h, double *S_out, double *g_out);
+
+/* Diagnostic: number of out-of-range accumulation targets caught by a -DFEBA_CHECK build of the
+ * kernels (compute-sanitizer stand-in); -1 in a normal build. */
+int feba_debug_oob(void);
+
+/* Device-resident variant for benchmarking with inputs already in HBM: identical to
+ * feba_iterate but never copies deltasum back unless asked (deltasum_out may be NULL). */
+int feba_iterate_async(feba_handle *h);
+int feba_iterate_solve_async(feba_handle *h); /* second half only (after the caller's all-reduce) */
+int feba_sync(feba_handle *h, double *deltasum_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEBA_H */

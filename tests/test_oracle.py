@@ -1,0 +1,142 @@
+"""The CPU oracle against (1) the reference's own BuildAwG.m statements executed from the
+reference source (when /root/reference is mounted), (2) the frozen outputs of those statements
+(tests/golden/cam0_refsrc_t*.npz), (3) finite differences, (4) its own independent
+block-sparse/Schur restatement, (5) the frozen Gauss-Newton runs."""
+import numpy as np
+import pytest
+
+import feba_b200 as fb
+from oracle import dense, model, refexpr, sparse
+from tests import golden
+
+TYPES = refexpr.TYPE_NAMES
+
+
+def _rel(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+@pytest.mark.parametrize("t", range(5))
+def test_model_matches_frozen_reference_statements(t):
+    prob = golden.load_cam0(type=TYPES[t])
+    err, xhat0, _ = fb.Buildxhat(prob)
+    eop, iop, xyz = model.gather_params(prob, xhat0)
+    q = model.observation_equations(prob, eop, iop, xyz)
+    z = np.load(golden.path(f"cam0_refsrc_t{t}.npz"))
+    assert _rel(q["fx"], z["fx"]) < 1e-13 and _rel(q["fy"], z["fy"]) < 1e-13
+    assert np.max(np.abs(q["w"] - z["w"])) < 1e-9          # w = f - obs: absolute, pixels
+    # generated closed forms cancel heavily (1e-15 .. 5e-13 over models)
+    for k in ("Je", "Jt", "Jc"):
+        assert _rel(q[k], z[k]) < 5e-11, k
+    assert _rel(model.G_rows(eop), z["G"]) < 1e-14
+    assert _rel(q["scale"][prob.img_cam[prob.obs_img]], z["scale"]) < 1e-15
+
+
+@pytest.mark.skipif(not refexpr.available(), reason="reference tree not mounted")
+@pytest.mark.parametrize("t", range(5))
+def test_model_matches_reference_source_live(t):
+    """Same comparison with the statements harvested NOW from /root/reference, at a perturbed
+    point (so it is not the same evaluation as the frozen one)."""
+    prob = golden.load_cam0(type=TYPES[t])
+    err, xhat0, _ = fb.Buildxhat(prob)
+    rng = np.random.default_rng(7 + t)
+    xhat = xhat0 * (1 + 1e-4 * rng.standard_normal(xhat0.size))
+    eop, iop, xyz = model.gather_params(prob, xhat)
+    q = model.observation_equations(prob, eop, iop, xyz)
+    r = refexpr.reference_observation_equations(prob, eop, iop, xyz)
+    for k in ("fx", "fy"):
+        assert _rel(q[k], r[k]) < 1e-13
+    for k in ("Je", "Jt", "Jc"):
+        assert _rel(q[k], r[k]) < 5e-11, k
+    assert _rel(model.G_rows(eop), r["G"]) < 1e-14
+
+
+def test_frozen_problem_equals_reference_files():
+    if not refexpr.available():
+        pytest.skip("reference tree not mounted")
+    a = fb.load_problem(refexpr.REFERENCE_ROOT)
+    b = golden.load_cam0()
+    for k in ("obs_x", "obs_y", "obs_img", "obs_pt", "img_cam", "eop0", "iop0", "cam_box", "xyz0", "pt_tie"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert a.settings == b.settings
+
+
+@pytest.mark.parametrize("t", [0, 1, 4])
+def test_jacobian_finite_differences(t):
+    prob = golden.load_cam0(type=TYPES[t])
+    err, xhat0, _ = fb.Buildxhat(prob)
+    eop, iop, xyz = model.gather_params(prob, xhat0)
+    q = model.observation_equations(prob, eop, iop, xyz)
+    idx = np.arange(0, prob.n_obs, 37)
+
+    def f(e, i, x):
+        o = model.observation_equations(prob, e, i, x, idx=idx)
+        return np.stack([o["fx"], o["fy"]], -1)
+
+    for col in range(6):
+        h = 1e-3 if col < 3 else 1e-7
+        ep, em = eop.copy(), eop.copy()
+        ep[:, col] += h; em[:, col] -= h
+        fd = (f(ep, iop, xyz) - f(em, iop, xyz)) / (2 * h)
+        assert np.max(np.abs(fd - q["Je"][idx, :, col])) < 2e-5 * max(1, np.max(np.abs(fd))), col
+    for col in range(3):
+        xp_, xm_ = xyz.copy(), xyz.copy()
+        xp_[:, col] += 1e-3; xm_[:, col] -= 1e-3
+        fd = (f(eop, iop, xp_) - f(eop, iop, xm_)) / 2e-3
+        assert np.max(np.abs(fd - q["Jt"][idx, :, col])) < 2e-5 * max(1, np.max(np.abs(fd)))
+    NK = prob.settings.NK
+    sc = q["scale"][0]
+    for col in range(3 + NK + 2):
+        mag = abs(iop[0, col])
+        h = 1e-4 if col < 3 else max(mag, 1e-12) * 1e-3
+        ip, im_ = iop.copy(), iop.copy()
+        ip[:, col] += h; im_[:, col] -= h
+        fd = (f(eop, ip, xyz) - f(eop, im_, xyz)) / (2 * h)
+        if 3 <= col < 3 + NK:
+            fd = fd / sc[col - 3]          # columns are pre-divided by r_max^(2j) (BuildAwG.m:433-434)
+        elif col >= 3 + NK:
+            fd = fd / sc[0]                # and by r_max^2 (BuildAwG.m:441-442)
+        an = q["Jc"][idx, :, col]
+        assert np.max(np.abs(fd - an)) < 1e-5 * max(1e-12, np.max(np.abs(an))), col
+
+
+@pytest.mark.parametrize("name", ["pinhole", "fisheye"])
+def test_dense_oracle_reproduces_frozen_run(name):
+    prob = golden.load_cam0(type=name)
+    z = np.load(golden.path(f"cam0_gn_{name}.npz"))
+    out = dense.gauss_newton(prob, z["xhat0"])
+    assert out["iterations"] == int(z["iterations"])
+    assert np.allclose(out["deltasum"][:3], z["deltasum"][:3], rtol=1e-6)
+    assert abs(out["sigma02"] - float(z["sigma02"])) < 1e-9 * float(z["sigma02"])
+    assert np.max(np.abs(out["v"] - z["v"])) < 1e-8
+    # survey-time anchors
+    if name == "pinhole":
+        assert out["iterations"] == 5 and abs(out["sigma02"] - 0.618691873512) < 1e-9
+        assert abs(out["deltasum"][0] - 0.1430413) < 1e-6
+
+
+def test_sparse_schur_path_agrees_with_dense():
+    prob = golden.load_cam0()
+    err, xhat0, _ = fb.Buildxhat(prob)
+    a = dense.gauss_newton(prob, xhat0)
+    b = sparse.gauss_newton(prob, xhat0)
+    assert a["iterations"] == b["iterations"]
+    assert np.max(np.abs(a["v"] - b["v"])) < 1e-8
+    assert abs(a["sigma02"] - b["sigma02"]) < 1e-10
+    # gauge-invariant IOP part
+    L = model.layout(prob)
+    sl = slice(L["off_cam"], L["off_tie"])
+    assert np.max(np.abs(a["xhat"][sl] - b["xhat"][sl]) / np.abs(a["xhat"][sl])) < 1e-9
+
+
+def test_sparse_path_on_small_synthetic_networks():
+    from feba_b200 import synth
+    for mode, kw in (("eop", {}), ("free", {}), ("mixed", dict(n_control=12))):
+        prob = synth.make_network(12, 300, 6, 99, mode=mode, **kw)
+        err, xhat0, _ = fb.Buildxhat(prob)
+        a = dense.gauss_newton(prob, xhat0)
+        b = sparse.gauss_newton(prob, xhat0)
+        assert a["iterations"] == b["iterations"], mode
+        assert np.max(np.abs(a["v"] - b["v"])) < 1e-8, mode
+        assert abs(a["sigma02"] - b["sigma02"]) < 1e-8 * a["sigma02"], mode
+        assert 0.5 < a["sigma02"] < 2.0, (mode, a["sigma02"])    # noise model consistent
