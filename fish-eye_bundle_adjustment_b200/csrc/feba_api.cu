@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -35,6 +36,7 @@ struct feba_handle {
     // device state
     double *eop = nullptr, *iop = nullptr, *cam_box = nullptr, *img_tab = nullptr, *cam_tab = nullptr;
     double *xhat = nullptr, *sol = nullptr, *dcam = nullptr, *dcam_unscaled = nullptr, *work = nullptr;
+    double *ywork = nullptr, *Linv = nullptr, *dvec = nullptr;
     double *scal = nullptr;       // [0] sumabs camera part, [1] sumabs points, [2] sum vx^2, [3] sum vy^2
     double *v_out = nullptr, *rsd_out = nullptr, *delta_out = nullptr;
     int *opt = nullptr, *tie_pt = nullptr, *info = nullptr;
@@ -46,6 +48,15 @@ struct feba_handle {
     int64_t launches = 0;
     int iterations = 0;           // completed iterations since the last set_xhat
     int phase = 0;                // 0 idle, 1 assembled (waiting for solve)
+    // CUDA graphs of the two halves of an iteration (launch-bound inner loops: ~1,900 kernels per
+    // iteration at u_c = 12,010).  Call 0 of a phase runs eagerly, call 1 is captured, later calls replay.
+    struct GraphSlot {
+        cudaGraphExec_t exec = nullptr;
+        int64_t launches = 0;
+        int calls = 0;
+    } g_assemble, g_solve;
+    bool use_graph = true;
+    bool capturing = false;
     double timing[6] = {0, 0, 0, 0, 0, 0};
     bool timing_valid = false;
     std::string err;
@@ -71,6 +82,20 @@ int fail(feba_handle* h, int code, const char* fmt, ...) {
             return fail(h, FEBA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
                         __LINE__);                                                                   \
     } while (0)
+
+// Event record that also works inside stream capture (external-record node keeps the timestamp).
+cudaError_t record(feba_handle* h, int i) {
+    return h->capturing ? cudaEventRecordWithFlags(h->ev[i], h->stream, cudaEventRecordExternal)
+                        : cudaEventRecord(h->ev[i], h->stream);
+}
+
+void drop_graphs(feba_handle* h) {
+    for (feba_handle::GraphSlot* g : {&h->g_assemble, &h->g_solve}) {
+        if (g->exec) cudaGraphExecDestroy(g->exec);
+        g->exec = nullptr;
+        if (g->calls > 1) g->calls = 1;
+    }
+}
 
 template <typename T>
 cudaError_t dev_alloc(feba_handle* h, T** p, size_t count) {
@@ -127,6 +152,7 @@ void feba_destroy(feba_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     if (h->scal_host) cudaFreeHost(h->scal_host);
     if (h->info_host) cudaFreeHost(h->info_host);
+    drop_graphs(h);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -159,6 +185,7 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
     h->own_stream = true;
     for (auto& e : h->ev) CU(h, cudaEventCreate(&e));
     h->cfg = pr->settings;
+    h->use_graph = std::getenv("FEBA_NO_GRAPH") == nullptr;
     const feba_settings& s = pr->settings;
 
     DevProblem& P = h->P;
@@ -272,6 +299,10 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
     CU(h, dev_alloc(h, &h->dcam_unscaled, (size_t)P.n_pad));
     CU(h, dev_alloc(h, &P.dpts, (size_t)pr->n_tie * 3));
     CU(h, dev_alloc(h, &h->work, 64));
+    CU(h, dev_alloc(h, &h->ywork, (size_t)P.n_pad));
+    CU(h, dev_alloc(h, &h->dvec, (size_t)P.n_pad));
+    CU(h, dev_alloc(h, &h->Linv, (size_t)(P.n_pad / kBlk) * kBlk * kBlk));
+    CU(h, dev_alloc(h, &P.Gt, (size_t)(P.off_cam > 0 ? P.off_cam : 1) * 8));
     CU(h, dev_alloc(h, &h->scal, 8));
     CU(h, dev_alloc(h, &h->info, 1));
     CU(h, cudaMallocHost((void**)&h->scal_host, 8 * sizeof(double)));
@@ -312,6 +343,7 @@ int feba_set_stream(feba_handle* h, void* stream) {
     if (!h) return FEBA_ERR_INVALID;
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamSynchronize(h->stream));
+    drop_graphs(h);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     h->stream = static_cast<cudaStream_t>(stream);
     h->own_stream = false;
@@ -363,18 +395,54 @@ int feba_get_delta(feba_handle* h, double* delta, size_t u) {
 }
 
 // ---- one Gauss-Newton step, first half: tables, zero S, fused BuildAwG + normal blocks + Schur.
-int feba_iterate_assemble(feba_handle* h) {
-    if (!h) return FEBA_ERR_INVALID;
-    CU(h, cudaSetDevice(h->device));
+static int enqueue_assemble(feba_handle* h) {
     DevProblem& P = h->P;
-    CU(h, cudaEventRecord(h->ev[0], h->stream));
+    CU(h, record(h, 0));
     CU(h, launch_tables(P, h->eop, h->iop, h->cam_box, h->img_tab, h->cam_tab, h->stream));
     CU(h, cudaMemsetAsync(P.S, 0, h->S_count * sizeof(double), h->stream));
     CU(h, cudaMemsetAsync(h->info, 0, sizeof(int), h->stream));
-    CU(h, cudaEventRecord(h->ev[1], h->stream));
+    CU(h, record(h, 1));
     CU(h, launch_assemble(P, h->sm_count, h->stream));
     h->launches += 2;
-    CU(h, cudaEventRecord(h->ev[2], h->stream));
+    CU(h, record(h, 2));
+    return FEBA_OK;
+}
+
+// Run one phase eagerly (first call: kernels set their attributes), capture it (second call) or
+// replay its graph.
+static int run_phase(feba_handle* h, feba_handle::GraphSlot& g, int (*fn)(feba_handle*)) {
+    const int call = g.calls++;
+    if (!h->use_graph || call == 0) return fn(h);
+    if (!g.exec) {
+        const int64_t before = h->launches;
+        CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        h->capturing = true;
+        const int rc = fn(h);
+        h->capturing = false;
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        CU(h, e);
+        g.launches = h->launches - before;
+        const cudaError_t ei = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        CU(h, ei);
+        CU(h, cudaGraphLaunch(g.exec, h->stream));
+        return FEBA_OK;
+    }
+    CU(h, cudaGraphLaunch(g.exec, h->stream));
+    h->launches += g.launches;
+    return FEBA_OK;
+}
+
+int feba_iterate_assemble(feba_handle* h) {
+    if (!h) return FEBA_ERR_INVALID;
+    CU(h, cudaSetDevice(h->device));
+    const int rc = run_phase(h, h->g_assemble, enqueue_assemble);
+    if (rc) return rc;
     h->phase = 1;
     return FEBA_OK;
 }
@@ -387,21 +455,16 @@ int feba_reduced_dev(feba_handle* h, double** dev_ptr, size_t* count) {
 }
 
 // ---- second half: inner-constraint border, factorisation, solve, update, back-substitution.
-static int solve_async(feba_handle* h) {
+static int enqueue_solve(feba_handle* h) {
     DevProblem& P = h->P;
-    if (h->phase != 1) return fail(h, FEBA_ERR_STATE, "feba_iterate_solve without feba_iterate_assemble");
-    if (P.inner) {
-        CU(h, launch_constraints(P, h->eop, h->stream));
-        h->launches += 2;
-    }
-    CU(h, launch_pad_diag(P, h->stream));
-    if (P.n_pad > P.n_red) ++h->launches;
+    CU(h, launch_border_scale(P, h->eop, h->dvec, h->info, h->stream, &h->launches));
     const int nb = P.n_pad / kBlk;
-    CU(h, chol_augmented(P.S, P.ld, nb, h->info, h->stream, &h->launches));
-    CU(h, cudaEventRecord(h->ev[3], h->stream));
-    CU(h, border_and_backsolve(P.S, P.ld, nb, P.inner, h->work, h->sol, h->info, h->stream, &h->launches));
-    CU(h, cudaEventRecord(h->ev[4], h->stream));
-    CU(h, launch_update_cam(P, h->sol, h->dcam, h->dcam_unscaled, h->eop, h->iop, h->scal, h->stream));
+    CU(h, chol_augmented(P.S, P.ld, nb, h->Linv, h->info, h->stream, &h->launches));
+    CU(h, record(h, 3));
+    CU(h, border_and_backsolve(P.S, P.ld, nb, h->Linv, P.inner, h->work, h->ywork, h->sol, h->info, h->sm_count,
+                               h->stream, &h->launches));
+    CU(h, record(h, 4));
+    CU(h, launch_update_cam(P, h->sol, h->dvec, h->dcam, h->dcam_unscaled, h->eop, h->iop, h->scal, h->stream));
     ++h->launches;
     if (P.n_tie > 0 && P.n_seg > 0) {
         CU(h, launch_backsub(P, h->sm_count, h->stream));
@@ -410,7 +473,14 @@ static int solve_async(feba_handle* h) {
     } else {
         CU(h, cudaMemsetAsync(h->scal + 1, 0, sizeof(double), h->stream));
     }
-    CU(h, cudaEventRecord(h->ev[5], h->stream));
+    CU(h, record(h, 5));
+    return FEBA_OK;
+}
+
+static int solve_async(feba_handle* h) {
+    if (h->phase != 1) return fail(h, FEBA_ERR_STATE, "feba_iterate_solve without feba_iterate_assemble");
+    const int rc = run_phase(h, h->g_solve, enqueue_solve);
+    if (rc) return rc;
     h->phase = 0;
     ++h->iterations;
     return FEBA_OK;

@@ -41,11 +41,14 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-template <bool LOWER>
+// MODE 0: C -= A B'   MODE 1: the same, tiles of the lower block triangle only (SYRK-shaped update)
+// MODE 2: C = A B' (overwrite).  MODE 2 may run in place (C == A, one tile column, K == 64): every
+// global read of the CTA's A rows has landed in shared memory before its first store.
+template <int MODE>
 __global__ void __launch_bounds__(128) k_gemm_nt(double* __restrict__ C, int ldc, const double* __restrict__ A,
                                                  int lda, const double* __restrict__ B, int ldb, int K) {
     const int bx = blockIdx.x, by = blockIdx.y;
-    if (LOWER && by > bx) return;
+    if (MODE == 1 && by > bx) return;
     extern __shared__ __align__(16) double gsm[];
     double(*As)[GK][GS] = reinterpret_cast<double(*)[GK][GS]>(gsm);
     double(*Bs)[GK][GS] = reinterpret_cast<double(*)[GK][GS]>(gsm + GSTAGES * GK * GS);
@@ -98,6 +101,7 @@ __global__ void __launch_bounds__(128) k_gemm_nt(double* __restrict__ C, int ldc
         }
     }
     cp_async_wait<0>();
+    if (MODE == 2) __syncthreads();
     double* Cg = C + (size_t)bx * GT + (size_t)ldc * by * GT;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -105,130 +109,146 @@ __global__ void __launch_bounds__(128) k_gemm_nt(double* __restrict__ C, int ldc
         for (int j = 0; j < 4; ++j) {
             const int r = wm * 32 + i * 8 + lr;
             const int c = wn * 32 + j * 8 + 2 * lk;
-            Cg[r + (size_t)ldc * c] -= acc[i][j][0];
-            Cg[r + (size_t)ldc * (c + 1)] -= acc[i][j][1];
+            if (MODE == 2) {
+                Cg[r + (size_t)ldc * c] = acc[i][j][0];
+                Cg[r + (size_t)ldc * (c + 1)] = acc[i][j][1];
+            } else {
+                Cg[r + (size_t)ldc * c] -= acc[i][j][0];
+                Cg[r + (size_t)ldc * (c + 1)] -= acc[i][j][1];
+            }
         }
 }
 
 // ------------------------------------------------------------------------------------------
-// 64x64 Cholesky of a diagonal block (lower), one CTA.
-__global__ void __launch_bounds__(256) k_potrf64(double* __restrict__ A, int ld, int* __restrict__ info) {
-    __shared__ double s[kBlk][kBlk + 1];
-    const int tid = threadIdx.x;
-    for (int q = tid; q < kBlk * kBlk; q += 256) {
-        const int r = q & 63, c = q >> 6;
-        s[r][c] = (r >= c) ? A[r + (size_t)ld * c] : 0.0;
-    }
-    __syncthreads();
-    for (int j = 0; j < kBlk; ++j) {
-        const double d = s[j][j];
-        if (!(d > 0.0)) {
-            if (tid == 0) atomicExch(info, 1);
-        }
-        const double rd = 1.0 / sqrt(d);
-        __syncthreads();
-        if (tid >= j && tid < kBlk) s[tid][j] = (tid == j) ? sqrt(d) : s[tid][j] * rd;
-        __syncthreads();
-        // trailing update: s[r][c] -= s[r][j]*s[c][j], j < c <= r
-        const int m = kBlk - 1 - j;
-        for (int q = tid; q < m * m; q += 256) {
-            const int r = j + 1 + q / m, c = j + 1 + q % m;
-            if (c <= r) s[r][c] -= s[r][j] * s[c][j];
-        }
-        __syncthreads();
-    }
-    for (int q = tid; q < kBlk * kBlk; q += 256) {
-        const int r = q & 63, c = q >> 6;
-        if (r >= c) A[r + (size_t)ld * c] = s[r][c];
-    }
-}
-
-// X (rows x 64) := X * L^-T, L the 64x64 lower-triangular diagonal block.  One thread per row.
-__global__ void __launch_bounds__(64) k_trsm64(double* __restrict__ X, int ldx, const double* __restrict__ L,
-                                               int ldl) {
-    __shared__ double sl[kBlk][kBlk + 1];
-    __shared__ double sinv[kBlk];
-    const int tid = threadIdx.x;
-    for (int q = tid; q < kBlk * kBlk; q += 64) {
-        const int r = q & 63, c = q >> 6;
-        sl[r][c] = L[r + (size_t)ldl * c];
-    }
-    __syncthreads();
-    sinv[tid] = 1.0 / sl[tid][tid];
-    __syncthreads();
-    double* xr = X + (size_t)blockIdx.x * kBlk + tid;
-    double x[kBlk];
+// 64x64 Cholesky of a diagonal block (lower) and the inverse of its factor, one CTA of 256 threads.
+// Thread (r, q) = (tid >> 2, tid & 3) keeps the entries (r, 4i+q), i = 0..15, of row r in registers.
+// Right-looking: at step j the owners publish the unscaled column j through shared memory
+// (double-buffered: one barrier per step); everyone scales by 1/d and updates its own entries.
+// Then Linv = L^-1 by forward substitution on the identity: thread (c, q) holds the entries
+// k = 4i+q of column c, the row dot products are closed with two shuffles.  Linv (full 64x64,
+// zero upper triangle) lets every later triangular solve with this block run as a DMMA GEMM.
+__global__ void __launch_bounds__(256) k_potrf64_inv(double* __restrict__ A, int ld, double* __restrict__ Linv,
+                                                    int* __restrict__ info) {
+    __shared__ double col[2][kBlk];
+    __shared__ double sL[kBlk][kBlk + 1];
+    const int tid = threadIdx.x, r = tid >> 2, q = tid & 3;
+    double a[16];
 #pragma unroll
-    for (int c = 0; c < kBlk; ++c) x[c] = xr[(size_t)ldx * c];
+    for (int i = 0; i < 16; ++i) {
+        const int c = 4 * i + q;
+        a[i] = (c <= r) ? A[r + (size_t)ld * c] : 0.0;
+    }
+    bool bad = false;
 #pragma unroll
     for (int j = 0; j < kBlk; ++j) {
-        x[j] *= sinv[j];
+        if (q == (j & 3)) col[j & 1][r] = a[j >> 2];          // unscaled column j (rows < j hold junk, unused)
+        __syncthreads();
+        const double d = col[j & 1][j];
+        if (!(d > 0.0)) bad = true;
+        const double inv_d = 1.0 / d;
+        const double xr = col[j & 1][r] * inv_d;              // l_rj / l_jj
+        if (r > j) {
 #pragma unroll
-        for (int k = j + 1; k < kBlk; ++k) x[k] -= x[j] * sl[k][j];
+            for (int i = (j + 1) >> 2; i < 16; ++i) {
+                const int c = 4 * i + q;
+                if (c > j && c <= r) a[i] -= xr * col[j & 1][c];
+            }
+        }
+        if (q == (j & 3) && r >= j) a[j >> 2] *= rsqrt(d);    // final L(r, j)
+    }
+    if (bad && tid == 0) atomicExch(info, 1);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int c = 4 * i + q;
+        if (c <= r) A[r + (size_t)ld * c] = a[i];
+        sL[r][c] = (c <= r) ? a[i] : 0.0;
+    }
+    __syncthreads();
+    // inverse: column c = r (reuse the (r, q) split as (column, k-phase))
+    const int c = r;
+    double x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < kBlk; ++i) {
+        double part = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const int k = 4 * kk + q;
+            if (k < i) part += sL[i][k] * x[kk];              // x[kk] is zero for k < c
+        }
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        const double xi = (i < c) ? 0.0 : (((i == c) ? 1.0 : 0.0) - part) / sL[i][i];
+        if (q == (i & 3)) x[i >> 2] = xi;
     }
 #pragma unroll
-    for (int c = 0; c < kBlk; ++c) xr[(size_t)ldx * c] = x[c];
+    for (int kk = 0; kk < 16; ++kk) Linv[(4 * kk + q) + (size_t)kBlk * c] = x[kk];
 }
 
 static cudaError_t gemm_nt(double* C, int ldc, const double* A, int lda, const double* B, int ldb, int mb,
-                           int nbk, int kb, bool lower, cudaStream_t st, int64_t* launches) {
+                           int nbk, int kb, int mode, cudaStream_t st, int64_t* launches) {
     const size_t smem = 2 * GSTAGES * GK * GS * sizeof(double);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_nt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_nt<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_gemm_nt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(k_gemm_nt<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_gemm_nt<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     dim3 grid(mb, nbk);
-    if (lower) k_gemm_nt<true><<<grid, 128, smem, st>>>(C, ldc, A, lda, B, ldb, kb * kBlk);
-    else k_gemm_nt<false><<<grid, 128, smem, st>>>(C, ldc, A, lda, B, ldb, kb * kBlk);
+    if (mode == 1) k_gemm_nt<1><<<grid, 128, smem, st>>>(C, ldc, A, lda, B, ldb, kb * kBlk);
+    else if (mode == 2) k_gemm_nt<2><<<grid, 128, smem, st>>>(C, ldc, A, lda, B, ldb, kb * kBlk);
+    else k_gemm_nt<0><<<grid, 128, smem, st>>>(C, ldc, A, lda, B, ldb, kb * kBlk);
     ++*launches;
     return cudaGetLastError();
 }
 
 #define AT(A, ld, br, bc) ((A) + (size_t)(br) * kBlk + (size_t)(ld) * (bc) * kBlk)
 
+#define LINV(W, b) ((W) + (size_t)(b) * kBlk * kBlk)
+
 // X (mr x n blocks at block (r0, c0)) := X * L^-T with L the n x n block triangle at (c0, c0).
-static cudaError_t rtrsm(double* A, int ld, int r0, int mr, int c0, int n, cudaStream_t st, int64_t* launches) {
-    if (n == 1) {
-        k_trsm64<<<mr, 64, 0, st>>>(AT(A, ld, r0, c0), ld, AT(A, ld, c0, c0), ld);
-        ++*launches;
-        return cudaGetLastError();
-    }
+// Leaves multiply by the inverted 64x64 diagonal factor (in place, DMMA).
+static cudaError_t rtrsm(double* A, int ld, const double* Linv, int r0, int mr, int c0, int n, cudaStream_t st,
+                         int64_t* launches) {
+    if (n == 1)
+        return gemm_nt(AT(A, ld, r0, c0), ld, AT(A, ld, r0, c0), ld, LINV(Linv, c0), kBlk, mr, 1, 1, 2, st, launches);
     const int n1 = n / 2, n2 = n - n1;
-    cudaError_t e = rtrsm(A, ld, r0, mr, c0, n1, st, launches);
+    cudaError_t e = rtrsm(A, ld, Linv, r0, mr, c0, n1, st, launches);
     if (e != cudaSuccess) return e;
     // X2 -= X1 * L21'
-    e = gemm_nt(AT(A, ld, r0, c0 + n1), ld, AT(A, ld, r0, c0), ld, AT(A, ld, c0 + n1, c0), ld, mr, n2, n1, false, st,
+    e = gemm_nt(AT(A, ld, r0, c0 + n1), ld, AT(A, ld, r0, c0), ld, AT(A, ld, c0 + n1, c0), ld, mr, n2, n1, 0, st,
                 launches);
     if (e != cudaSuccess) return e;
-    return rtrsm(A, ld, r0, mr, c0 + n1, n2, st, launches);
+    return rtrsm(A, ld, Linv, r0, mr, c0 + n1, n2, st, launches);
 }
 
 // Factor block range [b0, b0+n); the block with index aug_blk (if inside) is not factorised.
-static cudaError_t rchol(double* A, int ld, int b0, int n, int aug_blk, int* info, cudaStream_t st,
+static cudaError_t rchol(double* A, int ld, double* Linv, int b0, int n, int aug_blk, int* info, cudaStream_t st,
                          int64_t* launches) {
     if (n == 1) {
         if (b0 == aug_blk) return cudaSuccess;
-        k_potrf64<<<1, 256, 0, st>>>(AT(A, ld, b0, b0), ld, info);
+        k_potrf64_inv<<<1, 256, 0, st>>>(AT(A, ld, b0, b0), ld, LINV(Linv, b0), info);
         ++*launches;
         return cudaGetLastError();
     }
     const int n1 = n / 2, n2 = n - n1;
-    cudaError_t e = rchol(A, ld, b0, n1, aug_blk, info, st, launches);
+    cudaError_t e = rchol(A, ld, Linv, b0, n1, aug_blk, info, st, launches);
     if (e != cudaSuccess) return e;
-    e = rtrsm(A, ld, b0 + n1, n2, b0, n1, st, launches);
+    e = rtrsm(A, ld, Linv, b0 + n1, n2, b0, n1, st, launches);
     if (e != cudaSuccess) return e;
     e = gemm_nt(AT(A, ld, b0 + n1, b0 + n1), ld, AT(A, ld, b0 + n1, b0), ld, AT(A, ld, b0 + n1, b0), ld, n2, n2, n1,
-                true, st, launches);
+                1, st, launches);
     if (e != cudaSuccess) return e;
-    return rchol(A, ld, b0 + n1, n2, aug_blk, info, st, launches);
+    return rchol(A, ld, Linv, b0 + n1, n2, aug_blk, info, st, launches);
 }
 
-cudaError_t chol_augmented(double* A, int ld, int nb, int* info, cudaStream_t st, int64_t* launches) {
-    return rchol(A, ld, 0, nb + 1, nb, info, st, launches);
+cudaError_t chol_augmented(double* A, int ld, int nb, double* Linv, int* info, cudaStream_t st, int64_t* launches) {
+    return rchol(A, ld, Linv, 0, nb + 1, nb, info, st, launches);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -278,57 +298,59 @@ __global__ void k_combine(const double* __restrict__ A, int ld, int n_pad, int i
     y[j] = t;
 }
 
-// Backward substitution L' x = y, one 64-block at a time (right-looking):
-//   x_k = L_kk^-T y_k ;  y_j -= L_kj' x_k  for j < k.
-__global__ void __launch_bounds__(64) k_trsv_bwd64(const double* __restrict__ L, int ld, double* __restrict__ y) {
-    __shared__ double sl[kBlk][kBlk + 1];
+// Backward substitution L' x = y, one launch per 64-block step k = nb-1 .. 0:
+//   x_k = L_kk^-T y_k (every CTA recomputes it from the inverted diagonal factor -- 4096 FMAs -- so
+//   no second launch is needed), CTA 0 stores it, then y_c -= sum_r L[k*64+r][c] x_k[r] for the
+//   columns c < k*64, one warp per column.
+__global__ void __launch_bounds__(256) k_backstep(const double* __restrict__ A, int ld, int k,
+                                                  const double* __restrict__ Linv_k, double* __restrict__ y,
+                                                  double* __restrict__ x_out) {
     __shared__ double sx[kBlk];
-    const int tid = threadIdx.x;
-    for (int q = tid; q < kBlk * kBlk; q += 64) {
-        const int r = q & 63, c = q >> 6;
-        sl[r][c] = L[r + (size_t)ld * c];
-    }
-    sx[tid] = y[tid];
-    __syncthreads();
-    for (int j = kBlk - 1; j >= 0; --j) {
-        if (tid == j) sx[j] = sx[j] / sl[j][j];
-        __syncthreads();
-        if (tid < j) sx[tid] -= sl[j][tid] * sx[j];      // (L')[tid][j] = L[j][tid]
-        __syncthreads();
-    }
-    y[tid] = sx[tid];
-}
-
-// y[c] -= sum_r L[k*64+r][c] * x[r] for the columns c < k*64; one warp per column.
-__global__ void __launch_bounds__(256) k_gemv_bwd(const double* __restrict__ Lrow, int ld, int ncols,
-                                                  const double* __restrict__ xk, double* __restrict__ y) {
-    const int lane = threadIdx.x & 31;
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= ncols) return;
-    const double* col = Lrow + (size_t)ld * c;
-    double acc = col[lane] * xk[lane] + col[lane + 32] * xk[lane + 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* yk = y + (size_t)k * kBlk;
+    // x[j] = sum_i Linv[i][j] y[i]  (Linv^T y); 4 threads per j
+    {
+        const int j = tid >> 2, qq = tid & 3;
+        double acc = 0.0;
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (lane == 0) y[c] -= acc;
+        for (int t = 0; t < 16; ++t) {
+            const int i = 4 * t + qq;
+            acc += Linv_k[i + (size_t)kBlk * j] * yk[i];
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (qq == 0) sx[j] = acc;
+    }
+    __syncthreads();
+    const int ncols = k * kBlk;
+    const double x0 = sx[lane], x1 = sx[lane + 32];
+    for (int c = blockIdx.x * 8 + warp; c < ncols; c += gridDim.x * 8) {
+        const double* colp = A + (size_t)k * kBlk + (size_t)ld * c;
+        double acc = colp[lane] * x0 + colp[lane + 32] * x1;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+        if (lane == 0) y[c] -= acc;
+    }
+    // other CTAs may still be reading y_k, so the solution goes to a separate vector
+    if (blockIdx.x == 0 && tid < kBlk) x_out[(size_t)k * kBlk + tid] = sx[tid];
 }
 
-cudaError_t border_and_backsolve(double* A, int ld, int nb, int inner, double* work, double* sol, int* info,
-                                 cudaStream_t st, int64_t* launches) {
+cudaError_t border_and_backsolve(double* A, int ld, int nb, const double* Linv, int inner, double* work,
+                                 double* ywork, double* sol, int* info, int sm_count, cudaStream_t st,
+                                 int64_t* launches) {
     const int n_pad = nb * kBlk;
     if (inner) {
         k_border_solve<<<1, 32, 0, st>>>(A, ld, n_pad, work, info);
         ++*launches;
     }
-    k_combine<<<(n_pad + 255) / 256, 256, 0, st>>>(A, ld, n_pad, inner, work, sol);
+    k_combine<<<(n_pad + 255) / 256, 256, 0, st>>>(A, ld, n_pad, inner, work, ywork);
     ++*launches;
     for (int k = nb - 1; k >= 0; --k) {
-        k_trsv_bwd64<<<1, 64, 0, st>>>(AT(A, ld, k, k), ld, sol + (size_t)k * kBlk);
+        int grid = (k * kBlk + 7) / 8;
+        if (grid > 2 * sm_count) grid = 2 * sm_count;
+        if (grid < 1) grid = 1;
+        k_backstep<<<grid, 256, 0, st>>>(A, ld, k, LINV(Linv, k), ywork, sol);
         ++*launches;
-        if (k > 0) {
-            const int ncols = k * kBlk;
-            k_gemv_bwd<<<(ncols + 7) / 8, 256, 0, st>>>(A + (size_t)k * kBlk, ld, ncols, sol + (size_t)k * kBlk, sol);
-            ++*launches;
-        }
     }
     return cudaGetLastError();
 }

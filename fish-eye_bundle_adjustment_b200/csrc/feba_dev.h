@@ -44,6 +44,7 @@ struct DevProblem {
     const double* dcam_unscaled;  // un-scaled increment (main.m:458-482)
     double* dpts;                 // increment of the tie points, n_tie x 3
     double* partial;              // per-warp partial sums (deterministic final reduction)
+    double* Gt;                   // inner-constraint rows, compact: (6 n_img) x 8 row-major (col 7 unused)
 };
 
 }  // namespace feba

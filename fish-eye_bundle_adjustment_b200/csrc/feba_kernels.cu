@@ -82,30 +82,171 @@ __global__ void k_G_rows(DevProblem P, const double* __restrict__ eop) {
                       {0, 0, 0, -1, -sw * tp, cw * tp, 0},
                       {0, 0, 0, 0, -cw, -sw, 0},
                       {0, 0, 0, 0, sw * secp, -cw * secp, 0}};
-    for (int q = 0; q < 6; ++q)
-        for (int c = 0; c < 7; ++c)
+    for (int q = 0; q < 6; ++q) {
+        for (int c = 0; c < 7; ++c) {
             P.S[(size_t)(P.n_pad + 1 + c) + (size_t)P.ld * (6 * i + q)] = G[q][c];
+            P.Gt[8 * (size_t)(6 * i + q) + c] = G[q][c];
+        }
+        P.Gt[8 * (size_t)(6 * i + q) + 7] = 0.0;
+    }
 }
 
-// M = S + Gc Gc'  on the lower triangle of the EOP part: Gc is non-zero only
-// in EOP rows, so the border stays in the camera block.  G is read from the augmented rows.
-__global__ void k_add_GGt(DevProblem P) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const int c = blockIdx.y * blockDim.y + threadIdx.y;
-    const int ne = P.off_cam;
-    if (r >= ne || c >= ne || r < c) return;
-    double acc = 0.0;
+// Conditioning of the inner-constraint border.  The bordered solution (main.m:428-437) depends only
+// on the column SPACE of G (G' delta = 0), so G may be replaced by G C for any non-singular 7x7 C.
+// As written (BuildAwG.m:516-525) G mixes unit entries with coordinates in millimetres:
+// G G' reaches 4e7 on rows whose normal-matrix diagonal is 4e1, and M = S + G G' then loses the
+// digits of S that matter (measured: step error 9e-6 instead of 1e-7 on the bundled data).
+// C is chosen so that, in the Jacobi-scaled system, the datum directions get eigenvalue ~1:
+//   C C' = (G'G)^-1 (G' diag(S) G) (G'G)^-1,   C = diag(1/c) A1^-1 chol(A2)
+// with c the column norms of G, A1 = Gn'Gn, A2 = Gn' diag(S) Gn, Gn = G diag(1/c).
+// One CTA: Gram reductions over the 6 n_img rows, 7x7 algebra on thread 0, rows rewritten in place
+// (compact copy Gt and the augmented rows 1..7 of S).
+__global__ void __launch_bounds__(256) k_G_condition(DevProblem P, int* __restrict__ info) {
+    __shared__ double red[256];
+    __shared__ double A1[7][7], A2[7][7], Cm[7][7], cn[7];
+    const int tid = threadIdx.x, ne = P.off_cam;
+    // column norms
+    for (int k = 0; k < 7; ++k) {
+        double acc = 0.0;
+        for (int r = tid; r < ne; r += 256) { const double g = P.Gt[8 * (size_t)r + k]; acc += g * g; }
+        red[tid] = acc;
+        __syncthreads();
+        for (int st = 128; st > 0; st >>= 1) { if (tid < st) red[tid] += red[tid + st]; __syncthreads(); }
+        if (tid == 0) cn[k] = red[0] > 0.0 ? 1.0 / sqrt(red[0]) : 1.0;
+        __syncthreads();
+    }
+    for (int i = 0; i < 7; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double a1 = 0.0, a2 = 0.0;
+            for (int r = tid; r < ne; r += 256) {
+                const double gi = P.Gt[8 * (size_t)r + i] * cn[i], gj = P.Gt[8 * (size_t)r + j] * cn[j];
+                a1 += gi * gj;
+                a2 += gi * gj * P.S[(size_t)r + (size_t)P.ld * r];
+            }
+            red[tid] = a1;
+            __syncthreads();
+            for (int st = 128; st > 0; st >>= 1) { if (tid < st) red[tid] += red[tid + st]; __syncthreads(); }
+            if (tid == 0) A1[i][j] = A1[j][i] = red[0];
+            __syncthreads();
+            red[tid] = a2;
+            __syncthreads();
+            for (int st = 128; st > 0; st >>= 1) { if (tid < st) red[tid] += red[tid + st]; __syncthreads(); }
+            if (tid == 0) A2[i][j] = A2[j][i] = red[0];
+            __syncthreads();
+        }
+    if (tid == 0) {
+        // Lw = chol(A2) (lower); on failure fall back to sqrt(mean diagonal) * I
+        double Lw[7][7];
+        bool ok = true;
+        for (int i = 0; i < 7; ++i)
+            for (int j = 0; j < 7; ++j) Lw[i][j] = 0.0;
+        for (int j = 0; j < 7 && ok; ++j) {
+            double d = A2[j][j];
+            for (int k = 0; k < j; ++k) d -= Lw[j][k] * Lw[j][k];
+            if (!(d > 1e-14 * A2[j][j])) { ok = false; break; }
+            Lw[j][j] = sqrt(d);
+            for (int i = j + 1; i < 7; ++i) {
+                double v = A2[i][j];
+                for (int k = 0; k < j; ++k) v -= Lw[i][k] * Lw[j][k];
+                Lw[i][j] = v / Lw[j][j];
+            }
+        }
+        // X = A1^-1 Lw by Gaussian elimination with partial pivoting
+        double Q[7][14];
+        for (int i = 0; i < 7; ++i)
+            for (int j = 0; j < 7; ++j) { Q[i][j] = A1[i][j]; Q[i][7 + j] = Lw[i][j]; }
+        for (int c = 0; c < 7 && ok; ++c) {
+            int p = c;
+            for (int r = c + 1; r < 7; ++r) if (fabs(Q[r][c]) > fabs(Q[p][c])) p = r;
+            if (!(fabs(Q[p][c]) > 1e-13)) { ok = false; break; }
+            if (p != c) for (int j = 0; j < 14; ++j) { const double t = Q[c][j]; Q[c][j] = Q[p][j]; Q[p][j] = t; }
+            for (int r = 0; r < 7; ++r) {
+                if (r == c) continue;
+                const double f = Q[r][c] / Q[c][c];
+                for (int j = c; j < 14; ++j) Q[r][j] -= f * Q[c][j];
+            }
+        }
+        if (ok) {
+            for (int i = 0; i < 7; ++i)
+                for (int j = 0; j < 7; ++j) Cm[i][j] = cn[i] * Q[i][7 + j] / Q[i][i];
+        } else {
+            double tr = 0.0;
+            for (int i = 0; i < 7; ++i) tr += A2[i][i];
+            const double sc = tr > 0.0 ? sqrt(tr / 7.0) : 1.0;
+            for (int i = 0; i < 7; ++i)
+                for (int j = 0; j < 7; ++j) Cm[i][j] = (i == j) ? cn[i] * sc : 0.0;
+        }
+        (void)info;
+    }
+    __syncthreads();
+    for (int r = tid; r < ne; r += 256) {
+        double g[7], o[7];
 #pragma unroll
-    for (int k = 0; k < 7; ++k)
-        acc += P.S[(size_t)(P.n_pad + 1 + k) + (size_t)P.ld * r] *
-               P.S[(size_t)(P.n_pad + 1 + k) + (size_t)P.ld * c];
-    P.S[(size_t)r + (size_t)P.ld * c] += acc;
+        for (int k = 0; k < 7; ++k) g[k] = P.Gt[8 * (size_t)r + k];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) acc += g[k] * Cm[k][j];
+            o[j] = acc;
+        }
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            P.Gt[8 * (size_t)r + j] = o[j];
+            P.S[(size_t)(P.n_pad + 1 + j) + (size_t)P.ld * r] = o[j];
+        }
+    }
 }
 
 // Unit diagonal on the padding rows so the padded matrix stays positive definite.
 __global__ void k_pad_diag(DevProblem P) {
     const int i = P.n_red + blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P.n_pad) P.S[(size_t)i + (size_t)P.ld * i] = 1.0;
+}
+
+// Jacobi scaling of the system that is factorised:  M = S + Gc Gc' (Gc is non-zero
+// only in EOP rows, so the border stays in the camera block), d_i = 1/sqrt(M_ii).  The unknowns mix
+// millimetres, radians, pixels and scaled distortion terms (diag(M) spans 1e0..1e9 on the bundled
+// data, cond(M) ~ 1e11): Cholesky itself is insensitive to this scaling, the inverted 64x64
+// diagonal factors used by the DMMA triangular solves are not, so M is equilibrated first.
+__global__ void k_diag_scale(DevProblem P, double* __restrict__ dvec, int* __restrict__ info) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_pad) return;
+    double d = P.S[(size_t)i + (size_t)P.ld * i];
+    if (P.inner && i < P.off_cam) {
+        const double* g = P.Gt + 8 * (size_t)i;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) d += g[k] * g[k];
+    }
+    if (!(d > 0.0)) {
+        atomicExch(info, 1);
+        d = 1.0;
+    }
+    dvec[i] = rsqrt(d);
+}
+
+// One pass over the lower triangle: M~_rc = (S_rc + G_r . G_c) d_r d_c, and the augmented rows
+// (right-hand side g, columns of G) scaled by d_c.  x: rows (coalesced), y: columns.
+__global__ void __launch_bounds__(256) k_border_scale(DevProblem P, const double* __restrict__ dvec) {
+    const int r = blockIdx.x * 32 + threadIdx.x;
+    const int c = blockIdx.y * 8 + threadIdx.y;
+    if (blockIdx.x * 32 + 31 < blockIdx.y * 8) return;            // tile entirely above the diagonal
+    if (c >= P.n_pad) return;
+    const double dc = dvec[c];
+    if (r < P.n_pad) {
+        if (r >= c) {
+            double v = P.S[(size_t)r + (size_t)P.ld * c];
+            if (P.inner && r < P.off_cam) {                       // then c <= r < off_cam as well
+                const double4* gr = reinterpret_cast<const double4*>(P.Gt + 8 * (size_t)r);
+                const double4* gc = reinterpret_cast<const double4*>(P.Gt + 8 * (size_t)c);
+                const double4 r0 = gr[0], r1 = gr[1], c0 = gc[0], c1 = gc[1];
+                v += r0.x * c0.x + r0.y * c0.y + r0.z * c0.z + r0.w * c0.w + r1.x * c1.x + r1.y * c1.y + r1.z * c1.z;
+            }
+            P.S[(size_t)r + (size_t)P.ld * c] = v * dvec[r] * dc;
+        }
+    } else if (r < P.n_pad + kAugRows) {
+        P.S[(size_t)r + (size_t)P.ld * c] *= dc;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -524,7 +665,8 @@ __global__ void __launch_bounds__(128) k_assemble(DevProblem P) {
 // ------------------------------------------------------------------------------------------
 // Camera-part update (main.m:458-488 for the EOP/IOP unknowns): delta_c = -sol, un-scale the
 // distortion increments by r_max^(2j) / r_max^2, add to the parameter tables, partial sumabs.
-__global__ void k_update_cam(DevProblem P, const double* __restrict__ sol, double* __restrict__ dcam,
+__global__ void k_update_cam(DevProblem P, const double* __restrict__ sol, const double* __restrict__ dvec,
+                             double* __restrict__ dcam,
                              double* __restrict__ dcam_unscaled, double* __restrict__ eop,
                              double* __restrict__ iop, double* __restrict__ out_sumabs) {
     __shared__ double red[1024];
@@ -532,7 +674,7 @@ __global__ void k_update_cam(DevProblem P, const double* __restrict__ sol, doubl
     for (int i = threadIdx.x; i < P.n_pad; i += blockDim.x) {
         double d = 0.0, du = 0.0;
         if (i < P.n_red) {
-            d = -sol[i];
+            d = -sol[i] * dvec[i];                 // undo the Jacobi scaling of the reduced system
             du = d;
             if (i < P.off_cam) {
                 const int im = i / P.ui, slot = i - im * P.ui;
@@ -766,15 +908,21 @@ cudaError_t launch_tables(const DevProblem& P, const double* eop, const double* 
     return cudaGetLastError();
 }
 
-cudaError_t launch_constraints(const DevProblem& P, const double* eop, cudaStream_t st) {
-    k_G_rows<<<(P.n_img + 127) / 128, 128, 0, st>>>(P, eop);
-    dim3 blk(32, 8), grd((P.off_cam + 31) / 32, (P.off_cam + 7) / 8);
-    k_add_GGt<<<grd, blk, 0, st>>>(P);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_pad_diag(const DevProblem& P, cudaStream_t st) {
-    if (P.n_pad > P.n_red) k_pad_diag<<<1, 64, 0, st>>>(P);
+cudaError_t launch_border_scale(const DevProblem& P, const double* eop, double* dvec, int* info, cudaStream_t st,
+                                int64_t* launches) {
+    if (P.inner) {
+        k_G_rows<<<(P.n_img + 127) / 128, 128, 0, st>>>(P, eop);
+        k_G_condition<<<1, 256, 0, st>>>(P, info);
+        *launches += 2;
+    }
+    if (P.n_pad > P.n_red) {
+        k_pad_diag<<<1, 64, 0, st>>>(P);
+        ++*launches;
+    }
+    k_diag_scale<<<(P.n_pad + 255) / 256, 256, 0, st>>>(P, dvec, info);
+    dim3 blk(32, 8), grd((P.n_pad + kAugRows + 31) / 32, (P.n_pad + 7) / 8);
+    k_border_scale<<<grd, blk, 0, st>>>(P, dvec);
+    *launches += 2;
     return cudaGetLastError();
 }
 
@@ -817,9 +965,9 @@ cudaError_t launch_backsub(const DevProblem& P, int sm_count, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_update_cam(const DevProblem& P, const double* sol, double* dcam, double* dcam_unscaled,
-                              double* eop, double* iop, double* out_sumabs, cudaStream_t st) {
-    k_update_cam<<<1, 1024, 0, st>>>(P, sol, dcam, dcam_unscaled, eop, iop, out_sumabs);
+cudaError_t launch_update_cam(const DevProblem& P, const double* sol, const double* dvec, double* dcam,
+                              double* dcam_unscaled, double* eop, double* iop, double* out_sumabs, cudaStream_t st) {
+    k_update_cam<<<1, 1024, 0, st>>>(P, sol, dvec, dcam, dcam_unscaled, eop, iop, out_sumabs);
     return cudaGetLastError();
 }
 

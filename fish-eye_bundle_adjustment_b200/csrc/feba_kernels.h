@@ -14,13 +14,14 @@ cudaError_t launch_xhat_scatter(const DevProblem& P, int sm_count, const double*
 cudaError_t launch_xhat_gather(const DevProblem& P, int sm_count, double* xhat, const double* eop,
                                const double* iop, const int* tie_pt, cudaStream_t st);
 cudaError_t launch_delta_gather(const DevProblem& P, int sm_count, double* delta, cudaStream_t st);
-cudaError_t launch_constraints(const DevProblem& P, const double* eop, cudaStream_t st);
-cudaError_t launch_pad_diag(const DevProblem& P, cudaStream_t st);
+// G rows (inner constraints), padding diagonal, M = S + Gc Gc' and its Jacobi scaling d = diag(M)^-1/2
+cudaError_t launch_border_scale(const DevProblem& P, const double* eop, double* dvec, int* info, cudaStream_t st,
+                                int64_t* launches);
 cudaError_t launch_assemble(const DevProblem& P, int sm_count, cudaStream_t st);
 int backsub_warps(const DevProblem& P, int sm_count);
 cudaError_t launch_backsub(const DevProblem& P, int sm_count, cudaStream_t st);
-cudaError_t launch_update_cam(const DevProblem& P, const double* sol, double* dcam, double* dcam_unscaled,
-                              double* eop, double* iop, double* out_sumabs, cudaStream_t st);
+cudaError_t launch_update_cam(const DevProblem& P, const double* sol, const double* dvec, double* dcam,
+                              double* dcam_unscaled, double* eop, double* iop, double* out_sumabs, cudaStream_t st);
 cudaError_t launch_sum_partials(const double* partial, int n, int stride, int offset, double* out,
                                 cudaStream_t st);
 int debug_oob_count();   // -1 unless built with -DFEBA_CHECK
@@ -32,11 +33,13 @@ cudaError_t launch_residuals(const DevProblem& P, int sm_count, const int* opt, 
 // A: (nb+1)*kBlk square, column-major, leading dimension ld, lower triangle; the last block row is
 // the augmented block (right-hand side g in row 0, G columns in rows 1..7) and is not factorised:
 // on return A = [L 0; Y' T] with Y' = B' L^-T and T = -B' M^-1 B (Schur complement).
+// Linv: nb blocks of kBlk x kBlk (column-major): inverses of the diagonal factors.
 // info (device int) is set non-zero when a pivot is not positive.
-cudaError_t chol_augmented(double* A, int ld, int nb, int* info, cudaStream_t st, int64_t* launches);
-// y (n_pad) := combination of the augmented rows: y = Y'(0,:) + sum_k kvec[k] Y'(1+k,:) where kvec
+cudaError_t chol_augmented(double* A, int ld, int nb, double* Linv, int* info, cudaStream_t st, int64_t* launches);
+// ywork (n_pad) := combination of the augmented rows: y = Y'(0,:) + sum_k kvec[k] Y'(1+k,:) where kvec
 // solves the 7x7 border system (inner != 0), else y = Y'(0,:).  Then sol := L^-T y.
-cudaError_t border_and_backsolve(double* A, int ld, int nb, int inner, double* work, double* sol, int* info,
-                                 cudaStream_t st, int64_t* launches);
+cudaError_t border_and_backsolve(double* A, int ld, int nb, const double* Linv, int inner, double* work,
+                                 double* ywork, double* sol, int* info, int sm_count, cudaStream_t st,
+                                 int64_t* launches);
 
 }  // namespace feba
