@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfeba.so")
-SOURCES = ("feba_api.cu", "feba_kernels.cu", "feba_chol.cu")
+SOURCES = ("feba_api.cu", "feba_kernels.cu", "feba_assemble.cu", "feba_chol.cu")
 HEADERS = ("feba_dev.h", "feba_kernels.h", "feba_model.cuh", os.path.join("..", "..", "include", "feba.h"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall", "--use_fast_math=false"]
@@ -40,8 +40,6 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         return LIB
     objs, procs = [], []
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    if os.environ.get("FEBA_CHECK"):         # range-checked accumulation (debug builds only)
-        flags.append("-DFEBA_CHECK")
     for src in SOURCES:                      # translation units compile concurrently
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
         cmd = [_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj]

@@ -43,6 +43,7 @@ struct feba_handle {
     double* scal_host = nullptr;  // pinned mirror of scal
     int* info_host = nullptr;
     size_t S_count = 0;
+    long long n_pairs = 0;
     int64_t u = 0;
     int n_partial = 0;
     int64_t launches = 0;
@@ -240,7 +241,7 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
     }
     seg_start.push_back((int)n);
     P.n_seg = (int)seg_pt.size();
-    std::vector<int> perm((size_t)n), simg((size_t)n), spt((size_t)n);
+    std::vector<int> perm((size_t)n), simg((size_t)n), spt((size_t)n), oseg((size_t)n);
     std::vector<double> sx((size_t)n), sy((size_t)n);
     {
         std::vector<int> cur(start.begin(), start.end() - 1);
@@ -253,6 +254,16 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
             sx[d] = pr->obs_x[i];
             sy[d] = pr->obs_y[i];
         }
+    }
+    for (int sg = 0; sg < P.n_seg; ++sg)
+        for (int o = seg_start[sg]; o < seg_start[sg + 1]; ++o) oseg[o] = sg;
+    // observations grouped by image (indices into the point-major order), for the image pass
+    std::vector<int> img_start((size_t)pr->n_img + 1, 0), iobs((size_t)n);
+    for (int64_t o = 0; o < n; ++o) ++img_start[(size_t)simg[o] + 1];
+    for (int j = 0; j < pr->n_img; ++j) img_start[(size_t)j + 1] += img_start[j];
+    {
+        std::vector<int> cur(img_start.begin(), img_start.end() - 1);
+        for (int64_t o = 0; o < n; ++o) iobs[cur[simg[o]]++] = (int)o;
     }
     // tie index <-> CNT row (main.m:362-375, Buildxhat.m:108-135)
     std::vector<int> tie_pt((size_t)pr->n_tie, -1);
@@ -273,7 +284,7 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
 
     // ---- uploads
     double *ox, *oy, *xyz, *xyz_prev;
-    int *oimg, *operm, *dseg_start, *dseg_pt, *dimg_cam, *dpt_tie;
+    int *oimg, *operm, *dseg_start, *dseg_pt, *dimg_cam, *dpt_tie, *dimg_start, *diobs, *doseg;
     CU(h, upload(h, &ox, sx.data(), (size_t)n));
     CU(h, upload(h, &oy, sy.data(), (size_t)n));
     CU(h, upload(h, &oimg, simg.data(), (size_t)n));
@@ -284,6 +295,11 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
     CU(h, upload(h, &dimg_cam, pr->img_cam, (size_t)pr->n_img));
     CU(h, upload(h, &dpt_tie, pr->pt_tie, (size_t)pr->n_pts));
     CU(h, upload(h, &h->tie_pt, tie_pt.data(), tie_pt.size()));
+    CU(h, upload(h, &dimg_start, img_start.data(), img_start.size()));
+    CU(h, upload(h, &diobs, iobs.data(), iobs.size()));
+    CU(h, upload(h, &doseg, oseg.data(), oseg.size()));
+    CU(h, dev_alloc(h, &P.rec1, (size_t)n * kRec1));
+    CU(h, dev_alloc(h, &P.rec2, (size_t)n * (2 + 2 * P.NC)));
     CU(h, upload(h, &h->eop, pr->eop0, (size_t)pr->n_img * 6));
     CU(h, upload(h, &h->iop, pr->iop0, (size_t)pr->n_cam * P.NC));
     CU(h, upload(h, &h->cam_box, pr->cam_box, (size_t)pr->n_cam * 5));
@@ -318,6 +334,8 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
     P.seg_pt = dseg_pt;
     P.img_cam = dimg_cam;
     P.pt_tie = dpt_tie;
+    P.img_start = dimg_start;
+    P.iobs = diobs;
     P.img_tab = h->img_tab;
     P.cam_tab = h->cam_tab;
     P.xyz = xyz;
@@ -329,6 +347,14 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
         h->n_partial = a > b ? a : b;
     }
     CU(h, dev_alloc(h, &P.partial, (size_t)h->n_partial));
+    CU(h, dev_alloc(h, &P.cam_part, (size_t)assemble_warps(P, h->sm_count) * kCamPart));
+    {
+        // image-pair schedule of the Schur blocks: static for the life of the handle
+        void *kp = nullptr, *kb = nullptr;
+        CU(h, build_pair_schedule(P, doseg, &h->n_pairs, &kp, &kb, h->stream));
+        if (kp) h->allocs.push_back(kp);
+        if (kb) h->allocs.push_back(kb);
+    }
     // xhat = Buildxhat of the uploaded tables (Buildxhat.m:22-135)
     CU(h, cudaMemsetAsync(h->xhat, 0, (size_t)h->u * sizeof(double), h->stream));
     CU(h, launch_xhat_gather(P, h->sm_count, h->xhat, h->eop, h->iop, h->tie_pt, h->stream));
@@ -402,8 +428,8 @@ static int enqueue_assemble(feba_handle* h) {
     CU(h, cudaMemsetAsync(P.S, 0, h->S_count * sizeof(double), h->stream));
     CU(h, cudaMemsetAsync(h->info, 0, sizeof(int), h->stream));
     CU(h, record(h, 1));
-    CU(h, launch_assemble(P, h->sm_count, h->stream));
-    h->launches += 2;
+    ++h->launches;
+    CU(h, launch_assemble(P, h->sm_count, h->stream, &h->launches));
     CU(h, record(h, 2));
     return FEBA_OK;
 }
@@ -602,8 +628,6 @@ int feba_last_timing(const feba_handle* h, double ms[6]) {
     for (int i = 0; i < 6; ++i) ms[i] = h->timing[i];
     return FEBA_OK;
 }
-
-int feba_debug_oob(void) { return debug_oob_count(); }
 
 int64_t feba_launch_count(const feba_handle* h) { return h ? h->launches : 0; }
 

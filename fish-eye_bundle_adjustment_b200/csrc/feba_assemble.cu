@@ -1,0 +1,675 @@
+// Fused BuildAwG + block normal equations + Schur elimination of the object points, without
+// atomics on the reduced system: a point pass, an image pass and an image-pair pass over a
+// schedule that is built once per problem (the sparsity of the network does not change between
+// Gauss-Newton iterations).
+//
+// Reference path replaced: functions/BuildAwG.m:46-512 (A, w), main.m:424-425 (u = A'Pw, N = A'PA)
+// and the elimination of the tie-point unknowns that the explicit inverse of main.m:432/442
+// performs implicitly.  A and N are never formed.
+//
+// Algebra (per tie point p, observations a = 1..m in images i_a; P = diag(1/sx^2, 1/sy^2)):
+//   V  = sum_a Jt_a' P Jt_a = L L'                       3x3, Cholesky in registers
+//   Z_a = P Jt_a L^-T            (2x3)    ut = L^-1 u_p,  u_p = sum_a Jt_a' P w_a
+//   Fc  = Wc L^-T                (NC x 3) Wc = sum_a Jc_a' P Jt_a
+//   W V^-1 W' = (W L^-T)(W L^-T)'  so with  C_ab = Z_a Z_b' (2x2):
+//     S[i_a, i_b]   -= Je_a' C_ab Je_b                   image-pair pass   (a != b)
+//     S[i_a, i_a]   += Je_a' (P - C_aa) Je_a             image pass
+//     g[i_a]        += Je_a' r_a,   r_a = P w_a - Z_a ut
+//     S[cam, i_a]   += H_a Je_a,    H_a = Jc_a' P - Fc Z_a'
+//     S[cam, cam]   += sum_a Jc_a' P Jc_a - Fc Fc',  g[cam] += sum_a Jc_a' P w_a - Fc ut   point pass
+// Control points (not estimated) contribute the same terms with Z = 0, Fc = 0.
+// The point pass stores, per observation, rec1 = {Je (2x6), Z (2x3)} and rec2 = {r (2), H (NC x 2)};
+// the other two passes only read those records.  Every entry of S has exactly one writer per
+// kernel and partial sums are combined in a fixed order, so the result is run-to-run deterministic.
+#include <cub/cub.cuh>
+
+#include <vector>
+
+#include "feba_dev.h"
+#include "feba_kernels.h"
+#include "feba_model.cuh"
+
+namespace feba {
+
+// ------------------------------------------------------------------------------------------
+// point pass: one warp per object point, lanes over its observations (chunks of 32)
+template <int NK>
+struct PtSmem {
+    static constexpr int NC = NK + 5;
+    double rowJc[32][2][NC];
+    double rowJt[32][2][3];
+    double roww[32][2];
+    double Wc[NC][3];
+    double Fc[NC][3];
+    double V[6];
+    double up[3];
+};
+
+template <int NK, bool HAS_CAM>
+__global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
+    constexpr int NC = NK + 5;
+    constexpr int ND = NC * (NC + 1) / 2;          // packed camera-camera block
+    constexpr int DPL = (ND + 31) / 32;            // entries of D per lane
+    constexpr int WPL = (NC * 3 + 31) / 32;        // entries of Wc per lane
+    constexpr int R2 = 2 + 2 * NC;                 // doubles per rec2 record
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PtSmem<NK>* sm_all = reinterpret_cast<PtSmem<NK>*>(smem_raw);
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    PtSmem<NK>& sm = sm_all[wib];
+    const int nwarp = gridDim.x * (blockDim.x >> 5);
+    const int gw = blockIdx.x * (blockDim.x >> 5) + wib;
+    const double pw[2] = {P.px, P.py};
+    const int type = P.type;
+
+    int dI[DPL], dJ[DPL];
+    double dacc[DPL];
+#pragma unroll
+    for (int t = 0; t < DPL; ++t) {
+        const int e = lane + 32 * t;
+        int i = 0;
+        while ((i + 1) * (i + 2) / 2 <= e) ++i;    // row of packed lower-triangular index e
+        dI[t] = i;
+        dJ[t] = e - i * (i + 1) / 2;
+        dacc[t] = 0.0;
+    }
+    double gcacc = 0.0;
+
+    for (int seg = gw; seg < P.n_seg; seg += nwarp) {
+        const int beg = P.seg_start[seg], end = P.seg_start[seg + 1];
+        const int pt = P.seg_pt[seg];
+        const bool is_tie = P.pt_tie[pt] >= 0;
+        const double X = P.xyz[3 * pt], Y = P.xyz[3 * pt + 1], Z = P.xyz[3 * pt + 2];
+        const bool single = (end - beg) <= 32;
+        ObsJac<NK> J;
+        bool have_J = false;
+
+        // ---------------- pass 1: V, u_p, Wc and the direct camera-camera sums
+        double vacc = 0.0;                          // lanes 0..5: V entries, 6..8: u_p
+        double wcacc[WPL];
+#pragma unroll
+        for (int t = 0; t < WPL; ++t) wcacc[t] = 0.0;
+        if (is_tie || HAS_CAM) {
+            for (int c0 = beg; c0 < end; c0 += 32) {
+                const int o = c0 + lane;
+                const bool act = o < end;
+                if (act) {
+                    const int img = P.oimg[o];
+                    observation<NK, HAS_CAM>(type, P.ox[o], P.oy[o], P.img_tab + kImgStride * img, P.cam_tab, X, Y,
+                                             Z, J);
+                }
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    if (HAS_CAM) {
+#pragma unroll
+                        for (int j = 0; j < NC; ++j) sm.rowJc[lane][r][j] = act ? J.Jc[r][j] : 0.0;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) sm.rowJt[lane][r][k] = act ? J.Jt[r][k] : 0.0;
+                    sm.roww[lane][r] = act ? J.w[r] : 0.0;
+                }
+                __syncwarp();
+                const int nrow = min(32, end - c0);
+                if (HAS_CAM) {
+#pragma unroll
+                    for (int t = 0; t < DPL; ++t) {
+                        if (lane + 32 * t < ND) {
+                            double a = 0.0;
+                            for (int l = 0; l < nrow; ++l)
+                                a += sm.rowJc[l][0][dI[t]] * pw[0] * sm.rowJc[l][0][dJ[t]] +
+                                     sm.rowJc[l][1][dI[t]] * pw[1] * sm.rowJc[l][1][dJ[t]];
+                            dacc[t] += a;
+                        }
+                    }
+                    if (lane < NC) {
+                        double a = 0.0;
+                        for (int l = 0; l < nrow; ++l)
+                            a += sm.rowJc[l][0][lane] * pw[0] * sm.roww[l][0] +
+                                 sm.rowJc[l][1][lane] * pw[1] * sm.roww[l][1];
+                        gcacc += a;
+                    }
+                    if (is_tie) {
+#pragma unroll
+                        for (int t = 0; t < WPL; ++t) {
+                            const int e = lane + 32 * t;
+                            if (e < NC * 3) {
+                                const int i = e / 3, k = e - 3 * i;
+                                double a = 0.0;
+                                for (int l = 0; l < nrow; ++l)
+                                    a += sm.rowJc[l][0][i] * pw[0] * sm.rowJt[l][0][k] +
+                                         sm.rowJc[l][1][i] * pw[1] * sm.rowJt[l][1][k];
+                                wcacc[t] += a;
+                            }
+                        }
+                    }
+                }
+                if (is_tie && lane < 9) {
+                    double a = 0.0;
+                    if (lane < 6) {
+                        const int i = lane < 1 ? 0 : (lane < 3 ? 1 : 2);
+                        const int k = lane - i * (i + 1) / 2;
+                        for (int l = 0; l < nrow; ++l)
+                            a += sm.rowJt[l][0][i] * pw[0] * sm.rowJt[l][0][k] +
+                                 sm.rowJt[l][1][i] * pw[1] * sm.rowJt[l][1][k];
+                    } else {
+                        const int k = lane - 6;
+                        for (int l = 0; l < nrow; ++l)
+                            a += sm.rowJt[l][0][k] * pw[0] * sm.roww[l][0] +
+                                 sm.rowJt[l][1][k] * pw[1] * sm.roww[l][1];
+                    }
+                    vacc += a;
+                }
+                __syncwarp();
+            }
+            have_J = single;
+        }
+        // ---------------- V = L L', L^-1, ut = L^-1 u_p, Fc = Wc L^-T
+        double i00 = 0, i10 = 0, i11 = 0, i20 = 0, i21 = 0, i22 = 0;
+        double ut[3] = {0, 0, 0};
+        if (is_tie) {
+            if (lane < 6) sm.V[lane] = vacc;
+            else if (lane < 9) sm.up[lane - 6] = vacc;
+            if (HAS_CAM) {
+#pragma unroll
+                for (int t = 0; t < WPL; ++t) {
+                    const int e = lane + 32 * t;
+                    if (e < NC * 3) (&sm.Wc[0][0])[e] = wcacc[t];
+                }
+            }
+            __syncwarp();
+            const double v0 = sm.V[0], v1 = sm.V[1], v2 = sm.V[2], v3 = sm.V[3], v4 = sm.V[4], v5 = sm.V[5];
+            const double l00 = sqrt(v0);
+            const double l10 = v1 / l00, l20 = v3 / l00;
+            const double l11 = sqrt(v2 - l10 * l10);
+            const double l21 = (v4 - l20 * l10) / l11;
+            const double l22 = sqrt(v5 - l20 * l20 - l21 * l21);
+            i00 = 1.0 / l00; i11 = 1.0 / l11; i22 = 1.0 / l22;
+            i10 = -l10 * i00 * i11;
+            i21 = -l21 * i11 * i22;
+            i20 = -(l20 * i00 + l21 * i10) * i22;
+            const double u0 = sm.up[0], u1 = sm.up[1], u2 = sm.up[2];
+            ut[0] = i00 * u0;
+            ut[1] = i10 * u0 + i11 * u1;
+            ut[2] = i20 * u0 + i21 * u1 + i22 * u2;
+            if (HAS_CAM) {
+                if (lane < NC) {
+                    const double w0 = sm.Wc[lane][0], w1 = sm.Wc[lane][1], w2 = sm.Wc[lane][2];
+                    sm.Fc[lane][0] = w0 * i00;
+                    sm.Fc[lane][1] = w0 * i10 + w1 * i11;
+                    sm.Fc[lane][2] = w0 * i20 + w1 * i21 + w2 * i22;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < DPL; ++t) {
+                    if (lane + 32 * t < ND)
+                        dacc[t] -= sm.Fc[dI[t]][0] * sm.Fc[dJ[t]][0] + sm.Fc[dI[t]][1] * sm.Fc[dJ[t]][1] +
+                                   sm.Fc[dI[t]][2] * sm.Fc[dJ[t]][2];
+                }
+                if (lane < NC) gcacc -= sm.Fc[lane][0] * ut[0] + sm.Fc[lane][1] * ut[1] + sm.Fc[lane][2] * ut[2];
+            }
+        }
+        // ---------------- pass 2: per-observation records
+        for (int a0 = beg; a0 < end; a0 += 32) {
+            const int o = a0 + lane;
+            if (o >= end) continue;
+            if (!have_J) {
+                const int img = P.oimg[o];
+                observation<NK, HAS_CAM>(type, P.ox[o], P.oy[o], P.img_tab + kImgStride * img, P.cam_tab, X, Y, Z, J);
+            }
+            double Zm[2][3];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const double t0 = pw[r] * J.Jt[r][0], t1 = pw[r] * J.Jt[r][1], t2 = pw[r] * J.Jt[r][2];
+                Zm[r][0] = t0 * i00;                         // zero for control points (i.. = 0)
+                Zm[r][1] = t0 * i10 + t1 * i11;
+                Zm[r][2] = t0 * i20 + t1 * i21 + t2 * i22;
+            }
+            double* r1 = P.rec1 + (size_t)kRec1 * o;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) r1[6 * r + i] = J.Je[r][i];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) r1[12 + 3 * r + k] = Zm[r][k];
+            }
+            double* r2 = P.rec2 + (size_t)R2 * o;
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+                r2[r] = pw[r] * J.w[r] - (Zm[r][0] * ut[0] + Zm[r][1] * ut[1] + Zm[r][2] * ut[2]);
+            if (HAS_CAM) {
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    double f0 = 0, f1 = 0, f2 = 0;
+                    if (is_tie) { f0 = sm.Fc[j][0]; f1 = sm.Fc[j][1]; f2 = sm.Fc[j][2]; }
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+                        r2[2 + 2 * j + r] = J.Jc[r][j] * pw[r] - (f0 * Zm[r][0] + f1 * Zm[r][1] + f2 * Zm[r][2]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    // camera-camera block and camera right-hand side of this warp -> partial buffer (fixed-order sum later)
+    if (HAS_CAM) {
+        double* part = P.cam_part + (size_t)kCamPart * gw;
+#pragma unroll
+        for (int t = 0; t < DPL; ++t)
+            if (lane + 32 * t < ND) part[lane + 32 * t] = dacc[t];
+        if (lane < NC) part[ND + lane] = gcacc;
+    }
+}
+
+// Fixed-order sum of the per-warp camera partials into S (camera-camera block, lower) and g.
+// Thread (e, s): entry e, slice s of the warps; slices are combined in order.
+__global__ void __launch_bounds__(1024) k_cam_reduce(DevProblem P, int n_warps) {
+    __shared__ double part[8][128];
+    const int NC = P.NC, ND = NC * (NC + 1) / 2, NE = ND + NC;
+    const int e = threadIdx.x & 127, s = threadIdx.x >> 7;
+    double acc = 0.0;
+    if (e < NE)
+        for (int w = s; w < n_warps; w += 8) acc += P.cam_part[(size_t)kCamPart * w + e];
+    part[s][e] = acc;
+    __syncthreads();
+    if (s == 0 && e < NE) {
+        double tot = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tot += part[k][e];
+        if (e < ND) {
+            int i = 0;
+            while ((i + 1) * (i + 2) / 2 <= e) ++i;
+            const int j = e - i * (i + 1) / 2;
+            if (P.ccol[i] >= 0 && P.ccol[j] >= 0)      // slots are monotone in parameter order: row >= col
+                P.S[(size_t)(P.off_cam + P.ccol[i]) + (size_t)P.ld * (P.off_cam + P.ccol[j])] += tot;
+        } else {
+            const int j = e - ND;
+            if (P.ccol[j] >= 0) P.S[(size_t)P.n_pad + (size_t)P.ld * (P.off_cam + P.ccol[j])] += tot;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// image pass: one CTA per image, threads over its observations; diagonal 6x6 block, right-hand
+// side and camera x image block of the image.  Two sweeps keep the accumulators in registers.
+template <int NK, bool HAS_CAM>
+__global__ void __launch_bounds__(128) k_image_pass(DevProblem P) {
+    constexpr int NC = NK + 5;
+    constexpr int R2 = 2 + 2 * NC;
+    constexpr int NA = HAS_CAM ? (NC * 6 > 27 ? NC * 6 : 27) : 27;
+    __shared__ double part[4][NA];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int img = blockIdx.x; img < P.n_img; img += gridDim.x) {
+        const int beg = P.img_start[img], end = P.img_start[img + 1];
+        const size_t col0 = (size_t)P.ui * img;
+        // ---- sweep 1: Je' (P - Z Z') Je  (21 entries, lower) and Je' r (6)
+        {
+            double acc[27];
+#pragma unroll
+            for (int k = 0; k < 27; ++k) acc[k] = 0.0;
+            for (int t = beg + tid; t < end; t += 128) {
+                const int o = P.iobs[t];
+                const double* r1 = P.rec1 + (size_t)kRec1 * o;
+                const double* r2 = P.rec2 + (size_t)R2 * o;
+                double Je[2][6], Zm[2][3];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { Je[0][k] = r1[k]; Je[1][k] = r1[6 + k]; }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { Zm[0][k] = r1[12 + k]; Zm[1][k] = r1[15 + k]; }
+                const double ra0 = r2[0], ra1 = r2[1];
+                const double p00 = P.px - (Zm[0][0] * Zm[0][0] + Zm[0][1] * Zm[0][1] + Zm[0][2] * Zm[0][2]);
+                const double p01 = -(Zm[0][0] * Zm[1][0] + Zm[0][1] * Zm[1][1] + Zm[0][2] * Zm[1][2]);
+                const double p11 = P.py - (Zm[1][0] * Zm[1][0] + Zm[1][1] * Zm[1][1] + Zm[1][2] * Zm[1][2]);
+                int e = 0;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    const double t0 = p00 * Je[0][i] + p01 * Je[1][i], t1 = p01 * Je[0][i] + p11 * Je[1][i];
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) acc[e++] += t0 * Je[0][j] + t1 * Je[1][j];
+                }
+#pragma unroll
+                for (int i = 0; i < 6; ++i) acc[21 + i] += Je[0][i] * ra0 + Je[1][i] * ra1;
+            }
+#pragma unroll
+            for (int k = 0; k < 27; ++k) {
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], s);
+                if (lane == 0) part[warp][k] = acc[k];
+            }
+            __syncthreads();
+            if (tid < 27) {
+                const double tot = part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid];
+                if (tid < 21) {
+                    int i = 0;
+                    while ((i + 1) * (i + 2) / 2 <= tid) ++i;
+                    const int j = tid - i * (i + 1) / 2;
+                    if (P.ecol[i] >= 0 && P.ecol[j] >= 0)
+                        P.S[(col0 + P.ecol[i]) + (size_t)P.ld * (col0 + P.ecol[j])] += tot;
+                } else if (P.ecol[tid - 21] >= 0) {
+                    P.S[(size_t)P.n_pad + (size_t)P.ld * (col0 + P.ecol[tid - 21])] += tot;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- sweep 2: camera x image block  sum_a H_a Je_a  (NC x 6)
+        if (HAS_CAM) {
+            double acc[NC * 6];
+#pragma unroll
+            for (int k = 0; k < NC * 6; ++k) acc[k] = 0.0;
+            for (int t = beg + tid; t < end; t += 128) {
+                const int o = P.iobs[t];
+                const double* r1 = P.rec1 + (size_t)kRec1 * o;
+                const double* r2 = P.rec2 + (size_t)R2 * o + 2;
+                double Je[2][6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { Je[0][k] = r1[k]; Je[1][k] = r1[6 + k]; }
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    const double h0 = r2[2 * j], h1 = r2[2 * j + 1];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) acc[6 * j + i] += h0 * Je[0][i] + h1 * Je[1][i];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NC * 6; ++k) {
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], s);
+                if (lane == 0) part[warp][k] = acc[k];
+            }
+            __syncthreads();
+            if (tid < NC * 6) {
+                const int j = tid / 6, i = tid - 6 * j;
+                if (P.ccol[j] >= 0 && P.ecol[i] >= 0) {
+                    const double tot = part[0][tid] + part[1][tid] + part[2][tid] + part[3][tid];
+                    const int cam = P.img_cam[img];
+                    P.S[(size_t)(P.off_cam + P.uc * cam + P.ccol[j]) + (size_t)P.ld * (col0 + P.ecol[i])] += tot;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// image-pair pass: one warp per block (i_a >= i_b) of the schedule, lanes over the block's
+// (a, b) observation pairs (the tie points the two images share): S[i_a, i_b] -= sum Je_a' Z_a Z_b' Je_b.
+__global__ void __launch_bounds__(128) k_pair_pass(DevProblem P) {
+    const int lane = threadIdx.x & 31;
+    const int nwarp = gridDim.x * (blockDim.x >> 5);
+    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (int blk = gw; blk < P.n_blocks; blk += nwarp) {
+        const int4 b = P.blocks[blk];                  // x: image a, y: image b, z: first pair, w: pairs
+        double acc[36];
+#pragma unroll
+        for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+        for (int t = lane; t < b.w; t += 32) {
+            const int2 pr = P.pairs[(size_t)b.z + t];
+            const double* ra = P.rec1 + (size_t)kRec1 * pr.x;
+            const double* rb = P.rec1 + (size_t)kRec1 * pr.y;
+            double Za[2][3], Zb[2][3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                Za[0][k] = ra[12 + k]; Za[1][k] = ra[15 + k];
+                Zb[0][k] = rb[12 + k]; Zb[1][k] = rb[15 + k];
+            }
+            const double c00 = Za[0][0] * Zb[0][0] + Za[0][1] * Zb[0][1] + Za[0][2] * Zb[0][2];
+            const double c01 = Za[0][0] * Zb[1][0] + Za[0][1] * Zb[1][1] + Za[0][2] * Zb[1][2];
+            const double c10 = Za[1][0] * Zb[0][0] + Za[1][1] * Zb[0][1] + Za[1][2] * Zb[0][2];
+            const double c11 = Za[1][0] * Zb[1][0] + Za[1][1] * Zb[1][1] + Za[1][2] * Zb[1][2];
+            double Jb[2][6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { Jb[0][k] = rb[k]; Jb[1][k] = rb[6 + k]; }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const double ja0 = ra[i], ja1 = ra[6 + i];
+                const double e0 = ja0 * c00 + ja1 * c10, e1 = ja0 * c01 + ja1 * c11;     // (Je_a' C)(i, :)
+#pragma unroll
+                for (int j = 0; j < 6; ++j) acc[6 * i + j] += e0 * Jb[0][j] + e1 * Jb[1][j];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 36; ++k) {
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], s);
+        }
+        // lane k (and k + 32) writes entry k; every lane holds all sums after the butterfly
+        const size_t rowa = (size_t)P.ui * b.x, colb = (size_t)P.ui * b.y;
+        const bool diag = b.x == b.y;
+#pragma unroll
+        for (int k = 0; k < 36; ++k) {
+            if ((k & 31) == lane) {
+                const int i = k / 6, j = k - 6 * i;
+                if (P.ecol[i] >= 0 && P.ecol[j] >= 0 && (!diag || j <= i))
+                    P.S[(rowa + P.ecol[i]) + (size_t)P.ld * (colb + P.ecol[j])] -= acc[k];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// schedule construction (once per problem, on the device)
+
+__global__ void k_pair_count(int64_t n_obs, const int* __restrict__ oseg, const int* __restrict__ seg_start,
+                             const int* __restrict__ seg_pt, const int* __restrict__ pt_tie,
+                             const int* __restrict__ oimg, long long* __restrict__ cnt) {
+    const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (o >= n_obs) return;
+    const int seg = oseg[o];
+    long long c = 0;
+    if (pt_tie[seg_pt[seg]] >= 0) {
+        const int ia = oimg[o];
+        for (int b = seg_start[seg]; b < seg_start[seg + 1]; ++b) {
+            const int ib = oimg[b];
+            if (ib < ia || (ib == ia && b != o)) ++c;
+        }
+    }
+    cnt[o] = c;
+}
+
+__global__ void k_pair_fill(int64_t n_obs, int n_img, const int* __restrict__ oseg, const int* __restrict__ seg_start,
+                            const int* __restrict__ seg_pt, const int* __restrict__ pt_tie,
+                            const int* __restrict__ oimg, const long long* __restrict__ off,
+                            unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals) {
+    const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (o >= n_obs) return;
+    const int seg = oseg[o];
+    if (pt_tie[seg_pt[seg]] < 0) return;
+    const int ia = oimg[o];
+    long long q = off[o];
+    for (int b = seg_start[seg]; b < seg_start[seg + 1]; ++b) {
+        const int ib = oimg[b];
+        if (ib < ia || (ib == ia && b != o)) {
+            keys[q] = (unsigned long long)ia * (unsigned long long)n_img + (unsigned long long)ib;
+            vals[q] = ((unsigned long long)(unsigned)o << 32) | (unsigned)b;
+            ++q;
+        }
+    }
+}
+
+__global__ void k_blocks_fill(int n_blocks, int n_img, const unsigned long long* __restrict__ ukeys,
+                              const long long* __restrict__ starts, const long long* __restrict__ counts,
+                              int4* __restrict__ blocks) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_blocks) return;
+    const unsigned long long key = ukeys[k];
+    blocks[k] = make_int4((int)(key / (unsigned long long)n_img), (int)(key % (unsigned long long)n_img),
+                          (int)starts[k], (int)counts[k]);
+}
+
+__global__ void k_pairs_unpack(long long n, const unsigned long long* __restrict__ vals, int2* __restrict__ pairs) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) pairs[i] = make_int2((int)(vals[i] >> 32), (int)(vals[i] & 0xffffffffull));
+}
+
+#define SCHED_CU(call)                      \
+    do {                                    \
+        cudaError_t e_ = (call);            \
+        if (e_ != cudaSuccess) {            \
+            for (void* p_ : tmp) cudaFree(p_); \
+            return e_;                      \
+        }                                   \
+    } while (0)
+
+// Builds P.pairs / P.blocks / P.n_blocks.  oseg: segment of every (point-major) observation.
+// Device allocations that must outlive the call are returned through keep[].
+cudaError_t build_pair_schedule(DevProblem& P, const int* d_oseg, long long* n_pairs_out, void** keep_pairs,
+                                void** keep_blocks, cudaStream_t st) {
+    std::vector<void*> tmp;
+    auto talloc = [&](void** p, size_t bytes) {
+        cudaError_t e = cudaMalloc(p, bytes ? bytes : 8);
+        if (e == cudaSuccess) tmp.push_back(*p);
+        return e;
+    };
+    *n_pairs_out = 0;
+    *keep_pairs = *keep_blocks = nullptr;
+    P.pairs = nullptr;
+    P.blocks = nullptr;
+    P.n_blocks = 0;
+    const int64_t n = P.n_obs;
+    if (n == 0 || P.n_tie == 0) return cudaSuccess;
+    long long *cnt, *off;
+    SCHED_CU(talloc((void**)&cnt, (size_t)(n + 1) * sizeof(long long)));
+    SCHED_CU(talloc((void**)&off, (size_t)(n + 1) * sizeof(long long)));
+    SCHED_CU(cudaMemsetAsync(cnt, 0, (size_t)(n + 1) * sizeof(long long), st));
+    const int grid = (int)((n + 255) / 256);
+    k_pair_count<<<grid, 256, 0, st>>>(n, d_oseg, P.seg_start, P.seg_pt, P.pt_tie, P.oimg, cnt);
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    SCHED_CU(cub::DeviceScan::ExclusiveSum(nullptr, scratch_bytes, cnt, off, (int)(n + 1), st));
+    SCHED_CU(talloc(&scratch, scratch_bytes));
+    SCHED_CU(cub::DeviceScan::ExclusiveSum(scratch, scratch_bytes, cnt, off, (int)(n + 1), st));
+    long long n_pairs = 0;
+    SCHED_CU(cudaMemcpyAsync(&n_pairs, off + n, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    SCHED_CU(cudaStreamSynchronize(st));
+    *n_pairs_out = n_pairs;
+    if (n_pairs == 0) {
+        for (void* p_ : tmp) cudaFree(p_);
+        return cudaSuccess;
+    }
+    if (n_pairs > 2000000000LL) {
+        for (void* p_ : tmp) cudaFree(p_);
+        return cudaErrorInvalidValue;
+    }
+    unsigned long long *keys, *vals, *keys2, *vals2;
+    SCHED_CU(talloc((void**)&keys, (size_t)n_pairs * 8));
+    SCHED_CU(talloc((void**)&vals, (size_t)n_pairs * 8));
+    SCHED_CU(talloc((void**)&keys2, (size_t)n_pairs * 8));
+    SCHED_CU(talloc((void**)&vals2, (size_t)n_pairs * 8));
+    k_pair_fill<<<grid, 256, 0, st>>>(n, P.n_img, d_oseg, P.seg_start, P.seg_pt, P.pt_tie, P.oimg, off, keys, vals);
+    int bits = 1;
+    while (bits < 64 && (1ull << bits) < (unsigned long long)P.n_img * (unsigned long long)P.n_img) ++bits;
+    void* s2 = nullptr;
+    size_t s2_bytes = 0;
+    SCHED_CU(cub::DeviceRadixSort::SortPairs(nullptr, s2_bytes, keys, keys2, vals, vals2, (int)n_pairs, 0, bits, st));
+    SCHED_CU(talloc(&s2, s2_bytes));
+    SCHED_CU(cub::DeviceRadixSort::SortPairs(s2, s2_bytes, keys, keys2, vals, vals2, (int)n_pairs, 0, bits, st));
+    // runs of equal keys = blocks
+    unsigned long long* ukeys = keys;          // reuse: unique keys (at most n_pairs)
+    long long* counts;
+    int* d_runs;
+    SCHED_CU(talloc((void**)&counts, (size_t)n_pairs * sizeof(long long)));
+    SCHED_CU(talloc((void**)&d_runs, sizeof(int)));
+    void* s3 = nullptr;
+    size_t s3_bytes = 0;
+    SCHED_CU(cub::DeviceRunLengthEncode::Encode(nullptr, s3_bytes, keys2, ukeys, counts, d_runs, (int)n_pairs, st));
+    SCHED_CU(talloc(&s3, s3_bytes));
+    SCHED_CU(cub::DeviceRunLengthEncode::Encode(s3, s3_bytes, keys2, ukeys, counts, d_runs, (int)n_pairs, st));
+    int n_blocks = 0;
+    SCHED_CU(cudaMemcpyAsync(&n_blocks, d_runs, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SCHED_CU(cudaStreamSynchronize(st));
+    long long* starts;
+    SCHED_CU(talloc((void**)&starts, (size_t)n_blocks * sizeof(long long)));
+    {
+        void* s4 = nullptr;
+        size_t s4_bytes = 0;
+        SCHED_CU(cub::DeviceScan::ExclusiveSum(nullptr, s4_bytes, counts, starts, n_blocks, st));
+        SCHED_CU(talloc(&s4, s4_bytes));
+        SCHED_CU(cub::DeviceScan::ExclusiveSum(s4, s4_bytes, counts, starts, n_blocks, st));
+    }
+    int4* blocks = nullptr;
+    int2* pairs = nullptr;
+    cudaError_t e = cudaMalloc((void**)&blocks, (size_t)n_blocks * sizeof(int4));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&pairs, (size_t)n_pairs * sizeof(int2));
+    if (e != cudaSuccess) {
+        if (blocks) cudaFree(blocks);
+        for (void* p_ : tmp) cudaFree(p_);
+        return e;
+    }
+    k_blocks_fill<<<(n_blocks + 255) / 256, 256, 0, st>>>(n_blocks, P.n_img, ukeys, starts, counts, blocks);
+    k_pairs_unpack<<<(int)((n_pairs + 255) / 256), 256, 0, st>>>(n_pairs, vals2, pairs);
+    e = cudaStreamSynchronize(st);
+    for (void* p_ : tmp) cudaFree(p_);
+    if (e != cudaSuccess) {
+        cudaFree(blocks);
+        cudaFree(pairs);
+        return e;
+    }
+    P.pairs = pairs;
+    P.blocks = blocks;
+    P.n_blocks = n_blocks;
+    *keep_pairs = pairs;
+    *keep_blocks = blocks;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// launcher
+
+#define FEBA_NK_DISPATCH2(NKV, HASCAM, CALL)                                  \
+    switch (NKV) {                                                            \
+        case 1: { constexpr int NK_ = 1; if (HASCAM) { constexpr bool HC_ = true; CALL; } else { constexpr bool HC_ = false; CALL; } } break; \
+        case 2: { constexpr int NK_ = 2; if (HASCAM) { constexpr bool HC_ = true; CALL; } else { constexpr bool HC_ = false; CALL; } } break; \
+        case 3: { constexpr int NK_ = 3; if (HASCAM) { constexpr bool HC_ = true; CALL; } else { constexpr bool HC_ = false; CALL; } } break; \
+        case 4: { constexpr int NK_ = 4; if (HASCAM) { constexpr bool HC_ = true; CALL; } else { constexpr bool HC_ = false; CALL; } } break; \
+        case 5: { constexpr int NK_ = 5; if (HASCAM) { constexpr bool HC_ = true; CALL; } else { constexpr bool HC_ = false; CALL; } } break; \
+        case 6: { constexpr int NK_ = 6; if (HASCAM) { constexpr bool HC_ = true; CALL; } else { constexpr bool HC_ = false; CALL; } } break; \
+        case 7: { constexpr int NK_ = 7; if (HASCAM) { constexpr bool HC_ = true; CALL; } else { constexpr bool HC_ = false; CALL; } } break; \
+        case 8: { constexpr int NK_ = 8; if (HASCAM) { constexpr bool HC_ = true; CALL; } else { constexpr bool HC_ = false; CALL; } } break; \
+        default: return cudaErrorInvalidValue;                                \
+    }
+
+int assemble_warps(const DevProblem& P, int sm_count) {
+    int grid = (P.n_seg + 3) / 4;
+    const int cap = sm_count * 4;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    return grid * 4;
+}
+
+template <int NK, bool HC>
+static cudaError_t launch_point_pass_t(const DevProblem& P, int sm_count, cudaStream_t st) {
+    const size_t smem = 4 * sizeof(PtSmem<NK>);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_point_pass<NK, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    k_point_pass<NK, HC><<<assemble_warps(P, sm_count) / 4, 128, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_assemble(const DevProblem& P, int sm_count, cudaStream_t st, int64_t* launches) {
+    const bool hc = P.uc > 0;
+    if (P.n_seg > 0) {
+        cudaError_t e = cudaSuccess;
+        FEBA_NK_DISPATCH2(P.NK, hc, (e = launch_point_pass_t<NK_, HC_>(P, sm_count, st)));
+        if (e != cudaSuccess) return e;
+        ++*launches;
+        int grid = P.n_img < sm_count * 4 ? P.n_img : sm_count * 4;
+        FEBA_NK_DISPATCH2(P.NK, hc, (k_image_pass<NK_, HC_><<<grid, 128, 0, st>>>(P)));
+        ++*launches;
+        if (hc) {
+            k_cam_reduce<<<1, 1024, 0, st>>>(P, assemble_warps(P, sm_count));
+            ++*launches;
+        }
+        if (P.n_blocks > 0) {
+            int g2 = (P.n_blocks + 3) / 4;
+            if (g2 > sm_count * 8) g2 = sm_count * 8;
+            k_pair_pass<<<g2, 128, 0, st>>>(P);
+            ++*launches;
+        }
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace feba

@@ -7,6 +7,8 @@ namespace feba {
 
 constexpr int kBlk = 64;          // dense linear-algebra tile; reduced system is padded to it
 constexpr int kAugRows = 8;       // rows of the augmented block in use: [g ; G(:,1..7)]
+constexpr int kRec1 = 18;         // per-observation record 1: Je (2x6), Z (2x3)
+constexpr int kCamPart = 104;     // per-warp camera partial: packed NC(NC+1)/2 block + NC rhs (NC <= 13)
 
 // Everything a kernel needs, passed by value (lives in the constant bank).
 struct DevProblem {
@@ -44,6 +46,15 @@ struct DevProblem {
     const double* dcam_unscaled;  // un-scaled increment (main.m:458-482)
     double* dpts;                 // increment of the tie points, n_tie x 3
     double* partial;              // per-warp partial sums (deterministic final reduction)
+    // assembly schedule and per-observation records (feba_assemble.cu)
+    double* rec1;                 // n_obs x kRec1
+    double* rec2;                 // n_obs x (2 + 2 NC): r (2), H (NC x 2)
+    const int* img_start;         // n_img + 1: observations grouped by image ...
+    const int* iobs;              // ... as point-major observation indices
+    const int2* pairs;            // (a, b) observation pairs sharing a tie point, sorted by image block
+    const int4* blocks;           // (image a, image b <= a, first pair, pairs)
+    int n_blocks;
+    double* cam_part;             // per-warp camera-camera partial sums
     double* Gt;                   // inner-constraint rows, compact: (6 n_img) x 8 row-major (col 7 unused)
 };
 

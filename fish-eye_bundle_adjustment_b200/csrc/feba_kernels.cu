@@ -12,20 +12,6 @@
 
 namespace feba {
 
-// Accumulation into the reduced system.  A -DFEBA_CHECK build range-checks every target address
-// (compute-sanitizer is not available on the GPU pool) and counts violations instead of writing.
-#ifdef FEBA_CHECK
-__device__ int g_feba_oob = 0;
-#define RED_ADD(ptr, v)                                                                   \
-    do {                                                                                  \
-        double* p_ = (ptr);                                                               \
-        if (p_ < P.S || p_ >= P.S + (size_t)P.ld * (size_t)P.ld) atomicAdd(&g_feba_oob, 1); \
-        else atomicAdd(p_, (v));                                                          \
-    } while (0)
-#else
-#define RED_ADD(ptr, v) atomicAdd((ptr), (v))
-#endif
-
 // ------------------------------------------------------------------------------------------
 // K0: per-image and per-camera tables from the current parameters.
 // M = R3(kappa) R2(phi) R1(omega) as written in BuildAwG.m:163-165.
@@ -338,331 +324,6 @@ __device__ __forceinline__ double sym3(const double* m, int i, int j) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K1+K2: fused assembly of the block normal equations and Schur elimination of the points.
-// One warp per object point, lanes over its observations (chunks of 32).
-//
-// For a tie point p with observations a = 1..m (image i_a), per-observation blocks
-//   We_a = Je_a' P Jt_a (u_img x 3), Wc = sum_a Jc_a' P Jt_a (u_cam x 3), V = sum_a Jt_a' P Jt_a,
-// the contribution to the reduced system S = N_cc - W V^-1 W' (never forming N) is
-//   S[i_a,i_b] += delta_ab Je_a'PJe_a - (We_a V^-1) We_b'
-//   S[cam,i_a] += Jc_a'PJe_a - Wc V^-1 We_a'
-//   S[cam,cam] += sum_a Jc_a'PJc_a - Wc V^-1 Wc'
-//   g[i_a]     += Je_a'P w_a - We_a V^-1 u_p,   g[cam] += sum_a Jc_a'P w_a - Wc V^-1 u_p.
-// Control points contribute only the direct terms.  Only the lower triangle is written.
-// Single camera per problem in this kernel (n_cam == 1); camera block sums are kept in
-// lane-owned registers across the warp's points and flushed once.
-template <int NK>
-struct AsmSmem {
-    static constexpr int NC = NK + 5;
-    double rowJc[32][2][NC];
-    double rowJt[32][2][3];
-    double roww[32][2];
-    double We[32][18];
-    double Wc[NC][3];
-    double Yc[NC][3];
-    double V[6];
-    double up[3];
-    int img[32];
-};
-
-template <int NK, bool HAS_CAM>
-__global__ void __launch_bounds__(128) k_assemble(DevProblem P) {
-    constexpr int NC = NK + 5;
-    constexpr int ND = NC * (NC + 1) / 2;          // packed camera-camera block
-    constexpr int DPL = (ND + 31) / 32;            // entries of D per lane
-    constexpr int WPL = (NC * 3 + 31) / 32;        // entries of Wc per lane
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    AsmSmem<NK>* sm_all = reinterpret_cast<AsmSmem<NK>*>(smem_raw);
-    const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    AsmSmem<NK>& sm = sm_all[wib];
-    const int nwarp = gridDim.x * (blockDim.x >> 5);
-    const int gw = blockIdx.x * (blockDim.x >> 5) + wib;
-    const double pw[2] = {P.px, P.py};
-    const int type = P.type;
-
-    // static ownership of camera-block entries
-    int dI[DPL], dJ[DPL];
-    double dacc[DPL];
-#pragma unroll
-    for (int t = 0; t < DPL; ++t) {
-        const int e = lane + 32 * t;
-        int i = 0;
-        while ((i + 1) * (i + 2) / 2 <= e) ++i;    // row of packed lower-triangular index e
-        dI[t] = i;
-        dJ[t] = e - i * (i + 1) / 2;
-        dacc[t] = 0.0;
-    }
-    double gcacc = 0.0;
-
-    for (int seg = gw; seg < P.n_seg; seg += nwarp) {
-        const int beg = P.seg_start[seg], end = P.seg_start[seg + 1];
-        const int pt = P.seg_pt[seg];
-        const bool is_tie = P.pt_tie[pt] >= 0;
-        const double X = P.xyz[3 * pt], Y = P.xyz[3 * pt + 1], Z = P.xyz[3 * pt + 2];
-        const bool single = (end - beg) <= 32;
-        ObsJac<NK> J;
-        int img = -1;
-        bool act = false;
-
-        // ---------------- pass 1: V, u_p, Wc, and the direct camera-camera sums
-        double vacc = 0.0;                          // lanes 0..5: V entries, 6..8: u_p
-        double wcacc[WPL];
-#pragma unroll
-        for (int t = 0; t < WPL; ++t) wcacc[t] = 0.0;
-        if (is_tie || HAS_CAM) {
-            for (int c0 = beg; c0 < end; c0 += 32) {
-                const int o = c0 + lane;
-                act = o < end;
-                if (act) {
-                    img = P.oimg[o];
-                    observation<NK, HAS_CAM>(type, P.ox[o], P.oy[o], P.img_tab + kImgStride * img,
-                                             P.cam_tab, X, Y, Z, J);
-                }
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    if (HAS_CAM) {
-#pragma unroll
-                        for (int j = 0; j < NC; ++j) sm.rowJc[lane][r][j] = act ? J.Jc[r][j] : 0.0;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) sm.rowJt[lane][r][k] = act ? J.Jt[r][k] : 0.0;
-                    sm.roww[lane][r] = act ? J.w[r] : 0.0;
-                }
-                __syncwarp();
-                const int nrow = min(32, end - c0);
-                if (HAS_CAM) {
-#pragma unroll
-                    for (int t = 0; t < DPL; ++t) {
-                        if (lane + 32 * t < ND) {
-                            double a = 0.0;
-                            for (int l = 0; l < nrow; ++l)
-                                a += sm.rowJc[l][0][dI[t]] * pw[0] * sm.rowJc[l][0][dJ[t]] +
-                                     sm.rowJc[l][1][dI[t]] * pw[1] * sm.rowJc[l][1][dJ[t]];
-                            dacc[t] += a;
-                        }
-                    }
-                    if (lane < NC) {
-                        double a = 0.0;
-                        for (int l = 0; l < nrow; ++l)
-                            a += sm.rowJc[l][0][lane] * pw[0] * sm.roww[l][0] +
-                                 sm.rowJc[l][1][lane] * pw[1] * sm.roww[l][1];
-                        gcacc += a;
-                    }
-                    if (is_tie) {
-#pragma unroll
-                        for (int t = 0; t < WPL; ++t) {
-                            const int e = lane + 32 * t;
-                            if (e < NC * 3) {
-                                const int i = e / 3, k = e - 3 * i;
-                                double a = 0.0;
-                                for (int l = 0; l < nrow; ++l)
-                                    a += sm.rowJc[l][0][i] * pw[0] * sm.rowJt[l][0][k] +
-                                         sm.rowJc[l][1][i] * pw[1] * sm.rowJt[l][1][k];
-                                wcacc[t] += a;
-                            }
-                        }
-                    }
-                }
-                if (is_tie && lane < 9) {
-                    double a = 0.0;
-                    if (lane < 6) {
-                        const int i = lane < 1 ? 0 : (lane < 3 ? 1 : 2);
-                        const int k = lane - i * (i + 1) / 2;
-                        for (int l = 0; l < nrow; ++l)
-                            a += sm.rowJt[l][0][i] * pw[0] * sm.rowJt[l][0][k] +
-                                 sm.rowJt[l][1][i] * pw[1] * sm.rowJt[l][1][k];
-                    } else {
-                        const int k = lane - 6;
-                        for (int l = 0; l < nrow; ++l)
-                            a += sm.rowJt[l][0][k] * pw[0] * sm.roww[l][0] +
-                                 sm.rowJt[l][1][k] * pw[1] * sm.roww[l][1];
-                    }
-                    vacc += a;
-                }
-                __syncwarp();
-            }
-        }
-        double Vinv[6] = {0, 0, 0, 0, 0, 0};
-        double up[3] = {0, 0, 0};
-        if (is_tie) {
-            if (lane < 6) sm.V[lane] = vacc;
-            else if (lane < 9) sm.up[lane - 6] = vacc;
-            if (HAS_CAM) {
-#pragma unroll
-                for (int t = 0; t < WPL; ++t) {
-                    const int e = lane + 32 * t;
-                    if (e < NC * 3) (&sm.Wc[0][0])[e] = wcacc[t];
-                }
-            }
-            __syncwarp();
-            double Vp[6];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) Vp[k] = sm.V[k];
-            sym3_inverse(Vp, Vinv);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) up[k] = sm.up[k];
-            if (HAS_CAM) {
-                if (lane < NC) {
-#pragma unroll
-                    for (int k = 0; k < 3; ++k)
-                        sm.Yc[lane][k] = sm.Wc[lane][0] * sym3(Vinv, 0, k) +
-                                         sm.Wc[lane][1] * sym3(Vinv, 1, k) +
-                                         sm.Wc[lane][2] * sym3(Vinv, 2, k);
-                }
-                __syncwarp();
-#pragma unroll
-                for (int t = 0; t < DPL; ++t) {
-                    if (lane + 32 * t < ND)
-                        dacc[t] -= sm.Yc[dI[t]][0] * sm.Wc[dJ[t]][0] + sm.Yc[dI[t]][1] * sm.Wc[dJ[t]][1] +
-                                   sm.Yc[dI[t]][2] * sm.Wc[dJ[t]][2];
-                }
-                if (lane < NC)
-                    gcacc -= sm.Yc[lane][0] * up[0] + sm.Yc[lane][1] * up[1] + sm.Yc[lane][2] * up[2];
-            }
-        }
-
-        // ---------------- pass 2: image-keyed blocks
-        for (int a0 = beg; a0 < end; a0 += 32) {
-            const int oa = a0 + lane;
-            const bool acta = oa < end;
-            if (!single || !(is_tie || HAS_CAM)) {
-                act = acta;
-                if (acta) {
-                    img = P.oimg[oa];
-                    observation<NK, HAS_CAM>(type, P.ox[oa], P.oy[oa], P.img_tab + kImgStride * img,
-                                             P.cam_tab, X, Y, Z, J);
-                }
-            }
-            const int img_a = acta ? img : -1;
-            double We[6][3], Ye[6][3];
-            if (acta) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i)
-#pragma unroll
-                    for (int k = 0; k < 3; ++k)
-                        We[i][k] = J.Je[0][i] * pw[0] * J.Jt[0][k] + J.Je[1][i] * pw[1] * J.Jt[1][k];
-#pragma unroll
-                for (int i = 0; i < 6; ++i)
-#pragma unroll
-                    for (int k = 0; k < 3; ++k)
-                        Ye[i][k] = is_tie ? We[i][0] * sym3(Vinv, 0, k) + We[i][1] * sym3(Vinv, 1, k) +
-                                                We[i][2] * sym3(Vinv, 2, k)
-                                          : 0.0;
-                const size_t col0 = (size_t)P.ui * img_a;
-                // right-hand side of the image block -> augmented row 0
-#pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    if (P.ecol[i] >= 0) {
-                        double gval = J.Je[0][i] * pw[0] * J.w[0] + J.Je[1][i] * pw[1] * J.w[1] -
-                                      (Ye[i][0] * up[0] + Ye[i][1] * up[1] + Ye[i][2] * up[2]);
-                        RED_ADD(&P.S[(size_t)P.n_pad + (size_t)P.ld * (col0 + P.ecol[i])], gval);
-                    }
-                }
-                // direct diagonal block Je'PJe (lower)
-#pragma unroll
-                for (int i = 0; i < 6; ++i)
-#pragma unroll
-                    for (int j = 0; j <= i; ++j) {
-                        if (P.ecol[i] >= 0 && P.ecol[j] >= 0) {
-                            const double val = J.Je[0][i] * pw[0] * J.Je[0][j] + J.Je[1][i] * pw[1] * J.Je[1][j];
-                            RED_ADD(&P.S[(col0 + P.ecol[i]) + (size_t)P.ld * (col0 + P.ecol[j])], val);
-                        }
-                    }
-                if (HAS_CAM) {
-                    // camera x image block: Jc'PJe - Wc V^-1 We' = Jc'PJe - Wc Ye'
-#pragma unroll
-                    for (int j = 0; j < NC; ++j) {
-                        if (P.ccol[j] >= 0) {
-                            const size_t row = (size_t)P.off_cam + P.ccol[j];
-                            double wc0 = 0, wc1 = 0, wc2 = 0;
-                            if (is_tie) { wc0 = sm.Wc[j][0]; wc1 = sm.Wc[j][1]; wc2 = sm.Wc[j][2]; }
-#pragma unroll
-                            for (int i = 0; i < 6; ++i) {
-                                if (P.ecol[i] >= 0) {
-                                    const double val = J.Jc[0][j] * pw[0] * J.Je[0][i] +
-                                                       J.Jc[1][j] * pw[1] * J.Je[1][i] -
-                                                       (wc0 * Ye[i][0] + wc1 * Ye[i][1] + wc2 * Ye[i][2]);
-                                    RED_ADD(&P.S[row + (size_t)P.ld * (col0 + P.ecol[i])], val);
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-            if (is_tie) {
-                for (int b0 = beg; b0 < end; b0 += 32) {
-                    __syncwarp();
-                    if (b0 == a0) {
-                        sm.img[lane] = img_a;
-                        if (acta) {
-#pragma unroll
-                            for (int i = 0; i < 6; ++i)
-#pragma unroll
-                                for (int k = 0; k < 3; ++k) sm.We[lane][3 * i + k] = We[i][k];
-                        }
-                    } else {
-                        const int ob = b0 + lane;
-                        sm.img[lane] = -1;
-                        if (ob < end) {
-                            ObsJac<NK> Jb;
-                            const int ib = P.oimg[ob];
-                            observation<NK, false>(type, P.ox[ob], P.oy[ob], P.img_tab + kImgStride * ib,
-                                                   P.cam_tab, X, Y, Z, Jb);
-                            sm.img[lane] = ib;
-#pragma unroll
-                            for (int i = 0; i < 6; ++i)
-#pragma unroll
-                                for (int k = 0; k < 3; ++k)
-                                    sm.We[lane][3 * i + k] =
-                                        Jb.Je[0][i] * pw[0] * Jb.Jt[0][k] + Jb.Je[1][i] * pw[1] * Jb.Jt[1][k];
-                        }
-                    }
-                    __syncwarp();
-                    const int nb = min(32, end - b0);
-                    if (acta) {
-                        const size_t rowa = (size_t)P.ui * img_a;
-                        for (int b = 0; b < nb; ++b) {
-                            const int ib = sm.img[b];
-                            if (ib > img_a) continue;
-                            const bool diag = (ib == img_a);
-                            const size_t colb = (size_t)P.ui * ib;
-                            double wb[18];
-#pragma unroll
-                            for (int q = 0; q < 18; ++q) wb[q] = sm.We[b][q];
-#pragma unroll
-                            for (int i = 0; i < 6; ++i)
-#pragma unroll
-                                for (int j = 0; j < 6; ++j) {
-                                    if (P.ecol[i] >= 0 && P.ecol[j] >= 0 && (!diag || j <= i)) {
-                                        const double val = -(Ye[i][0] * wb[3 * j] + Ye[i][1] * wb[3 * j + 1] +
-                                                             Ye[i][2] * wb[3 * j + 2]);
-                                        RED_ADD(&P.S[(rowa + P.ecol[i]) + (size_t)P.ld * (colb + P.ecol[j])], val);
-                                    }
-                                }
-                        }
-                    }
-                }
-            }
-        }
-    }
-    // flush the camera block (one camera)
-    if (HAS_CAM) {
-#pragma unroll
-        for (int t = 0; t < DPL; ++t) {
-            if (lane + 32 * t < ND && P.ccol[dI[t]] >= 0 && P.ccol[dJ[t]] >= 0) {
-                // packed index (i >= j) in parameter order; slots are monotone so row >= col
-                const size_t row = (size_t)P.off_cam + P.ccol[dI[t]];
-                const size_t col = (size_t)P.off_cam + P.ccol[dJ[t]];
-                RED_ADD(&P.S[row + (size_t)P.ld * col], dacc[t]);
-            }
-        }
-        if (lane < NC && P.ccol[lane] >= 0)
-            RED_ADD(&P.S[(size_t)P.n_pad + (size_t)P.ld * ((size_t)P.off_cam + P.ccol[lane])], gcacc);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // Camera-part update (main.m:458-488 for the EOP/IOP unknowns): delta_c = -sol, un-scale the
 // distortion increments by r_max^(2j) / r_max^2, add to the parameter tables, partial sumabs.
 __global__ void k_update_cam(DevProblem P, const double* __restrict__ sol, const double* __restrict__ dvec,
@@ -926,30 +587,6 @@ cudaError_t launch_border_scale(const DevProblem& P, const double* eop, double* 
     return cudaGetLastError();
 }
 
-template <int NK, bool HC>
-static cudaError_t launch_assemble_t(const DevProblem& P, int sm_count, cudaStream_t st) {
-    const size_t smem = 4 * sizeof(AsmSmem<NK>);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_assemble<NK, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    int grid = (P.n_seg + 3) / 4;
-    const int cap = sm_count * 4;
-    if (grid > cap) grid = cap;
-    if (grid < 1) grid = 1;
-    k_assemble<NK, HC><<<grid, 128, smem, st>>>(P);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_assemble(const DevProblem& P, int sm_count, cudaStream_t st) {
-    const bool hc = P.uc > 0;
-    FEBA_NK_DISPATCH(P.NK, hc, return (launch_assemble_t<NK_, HC_>(P, sm_count, st)));
-    return cudaSuccess;
-}
-
 int backsub_warps(const DevProblem& P, int sm_count) {
     int grid = (P.n_seg + 3) / 4;
     const int cap = sm_count * 8;
@@ -1000,16 +637,6 @@ cudaError_t launch_xhat_gather(const DevProblem& P, int sm_count, double* xhat, 
 cudaError_t launch_delta_gather(const DevProblem& P, int sm_count, double* delta, cudaStream_t st) {
     k_delta_gather<<<stream_grid((int64_t)P.n_red + 3 * (int64_t)P.n_tie, sm_count), 256, 0, st>>>(P, delta);
     return cudaGetLastError();
-}
-
-int debug_oob_count() {
-#ifdef FEBA_CHECK
-    int v = 0;
-    cudaMemcpyFromSymbol(&v, g_feba_oob, sizeof(int));
-    return v;
-#else
-    return -1;
-#endif
 }
 
 int residual_blocks(const DevProblem& P, int sm_count) {

@@ -17,14 +17,17 @@ cudaError_t launch_delta_gather(const DevProblem& P, int sm_count, double* delta
 // G rows (inner constraints), padding diagonal, M = S + Gc Gc' and its Jacobi scaling d = diag(M)^-1/2
 cudaError_t launch_border_scale(const DevProblem& P, const double* eop, double* dvec, int* info, cudaStream_t st,
                                 int64_t* launches);
-cudaError_t launch_assemble(const DevProblem& P, int sm_count, cudaStream_t st);
+// feba_assemble.cu: schedule (once) and the three assembly passes (per iteration)
+cudaError_t build_pair_schedule(DevProblem& P, const int* d_oseg, long long* n_pairs_out, void** keep_pairs,
+                                void** keep_blocks, cudaStream_t st);
+int assemble_warps(const DevProblem& P, int sm_count);
+cudaError_t launch_assemble(const DevProblem& P, int sm_count, cudaStream_t st, int64_t* launches);
 int backsub_warps(const DevProblem& P, int sm_count);
 cudaError_t launch_backsub(const DevProblem& P, int sm_count, cudaStream_t st);
 cudaError_t launch_update_cam(const DevProblem& P, const double* sol, const double* dvec, double* dcam,
                               double* dcam_unscaled, double* eop, double* iop, double* out_sumabs, cudaStream_t st);
 cudaError_t launch_sum_partials(const double* partial, int n, int stride, int offset, double* out,
                                 cudaStream_t st);
-int debug_oob_count();   // -1 unless built with -DFEBA_CHECK
 int residual_blocks(const DevProblem& P, int sm_count);
 cudaError_t launch_residuals(const DevProblem& P, int sm_count, const int* opt, const double* xyz_prev,
                              const double* iop_new, double* v_out, double* rsd_out, cudaStream_t st);

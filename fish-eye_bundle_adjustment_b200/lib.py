@@ -24,7 +24,7 @@ EXPORTS = (
     "feba_create", "feba_destroy", "feba_last_error", "feba_set_stream", "feba_num_unknowns",
     "feba_set_xhat", "feba_get_xhat", "feba_iterate", "feba_iterate_assemble", "feba_reduced_dev",
     "feba_iterate_solve", "feba_get_delta", "feba_residuals", "feba_solve", "feba_last_timing",
-    "feba_launch_count", "feba_debug_reduced", "feba_debug_oob", "feba_iterate_async", "feba_iterate_solve_async", "feba_sync",
+    "feba_launch_count", "feba_debug_reduced", "feba_iterate_async", "feba_iterate_solve_async", "feba_sync",
 )
 
 
@@ -87,7 +87,6 @@ def load() -> C.CDLL:
     lib.feba_launch_count.argtypes = [H]
     lib.feba_launch_count.restype = C.c_int64
     lib.feba_debug_reduced.argtypes = [H, _pd, _pd]
-    lib.feba_debug_oob.argtypes = []
     lib.feba_iterate_async.argtypes = [H]
     lib.feba_iterate_solve_async.argtypes = [H]
     lib.feba_sync.argtypes = [H, _pd]

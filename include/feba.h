@@ -149,10 +149,6 @@ int64_t feba_launch_count(const feba_handle *h);
  * S_out [u_c*u_c] column-major full symmetric, g_out [u_c]; either may be NULL. */
 int feba_debug_reduced(feba_handle *h, double *S_out, double *g_out);
 
-/* Diagnostic: number of out-of-range accumulation targets caught by a -DFEBA_CHECK build of the
- * kernels (compute-sanitizer stand-in); -1 in a normal build. */
-int feba_debug_oob(void);
-
 /* Device-resident variant for benchmarking with inputs already in HBM: identical to
  * feba_iterate but never copies deltasum back unless asked (deltasum_out may be NULL). */
 int feba_iterate_async(feba_handle *h);

@@ -54,4 +54,3 @@ if __name__ == "__main__":
         stage_report("synthetic mixed", synth.make_network(12, 400, 8, 33, mode="mixed", n_control=40))
     if "big" in which:
         stage_report("synthetic >32 obs/pt", synth.make_network(64, 120, 40, 5, mode="mixed", n_control=20))
-    print("oob count:", fb.lib.load().feba_debug_oob())
