@@ -257,13 +257,13 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
     }
     for (int sg = 0; sg < P.n_seg; ++sg)
         for (int o = seg_start[sg]; o < seg_start[sg + 1]; ++o) oseg[o] = sg;
-    // observations grouped by image (indices into the point-major order), for the image pass
-    std::vector<int> img_start((size_t)pr->n_img + 1, 0), iobs((size_t)n);
+    // image-major record positions (stable: point-major order is kept inside an image)
+    std::vector<int> img_start((size_t)pr->n_img + 1, 0), ipos((size_t)n);
     for (int64_t o = 0; o < n; ++o) ++img_start[(size_t)simg[o] + 1];
     for (int j = 0; j < pr->n_img; ++j) img_start[(size_t)j + 1] += img_start[j];
     {
         std::vector<int> cur(img_start.begin(), img_start.end() - 1);
-        for (int64_t o = 0; o < n; ++o) iobs[cur[simg[o]]++] = (int)o;
+        for (int64_t o = 0; o < n; ++o) ipos[o] = cur[simg[o]]++;
     }
     // tie index <-> CNT row (main.m:362-375, Buildxhat.m:108-135)
     std::vector<int> tie_pt((size_t)pr->n_tie, -1);
@@ -296,7 +296,7 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
     CU(h, upload(h, &dpt_tie, pr->pt_tie, (size_t)pr->n_pts));
     CU(h, upload(h, &h->tie_pt, tie_pt.data(), tie_pt.size()));
     CU(h, upload(h, &dimg_start, img_start.data(), img_start.size()));
-    CU(h, upload(h, &diobs, iobs.data(), iobs.size()));
+    CU(h, upload(h, &diobs, ipos.data(), ipos.size()));
     CU(h, upload(h, &doseg, oseg.data(), oseg.size()));
     CU(h, dev_alloc(h, &P.rec1, (size_t)n * kRec1));
     CU(h, dev_alloc(h, &P.rec2, (size_t)n * (2 + 2 * P.NC)));
@@ -335,7 +335,7 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
     P.img_cam = dimg_cam;
     P.pt_tie = dpt_tie;
     P.img_start = dimg_start;
-    P.iobs = diobs;
+    P.ipos = diobs;
     P.img_tab = h->img_tab;
     P.cam_tab = h->cam_tab;
     P.xyz = xyz;

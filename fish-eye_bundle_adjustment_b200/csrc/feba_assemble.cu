@@ -18,8 +18,9 @@
 //     S[cam, i_a]   += H_a Je_a,    H_a = Jc_a' P - Fc Z_a'
 //     S[cam, cam]   += sum_a Jc_a' P Jc_a - Fc Fc',  g[cam] += sum_a Jc_a' P w_a - Fc ut   point pass
 // Control points (not estimated) contribute the same terms with Z = 0, Fc = 0.
-// The point pass stores, per observation, rec1 = {Je (2x6), Z (2x3)} and rec2 = {r (2), H (NC x 2)};
-// the other two passes only read those records.  Every entry of S has exactly one writer per
+// The point pass stores, per observation, rec1 = {Je (2x6), Z (2x3)} and rec2 = {r (2), H (NC x 2)} in
+// IMAGE-MAJOR order (an image's records are contiguous: the image pass streams them, the pair pass
+// gathers monotonically inside two images' ranges); the other two passes only read those records.  Every entry of S has exactly one writer per
 // kernel and partial sums are combined in a fixed order, so the result is run-to-run deterministic.
 #include <cub/cub.cuh>
 
@@ -34,7 +35,7 @@ namespace feba {
 // ------------------------------------------------------------------------------------------
 // point pass: one warp per object point, lanes over its observations (chunks of 32)
 template <int NK>
-struct PtSmem {
+struct alignas(16) PtSmem {
     static constexpr int NC = NK + 5;
     double rowJc[32][2][NC];
     double rowJt[32][2][3];
@@ -43,6 +44,7 @@ struct PtSmem {
     double Fc[NC][3];
     double V[6];
     double up[3];
+    int pos[32];
 };
 
 template <int NK, bool HAS_CAM>
@@ -208,46 +210,72 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
                 if (lane < NC) gcacc -= sm.Fc[lane][0] * ut[0] + sm.Fc[lane][1] * ut[1] + sm.Fc[lane][2] * ut[2];
             }
         }
-        // ---------------- pass 2: per-observation records
+        // ---------------- pass 2: per-observation records, staged through shared memory (the
+        // pass-1 row buffers are dead by now) and written as 16-byte units, contiguous per record,
+        // at the observation's position in the image-major record arrays
+        double* buf = &sm.rowJc[0][0][0];              // (2 NC + 8) * 32 doubles, >= 32 * max(18, R2)
         for (int a0 = beg; a0 < end; a0 += 32) {
             const int o = a0 + lane;
-            if (o >= end) continue;
-            if (!have_J) {
-                const int img = P.oimg[o];
-                observation<NK, HAS_CAM>(type, P.ox[o], P.oy[o], P.img_tab + kImgStride * img, P.cam_tab, X, Y, Z, J);
-            }
-            double Zm[2][3];
+            const bool act = o < end;
+            const int nrow = min(32, end - a0);
+            double Zm[2][3], ra[2];
+            if (act) {
+                if (!have_J) {
+                    const int img = P.oimg[o];
+                    observation<NK, HAS_CAM>(type, P.ox[o], P.oy[o], P.img_tab + kImgStride * img, P.cam_tab, X, Y,
+                                             Z, J);
+                }
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const double t0 = pw[r] * J.Jt[r][0], t1 = pw[r] * J.Jt[r][1], t2 = pw[r] * J.Jt[r][2];
-                Zm[r][0] = t0 * i00;                         // zero for control points (i.. = 0)
-                Zm[r][1] = t0 * i10 + t1 * i11;
-                Zm[r][2] = t0 * i20 + t1 * i21 + t2 * i22;
-            }
-            double* r1 = P.rec1 + (size_t)kRec1 * o;
+                for (int r = 0; r < 2; ++r) {
+                    const double t0 = pw[r] * J.Jt[r][0], t1 = pw[r] * J.Jt[r][1], t2 = pw[r] * J.Jt[r][2];
+                    Zm[r][0] = t0 * i00;                     // zero for control points (i.. = 0)
+                    Zm[r][1] = t0 * i10 + t1 * i11;
+                    Zm[r][2] = t0 * i20 + t1 * i21 + t2 * i22;
+                    ra[r] = pw[r] * J.w[r] - (Zm[r][0] * ut[0] + Zm[r][1] * ut[1] + Zm[r][2] * ut[2]);
+                }
+                sm.pos[lane] = P.ipos[o];
+                double* r1 = buf + kRec1 * lane;
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
+                for (int r = 0; r < 2; ++r) {
 #pragma unroll
-                for (int i = 0; i < 6; ++i) r1[6 * r + i] = J.Je[r][i];
+                    for (int i = 0; i < 6; ++i) r1[6 * r + i] = J.Je[r][i];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) r1[12 + 3 * r + k] = Zm[r][k];
-            }
-            double* r2 = P.rec2 + (size_t)R2 * o;
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-                r2[r] = pw[r] * J.w[r] - (Zm[r][0] * ut[0] + Zm[r][1] * ut[1] + Zm[r][2] * ut[2]);
-            if (HAS_CAM) {
-#pragma unroll
-                for (int j = 0; j < NC; ++j) {
-                    double f0 = 0, f1 = 0, f2 = 0;
-                    if (is_tie) { f0 = sm.Fc[j][0]; f1 = sm.Fc[j][1]; f2 = sm.Fc[j][2]; }
-#pragma unroll
-                    for (int r = 0; r < 2; ++r)
-                        r2[2 + 2 * j + r] = J.Jc[r][j] * pw[r] - (f0 * Zm[r][0] + f1 * Zm[r][1] + f2 * Zm[r][2]);
+                    for (int k = 0; k < 3; ++k) r1[12 + 3 * r + k] = Zm[r][k];
                 }
             }
+            __syncwarp();
+            for (int u = lane; u < nrow * (kRec1 / 2); u += 32) {
+                const int k = u / (kRec1 / 2), part = u - k * (kRec1 / 2);
+                reinterpret_cast<double2*>(P.rec1 + (size_t)kRec1 * sm.pos[k])[part] =
+                    reinterpret_cast<const double2*>(buf + kRec1 * k)[part];
+            }
+            __syncwarp();
+            if (act) {
+                double* r2 = buf + R2 * lane;
+                r2[0] = ra[0];
+                r2[1] = ra[1];
+                if (HAS_CAM) {
+#pragma unroll
+                    for (int j = 0; j < NC; ++j) {
+                        double f0 = 0, f1 = 0, f2 = 0;
+                        if (is_tie) { f0 = sm.Fc[j][0]; f1 = sm.Fc[j][1]; f2 = sm.Fc[j][2]; }
+#pragma unroll
+                        for (int r = 0; r < 2; ++r)
+                            r2[2 + 2 * j + r] = J.Jc[r][j] * pw[r] - (f0 * Zm[r][0] + f1 * Zm[r][1] + f2 * Zm[r][2]);
+                    }
+                }
+            }
+            __syncwarp();
+            {
+                constexpr int U2 = HAS_CAM ? R2 / 2 : 1;     // without camera unknowns only r (2) is used
+                for (int u = lane; u < nrow * U2; u += 32) {
+                    const int k = u / U2, part = u - k * U2;
+                    reinterpret_cast<double2*>(P.rec2 + (size_t)R2 * sm.pos[k])[part] =
+                        reinterpret_cast<const double2*>(buf + R2 * k)[part];
+                }
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
     // camera-camera block and camera right-hand side of this warp -> partial buffer (fixed-order sum later)
     if (HAS_CAM) {
@@ -306,9 +334,8 @@ __global__ void __launch_bounds__(128) k_image_pass(DevProblem P) {
 #pragma unroll
             for (int k = 0; k < 27; ++k) acc[k] = 0.0;
             for (int t = beg + tid; t < end; t += 128) {
-                const int o = P.iobs[t];
-                const double* r1 = P.rec1 + (size_t)kRec1 * o;
-                const double* r2 = P.rec2 + (size_t)R2 * o;
+                const double* r1 = P.rec1 + (size_t)kRec1 * t;
+                const double* r2 = P.rec2 + (size_t)R2 * t;
                 double Je[2][6], Zm[2][3];
 #pragma unroll
                 for (int k = 0; k < 6; ++k) { Je[0][k] = r1[k]; Je[1][k] = r1[6 + k]; }
@@ -355,9 +382,8 @@ __global__ void __launch_bounds__(128) k_image_pass(DevProblem P) {
 #pragma unroll
             for (int k = 0; k < NC * 6; ++k) acc[k] = 0.0;
             for (int t = beg + tid; t < end; t += 128) {
-                const int o = P.iobs[t];
-                const double* r1 = P.rec1 + (size_t)kRec1 * o;
-                const double* r2 = P.rec2 + (size_t)R2 * o + 2;
+                const double* r1 = P.rec1 + (size_t)kRec1 * t;
+                const double* r2 = P.rec2 + (size_t)R2 * t + 2;
                 double Je[2][6];
 #pragma unroll
                 for (int k = 0; k < 6; ++k) { Je[0][k] = r1[k]; Je[1][k] = r1[6 + k]; }
@@ -494,9 +520,10 @@ __global__ void k_blocks_fill(int n_blocks, int n_img, const unsigned long long*
                           (int)starts[k], (int)counts[k]);
 }
 
-__global__ void k_pairs_unpack(long long n, const unsigned long long* __restrict__ vals, int2* __restrict__ pairs) {
+__global__ void k_pairs_unpack(long long n, const unsigned long long* __restrict__ vals,
+                               const int* __restrict__ ipos, int2* __restrict__ pairs) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i < n) pairs[i] = make_int2((int)(vals[i] >> 32), (int)(vals[i] & 0xffffffffull));
+    if (i < n) pairs[i] = make_int2(ipos[(int)(vals[i] >> 32)], ipos[(int)(vals[i] & 0xffffffffull)]);
 }
 
 #define SCHED_CU(call)                      \
@@ -594,7 +621,7 @@ cudaError_t build_pair_schedule(DevProblem& P, const int* d_oseg, long long* n_p
         return e;
     }
     k_blocks_fill<<<(n_blocks + 255) / 256, 256, 0, st>>>(n_blocks, P.n_img, ukeys, starts, counts, blocks);
-    k_pairs_unpack<<<(int)((n_pairs + 255) / 256), 256, 0, st>>>(n_pairs, vals2, pairs);
+    k_pairs_unpack<<<(int)((n_pairs + 255) / 256), 256, 0, st>>>(n_pairs, vals2, P.ipos, pairs);
     e = cudaStreamSynchronize(st);
     for (void* p_ : tmp) cudaFree(p_);
     if (e != cudaSuccess) {

@@ -49,9 +49,9 @@ struct DevProblem {
     // assembly schedule and per-observation records (feba_assemble.cu)
     double* rec1;                 // n_obs x kRec1
     double* rec2;                 // n_obs x (2 + 2 NC): r (2), H (NC x 2)
-    const int* img_start;         // n_img + 1: observations grouped by image ...
-    const int* iobs;              // ... as point-major observation indices
-    const int2* pairs;            // (a, b) observation pairs sharing a tie point, sorted by image block
+    const int* img_start;         // n_img + 1: record ranges of the images
+    const int* ipos;              // point-major observation index -> position in the image-major records
+    const int2* pairs;            // (a, b) record positions of observation pairs sharing a tie point, by block
     const int4* blocks;           // (image a, image b <= a, first pair, pairs)
     int n_blocks;
     double* cam_part;             // per-warp camera-camera partial sums
