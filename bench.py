@@ -126,21 +126,21 @@ def make_workload(name: str, scale: float):
 
 # --------------------------------------------------------------------------- CPU baseline
 
-def cpu_iteration_seconds(prob, sample_points: int, seed: int = 0):
-    """Time of ONE Gauss-Newton iteration of the CPU restatement (oracle/sparse.py: block normal
-    equations, Schur complement, LAPACK Cholesky + border, back-substitution) for ``prob``,
-    measured on a bounded sample: assembly + point elimination + back-substitution on the first
-    ``sample_points`` object points with all their observations (cost linear in observations,
-    scaled up), the dense reduced solve at the FULL reduced size u_c.  Returns (seconds, parts)."""
+def cpu_iteration_seconds(prob, fraction: float = 1.0):
+    """Time of ONE Gauss-Newton iteration of the CPU restatement of the reference algorithm
+    (oracle/cport.py: C + OpenMP block normal equations and Schur complement on all host cores,
+    LAPACK dpotrf/dpotrs for the bordered reduced solve, C back-substitution).
+    fraction = 1: the full workload.  fraction < 1 (bounded sample for the multi-step reference arm):
+    assembly and back-substitution run on the first ``fraction`` of the object points with all their
+    observations and are scaled by the observation ratio (their cost is linear in observations); the
+    dense reduced solve is always timed at the FULL reduced size u_c.  Returns (seconds, parts)."""
     import copy
-    from oracle import sparse
+    from oracle import cport
     import feba_b200 as fb
     nP = prob.numPts
-    k = min(sample_points, nP)
+    k = nP if fraction >= 1.0 else max(int(nP * fraction), min(nP, 1000))
     if k < nP:
-        keep_pt = np.zeros(nP, dtype=bool)
-        keep_pt[:k] = True
-        rows = np.nonzero(keep_pt[prob.obs_pt])[0]
+        rows = np.nonzero(prob.obs_pt < k)[0]
         sub = copy.copy(prob)
         sub.obs_x, sub.obs_y = prob.obs_x[rows], prob.obs_y[rows]
         sub.obs_img, sub.obs_pt = prob.obs_img[rows], prob.obs_pt[rows]
@@ -154,48 +154,46 @@ def cpu_iteration_seconds(prob, sample_points: int, seed: int = 0):
     else:
         sub = prob
     err, x0, _ = fb.Buildxhat(sub)
-    t0 = time.perf_counter()
-    nb = sparse.normal_blocks(sub, x0)
-    S, g, Vinv = sparse.reduce(sub, nb)
-    t1 = time.perf_counter()
-    # thinning the points can leave the sampled S rank deficient beyond the datum: the timing of
-    # the factorisation does not depend on the values, so factor a safely definite matrix.
-    S[np.diag_indices_from(S)] += 1e-3 * np.abs(np.diag(S)).max()
-    d_c = sparse.solve_reduced(sub, S, g, nb.get("Gc"))
-    t2 = time.perf_counter()
-    sparse.back_substitute(sub, nb, Vinv, d_c)
-    t3 = time.perf_counter()
+    cp = cport.CPort(sub)
+    tm = {}
+    cp.iterate(x0, tm, diag_shift=0.0 if k == nP else 1e-3)
     ratio = prob.n_obs / max(sub.n_obs, 1)
-    t_lin = (t1 - t0) + (t3 - t2)
-    total = t_lin * ratio + (t2 - t1)
-    return total, dict(sample_obs=int(sub.n_obs), sample_points=int(k), assemble_schur_s=t1 - t0,
-                       solve_s=t2 - t1, backsub_s=t3 - t2, scale=ratio)
+    total = (tm["assemble_s"] + tm["backsub_s"]) * ratio + tm["solve_s"]
+    return total, dict(sample_obs=int(sub.n_obs), sample_points=int(k), assemble_schur_s=tm["assemble_s"],
+                       solve_s=tm["solve_s"], backsub_s=tm["backsub_s"], scale=ratio,
+                       threads=int(cport.lib().feba_oracle_threads()))
+
+
+def cpu_sample_text(prob, parts):
+    if parts["sample_points"] == prob.numPts:
+        return (f"full workload, one iteration: C/OpenMP assembly+Schur {parts['assemble_schur_s']:.2f} s, LAPACK "
+                f"bordered solve at u_c={prob.u_c} {parts['solve_s']:.2f} s, back-substitution {parts['backsub_s']:.2f} s")
+    return (f"assembly+Schur+back-substitution on {parts['sample_points']} of {prob.numPts} points "
+            f"({parts['sample_obs']} obs, scaled x{parts['scale']:.2f}: {parts['assemble_schur_s']:.2f} s + "
+            f"{parts['backsub_s']:.2f} s measured); LAPACK bordered solve at full u_c={prob.u_c} {parts['solve_s']:.2f} s")
 
 
 def run_reference(args, rank):
-    """--impl reference: the CPU restatement of the reference algorithm on the host cores."""
+    """--impl reference: the CPU restatement of the reference algorithm on the host cores (MATLAB /
+    Octave do not exist in this image, and literal main.m cannot hold these sizes: SURVEY.md 8d)."""
     if rank != 0:
         return
     prob, desc = make_workload(args.workload, args.scale)
-    cores = os.cpu_count() or 1
-    times = []
-    parts = None
+    times, parts = [], None
     for i in range(args.warmup + args.steps):
-        t, parts = cpu_iteration_seconds(prob, args.cpu_sample_points)
+        t, parts = cpu_iteration_seconds(prob, args.cpu_fraction)
         if i >= args.warmup:
             times.append(t)
     sec = float(np.mean(times))
     val = prob.n_obs / sec
-    sample = (f"assembly+Schur+back-substitution timed on {parts['sample_points']} of {prob.numPts} points "
-              f"({parts['sample_obs']} obs, scaled x{parts['scale']:.1f}); dense reduced solve timed at full "
-              f"u_c={prob.u_c} (LAPACK dpotrf, all BLAS threads)")
     line = {"impl": "reference", "metric": "observations/sec per Gauss-Newton iteration", "value": val,
             "unit": "obs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "desc": desc, "n_obs": prob.n_obs, "n_img": prob.numImg,
                        "n_pts": prob.numPts, "u": prob.u, "u_c": prob.u_c},
-            "cpu_baseline": {"value": val, "unit": "obs/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "obs/s", "cores": parts["threads"], "kind": "port",
+                             "sample": cpu_sample_text(prob, parts)},
             "e2e": {"value": val, "unit": "obs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -335,12 +333,9 @@ def run_ours(args, rank, world, local_rank):
     # CPU baseline: bounded sample on the host cores (rank 0, N=1 only)
     cpu = None
     if world == 1 and not args.no_cpu:
-        sec, parts = cpu_iteration_seconds(prob, args.cpu_sample_points)
-        cpu = {"value": prob.n_obs / sec, "unit": "obs/s", "cores": os.cpu_count() or 1, "kind": "port",
-               "ms_per_step": sec * 1e3,
-               "sample": (f"assembly+Schur+back-substitution on {parts['sample_points']} of {prob.numPts} points "
-                          f"({parts['sample_obs']} obs, scaled x{parts['scale']:.1f}); dense reduced solve at full "
-                          f"u_c={prob.u_c} (LAPACK, all BLAS threads)")}
+        sec, parts = cpu_iteration_seconds(prob, 1.0)
+        cpu = {"value": prob.n_obs / sec, "unit": "obs/s", "cores": parts["threads"], "kind": "port",
+               "ms_per_step": sec * 1e3, "sample": cpu_sample_text(prob, parts)}
     line = {
         "metric": "observations/sec per Gauss-Newton iteration", "value": value, "unit": "obs/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
@@ -370,7 +365,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config4", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (tests only)")
-    ap.add_argument("--cpu-sample-points", type=int, default=20000)
+    ap.add_argument("--cpu-fraction", type=float, default=0.25,
+                    help="--impl reference: fraction of the points the linear stages are timed on per step")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

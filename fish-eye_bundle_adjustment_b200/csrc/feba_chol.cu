@@ -19,7 +19,12 @@ namespace feba {
 
 // ------------------------------------------------------------------------------------------
 // C (M x N) -= A (M x K) * B (N x K)'   -- column-major, all dimensions multiples of 64.
-// CTA tile 64x64, 4 warps of 32x32, K tile 16, 3-stage cp.async pipeline, DMMA m8n8k4.
+// CTA tile 64x64, 4 warps of 32x32, K tile 16, 3-stage cp.async pipeline, DMMA m8n8k4 -- the only
+// FP64 tensor shape sm_100a has in SASS (m16n8k{4,8,16} all lower to DMMA.8x8x4; measured issue peak
+// 37.1 TFLOP/s, scripts/ubench/dmma_rate.cu).  Measured on the top-level trailing update of the
+// u_c = 12,010 system (95x95 lower tiles, K = 6016): 33.9 TFLOP/s, tensor pipe 82 % active
+// (profiles/).  A 128x128-tile variant (8 warps of 64x32, 164 registers, one CTA per SM) was tried
+// and was slower at every size of this recursion (factorisation 36.8 -> 38.9..54.6 ms).
 constexpr int GT = 64;      // CTA tile
 constexpr int GK = 16;      // K tile
 constexpr int GS = 68;      // smem row stride in doubles (== 4 mod 16: conflict-free fragments)

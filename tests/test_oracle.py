@@ -140,3 +140,40 @@ def test_sparse_path_on_small_synthetic_networks():
         assert np.max(np.abs(a["v"] - b["v"])) < 1e-8, mode
         assert abs(a["sigma02"] - b["sigma02"]) < 1e-8 * a["sigma02"], mode
         assert 0.5 < a["sigma02"] < 2.0, (mode, a["sigma02"])    # noise model consistent
+
+
+def two_camera_variant(prob):
+    """Same network, images split between two (identical) cameras: exercises the per-camera blocks."""
+    import copy
+    q = copy.copy(prob)
+    q.settings = copy.copy(prob.settings)
+    q.img_cam = (np.arange(prob.numImg) % 2).astype(np.int32)
+    q.iop0 = np.repeat(prob.iop0, 2, axis=0)
+    q.iop0[1, :3] += [0.7, -0.4, 1.3]
+    q.cam_box = np.repeat(prob.cam_box, 2, axis=0)
+    q.camera_ids = ["0", "1"]
+    return q
+
+
+def test_c_restatement_matches_numpy_oracle():
+    """oracle/feba_oracle.c (the fast checker / CPU baseline) against oracle/model.py + sparse.py."""
+    from feba_b200 import synth
+    from oracle import cport
+    cases = [golden.load_cam0(), golden.load_cam0(type="fisheye", inner=0),
+             synth.make_network(12, 300, 6, 99, mode="free"),
+             synth.make_network(12, 300, 6, 98, mode="eop"),
+             two_camera_variant(synth.make_network(12, 300, 6, 97, mode="mixed", n_control=12))]
+    for prob in cases:
+        err, xhat0, _ = fb.Buildxhat(prob)
+        eop, iop, xyz = model.gather_params(prob, xhat0)
+        q = model.observation_equations(prob, eop, iop, xyz)
+        c = cport.observation_equations(prob, eop, iop, xyz)
+        for k in ("Je", "Jc", "Jt"):
+            assert _rel(c[k], q[k]) < 1e-14, k
+        assert np.max(np.abs(c["w"] - q["w"])) < 1e-10
+        a = sparse.gauss_newton(prob, xhat0)
+        b = cport.CPort(prob).gauss_newton(xhat0)
+        assert a["iterations"] == b["iterations"]
+        assert np.max(np.abs(a["v"] - b["v"])) < 1e-9
+        assert abs(a["sigma02"] - b["sigma02"]) < 1e-9 * a["sigma02"]
+        assert np.linalg.norm(a["xhat"] - b["xhat"]) < 1e-11 * np.linalg.norm(a["xhat"])
