@@ -60,7 +60,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -235,8 +235,11 @@ def run_ours(args, rank, world, local_rank):
     err, x0 = fb.Buildxhat(shard.prob)[:2]
     assert err == 0
     h = fb.Handle(shard.prob)
-    stream = torch.cuda.current_stream()
-    h.set_stream(stream.cuda_stream)            # torch events then see the library's kernels
+    # one non-default torch stream carries the library's kernels (graph capture is not allowed on the
+    # legacy default stream), the NCCL all-reduce and the timing events
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    h.set_stream(stream.cuda_stream)
     adj = sh.ShardedAdjustment(h, shard)
     h.set_xhat(x0)
 

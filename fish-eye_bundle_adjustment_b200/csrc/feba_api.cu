@@ -373,6 +373,8 @@ int feba_set_stream(feba_handle* h, void* stream) {
     if (h->own_stream) cudaStreamDestroy(h->stream);
     h->stream = static_cast<cudaStream_t>(stream);
     h->own_stream = false;
+    // stream capture is not permitted on the legacy default stream: run eagerly there
+    if (h->stream == nullptr || h->stream == cudaStreamLegacy) h->use_graph = false;
     return FEBA_OK;
 }
 

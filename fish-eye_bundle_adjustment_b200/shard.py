@@ -99,7 +99,8 @@ class ShardedAdjustment:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._red = None
         if self.world > 1:
-            # kernels, copies and the collective are all ordered on torch's current stream
+            # kernels, copies and the collective are all ordered on torch's current stream (callers
+            # should make a non-default stream current: the library captures CUDA graphs on it)
             handle.set_stream(torch.cuda.current_stream().cuda_stream)
             ptr, count = handle.reduced_dev()
             self._red = torch.as_tensor(DeviceBuffer(ptr, count), device=torch.device("cuda", torch.cuda.current_device()))
