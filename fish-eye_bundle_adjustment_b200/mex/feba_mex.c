@@ -1,0 +1,147 @@
+/*
+ * feba_mex.c -- MEX gateway: MATLAB <-> the C ABI of include/feba.h (libfeba.so).
+ *
+ * Build (where MATLAB exists):  mex -I<repo>/include feba_mex.c -L<repo>/fish-eye_bundle_adjustment_b200 -lfeba
+ * Usage from the reference's main.m (see INTEGRATION.md and feba_main_loop.m):
+ *     h        = feba_mex('create', S);          S: packed numeric struct built once after main.m:384
+ *                feba_mex('set_xhat', h, xhat);  after Buildxhat (main.m:388)
+ *     deltasum = feba_mex('iterate', h);         replaces the while-body main.m:416-487
+ *     xhat     = feba_mex('get_xhat', h);
+ *     [v, rsd, stats] = feba_mex('residuals', h);   replaces main.m:569-601 (rsd: n_obs x 5 = r vx vy vr vt)
+ *                feba_mex('destroy', h);
+ * Recoverable errors are NOT raised with mexErrMsgIdAndTxt: like the reference's 0/1 `error` flags
+ * (main.m:417-421) the gateway returns the status as the LAST output and prints feba_last_error.
+ * The handle travels as a uint64 scalar; all arrays stay owned by MATLAB.
+ */
+#include <string.h>
+
+#include "feba.h"
+#include "mex.h"
+
+static feba_handle* get_handle(const mxArray* a) {
+    if (!mxIsClass(a, "uint64") || mxGetNumberOfElements(a) != 1)
+        mexErrMsgIdAndTxt("feba:handle", "handle must be a uint64 scalar");
+    return (feba_handle*)(uintptr_t)(*(uint64_t*)mxGetData(a));
+}
+
+static const mxArray* field(const mxArray* s, const char* name) {
+    const mxArray* f = mxGetField(s, 0, name);
+    if (!f) mexErrMsgIdAndTxt("feba:field", "missing field %s", name);
+    return f;
+}
+
+static const double* dfield(const mxArray* s, const char* name, size_t count) {
+    const mxArray* f = field(s, name);
+    if (!mxIsDouble(f) || mxGetNumberOfElements(f) != count)
+        mexErrMsgIdAndTxt("feba:field", "field %s must be double with %d elements", name, (int)count);
+    return mxGetPr(f);
+}
+
+static const int32_t* ifield(const mxArray* s, const char* name, size_t count) {
+    const mxArray* f = field(s, name);
+    if (!mxIsClass(f, "int32") || mxGetNumberOfElements(f) != count)
+        mexErrMsgIdAndTxt("feba:field", "field %s must be int32 with %d elements", name, (int)count);
+    return (const int32_t*)mxGetData(f);
+}
+
+static double sfield(const mxArray* s, const char* name) { return mxGetScalar(field(s, name)); }
+
+static void status_out(int nlhs, mxArray* plhs[], int slot, int rc, const feba_handle* h) {
+    if (rc) mexPrintf("%s\n", feba_last_error(h));      /* main.m:418 disp('Error building A and w') follows */
+    if (nlhs > slot) plhs[slot] = mxCreateDoubleScalar((double)(rc != 0));
+}
+
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    char cmd[32];
+    if (nrhs < 1 || mxGetString(prhs[0], cmd, sizeof(cmd))) mexErrMsgIdAndTxt("feba:cmd", "first argument: command");
+    if (!strcmp(cmd, "create")) {
+        /* S: n_obs n_img n_cam n_pts n_tie | obs_x obs_y (double) obs_img obs_pt (int32, 0-based) img_cam
+         * pt_tie (int32) | eop0 (6 x n_img) iop0 ((3+NK+2) x n_cam) cam_box (5 x n_cam) xyz0 (3 x n_pts),
+         * column-major = the row-major layout of feba.h | settings fields */
+        const mxArray* S = prhs[1];
+        feba_problem p;
+        memset(&p, 0, sizeof(p));
+        if (nrhs < 2 || !mxIsStruct(S)) mexErrMsgIdAndTxt("feba:create", "create needs the packed problem struct");
+        p.n_obs = (int64_t)sfield(S, "n_obs");
+        p.n_img = (int32_t)sfield(S, "n_img");
+        p.n_cam = (int32_t)sfield(S, "n_cam");
+        p.n_pts = (int32_t)sfield(S, "n_pts");
+        p.n_tie = (int32_t)sfield(S, "n_tie");
+        feba_settings* s = &p.settings;
+        const double* ee = dfield(S, "estimate_eop", 6);
+        for (int q = 0; q < 6; ++q) s->estimate_eop[q] = (int32_t)ee[q];
+        s->estimate_xp = (int32_t)sfield(S, "Estimate_xp");
+        s->estimate_yp = (int32_t)sfield(S, "Estimate_yp");
+        s->estimate_c = (int32_t)sfield(S, "Estimate_c");
+        s->estimate_radial = (int32_t)sfield(S, "Estimate_radial");
+        s->num_radial = (int32_t)sfield(S, "Num_Radial_Distortions");
+        if (s->num_radial < 1) s->num_radial = 1;                           /* BuildAwG.m:18-20 */
+        s->estimate_decent = (int32_t)sfield(S, "Estimate_decent");
+        s->inner_constraints = (int32_t)sfield(S, "Inner_Constraints");
+        s->type = (int32_t)sfield(S, "typeint");
+        s->iteration_cap = (int32_t)sfield(S, "Iteration_Cap");
+        s->sigma_x = sfield(S, "Meas_std");
+        s->sigma_y = sfield(S, "Meas_std_y");
+        s->threshold = sfield(S, "threshold");
+        const size_t n = (size_t)p.n_obs, NC = (size_t)s->num_radial + 5;
+        p.obs_x = dfield(S, "obs_x", n);
+        p.obs_y = dfield(S, "obs_y", n);
+        p.obs_img = ifield(S, "obs_img", n);
+        p.obs_pt = ifield(S, "obs_pt", n);
+        p.img_cam = ifield(S, "img_cam", (size_t)p.n_img);
+        p.pt_tie = ifield(S, "pt_tie", (size_t)p.n_pts);
+        p.eop0 = dfield(S, "eop0", 6 * (size_t)p.n_img);
+        p.iop0 = dfield(S, "iop0", NC * (size_t)p.n_cam);
+        p.cam_box = dfield(S, "cam_box", 5 * (size_t)p.n_cam);
+        p.xyz0 = dfield(S, "xyz0", 3 * (size_t)p.n_pts);
+        feba_handle* h = NULL;
+        const int rc = feba_create(&p, &h);
+        plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
+        *(uint64_t*)mxGetData(plhs[0]) = (uint64_t)(uintptr_t)h;
+        status_out(nlhs, plhs, 1, rc, NULL);
+        return;
+    }
+    if (nrhs < 2) mexErrMsgIdAndTxt("feba:cmd", "%s needs a handle", cmd);
+    feba_handle* h = get_handle(prhs[1]);
+    int64_t u = 0, uc = 0;
+    feba_num_unknowns(h, &u, &uc);
+    if (!strcmp(cmd, "destroy")) {
+        feba_destroy(h);
+    } else if (!strcmp(cmd, "set_xhat")) {
+        if (nrhs < 3 || !mxIsDouble(prhs[2])) mexErrMsgIdAndTxt("feba:xhat", "set_xhat needs a double vector");
+        status_out(nlhs, plhs, 0, feba_set_xhat(h, mxGetPr(prhs[2]), mxGetNumberOfElements(prhs[2])), h);
+    } else if (!strcmp(cmd, "get_xhat") || !strcmp(cmd, "get_delta")) {
+        plhs[0] = mxCreateDoubleMatrix((mwSize)u, 1, mxREAL);
+        const int rc = cmd[4] == 'x' ? feba_get_xhat(h, mxGetPr(plhs[0]), (size_t)u)
+                                     : feba_get_delta(h, mxGetPr(plhs[0]), (size_t)u);
+        status_out(nlhs, plhs, 1, rc, h);
+    } else if (!strcmp(cmd, "iterate")) {
+        double deltasum = 0.0;
+        const int rc = feba_iterate(h, &deltasum);
+        plhs[0] = mxCreateDoubleScalar(deltasum);                          /* main.m:487 */
+        status_out(nlhs, plhs, 1, rc, h);
+    } else if (!strcmp(cmd, "solve")) {
+        int32_t it = 0;
+        const int cap = 4096;
+        double* trace = (double*)mxMalloc(sizeof(double) * cap);
+        const int rc = feba_solve(h, &it, trace, cap);
+        plhs[0] = mxCreateDoubleScalar((double)it);
+        if (nlhs > 1) {
+            plhs[1] = mxCreateDoubleMatrix(1, (mwSize)(it < cap ? it : cap), mxREAL);   /* deltasumarr, main.m:488 */
+            memcpy(mxGetPr(plhs[1]), trace, sizeof(double) * (size_t)(it < cap ? it : cap));
+        }
+        mxFree(trace);
+        status_out(nlhs, plhs, 2, rc, h);
+    } else if (!strcmp(cmd, "residuals")) {
+        const size_t n = (size_t)mxGetScalar(prhs[2]);                     /* n_obs */
+        plhs[0] = mxCreateDoubleMatrix((mwSize)(2 * n), 1, mxREAL);        /* v, main.m:569 */
+        mxArray* rsd = mxCreateDoubleMatrix(5, (mwSize)n, mxREAL);         /* 5 x n_obs column-major = n_obs x 5 row-major */
+        mxArray* st = mxCreateDoubleMatrix(1, 6, mxREAL);
+        const int rc = feba_residuals(h, mxGetPr(plhs[0]), mxGetPr(rsd), mxGetPr(st));
+        if (nlhs > 1) plhs[1] = rsd;
+        if (nlhs > 2) plhs[2] = st;                                        /* RMSx RMSy RMS sigma02 sum_vx2 sum_vy2 */
+        status_out(nlhs, plhs, 3, rc, h);
+    } else {
+        mexErrMsgIdAndTxt("feba:cmd", "unknown command %s", cmd);
+    }
+}
