@@ -24,6 +24,7 @@
 // kernel and partial sums are combined in a fixed order, so the result is run-to-run deterministic.
 #include <cub/cub.cuh>
 
+#include <cstdlib>
 #include <vector>
 
 #include "feba_dev.h"
@@ -33,34 +34,37 @@
 namespace feba {
 
 // ------------------------------------------------------------------------------------------
-// point pass: one warp per object point, lanes over its observations (chunks of 32)
-template <int NK>
+// point pass: one GROUP of G lanes (G = 32, or 16 when points have few observations: two points per
+// warp, the halves run independently with their own __syncwarp masks) per object point, lanes over
+// its observations (chunks of G)
+template <int NK, int G>
 struct alignas(16) PtSmem {
     static constexpr int NC = NK + 5;
-    double rowJc[32][2][NC];
-    double rowJt[32][2][3];
-    double roww[32][2];
+    double rowJc[G][2][NC];
+    double rowJt[G][2][3];
+    double roww[G][2];
     double Wc[NC][3];
     double Fc[NC][3];
     double V[6];
     double up[3];
-    int pos[32];
+    int pos[G];
 };
 
-template <int NK, bool HAS_CAM>
+template <int NK, bool HAS_CAM, int G>
 __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
     constexpr int NC = NK + 5;
     constexpr int ND = NC * (NC + 1) / 2;          // packed camera-camera block
-    constexpr int DPL = (ND + 31) / 32;            // entries of D per lane
-    constexpr int WPL = (NC * 3 + 31) / 32;        // entries of Wc per lane
+    constexpr int DPL = (ND + G - 1) / G;          // entries of D per lane
+    constexpr int WPL = (NC * 3 + G - 1) / G;      // entries of Wc per lane
     constexpr int R2 = 2 + 2 * NC;                 // doubles per rec2 record
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    PtSmem<NK>* sm_all = reinterpret_cast<PtSmem<NK>*>(smem_raw);
-    const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    PtSmem<NK>& sm = sm_all[wib];
-    const int nwarp = gridDim.x * (blockDim.x >> 5);
-    const int gw = blockIdx.x * (blockDim.x >> 5) + wib;
+    PtSmem<NK, G>* sm_all = reinterpret_cast<PtSmem<NK, G>*>(smem_raw);
+    const int lane = threadIdx.x & (G - 1);                  // lane inside the group
+    const int wib = threadIdx.x / G;                         // group inside the CTA
+    PtSmem<NK, G>& sm = sm_all[wib];
+    const int nwarp = gridDim.x * (blockDim.x / G);          // groups in the grid
+    const int gw = blockIdx.x * (blockDim.x / G) + wib;      // this group
+    const unsigned gmask = G == 32 ? 0xffffffffu : (0xffffu << (16 * ((threadIdx.x & 31) >> 4)));
     const double pw[2] = {P.px, P.py};
     const int type = P.type;
 
@@ -68,7 +72,7 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
     double dacc[DPL];
 #pragma unroll
     for (int t = 0; t < DPL; ++t) {
-        const int e = lane + 32 * t;
+        const int e = lane + G * t;
         int i = 0;
         while ((i + 1) * (i + 2) / 2 <= e) ++i;    // row of packed lower-triangular index e
         dI[t] = i;
@@ -82,7 +86,7 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
         const int pt = P.seg_pt[seg];
         const bool is_tie = P.pt_tie[pt] >= 0;
         const double X = P.xyz[3 * pt], Y = P.xyz[3 * pt + 1], Z = P.xyz[3 * pt + 2];
-        const bool single = (end - beg) <= 32;
+        const bool single = (end - beg) <= G;
         ObsJac<NK> J;
         bool have_J = false;
 
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
 #pragma unroll
         for (int t = 0; t < WPL; ++t) wcacc[t] = 0.0;
         if (is_tie || HAS_CAM) {
-            for (int c0 = beg; c0 < end; c0 += 32) {
+            for (int c0 = beg; c0 < end; c0 += G) {
                 const int o = c0 + lane;
                 const bool act = o < end;
                 if (act) {
@@ -110,12 +114,12 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
                     for (int k = 0; k < 3; ++k) sm.rowJt[lane][r][k] = act ? J.Jt[r][k] : 0.0;
                     sm.roww[lane][r] = act ? J.w[r] : 0.0;
                 }
-                __syncwarp();
-                const int nrow = min(32, end - c0);
+                __syncwarp(gmask);
+                const int nrow = min(G, end - c0);
                 if (HAS_CAM) {
 #pragma unroll
                     for (int t = 0; t < DPL; ++t) {
-                        if (lane + 32 * t < ND) {
+                        if (lane + G * t < ND) {
                             double a = 0.0;
                             for (int l = 0; l < nrow; ++l)
                                 a += sm.rowJc[l][0][dI[t]] * pw[0] * sm.rowJc[l][0][dJ[t]] +
@@ -133,7 +137,7 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
                     if (is_tie) {
 #pragma unroll
                         for (int t = 0; t < WPL; ++t) {
-                            const int e = lane + 32 * t;
+                            const int e = lane + G * t;
                             if (e < NC * 3) {
                                 const int i = e / 3, k = e - 3 * i;
                                 double a = 0.0;
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
                     }
                     vacc += a;
                 }
-                __syncwarp();
+                __syncwarp(gmask);
             }
             have_J = single;
         }
@@ -174,11 +178,11 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
             if (HAS_CAM) {
 #pragma unroll
                 for (int t = 0; t < WPL; ++t) {
-                    const int e = lane + 32 * t;
+                    const int e = lane + G * t;
                     if (e < NC * 3) (&sm.Wc[0][0])[e] = wcacc[t];
                 }
             }
-            __syncwarp();
+            __syncwarp(gmask);
             const double v0 = sm.V[0], v1 = sm.V[1], v2 = sm.V[2], v3 = sm.V[3], v4 = sm.V[4], v5 = sm.V[5];
             const double l00 = sqrt(v0);
             const double l10 = v1 / l00, l20 = v3 / l00;
@@ -200,10 +204,10 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
                     sm.Fc[lane][1] = w0 * i10 + w1 * i11;
                     sm.Fc[lane][2] = w0 * i20 + w1 * i21 + w2 * i22;
                 }
-                __syncwarp();
+                __syncwarp(gmask);
 #pragma unroll
                 for (int t = 0; t < DPL; ++t) {
-                    if (lane + 32 * t < ND)
+                    if (lane + G * t < ND)
                         dacc[t] -= sm.Fc[dI[t]][0] * sm.Fc[dJ[t]][0] + sm.Fc[dI[t]][1] * sm.Fc[dJ[t]][1] +
                                    sm.Fc[dI[t]][2] * sm.Fc[dJ[t]][2];
                 }
@@ -213,11 +217,11 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
         // ---------------- pass 2: per-observation records, staged through shared memory (the
         // pass-1 row buffers are dead by now) and written as 16-byte units, contiguous per record,
         // at the observation's position in the image-major record arrays
-        double* buf = &sm.rowJc[0][0][0];              // (2 NC + 8) * 32 doubles, >= 32 * max(18, R2)
-        for (int a0 = beg; a0 < end; a0 += 32) {
+        double* buf = &sm.rowJc[0][0][0];              // (2 NC + 8) * G doubles, >= G * max(18, R2)
+        for (int a0 = beg; a0 < end; a0 += G) {
             const int o = a0 + lane;
             const bool act = o < end;
-            const int nrow = min(32, end - a0);
+            const int nrow = min(G, end - a0);
             double Zm[2][3], ra[2];
             if (act) {
                 if (!have_J) {
@@ -243,13 +247,13 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
                     for (int k = 0; k < 3; ++k) r1[12 + 3 * r + k] = Zm[r][k];
                 }
             }
-            __syncwarp();
-            for (int u = lane; u < nrow * (kRec1 / 2); u += 32) {
+            __syncwarp(gmask);
+            for (int u = lane; u < nrow * (kRec1 / 2); u += G) {
                 const int k = u / (kRec1 / 2), part = u - k * (kRec1 / 2);
                 reinterpret_cast<double2*>(P.rec1 + (size_t)kRec1 * sm.pos[k])[part] =
                     reinterpret_cast<const double2*>(buf + kRec1 * k)[part];
             }
-            __syncwarp();
+            __syncwarp(gmask);
             if (act) {
                 double* r2 = buf + R2 * lane;
                 r2[0] = ra[0];
@@ -265,16 +269,16 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
                     }
                 }
             }
-            __syncwarp();
+            __syncwarp(gmask);
             {
                 constexpr int U2 = HAS_CAM ? R2 / 2 : 1;     // without camera unknowns only r (2) is used
-                for (int u = lane; u < nrow * U2; u += 32) {
+                for (int u = lane; u < nrow * U2; u += G) {
                     const int k = u / U2, part = u - k * U2;
                     reinterpret_cast<double2*>(P.rec2 + (size_t)R2 * sm.pos[k])[part] =
                         reinterpret_cast<const double2*>(buf + R2 * k)[part];
                 }
             }
-            __syncwarp();
+            __syncwarp(gmask);
         }
     }
     // camera-camera block and camera right-hand side of this warp -> partial buffer (fixed-order sum later)
@@ -282,7 +286,7 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
         double* part = P.cam_part + (size_t)kCamPart * gw;
 #pragma unroll
         for (int t = 0; t < DPL; ++t)
-            if (lane + 32 * t < ND) part[lane + 32 * t] = dacc[t];
+            if (lane + G * t < ND) part[lane + G * t] = dacc[t];
         if (lane < NC) part[ND + lane] = gcacc;
     }
 }
@@ -653,25 +657,31 @@ cudaError_t build_pair_schedule(DevProblem& P, const int* d_oseg, long long* n_p
         default: return cudaErrorInvalidValue;                                \
     }
 
-int assemble_warps(const DevProblem& P, int sm_count) {
-    int grid = (P.n_seg + 3) / 4;
+// lanes per object point: 16 when points have few observations on average (two points per warp)
+static int group_lanes(const DevProblem& P) { return (P.n_seg > 0 && P.n_obs <= 12 * (int64_t)P.n_seg) ? 16 : 32; }
+
+static int point_pass_grid(const DevProblem& P, int sm_count) {
+    const int per_cta = 128 / group_lanes(P);
+    int grid = (P.n_seg + per_cta - 1) / per_cta;
     const int cap = sm_count * 4;
     if (grid > cap) grid = cap;
-    if (grid < 1) grid = 1;
-    return grid * 4;
+    return grid < 1 ? 1 : grid;
 }
 
-template <int NK, bool HC>
+// number of point groups in the grid = rows of the camera partial buffer
+int assemble_warps(const DevProblem& P, int sm_count) { return point_pass_grid(P, sm_count) * (128 / group_lanes(P)); }
+
+template <int NK, bool HC, int G>
 static cudaError_t launch_point_pass_t(const DevProblem& P, int sm_count, cudaStream_t st) {
-    const size_t smem = 4 * sizeof(PtSmem<NK>);
+    const size_t smem = (128 / G) * sizeof(PtSmem<NK, G>);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_point_pass<NK, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(k_point_pass<NK, HC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    k_point_pass<NK, HC><<<assemble_warps(P, sm_count) / 4, 128, smem, st>>>(P);
+    k_point_pass<NK, HC, G><<<point_pass_grid(P, sm_count), 128, smem, st>>>(P);
     return cudaGetLastError();
 }
 
@@ -679,7 +689,11 @@ cudaError_t launch_assemble(const DevProblem& P, int sm_count, cudaStream_t st, 
     const bool hc = P.uc > 0;
     if (P.n_seg > 0) {
         cudaError_t e = cudaSuccess;
-        FEBA_NK_DISPATCH2(P.NK, hc, (e = launch_point_pass_t<NK_, HC_>(P, sm_count, st)));
+        if (group_lanes(P) == 16) {
+            FEBA_NK_DISPATCH2(P.NK, hc, (e = launch_point_pass_t<NK_, HC_, 16>(P, sm_count, st)));
+        } else {
+            FEBA_NK_DISPATCH2(P.NK, hc, (e = launch_point_pass_t<NK_, HC_, 32>(P, sm_count, st)));
+        }
         if (e != cudaSuccess) return e;
         ++*launches;
         int grid = P.n_img < sm_count * 4 ? P.n_img : sm_count * 4;
@@ -690,8 +704,17 @@ cudaError_t launch_assemble(const DevProblem& P, int sm_count, cudaStream_t st, 
             ++*launches;
         }
         if (P.n_blocks > 0) {
+            // few resident warps on purpose: the grid sweeps the block list (image-row major) in
+            // waves, and the records a wave touches (its rows' images + their lower neighbours)
+            // should stay in L2
+            static int per_sm = -1;
+            if (per_sm < 0) {
+                const char* e = std::getenv("FEBA_PAIR_CTAS_PER_SM");
+                per_sm = e ? std::atoi(e) : 2;
+                if (per_sm < 1) per_sm = 1;
+            }
             int g2 = (P.n_blocks + 3) / 4;
-            if (g2 > sm_count * 8) g2 = sm_count * 8;
+            if (g2 > sm_count * per_sm) g2 = sm_count * per_sm;
             k_pair_pass<<<g2, 128, 0, st>>>(P);
             ++*launches;
         }

@@ -263,6 +263,133 @@ __global__ void __launch_bounds__(256) k_potrf64_inv(double* __restrict__ A, int
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused triangular solve against up to four 64-column blocks: X (64 rows per CTA, nt*64 columns)
+// := X * L^-T with L the nt x nt block triangle at (c0, c0):
+//   for j = 0..nt-1:  X_j := (X_j - sum_{i<j} X_i L_ji') * Linv_j'
+// The CTA keeps its 64 x (nt*64) row block in shared memory (139 KB), streams the L_ji / Linv_j
+// tiles through a double buffer with cp.async and runs every product on DMMA.  One launch replaces
+// the 2 nt - 1 launches (nt leaf multiplications + nt - 1 small GEMMs) of the recursion below four
+// blocks: those small launches were latency-bound (profiles/: 685 leaf + ~370 small GEMM launches,
+// ~13 ms of a 42 ms factorisation under ncu).
+constexpr int TS = 68;                      // smem stride (doubles) of a 64-wide tile row: == 4 mod 16
+constexpr int TF_MAX = 4;
+constexpr size_t kTrsmFusedSmem = (size_t)(TF_MAX + 2) * 64 * TS * sizeof(double);
+
+__device__ __forceinline__ void load_tile64(double (*dst)[TS], const double* __restrict__ src, int ld, int tid) {
+    // dst[k][i] = src[i + ld * k], 64 x 64, 16-byte chunks, 256 threads -> 8 chunks each
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int q = tid + 256 * t;
+        const int k = q >> 5, i2 = (q & 31) * 2;
+        cp_async16(&dst[k][i2], src + i2 + (size_t)ld * k);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_trsm_fused(double* __restrict__ A, int ld, const double* __restrict__ Linv,
+                                                    int r0, int c0, int nt) {
+    extern __shared__ __align__(16) double fsm[];
+    double(*Xs)[64][TS] = reinterpret_cast<double(*)[64][TS]>(fsm);                          // [tile][k][row]
+    double(*Ls)[64][TS] = reinterpret_cast<double(*)[64][TS]>(fsm + (size_t)TF_MAX * 64 * TS); // [buf][k][n]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 1, wn = warp >> 1;                 // 2 x 4 warps, each 32 rows x 16 columns
+    const int lr = lane >> 2, lk = lane & 3;
+    double* Xg = A + (size_t)(r0 + blockIdx.x) * kBlk + (size_t)ld * c0 * kBlk;
+    auto Btile = [&](int seq, const double*& src, int& bld) {
+        // sequence: j = 0: Linv_0 | j = 1: L_10, Linv_1 | j = 2: L_20, L_21, Linv_2 | ...
+        int j = 0;
+        while ((j + 1) * (j + 2) / 2 <= seq) ++j;
+        const int i = seq - j * (j + 1) / 2;
+        if (i == j) {
+            src = Linv + (size_t)(c0 + j) * kBlk * kBlk;
+            bld = kBlk;
+        } else {
+            src = A + (size_t)(c0 + j) * kBlk + (size_t)ld * (c0 + i) * kBlk;
+            bld = ld;
+        }
+    };
+    const int nseq = nt * (nt + 1) / 2;
+    for (int t = 0; t < nt; ++t) load_tile64(Xs[t], Xg + (size_t)ld * t * kBlk, ld, tid);
+    {
+        const double* src;
+        int bld;
+        Btile(0, src, bld);
+        load_tile64(Ls[0], src, bld, tid);
+    }
+    cp_async_commit();
+    int seq = 0;
+    double acc[4][2][2];
+    auto mma_tile = [&](const double (*Xa)[TS], const double (*Lb)[TS]) {
+#pragma unroll 4
+        for (int kk = 0; kk < 16; ++kk) {
+            double a[4], b[2];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) a[t] = Xa[kk * 4 + lk][wm * 32 + t * 8 + lr];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) b[t] = Lb[kk * 4 + lk][wn * 16 + t * 8 + lr];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    };
+    auto next_tile = [&]() {        // prefetch tile seq+1, then make tile seq visible to the whole CTA
+        if (seq + 1 < nseq) {
+            const double* src;
+            int bld;
+            Btile(seq + 1, src, bld);
+            load_tile64(Ls[(seq + 1) & 1], src, bld, tid);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+    };
+    for (int j = 0; j < nt; ++j) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) acc[i][jj][0] = acc[i][jj][1] = 0.0;
+        for (int i = 0; i < j; ++i) {
+            next_tile();
+            mma_tile(Xs[i], Ls[seq & 1]);
+            __syncthreads();                                  // Ls[seq & 1] may be refilled two tiles later
+            ++seq;
+        }
+        if (j > 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int r = wm * 32 + i * 8 + lr, c = wn * 16 + jj * 8 + 2 * lk;
+                    Xs[j][c][r] -= acc[i][jj][0];
+                    Xs[j][c + 1][r] -= acc[i][jj][1];
+                    acc[i][jj][0] = acc[i][jj][1] = 0.0;
+                }
+        }
+        next_tile();                                          // also orders the X_j update above
+        mma_tile(Xs[j], Ls[seq & 1]);
+        __syncthreads();                                      // everyone has read X_j
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int r = wm * 32 + i * 8 + lr, c = wn * 16 + jj * 8 + 2 * lk;
+                Xs[j][c][r] = acc[i][jj][0];
+                Xs[j][c + 1][r] = acc[i][jj][1];
+            }
+        __syncthreads();
+        ++seq;
+    }
+    cp_async_wait<0>();
+    // write the row block back (coalesced over rows)
+    for (int t = 0; t < nt; ++t)
+        for (int q = tid; q < 64 * 32; q += 256) {
+            const int k = q >> 5, i2 = (q & 31) * 2;
+            *reinterpret_cast<double2*>(Xg + i2 + (size_t)ld * (t * kBlk + k)) =
+                *reinterpret_cast<const double2*>(&Xs[t][k][i2]);
+        }
+}
+
 static cudaError_t gemm_nt(double* C, int ldc, const double* A, int lda, const double* B, int ldb, int mb,
                            int nbk, int kb, int mode, cudaStream_t st, int64_t* launches) {
     const size_t smem = 2 * GSTAGES * GK * GS * sizeof(double);
@@ -289,11 +416,21 @@ static cudaError_t gemm_nt(double* C, int ldc, const double* A, int lda, const d
 #define LINV(W, b) ((W) + (size_t)(b) * kBlk * kBlk)
 
 // X (mr x n blocks at block (r0, c0)) := X * L^-T with L the n x n block triangle at (c0, c0).
-// Leaves multiply by the inverted 64x64 diagonal factor (in place, DMMA).
+// Below five blocks the whole solve is one fused launch (k_trsm_fused).
 static cudaError_t rtrsm(double* A, int ld, const double* Linv, int r0, int mr, int c0, int n, cudaStream_t st,
                          int64_t* launches) {
-    if (n == 1)
-        return gemm_nt(AT(A, ld, r0, c0), ld, AT(A, ld, r0, c0), ld, LINV(Linv, c0), kBlk, mr, 1, 1, 2, st, launches);
+    if (n <= TF_MAX) {
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(k_trsm_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)kTrsmFusedSmem);
+            if (e != cudaSuccess) return e;
+            configured = true;
+        }
+        k_trsm_fused<<<mr, 256, kTrsmFusedSmem, st>>>(A, ld, Linv, r0, c0, n);
+        ++*launches;
+        return cudaGetLastError();
+    }
     const int n1 = n / 2, n2 = n - n1;
     cudaError_t e = rtrsm(A, ld, Linv, r0, mr, c0, n1, st, launches);
     if (e != cudaSuccess) return e;

@@ -91,35 +91,46 @@ __global__ void __launch_bounds__(256) k_G_condition(DevProblem P, int* __restri
     __shared__ double red[256];
     __shared__ double A1[7][7], A2[7][7], Cm[7][7], cn[7];
     const int tid = threadIdx.x, ne = P.off_cam;
-    // column norms
-    for (int k = 0; k < 7; ++k) {
-        double acc = 0.0;
-        for (int r = tid; r < ne; r += 256) { const double g = P.Gt[8 * (size_t)r + k]; acc += g * g; }
-        red[tid] = acc;
-        __syncthreads();
-        for (int st = 128; st > 0; st >>= 1) { if (tid < st) red[tid] += red[tid + st]; __syncthreads(); }
-        if (tid == 0) cn[k] = red[0] > 0.0 ? 1.0 / sqrt(red[0]) : 1.0;
+    // one sweep over the rows: column norms, then both Gram matrices from the raw sums
+    // (A1 = Gn'Gn and A2 = Gn' diag(S) Gn with Gn = G diag(cn): scale the raw sums by cn_i cn_j)
+    {
+        double a1[28], a2[28];
+#pragma unroll
+        for (int e = 0; e < 28; ++e) a1[e] = a2[e] = 0.0;
+        for (int r = tid; r < ne; r += 256) {
+            double g[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) g[k] = P.Gt[8 * (size_t)r + k];
+            const double sd = P.S[(size_t)r + (size_t)P.ld * r];
+            int e = 0;
+#pragma unroll
+            for (int i = 0; i < 7; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) {
+                    const double p = g[i] * g[j];
+                    a1[e] += p;
+                    a2[e] += p * sd;
+                    ++e;
+                }
+        }
+        int e = 0;
+        for (int i = 0; i < 7; ++i)
+            for (int j = 0; j <= i; ++j, ++e) {
+                for (int pass = 0; pass < 2; ++pass) {
+                    red[tid] = pass ? a2[e] : a1[e];
+                    __syncthreads();
+                    for (int st = 128; st > 0; st >>= 1) { if (tid < st) red[tid] += red[tid + st]; __syncthreads(); }
+                    if (tid == 0) { if (pass) A2[i][j] = A2[j][i] = red[0]; else A1[i][j] = A1[j][i] = red[0]; }
+                    __syncthreads();
+                }
+            }
+        if (tid == 0) {
+            for (int k = 0; k < 7; ++k) cn[k] = A1[k][k] > 0.0 ? 1.0 / sqrt(A1[k][k]) : 1.0;
+            for (int i = 0; i < 7; ++i)
+                for (int j = 0; j < 7; ++j) { A1[i][j] *= cn[i] * cn[j]; A2[i][j] *= cn[i] * cn[j]; }
+        }
         __syncthreads();
     }
-    for (int i = 0; i < 7; ++i)
-        for (int j = 0; j <= i; ++j) {
-            double a1 = 0.0, a2 = 0.0;
-            for (int r = tid; r < ne; r += 256) {
-                const double gi = P.Gt[8 * (size_t)r + i] * cn[i], gj = P.Gt[8 * (size_t)r + j] * cn[j];
-                a1 += gi * gj;
-                a2 += gi * gj * P.S[(size_t)r + (size_t)P.ld * r];
-            }
-            red[tid] = a1;
-            __syncthreads();
-            for (int st = 128; st > 0; st >>= 1) { if (tid < st) red[tid] += red[tid + st]; __syncthreads(); }
-            if (tid == 0) A1[i][j] = A1[j][i] = red[0];
-            __syncthreads();
-            red[tid] = a2;
-            __syncthreads();
-            for (int st = 128; st > 0; st >>= 1) { if (tid < st) red[tid] += red[tid + st]; __syncthreads(); }
-            if (tid == 0) A2[i][j] = A2[j][i] = red[0];
-            __syncthreads();
-        }
     if (tid == 0) {
         // Lw = chol(A2) (lower); on failure fall back to sqrt(mean diagonal) * I
         double Lw[7][7];
