@@ -11,6 +11,7 @@
 // tensor pipe: mma.sync.m8n8k4.f64 (DMMA).  tcgen05 has no FP64 kind, so the warp-level DMMA is
 // the tensor path for doubles on sm_100a as well.
 #include <cstdio>
+#include <cstdlib>
 
 #include "feba_dev.h"
 #include "feba_kernels.h"
@@ -275,26 +276,38 @@ __global__ void __launch_bounds__(256) k_potrf64_inv(double* __restrict__ A, int
 constexpr int TS = 68;                      // smem stride (doubles) of a 64-wide tile row: == 4 mod 16
 constexpr int TF_MAX = 4;
 constexpr size_t kTrsmFusedSmem = (size_t)(TF_MAX + 2) * 64 * TS * sizeof(double);
+constexpr size_t kTrsmFusedSmem16 = (size_t)(TF_MAX * 64 * 20 + 2 * 64 * TS) * sizeof(double);
 
-__device__ __forceinline__ void load_tile64(double (*dst)[TS], const double* __restrict__ src, int ld, int tid) {
-    // dst[k][i] = src[i + ld * k], 64 x 64, 16-byte chunks, 256 threads -> 8 chunks each
+// dst[k][i] = src[i + ld * k] for ROWS rows x 64 columns, 16-byte chunks, 256 threads
+template <int ROWS, int STRIDE>
+__device__ __forceinline__ void load_tile(double (*dst)[STRIDE], const double* __restrict__ src, int ld, int tid) {
+    constexpr int CH = ROWS / 2;                   // 16-byte chunks per column
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
+    for (int t = 0; t < (64 * CH + 255) / 256; ++t) {
         const int q = tid + 256 * t;
-        const int k = q >> 5, i2 = (q & 31) * 2;
-        cp_async16(&dst[k][i2], src + i2 + (size_t)ld * k);
+        if (64 * CH % 256 == 0 || q < 64 * CH) {
+            const int k = q / CH, i2 = (q % CH) * 2;
+            cp_async16(&dst[k][i2], src + i2 + (size_t)ld * k);
+        }
     }
 }
 
+// RM = rows of X per CTA: 64 (one 64-row block per CTA) or 16 (four CTAs per block: more CTAs for the
+// deep levels of the recursion where only a few row blocks exist).
+template <int RM>
 __global__ void __launch_bounds__(256) k_trsm_fused(double* __restrict__ A, int ld, const double* __restrict__ Linv,
                                                     int r0, int c0, int nt) {
     extern __shared__ __align__(16) double fsm[];
-    double(*Xs)[64][TS] = reinterpret_cast<double(*)[64][TS]>(fsm);                          // [tile][k][row]
-    double(*Ls)[64][TS] = reinterpret_cast<double(*)[64][TS]>(fsm + (size_t)TF_MAX * 64 * TS); // [buf][k][n]
+    constexpr int XS = RM == 64 ? TS : 20;        // row stride of the X tiles (== 4 mod 16 either way)
+    double(*Xs)[64][XS] = reinterpret_cast<double(*)[64][XS]>(fsm);                          // [tile][k][row]
+    double(*Ls)[64][TS] = reinterpret_cast<double(*)[64][TS]>(fsm + (size_t)TF_MAX * 64 * XS); // [buf][k][n]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp & 1, wn = warp >> 1;                 // 2 x 4 warps, each 32 rows x 16 columns
+    // RM = 64: 2 x 4 warps of 32 rows x 16 columns; RM = 16: 1 x 8 warps of 16 rows x 8 columns
+    constexpr int MF = RM == 64 ? 4 : 2, NF = RM == 64 ? 2 : 1;
+    const int wm = RM == 64 ? (warp & 1) : 0, wn = RM == 64 ? (warp >> 1) : warp;
+    const int row0 = wm * 32, col0 = wn * (8 * NF);
     const int lr = lane >> 2, lk = lane & 3;
-    double* Xg = A + (size_t)(r0 + blockIdx.x) * kBlk + (size_t)ld * c0 * kBlk;
+    double* Xg = A + (size_t)r0 * kBlk + (size_t)blockIdx.x * RM + (size_t)ld * c0 * kBlk;
     auto Btile = [&](int seq, const double*& src, int& bld) {
         // sequence: j = 0: Linv_0 | j = 1: L_10, Linv_1 | j = 2: L_20, L_21, Linv_2 | ...
         int j = 0;
@@ -309,28 +322,28 @@ __global__ void __launch_bounds__(256) k_trsm_fused(double* __restrict__ A, int 
         }
     };
     const int nseq = nt * (nt + 1) / 2;
-    for (int t = 0; t < nt; ++t) load_tile64(Xs[t], Xg + (size_t)ld * t * kBlk, ld, tid);
+    for (int t = 0; t < nt; ++t) load_tile<RM, XS>(Xs[t], Xg + (size_t)ld * t * kBlk, ld, tid);
     {
         const double* src;
         int bld;
         Btile(0, src, bld);
-        load_tile64(Ls[0], src, bld, tid);
+        load_tile<64, TS>(Ls[0], src, bld, tid);
     }
     cp_async_commit();
     int seq = 0;
-    double acc[4][2][2];
-    auto mma_tile = [&](const double (*Xa)[TS], const double (*Lb)[TS]) {
+    double acc[MF][NF][2];
+    auto mma_tile = [&](const double (*Xa)[XS], const double (*Lb)[TS]) {
 #pragma unroll 4
         for (int kk = 0; kk < 16; ++kk) {
-            double a[4], b[2];
+            double a[MF], b[NF];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) a[t] = Xa[kk * 4 + lk][wm * 32 + t * 8 + lr];
+            for (int t = 0; t < MF; ++t) a[t] = Xa[kk * 4 + lk][row0 + t * 8 + lr];
 #pragma unroll
-            for (int t = 0; t < 2; ++t) b[t] = Lb[kk * 4 + lk][wn * 16 + t * 8 + lr];
+            for (int t = 0; t < NF; ++t) b[t] = Lb[kk * 4 + lk][col0 + t * 8 + lr];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < MF; ++i)
 #pragma unroll
-                for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < NF; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
     };
     auto next_tile = [&]() {        // prefetch tile seq+1, then make tile seq visible to the whole CTA
@@ -338,7 +351,7 @@ __global__ void __launch_bounds__(256) k_trsm_fused(double* __restrict__ A, int 
             const double* src;
             int bld;
             Btile(seq + 1, src, bld);
-            load_tile64(Ls[(seq + 1) & 1], src, bld, tid);
+            load_tile<64, TS>(Ls[(seq + 1) & 1], src, bld, tid);
         }
         cp_async_commit();
         cp_async_wait<1>();
@@ -346,9 +359,9 @@ __global__ void __launch_bounds__(256) k_trsm_fused(double* __restrict__ A, int 
     };
     for (int j = 0; j < nt; ++j) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < MF; ++i)
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj) acc[i][jj][0] = acc[i][jj][1] = 0.0;
+            for (int jj = 0; jj < NF; ++jj) acc[i][jj][0] = acc[i][jj][1] = 0.0;
         for (int i = 0; i < j; ++i) {
             next_tile();
             mma_tile(Xs[i], Ls[seq & 1]);
@@ -357,10 +370,10 @@ __global__ void __launch_bounds__(256) k_trsm_fused(double* __restrict__ A, int 
         }
         if (j > 0) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < MF; ++i)
 #pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    const int r = wm * 32 + i * 8 + lr, c = wn * 16 + jj * 8 + 2 * lk;
+                for (int jj = 0; jj < NF; ++jj) {
+                    const int r = row0 + i * 8 + lr, c = col0 + jj * 8 + 2 * lk;
                     Xs[j][c][r] -= acc[i][jj][0];
                     Xs[j][c + 1][r] -= acc[i][jj][1];
                     acc[i][jj][0] = acc[i][jj][1] = 0.0;
@@ -370,10 +383,10 @@ __global__ void __launch_bounds__(256) k_trsm_fused(double* __restrict__ A, int 
         mma_tile(Xs[j], Ls[seq & 1]);
         __syncthreads();                                      // everyone has read X_j
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < MF; ++i)
 #pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                const int r = wm * 32 + i * 8 + lr, c = wn * 16 + jj * 8 + 2 * lk;
+            for (int jj = 0; jj < NF; ++jj) {
+                const int r = row0 + i * 8 + lr, c = col0 + jj * 8 + 2 * lk;
                 Xs[j][c][r] = acc[i][jj][0];
                 Xs[j][c + 1][r] = acc[i][jj][1];
             }
@@ -381,13 +394,25 @@ __global__ void __launch_bounds__(256) k_trsm_fused(double* __restrict__ A, int 
         ++seq;
     }
     cp_async_wait<0>();
-    // write the row block back (coalesced over rows)
+    // write the rows back (coalesced over rows)
+    constexpr int CH = RM / 2;
     for (int t = 0; t < nt; ++t)
-        for (int q = tid; q < 64 * 32; q += 256) {
-            const int k = q >> 5, i2 = (q & 31) * 2;
+        for (int q = tid; q < 64 * CH; q += 256) {
+            const int k = q / CH, i2 = (q % CH) * 2;
             *reinterpret_cast<double2*>(Xg + i2 + (size_t)ld * (t * kBlk + k)) =
                 *reinterpret_cast<const double2*>(&Xs[t][k][i2]);
         }
+}
+
+// Timing experiments only (results are garbage): FEBA_CHOL_SKIP bitmask drops kernel classes from the
+// factorisation -- 1: potrf64, 2: fused triangular leaves, 4: products with < 256 tiles, 8: the rest.
+static int chol_skip() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = std::getenv("FEBA_CHOL_SKIP");
+        v = e ? std::atoi(e) : 0;
+    }
+    return v;
 }
 
 static cudaError_t gemm_nt(double* C, int ldc, const double* A, int lda, const double* B, int ldb, int mb,
@@ -402,6 +427,10 @@ static cudaError_t gemm_nt(double* C, int ldc, const double* A, int lda, const d
         e = cudaFuncSetAttribute(k_gemm_nt<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = true;
+    }
+    {
+        const long long tiles = (long long)mb * nbk / (mode == 1 ? 2 : 1);
+        if (chol_skip() & (tiles < 256 ? 4 : 8)) return cudaSuccess;
     }
     dim3 grid(mb, nbk);
     if (mode == 1) k_gemm_nt<1><<<grid, 128, smem, st>>>(C, ldc, A, lda, B, ldb, kb * kBlk);
@@ -422,12 +451,18 @@ static cudaError_t rtrsm(double* A, int ld, const double* Linv, int r0, int mr, 
     if (n <= TF_MAX) {
         static bool configured = false;
         if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(k_trsm_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            cudaError_t e = cudaFuncSetAttribute(k_trsm_fused<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)kTrsmFusedSmem);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(k_trsm_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kTrsmFusedSmem16);
             if (e != cudaSuccess) return e;
             configured = true;
         }
-        k_trsm_fused<<<mr, 256, kTrsmFusedSmem, st>>>(A, ld, Linv, r0, c0, n);
+        if (chol_skip() & 2) return cudaSuccess;
+        // few row blocks (deep recursion levels): 16-row strips give four times the CTAs
+        if (mr <= 74) k_trsm_fused<16><<<mr * 4, 256, kTrsmFusedSmem16, st>>>(A, ld, Linv, r0, c0, n);
+        else k_trsm_fused<64><<<mr, 256, kTrsmFusedSmem, st>>>(A, ld, Linv, r0, c0, n);
         ++*launches;
         return cudaGetLastError();
     }
@@ -453,6 +488,7 @@ static cudaError_t rchol(double* A, int ld, double* Linv, int b0, int n, int aug
             if (e != cudaSuccess) return e;
             configured = true;
         }
+        if (chol_skip() & 1) return cudaSuccess;
         k_potrf64_inv<<<1, 256, psmem, st>>>(AT(A, ld, b0, b0), ld, LINV(Linv, b0), info);
         ++*launches;
         return cudaGetLastError();

@@ -381,12 +381,14 @@ __global__ void k_update_cam(DevProblem P, const double* __restrict__ sol, const
 // K4: back-substitution of the tie points, d_p = -V_p^-1 (u_p + W_p' d_c), X += d_p, sumabs.
 // Recomputes the Jacobians at the linearisation point (W_p is never stored):
 //   W_p' d_c = sum_a Jt_a' P (Je_a d_e(i_a) + Jc_a d_cam).
-template <int NK, bool HAS_CAM>
+// One group of G lanes per point (G = 16: two points per warp when points have few observations).
+template <int NK, bool HAS_CAM, int G>
 __global__ void __launch_bounds__(128) k_backsub(DevProblem P) {
     constexpr int NC = NK + 5;
-    const int lane = threadIdx.x & 31;
-    const int nwarp = gridDim.x * (blockDim.x >> 5);
-    const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & (G - 1);
+    const int nwarp = gridDim.x * (blockDim.x / G);
+    const int gw = blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
+    const unsigned gmask = G == 32 ? 0xffffffffu : (0xffffu << (16 * ((threadIdx.x & 31) >> 4)));
     const double pw[2] = {P.px, P.py};
     double dsum = 0.0;
     for (int seg = gw; seg < P.n_seg; seg += nwarp) {
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(128) k_backsub(DevProblem P) {
         double acc[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) acc[k] = 0.0;
-        for (int o = beg + lane; o < end; o += 32) {
+        for (int o = beg + lane; o < end; o += G) {
             ObsJac<NK> J;
             const int img = P.oimg[o];
             observation<NK, HAS_CAM>(P.type, P.ox[o], P.oy[o], P.img_tab + kImgStride * img, P.cam_tab,
@@ -437,7 +439,7 @@ __global__ void __launch_bounds__(128) k_backsub(DevProblem P) {
 #pragma unroll
         for (int k = 0; k < 12; ++k)
 #pragma unroll
-            for (int s = 16; s > 0; s >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], s);
+            for (int s = G / 2; s > 0; s >>= 1) acc[k] += __shfl_xor_sync(gmask, acc[k], s);
         double Vinv[6];
         sym3_inverse(acc, Vinv);
         double t[3] = {acc[6] + acc[9], acc[7] + acc[10], acc[8] + acc[11]};
@@ -598,18 +600,27 @@ cudaError_t launch_border_scale(const DevProblem& P, const double* eop, double* 
     return cudaGetLastError();
 }
 
+static int backsub_lanes(const DevProblem& P) { return (P.n_seg > 0 && P.n_obs <= 12 * (int64_t)P.n_seg) ? 16 : 32; }
+
+// number of point groups of the back-substitution grid (= partial sums it writes)
 int backsub_warps(const DevProblem& P, int sm_count) {
-    int grid = (P.n_seg + 3) / 4;
+    const int per_cta = 128 / backsub_lanes(P);
+    int grid = (P.n_seg + per_cta - 1) / per_cta;
     const int cap = sm_count * 8;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    return grid * 4;
+    return grid * per_cta;
 }
 
 cudaError_t launch_backsub(const DevProblem& P, int sm_count, cudaStream_t st) {
     const bool hc = P.uc > 0;
-    const int grid = backsub_warps(P, sm_count) / 4;
-    FEBA_NK_DISPATCH(P.NK, hc, (k_backsub<NK_, HC_><<<grid, 128, 0, st>>>(P)));
+    const int G = backsub_lanes(P);
+    const int grid = backsub_warps(P, sm_count) / (128 / G);
+    if (G == 16) {
+        FEBA_NK_DISPATCH(P.NK, hc, (k_backsub<NK_, HC_, 16><<<grid, 128, 0, st>>>(P)));
+    } else {
+        FEBA_NK_DISPATCH(P.NK, hc, (k_backsub<NK_, HC_, 32><<<grid, 128, 0, st>>>(P)));
+    }
     return cudaGetLastError();
 }
 
