@@ -704,13 +704,15 @@ cudaError_t launch_assemble(const DevProblem& P, int sm_count, cudaStream_t st, 
             ++*launches;
         }
         if (P.n_blocks > 0) {
-            // few resident warps on purpose: the grid sweeps the block list (image-row major) in
-            // waves, and the records a wave touches (its rows' images + their lower neighbours)
-            // should stay in L2
+            // resident CTAs per SM (measured 1, 2, 4, 8 on config 4: 13.4, 11.3, 12.0, 11.1 ms assembly).
+            // Tried and rejected: a cooperative gather (nine lanes per 144-byte record, staged through
+            // shared memory) -- 19 ms instead of 10.6 ms: the exposed load latency per 32-pair step is
+            // not hidden with 12 warps per SM, while the lane-per-record version has all 36 loads of a
+            // pair in flight at once.
             static int per_sm = -1;
             if (per_sm < 0) {
                 const char* e = std::getenv("FEBA_PAIR_CTAS_PER_SM");
-                per_sm = e ? std::atoi(e) : 2;
+                per_sm = e ? std::atoi(e) : 8;
                 if (per_sm < 1) per_sm = 1;
             }
             int g2 = (P.n_blocks + 3) / 4;
