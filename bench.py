@@ -251,7 +251,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- device-resident timing: inputs already in HBM, nothing read back inside the region
     for _ in range(max(args.warmup, 3)):
         adj.iterate_async()
-    deltasum_warm = h.sync()
+    h.sync()
     sampler = ClockSampler(local_rank)
     launches0 = h.launch_count()
     barrier()
@@ -310,6 +310,12 @@ def run_ours(args, rank, world, local_rank):
     t0 = time.perf_counter()
     res = h.residuals()
     rsd_ms = (time.perf_counter() - t0) * 1e3
+    # variance factor over ALL ranks (main.m:601): sum the squared residuals of the shards
+    ss = torch.tensor([res["sxx"], res["syy"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ss, op=dist.ReduceOp.SUM)
+    st = prob.settings
+    sigma02 = float((ss[0] / st.sigma_x ** 2 + ss[1] / st.sigma_y ** 2).item()) / (2 * prob.n_obs - prob.u)
 
     if rank != 0:
         if world > 1:
@@ -325,10 +331,15 @@ def run_ours(args, rank, world, local_rank):
         "update_backsub": {"ms": float(phase_ms[4])},
     }
     if phase_ms[2] >= phase_ms[1]:
-        roof = {"kernel": "k_gemm_nt (DMMA trailing updates of the blocked Cholesky)", "bound": "tensor",
+        roof = {"kernel": "k_gemm_nt (FP64 DMMA products of the blocked Cholesky; achieved = u_c^3/3 flop over the "
+                          "WHOLE factorisation phase incl. its latency-bound leaves)", "bound": "tensor",
                 "achieved": kernels["cholesky"]["TFLOPs"], "peak": dgemm_peak, "unit": "TFLOP/s",
-                "frac": kernels["cholesky"]["TFLOPs"] / dgemm_peak if dgemm_peak else None, "traffic": None,
-                "peak_source": "cuBLAS DGEMM 8192^3 measured live (FP64 tensor peak is not in MEASURED_PEAKS.json)"}
+                "frac": kernels["cholesky"]["TFLOPs"] / dgemm_peak if dgemm_peak else None,
+                "traffic": 6.02e9 if args.workload == "config4" else None,
+                "traffic_note": "dram read+write of the top-level trailing-update launch (2.25e11 flop, 6.62 ms, "
+                                "33.9 TFLOP/s, DMMA pipe 92 % active): ncu --set full, profiles/r1e_end_state_config4.md",
+                "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run (FP64 is not in MEASURED_PEAKS.json); "
+                               "DMMA issue peak by microbenchmark 37.1 TFLOP/s (profiles/r1_dmma_rate_microbench.txt)"}
     else:
         roof = {"kernel": "k_assemble (fused BuildAwG + normal blocks + Schur)", "bound": "hbm",
                 "achieved": kernels["assemble_schur"]["GBps"], "peak": hbm_peak, "unit": "GB/s",
@@ -351,7 +362,7 @@ def run_ours(args, rank, world, local_rank):
                 "d2h_bytes_per_step": int(8 * u_loc + 16)},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels,
         "fp64_dgemm_peak_tflops": dgemm_peak, "residual_stage_ms": rsd_ms,
-        "sigma02": float(res["sigma02"]), "deltasum_after_warmup": deltasum_warm,
+        "sigma02": sigma02,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
