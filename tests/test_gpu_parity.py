@@ -2,6 +2,8 @@
 blocks of the reduced normal equations 1e-12 relative (block max-norm); per-iteration delta
 max(1e-9, 100*cond*eps) relative; end to end xhat 1e-9 (group-normalised), v 1e-8*max|v|,
 sigma02 1e-8 relative; identical iteration counts."""
+import os
+
 import numpy as np
 import pytest
 
@@ -258,3 +260,74 @@ def test_full_size_properties_config4_shape():
     assert np.max(np.abs(c["v"] - a["v"][np.stack([2 * perm, 2 * perm + 1], 1).ravel()])) < 1e-9
     assert group_rel(prob, c["xhat"], a["xhat"]) < 1e-10
     assert 0.95 < a["sigma02"] < 1.05
+
+
+def test_main_and_batchrun_over_text_files(tmp_path):
+    """main(folder, plot) / BatchRun over the reference's five text formats + .cfg (written by
+    save_problem), as BatchRun.m:42-65 drives main.m: same console protocol, 0/1 return, .rsd written."""
+    folders = []
+    for k, mode in enumerate(("free", "mixed")):
+        prob = synth.make_network(10, 400, 7, 300 + k, mode=mode, n_control=25 if mode == "mixed" else 0)
+        d = tmp_path / "root" / f"set{k}"
+        fb.save_problem(prob, str(d), stem=f"net{k}")
+        folders.append((str(d), prob))
+    (tmp_path / "root" / "empty").mkdir()
+    assert sorted(fb.findfiles(str(tmp_path / "root"))) == sorted(f for f, _ in folders)
+    for d, prob in folders:
+        assert fb.main(d, False, verbose=False) == 0
+        out = fb.main.last
+        err, xhat0, _ = fb.Buildxhat(out["problem"])
+        ref = sparse.gauss_newton(out["problem"], xhat0)
+        assert out["iterations"] == ref["iterations"]
+        assert np.max(np.abs(out["v"] - ref["v"])) < 1e-8 * np.max(np.abs(ref["v"]))
+        rsd = [l.split("\t") for l in open(os.path.join(d, os.path.basename(d) + ".rsd")).read().splitlines()]
+        assert len(rsd) == prob.n_obs and len(rsd[0]) == 9                       # BuildRSD.m:5-6
+        assert abs(float(rsd[3][5]) - out["RSD"][3, 1]) < 1e-12
+    assert fb.BatchRun([str(tmp_path / "root")]) == 0
+    # a broken data set stops the batch with error 1 (BatchRun.m:60-64)
+    bad = tmp_path / "root" / "set0" / "net0.cfg"
+    bad.write_text(bad.read_text().replace("'fisheye'", "'no-such-model'"))
+    assert fb.BatchRun([str(tmp_path / "root")]) == 1
+
+
+def test_degenerate_inputs_fail_cleanly():
+    """The reference produces Inf/NaN (singular N, main.m:432/442) for these; the library must
+    return an error status, not crash or hang."""
+    prob = synth.make_network(10, 300, 6, 11, mode="mixed", n_control=40)
+    err, xhat0, _ = fb.Buildxhat(prob)
+    # an image that lost all its observations -> zero diagonal block
+    keep = prob.obs_img != 3
+    p2 = synth.make_network(10, 300, 6, 11, mode="mixed", n_control=40)
+    for k in ("obs_x", "obs_y", "obs_img", "obs_pt"):
+        setattr(p2, k, getattr(prob, k)[keep])
+    with fb.Handle(p2) as h:
+        h.set_xhat(xhat0)
+        with pytest.raises(fb.FebaError) as ei:
+            h.iterate()
+        assert ei.value.code == fb.lib.FEBA_ERR_NUMERIC
+    # no observations at all
+    p3 = synth.make_network(10, 300, 6, 11, mode="mixed", n_control=40)
+    for k in ("obs_x", "obs_y", "obs_img", "obs_pt"):
+        setattr(p3, k, getattr(prob, k)[:0])
+    with fb.Handle(p3) as h:
+        with pytest.raises(fb.FebaError):
+            h.iterate()
+
+
+def test_iteration_cap_and_solve_entry_point():
+    """feba_solve = the whole while loop (main.m:412-494) incl. the Iteration_Cap break (main.m:490-493)."""
+    prob = synth.make_network(10, 300, 6, 12, mode="free")
+    err, xhat0, _ = fb.Buildxhat(prob)
+    ref = sparse.gauss_newton(prob, xhat0)
+    with fb.Handle(prob) as h:
+        h.set_xhat(xhat0)
+        it, trace = h.solve()
+        assert it == ref["iterations"] and np.allclose(trace[:2], ref["deltasum"][:2], rtol=1e-4)
+    prob.settings.Iteration_Cap = 2
+    with fb.Handle(prob) as h:
+        h.set_xhat(xhat0)
+        it, trace = h.solve()
+        assert it == 2 and trace.size == 2
+        x2 = h.get_xhat()
+    ref2 = sparse.gauss_newton(prob, xhat0, max_iter=2)
+    assert np.linalg.norm(x2 - ref2["xhat"]) < 1e-9 * np.linalg.norm(ref2["xhat"])
