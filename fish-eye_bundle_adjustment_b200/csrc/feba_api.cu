@@ -134,9 +134,6 @@ int check_settings(const feba_problem* pr) {
     if (pr->n_obs < 0 || pr->n_obs > 2000000000LL || pr->n_img < 1 || pr->n_cam < 1 || pr->n_pts < 0 ||
         pr->n_tie < 0)
         return fail(nullptr, FEBA_ERR_INVALID, "bad problem sizes");
-    if (pr->n_cam != 1)
-        return fail(nullptr, FEBA_ERR_INVALID, "this build supports one camera per adjustment (n_cam = %d)",
-                    pr->n_cam);
     return FEBA_OK;
 }
 
@@ -431,7 +428,7 @@ static int enqueue_assemble(feba_handle* h) {
     CU(h, cudaMemsetAsync(h->info, 0, sizeof(int), h->stream));
     CU(h, record(h, 1));
     ++h->launches;
-    CU(h, launch_assemble(P, h->sm_count, h->stream, &h->launches));
+    CU(h, launch_assemble(P, h->sm_count, h->info, h->stream, &h->launches));
     CU(h, record(h, 2));
     return FEBA_OK;
 }
@@ -533,6 +530,8 @@ static int finish_iteration(feba_handle* h, double* dcam_sum, double* dpts_sum) 
     if (*h->info_host == 1)
         return fail(h, FEBA_ERR_NUMERIC, "reduced normal matrix is not positive definite");
     if (*h->info_host == 2) return fail(h, FEBA_ERR_NUMERIC, "inner-constraint border system is singular");
+    if (*h->info_host == 3)
+        return fail(h, FEBA_ERR_INVALID, "an object point is observed by more than 4 different cameras (unsupported)");
     if (!std::isfinite(h->scal_host[0]) || !std::isfinite(h->scal_host[1]))
         return fail(h, FEBA_ERR_NUMERIC, "non-finite increment (R = 0 on the optical axis? BuildAwG.m:186)");
     return FEBA_OK;

@@ -101,8 +101,8 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
                 const bool act = o < end;
                 if (act) {
                     const int img = P.oimg[o];
-                    observation<NK, HAS_CAM>(type, P.ox[o], P.oy[o], P.img_tab + kImgStride * img, P.cam_tab, X, Y,
-                                             Z, J);
+                    observation<NK, HAS_CAM>(type, P.ox[o], P.oy[o], P.img_tab + kImgStride * img,
+                                             P.cam_tab + kCamStride * P.img_cam[img], X, Y, Z, J);
                 }
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
             if (act) {
                 if (!have_J) {
                     const int img = P.oimg[o];
-                    observation<NK, HAS_CAM>(type, P.ox[o], P.oy[o], P.img_tab + kImgStride * img, P.cam_tab, X, Y,
-                                             Z, J);
+                    observation<NK, HAS_CAM>(type, P.ox[o], P.oy[o], P.img_tab + kImgStride * img,
+                                             P.cam_tab + kCamStride * P.img_cam[img], X, Y, Z, J);
                 }
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
@@ -288,6 +288,291 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
         for (int t = 0; t < DPL; ++t)
             if (lane + G * t < ND) part[lane + G * t] = dacc[t];
         if (lane < NC) part[ND + lane] = gcacc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Multi-camera variant of the point pass (n_cam > 1 with camera unknowns): a point may be seen by
+// images of up to kMaxCamPt different cameras.  Per camera c of the point: Wc_c = sum_{a in c} Jc_a'PJt_a,
+// Fc_c = Wc_c L^-T.  Own-camera terms go through the records exactly as in the single-camera
+// kernel (H_a uses Fc of the observation's camera, the image pass adds H Je to that camera's rows);
+// camera x camera blocks (all pairs), the camera right-hand sides and the cross terms
+// -(Fc_c Z_a') Je_a for c != camera(a) are added to S with atomics (this path is not bit-reproducible
+// from run to run; the single-camera path is).
+constexpr int kMaxCamPt = 4;
+
+template <int NK, int G>
+struct alignas(16) PtSmemMC {
+    static constexpr int NC = NK + 5;
+    double rowJc[G][2][NC];
+    double rowJt[G][2][3];
+    double roww[G][2];
+    double Wc[kMaxCamPt][NC][3];
+    double Fc[kMaxCamPt][NC][3];
+    double V[6];
+    double up[3];
+    int pos[G];
+    int camrow[G];
+};
+
+template <int NK, int G>
+__global__ void __launch_bounds__(128) k_point_pass_mc(DevProblem P, int* __restrict__ info) {
+    constexpr int NC = NK + 5;
+    constexpr int ND = NC * (NC + 1) / 2;
+    constexpr int R2 = 2 + 2 * NC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    PtSmemMC<NK, G>* sm_all = reinterpret_cast<PtSmemMC<NK, G>*>(smem_raw);
+    const int lane = threadIdx.x & (G - 1);
+    const int wib = threadIdx.x / G;
+    PtSmemMC<NK, G>& sm = sm_all[wib];
+    const int nwarp = gridDim.x * (blockDim.x / G);
+    const int gw = blockIdx.x * (blockDim.x / G) + wib;
+    const unsigned gmask = G == 32 ? 0xffffffffu : (0xffffu << (16 * ((threadIdx.x & 31) >> 4)));
+    const double pw[2] = {P.px, P.py};
+    const int type = P.type;
+    const size_t aug = (size_t)P.n_pad;
+
+    for (int seg = gw; seg < P.n_seg; seg += nwarp) {
+        const int beg = P.seg_start[seg], end = P.seg_start[seg + 1];
+        const int pt = P.seg_pt[seg];
+        const bool is_tie = P.pt_tie[pt] >= 0;
+        const double X = P.xyz[3 * pt], Y = P.xyz[3 * pt + 1], Z = P.xyz[3 * pt + 2];
+        const bool single = (end - beg) <= G;
+        ObsJac<NK> J;
+        int mycam = 0;
+        int cams[kMaxCamPt] = {-1, -1, -1, -1};
+        int ncam = 0;
+        // zero the per-camera accumulators
+        for (int e = lane; e < kMaxCamPt * NC * 3; e += G) (&sm.Wc[0][0][0])[e] = 0.0;
+        double vacc = 0.0;
+        __syncwarp(gmask);
+        // ---------------- pass 1
+        for (int c0 = beg; c0 < end; c0 += G) {
+            const int o = c0 + lane;
+            const bool act = o < end;
+            if (act) {
+                const int img = P.oimg[o];
+                mycam = P.img_cam[img];
+                observation<NK, true>(type, P.ox[o], P.oy[o], P.img_tab + kImgStride * img,
+                                      P.cam_tab + kCamStride * mycam, X, Y, Z, J);
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+#pragma unroll
+                for (int j = 0; j < NC; ++j) sm.rowJc[lane][r][j] = act ? J.Jc[r][j] : 0.0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) sm.rowJt[lane][r][k] = act ? J.Jt[r][k] : 0.0;
+                sm.roww[lane][r] = act ? J.w[r] : 0.0;
+            }
+            sm.camrow[lane] = act ? mycam : -1;
+            __syncwarp(gmask);
+            const int nrow = min(G, end - c0);
+            // camera list of the point, first-occurrence order (every lane builds the same list)
+            for (int l = 0; l < nrow; ++l) {
+                const int c = sm.camrow[l];
+                bool found = false;
+#pragma unroll
+                for (int k = 0; k < kMaxCamPt; ++k) found = found || (k < ncam && cams[k] == c);
+                if (!found) {
+                    if (ncam < kMaxCamPt) {
+#pragma unroll
+                        for (int k = 0; k < kMaxCamPt; ++k)
+                            if (k == ncam) cams[k] = c;
+                        ++ncam;
+                    } else if (lane == 0) {
+                        atomicExch(info, 3);
+                    }
+                }
+            }
+            // direct camera terms of this chunk: Jc'PJc (lower, own camera) and Jc'Pw
+            for (int e = lane; e < ND + NC; e += G) {
+                int i = 0, j = 0;
+                if (e < ND) {
+                    while ((i + 1) * (i + 2) / 2 <= e) ++i;
+                    j = e - i * (i + 1) / 2;
+                } else {
+                    i = e - ND;
+                }
+                for (int k = 0; k < ncam; ++k) {
+                    double a = 0.0;
+                    for (int l = 0; l < nrow; ++l) {
+                        if (sm.camrow[l] != cams[k]) continue;
+                        if (e < ND)
+                            a += sm.rowJc[l][0][i] * pw[0] * sm.rowJc[l][0][j] + sm.rowJc[l][1][i] * pw[1] * sm.rowJc[l][1][j];
+                        else
+                            a += sm.rowJc[l][0][i] * pw[0] * sm.roww[l][0] + sm.rowJc[l][1][i] * pw[1] * sm.roww[l][1];
+                    }
+                    if (a == 0.0) continue;
+                    const size_t rc = (size_t)P.off_cam + (size_t)P.uc * cams[k];
+                    if (e < ND) {
+                        if (P.ccol[i] >= 0 && P.ccol[j] >= 0)
+                            atomicAdd(&P.S[(rc + P.ccol[i]) + (size_t)P.ld * (rc + P.ccol[j])], a);
+                    } else if (P.ccol[i] >= 0) {
+                        atomicAdd(&P.S[aug + (size_t)P.ld * (rc + P.ccol[i])], a);
+                    }
+                }
+            }
+            if (is_tie) {
+                for (int e = lane; e < NC * 3; e += G) {
+                    const int i = e / 3, k3 = e - 3 * i;
+                    for (int k = 0; k < ncam; ++k) {
+                        double a = 0.0;
+                        for (int l = 0; l < nrow; ++l)
+                            if (sm.camrow[l] == cams[k])
+                                a += sm.rowJc[l][0][i] * pw[0] * sm.rowJt[l][0][k3] + sm.rowJc[l][1][i] * pw[1] * sm.rowJt[l][1][k3];
+                        sm.Wc[k][i][k3] += a;                  // entry owned by this lane
+                    }
+                }
+                if (lane < 9) {
+                    double a = 0.0;
+                    if (lane < 6) {
+                        const int i = lane < 1 ? 0 : (lane < 3 ? 1 : 2);
+                        const int k = lane - i * (i + 1) / 2;
+                        for (int l = 0; l < nrow; ++l)
+                            a += sm.rowJt[l][0][i] * pw[0] * sm.rowJt[l][0][k] + sm.rowJt[l][1][i] * pw[1] * sm.rowJt[l][1][k];
+                    } else {
+                        const int k = lane - 6;
+                        for (int l = 0; l < nrow; ++l)
+                            a += sm.rowJt[l][0][k] * pw[0] * sm.roww[l][0] + sm.rowJt[l][1][k] * pw[1] * sm.roww[l][1];
+                    }
+                    vacc += a;
+                }
+            }
+            __syncwarp(gmask);
+        }
+        const bool have_J = single;
+        // ---------------- V = L L', ut, Fc per camera, camera x camera Schur terms
+        double i00 = 0, i10 = 0, i11 = 0, i20 = 0, i21 = 0, i22 = 0;
+        double ut[3] = {0, 0, 0};
+        if (is_tie) {
+            if (lane < 6) sm.V[lane] = vacc;
+            else if (lane < 9) sm.up[lane - 6] = vacc;
+            __syncwarp(gmask);
+            const double v0 = sm.V[0], v1 = sm.V[1], v2 = sm.V[2], v3 = sm.V[3], v4 = sm.V[4], v5 = sm.V[5];
+            const double l00 = sqrt(v0);
+            const double l10 = v1 / l00, l20 = v3 / l00;
+            const double l11 = sqrt(v2 - l10 * l10);
+            const double l21 = (v4 - l20 * l10) / l11;
+            const double l22 = sqrt(v5 - l20 * l20 - l21 * l21);
+            i00 = 1.0 / l00; i11 = 1.0 / l11; i22 = 1.0 / l22;
+            i10 = -l10 * i00 * i11;
+            i21 = -l21 * i11 * i22;
+            i20 = -(l20 * i00 + l21 * i10) * i22;
+            const double u0 = sm.up[0], u1 = sm.up[1], u2 = sm.up[2];
+            ut[0] = i00 * u0;
+            ut[1] = i10 * u0 + i11 * u1;
+            ut[2] = i20 * u0 + i21 * u1 + i22 * u2;
+            for (int e = lane; e < ncam * NC; e += G) {
+                const int k = e / NC, j = e - k * NC;
+                const double w0 = sm.Wc[k][j][0], w1 = sm.Wc[k][j][1], w2 = sm.Wc[k][j][2];
+                sm.Fc[k][j][0] = w0 * i00;
+                sm.Fc[k][j][1] = w0 * i10 + w1 * i11;
+                sm.Fc[k][j][2] = w0 * i20 + w1 * i21 + w2 * i22;
+            }
+            __syncwarp(gmask);
+            for (int k1 = 0; k1 < ncam; ++k1) {
+                const size_t r1 = (size_t)P.off_cam + (size_t)P.uc * cams[k1];
+                for (int e = lane; e < NC; e += G)             // right-hand side: -Fc ut
+                    if (P.ccol[e] >= 0)
+                        atomicAdd(&P.S[aug + (size_t)P.ld * (r1 + P.ccol[e])],
+                                  -(sm.Fc[k1][e][0] * ut[0] + sm.Fc[k1][e][1] * ut[1] + sm.Fc[k1][e][2] * ut[2]));
+                for (int k2 = 0; k2 < ncam; ++k2) {
+                    const size_t r2 = (size_t)P.off_cam + (size_t)P.uc * cams[k2];
+                    if (r1 < r2) continue;                      // lower block triangle: (k1 rows, k2 columns)
+                    for (int e = lane; e < NC * NC; e += G) {
+                        const int i = e / NC, j = e - i * NC;
+                        if (P.ccol[i] < 0 || P.ccol[j] < 0) continue;
+                        if (k1 == k2 && j > i) continue;
+                        atomicAdd(&P.S[(r1 + P.ccol[i]) + (size_t)P.ld * (r2 + P.ccol[j])],
+                                  -(sm.Fc[k1][i][0] * sm.Fc[k2][j][0] + sm.Fc[k1][i][1] * sm.Fc[k2][j][1] +
+                                    sm.Fc[k1][i][2] * sm.Fc[k2][j][2]));
+                    }
+                }
+            }
+        }
+        // ---------------- pass 2: records + cross-camera terms
+        double* buf = &sm.rowJc[0][0][0];
+        for (int a0 = beg; a0 < end; a0 += G) {
+            const int o = a0 + lane;
+            const bool act = o < end;
+            const int nrow = min(G, end - a0);
+            double Zm[2][3], ra[2];
+            int img = 0;
+            if (act) {
+                img = P.oimg[o];
+                if (!have_J) {
+                    mycam = P.img_cam[img];
+                    observation<NK, true>(type, P.ox[o], P.oy[o], P.img_tab + kImgStride * img,
+                                          P.cam_tab + kCamStride * mycam, X, Y, Z, J);
+                }
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const double t0 = pw[r] * J.Jt[r][0], t1 = pw[r] * J.Jt[r][1], t2 = pw[r] * J.Jt[r][2];
+                    Zm[r][0] = t0 * i00;
+                    Zm[r][1] = t0 * i10 + t1 * i11;
+                    Zm[r][2] = t0 * i20 + t1 * i21 + t2 * i22;
+                    ra[r] = pw[r] * J.w[r] - (Zm[r][0] * ut[0] + Zm[r][1] * ut[1] + Zm[r][2] * ut[2]);
+                }
+                sm.pos[lane] = P.ipos[o];
+                double* r1 = buf + kRec1 * lane;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) r1[6 * r + i] = J.Je[r][i];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) r1[12 + 3 * r + k] = Zm[r][k];
+                }
+            }
+            __syncwarp(gmask);
+            for (int u = lane; u < nrow * (kRec1 / 2); u += G) {
+                const int k = u / (kRec1 / 2), part = u - k * (kRec1 / 2);
+                reinterpret_cast<double2*>(P.rec1 + (size_t)kRec1 * sm.pos[k])[part] =
+                    reinterpret_cast<const double2*>(buf + kRec1 * k)[part];
+            }
+            __syncwarp(gmask);
+            if (act) {
+                int kown = 0;
+#pragma unroll
+                for (int k = 0; k < kMaxCamPt; ++k)
+                    if (cams[k] == mycam) kown = k;
+                double* r2 = buf + R2 * lane;
+                r2[0] = ra[0];
+                r2[1] = ra[1];
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    double f0 = 0, f1 = 0, f2 = 0;
+                    if (is_tie) { f0 = sm.Fc[kown][j][0]; f1 = sm.Fc[kown][j][1]; f2 = sm.Fc[kown][j][2]; }
+#pragma unroll
+                    for (int r = 0; r < 2; ++r)
+                        r2[2 + 2 * j + r] = J.Jc[r][j] * pw[r] - (f0 * Zm[r][0] + f1 * Zm[r][1] + f2 * Zm[r][2]);
+                }
+                // cross terms: rows of the OTHER cameras of this point x columns of this image
+                if (is_tie) {
+                    const size_t col0 = (size_t)P.ui * img;
+                    for (int k = 0; k < ncam; ++k) {
+                        if (k == kown) continue;
+                        const size_t rc = (size_t)P.off_cam + (size_t)P.uc * cams[k];
+                        for (int j = 0; j < NC; ++j) {
+                            if (P.ccol[j] < 0) continue;
+                            const double h0 = -(sm.Fc[k][j][0] * Zm[0][0] + sm.Fc[k][j][1] * Zm[0][1] + sm.Fc[k][j][2] * Zm[0][2]);
+                            const double h1 = -(sm.Fc[k][j][0] * Zm[1][0] + sm.Fc[k][j][1] * Zm[1][1] + sm.Fc[k][j][2] * Zm[1][2]);
+#pragma unroll
+                            for (int i = 0; i < 6; ++i)
+                                if (P.ecol[i] >= 0)
+                                    atomicAdd(&P.S[(rc + P.ccol[j]) + (size_t)P.ld * (col0 + P.ecol[i])],
+                                              h0 * J.Je[0][i] + h1 * J.Je[1][i]);
+                        }
+                    }
+                }
+            }
+            __syncwarp(gmask);
+            for (int u = lane; u < nrow * (R2 / 2); u += G) {
+                const int k = u / (R2 / 2), part = u - k * (R2 / 2);
+                reinterpret_cast<double2*>(P.rec2 + (size_t)R2 * sm.pos[k])[part] =
+                    reinterpret_cast<const double2*>(buf + R2 * k)[part];
+            }
+            __syncwarp(gmask);
+        }
     }
 }
 
@@ -685,11 +970,36 @@ static cudaError_t launch_point_pass_t(const DevProblem& P, int sm_count, cudaSt
     return cudaGetLastError();
 }
 
-cudaError_t launch_assemble(const DevProblem& P, int sm_count, cudaStream_t st, int64_t* launches) {
+template <int NK, int G>
+static cudaError_t launch_point_pass_mc_t(const DevProblem& P, int sm_count, int* info, cudaStream_t st) {
+    const size_t smem = (128 / G) * sizeof(PtSmemMC<NK, G>);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_point_pass_mc<NK, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    k_point_pass_mc<NK, G><<<point_pass_grid(P, sm_count), 128, smem, st>>>(P, info);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_assemble(const DevProblem& P, int sm_count, int* info, cudaStream_t st, int64_t* launches) {
     const bool hc = P.uc > 0;
+    const bool mc = hc && P.n_cam > 1;
     if (P.n_seg > 0) {
         cudaError_t e = cudaSuccess;
-        if (group_lanes(P) == 16) {
+        if (mc) {
+            const bool g16 = group_lanes(P) == 16;
+            switch (P.NK) {
+#define FEBA_MC_CASE(N) \
+    case N: e = g16 ? launch_point_pass_mc_t<N, 16>(P, sm_count, info, st) : launch_point_pass_mc_t<N, 32>(P, sm_count, info, st); break;
+                FEBA_MC_CASE(1) FEBA_MC_CASE(2) FEBA_MC_CASE(3) FEBA_MC_CASE(4)
+                FEBA_MC_CASE(5) FEBA_MC_CASE(6) FEBA_MC_CASE(7) FEBA_MC_CASE(8)
+#undef FEBA_MC_CASE
+                default: return cudaErrorInvalidValue;
+            }
+        } else if (group_lanes(P) == 16) {
             FEBA_NK_DISPATCH2(P.NK, hc, (e = launch_point_pass_t<NK_, HC_, 16>(P, sm_count, st)));
         } else {
             FEBA_NK_DISPATCH2(P.NK, hc, (e = launch_point_pass_t<NK_, HC_, 32>(P, sm_count, st)));
@@ -699,7 +1009,7 @@ cudaError_t launch_assemble(const DevProblem& P, int sm_count, cudaStream_t st, 
         int grid = P.n_img < sm_count * 4 ? P.n_img : sm_count * 4;
         FEBA_NK_DISPATCH2(P.NK, hc, (k_image_pass<NK_, HC_><<<grid, 128, 0, st>>>(P)));
         ++*launches;
-        if (hc) {
+        if (hc && !mc) {
             k_cam_reduce<<<1, 1024, 0, st>>>(P, assemble_warps(P, sm_count));
             ++*launches;
         }

@@ -403,8 +403,9 @@ __global__ void __launch_bounds__(128) k_backsub(DevProblem P) {
         for (int o = beg + lane; o < end; o += G) {
             ObsJac<NK> J;
             const int img = P.oimg[o];
-            observation<NK, HAS_CAM>(P.type, P.ox[o], P.oy[o], P.img_tab + kImgStride * img, P.cam_tab,
-                                     X, Y, Z, J);
+            const int cam = P.img_cam[img];
+            observation<NK, HAS_CAM>(P.type, P.ox[o], P.oy[o], P.img_tab + kImgStride * img,
+                                     P.cam_tab + kCamStride * cam, X, Y, Z, J);
             double q[2] = {0.0, 0.0};
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(128) k_backsub(DevProblem P) {
 #pragma unroll
                 for (int j = 0; j < NC; ++j) {
                     if (P.ccol[j] >= 0) {
-                        const double d = P.dcam[P.off_cam + P.ccol[j]];
+                        const double d = P.dcam[P.off_cam + P.uc * cam + P.ccol[j]];
                         q[0] += J.Jc[0][j] * d;
                         q[1] += J.Jc[1][j] * d;
                     }
@@ -494,8 +495,9 @@ __global__ void __launch_bounds__(256) k_residuals(DevProblem P, const int* __re
         const int tie = P.pt_tie[pt];
         ObsJac<NK> J;
         const double x = P.ox[o], y = P.oy[o];
-        observation<NK, HAS_CAM>(P.type, x, y, P.img_tab + kImgStride * img, P.cam_tab, xyz_prev[3 * pt],
-                                 xyz_prev[3 * pt + 1], xyz_prev[3 * pt + 2], J);
+        const int cam = P.img_cam[img];
+        observation<NK, HAS_CAM>(P.type, x, y, P.img_tab + kImgStride * img, P.cam_tab + kCamStride * cam,
+                                 xyz_prev[3 * pt], xyz_prev[3 * pt + 1], xyz_prev[3 * pt + 2], J);
         double v[2] = {J.w[0], J.w[1]};
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
@@ -509,7 +511,7 @@ __global__ void __launch_bounds__(256) k_residuals(DevProblem P, const int* __re
 #pragma unroll
             for (int j = 0; j < NC; ++j) {
                 if (P.ccol[j] >= 0) {
-                    const double d = P.dcam_unscaled[P.off_cam + P.ccol[j]];
+                    const double d = P.dcam_unscaled[P.off_cam + P.uc * cam + P.ccol[j]];
                     v[0] += J.Jc[0][j] * d;
                     v[1] += J.Jc[1][j] * d;
                 }
@@ -531,7 +533,6 @@ __global__ void __launch_bounds__(256) k_residuals(DevProblem P, const int* __re
             v_out[2 * (size_t)row + 1] = v[1];
         }
         if (rsd_out) {
-            const int cam = P.img_cam[img];
             const double xb = x - iop_new[P.NC * cam], yb = y - iop_new[P.NC * cam + 1];
             const double theta = atan2(yb, xb), Phi = atan2(v[1], v[0]);
             const double vd = sqrt(v[0] * v[0] + v[1] * v[1]);

@@ -21,7 +21,7 @@ cudaError_t launch_border_scale(const DevProblem& P, const double* eop, double* 
 cudaError_t build_pair_schedule(DevProblem& P, const int* d_oseg, long long* n_pairs_out, void** keep_pairs,
                                 void** keep_blocks, cudaStream_t st);
 int assemble_warps(const DevProblem& P, int sm_count);
-cudaError_t launch_assemble(const DevProblem& P, int sm_count, cudaStream_t st, int64_t* launches);
+cudaError_t launch_assemble(const DevProblem& P, int sm_count, int* info, cudaStream_t st, int64_t* launches);
 int backsub_warps(const DevProblem& P, int sm_count);
 cudaError_t launch_backsub(const DevProblem& P, int sm_count, cudaStream_t st);
 cudaError_t launch_update_cam(const DevProblem& P, const double* sol, const double* dvec, double* dcam,

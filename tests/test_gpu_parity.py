@@ -331,3 +331,36 @@ def test_iteration_cap_and_solve_entry_point():
         x2 = h.get_xhat()
     ref2 = sparse.gauss_newton(prob, xhat0, max_iter=2)
     assert np.linalg.norm(x2 - ref2["xhat"]) < 1e-9 * np.linalg.norm(ref2["xhat"])
+
+
+@pytest.mark.parametrize("mode,ncams", [("free", 2), ("mixed", 2), ("mixed", 3)])
+def test_multi_camera_networks(mode, ncams):
+    """Several cameras (cam_num of main.m:322, per-camera IOP blocks of BuildAwG.m:110-155,448): images
+    are dealt round-robin to the cameras, so every object point is seen by all of them."""
+    import copy
+    base = synth.make_network(15, 900, 8, 555, mode=mode, n_control=60 if mode == "mixed" else 0)
+    prob = copy.copy(base)
+    prob.settings = copy.copy(base.settings)
+    prob.img_cam = (np.arange(base.numImg) % ncams).astype(np.int32)
+    prob.iop0 = np.repeat(base.iop0, ncams, axis=0)
+    prob.iop0[1:, :3] += np.arange(1, ncams)[:, None] * np.array([0.6, -0.4, 1.1])
+    prob.cam_box = np.repeat(base.cam_box, ncams, axis=0)
+    prob.camera_ids = [str(c) for c in range(ncams)]
+    err, xhat0, names = fb.Buildxhat(prob)
+    assert prob.u == base.u + (ncams - 1) * prob.settings.u_percam and f"xp_{ncams - 1}" in names
+    ref = sparse.gauss_newton(prob, xhat0)
+    # reduced system of the first step
+    S_ref, g_ref = reduced_oracle(prob, xhat0)
+    with fb.Handle(prob) as h:
+        h.set_xhat(xhat0)
+        h.iterate_assemble()
+        S, g = h.debug_reduced()
+        h.iterate_solve()
+    sc = np.sqrt(np.abs(np.diag(S_ref)))
+    assert np.max(np.abs(S - S_ref) / np.outer(sc, sc)) < 1e-11
+    out = fb.adjust(prob, xhat0, verbose=False)
+    assert out["iterations"] == ref["iterations"]
+    assert np.max(np.abs(out["v"] - ref["v"])) < 1e-8 * np.max(np.abs(ref["v"]))
+    assert abs(out["sigma02"] - ref["sigma02"]) < 1e-8 * ref["sigma02"]
+    assert group_rel(prob, out["xhat"], ref["xhat"]) < 1e-9
+    assert np.max(np.abs(out["RSD"] - ref["RSD"])) < 1e-8
