@@ -1,0 +1,63 @@
+"""Many independent adjustments on one GPU, run concurrently (BASELINE.json configs[4]: the
+BatchRun.m sweep).
+
+The reference's ``BatchRun.m:57-65`` calls ``main`` on one data folder after the other.  Small
+blocks (u_c ~ 1,200) are launch- and latency-bound on a B200, so here every block gets its own
+handle -- and with it its own CUDA stream and CUDA graphs -- and the Gauss-Newton loops advance in
+lock step: one ``feba_iterate_async`` per still-active block, then one ``feba_sync`` each.  Kernels of
+different blocks overlap on the device; there is no exchange between blocks (replicas only).
+Results are bit-identical to running the blocks one at a time (each block's arithmetic is untouched).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .lib import Handle
+from .problem import Buildxhat, Problem
+
+
+def adjust_batch(problems: Sequence[Problem], xhat0s: Optional[Sequence[np.ndarray]] = None,
+                 want_residuals: bool = True, handles: Optional[List[Handle]] = None) -> List[dict]:
+    """main.m:386-602 for every problem; returns one result dict per problem (as ``adjust``)."""
+    own = handles is None
+    if own:
+        handles = [Handle(p) for p in problems]
+    try:
+        n = len(problems)
+        if xhat0s is None:
+            xhat0s = []
+            for p in problems:
+                err, x0, _ = Buildxhat(p)
+                if err:
+                    raise ValueError("Error building xhat")
+                xhat0s.append(x0)
+        for h, x0 in zip(handles, xhat0s):
+            h.set_xhat(x0)
+        deltasum = [100.0] * n                                  # main.m:407
+        count = [0] * n
+        trace: List[List[float]] = [[] for _ in range(n)]
+        active = [i for i in range(n) if deltasum[i] > problems[i].settings.threshold]
+        while active:
+            for i in active:                                     # enqueue one iteration of every active block
+                handles[i].iterate_async()
+            nxt = []
+            for i in active:                                     # main.m:484-493 per block
+                deltasum[i] = handles[i].sync()
+                count[i] += 1
+                trace[i].append(deltasum[i])
+                s = problems[i].settings
+                if deltasum[i] > s.threshold and count[i] < s.Iteration_Cap:
+                    nxt.append(i)
+            active = nxt
+        out = []
+        for i, h in enumerate(handles):
+            res = h.residuals() if want_residuals else {}
+            res.update(xhat=h.get_xhat(), iterations=count[i], deltasum=trace[i])
+            out.append(res)
+        return out
+    finally:
+        if own:
+            for h in handles:
+                h.close()

@@ -122,14 +122,45 @@ def findfiles(root: str, exts: Sequence[str] = (".pho", ".ext", ".cnt", ".int"))
     return found
 
 
-def BatchRun(selpath: Sequence[str], cfg_folder: Optional[str] = None, verbose: bool = False) -> int:
+def BatchRun(selpath: Sequence[str], cfg_folder: Optional[str] = None, verbose: bool = False,
+             concurrent: bool = False) -> int:
     """BatchRun.m:42-65: run ``main(folder, false)`` over every data folder; stop at the first
-    error.  The reference runs them one at a time on the host; each adjustment here runs on the
-    current CUDA device (the multi-GPU sweep shards folders over ranks, see ``bench.py``)."""
+    error.  The reference runs them one at a time on the host.  ``concurrent=True`` loads every
+    folder first and advances all adjustments together on the current CUDA device
+    (``batch.adjust_batch``; same results, .rsd files written at the end); the multi-GPU sweep
+    shards folders over ranks (``bench.py --workload config5``)."""
     allfolders: List[str] = []
     for p in selpath:
         allfolders += findfiles(p)
+    if not concurrent:
+        for folder in allfolders:
+            if main(folder, False, cfg_folder=cfg_folder, verbose=verbose) == 1:
+                return 1
+        return 0
+    from .batch import adjust_batch
+    probs = []
     for folder in allfolders:
-        if main(folder, False, cfg_folder=cfg_folder, verbose=verbose) == 1:
+        try:
+            prob = load_problem(folder, cfg_folder=cfg_folder)
+            if prob is not None:
+                prob.validate()
+        except (OSError, IndexError, ValueError) as exc:
+            print(f"Error reading files ({exc})")
+            prob = None
+        if prob is None:
             return 1
+        probs.append(prob)
+    try:
+        outs = adjust_batch(probs)
+    except (FebaError, ValueError) as exc:
+        print("Error building A and w")
+        print(str(exc))
+        return 1
+    for folder, prob, out in zip(allfolders, probs, outs):
+        name = os.path.splitext(os.path.basename(prob.settings.Output_Filename))[0]
+        write_rsd(os.path.join(folder, name + ".rsd"), prob, out["RSD"])
+    BatchRun.last = outs
     return 0
+
+
+BatchRun.last = None

@@ -364,3 +364,23 @@ def test_multi_camera_networks(mode, ncams):
     assert abs(out["sigma02"] - ref["sigma02"]) < 1e-8 * ref["sigma02"]
     assert group_rel(prob, out["xhat"], ref["xhat"]) < 1e-9
     assert np.max(np.abs(out["RSD"] - ref["RSD"])) < 1e-8
+
+
+def test_concurrent_batch_equals_one_at_a_time(tmp_path):
+    """BASELINE configs[4] shape (many independent blocks): advancing all Gauss-Newton loops together
+    on one GPU gives bit-identical results to running the blocks one after the other."""
+    probs = [synth.make_network(10, 300 + 20 * k, 6, 900 + k, mode=("free" if k % 2 else "mixed"),
+                                n_control=30) for k in range(6)]
+    probs[2].settings.Iteration_Cap = 2                       # one block stops at its cap
+    outs = fb.adjust_batch(probs)
+    for prob, out in zip(probs, outs):
+        err, x0, _ = fb.Buildxhat(prob)
+        one = fb.adjust(prob, x0, verbose=False)
+        assert out["iterations"] == one["iterations"]
+        assert np.array_equal(out["xhat"], one["xhat"]) and np.array_equal(out["v"], one["v"])
+        assert out["deltasum"] == one["deltasum"]
+    assert outs[2]["iterations"] == 2
+    for k, prob in enumerate(probs[:3]):
+        fb.save_problem(prob, str(tmp_path / f"b{k}"), stem="blk")
+    assert fb.BatchRun([str(tmp_path)], concurrent=True) == 0
+    assert len(fb.BatchRun.last) == 3 and os.path.exists(tmp_path / "b1" / "b1.rsd")
