@@ -37,6 +37,8 @@ struct feba_handle {
     double *eop = nullptr, *iop = nullptr, *cam_box = nullptr, *img_tab = nullptr, *cam_tab = nullptr;
     double *xhat = nullptr, *sol = nullptr, *dcam = nullptr, *dcam_unscaled = nullptr, *work = nullptr;
     double *ywork = nullptr, *Linv = nullptr, *dvec = nullptr;
+    double *covU = nullptr, *covQ = nullptr, *covY = nullptr, *covT = nullptr;   // covariance stage (lazy)
+    bool cov_ready = false;
     double *scal = nullptr;       // [0] sumabs camera part, [1] sumabs points, [2] sum vx^2, [3] sum vy^2
     double *v_out = nullptr, *rsd_out = nullptr, *delta_out = nullptr;
     int *opt = nullptr, *tie_pt = nullptr, *info = nullptr;
@@ -469,6 +471,7 @@ int feba_iterate_assemble(feba_handle* h) {
     const int rc = run_phase(h, h->g_assemble, enqueue_assemble);
     if (rc) return rc;
     h->phase = 1;
+    h->cov_ready = false;
     return FEBA_OK;
 }
 
@@ -620,6 +623,66 @@ int feba_residuals(feba_handle* h, double* v, double* rsd, double stats[6]) {
         stats[4] = sxx;
         stats[5] = syy;
     }
+    return FEBA_OK;
+}
+
+// ---- covariance stage
+int feba_cov_prepare(feba_handle* h) {
+    if (!h) return FEBA_ERR_INVALID;
+    if (h->iterations < 1 || h->phase != 0)
+        return fail(h, FEBA_ERR_STATE, "feba_cov_prepare needs a completed iteration (Cx comes from the last N, main.m:432-444)");
+    if (h->cov_ready) return FEBA_OK;
+    CU(h, cudaSetDevice(h->device));
+    DevProblem& P = h->P;
+    const size_t nn = (size_t)P.n_pad * (size_t)P.n_pad;
+    if (!h->covU) {
+        CU(h, dev_alloc(h, &h->covU, nn));
+        CU(h, dev_alloc(h, &h->covQ, nn));
+        CU(h, dev_alloc(h, &h->covY, (size_t)P.n_pad * 8));
+        CU(h, dev_alloc(h, &h->covT, 64));
+    }
+    CU(h, chol_inverse(P.S, P.ld, P.n_pad / kBlk, h->Linv, P.inner, h->covU, h->covQ, h->covY, h->covT, h->info,
+                       h->stream, &h->launches));
+    CU(h, cudaMemcpyAsync(h->info_host, h->info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (*h->info_host) return fail(h, FEBA_ERR_NUMERIC, "covariance stage: singular border system");
+    h->cov_ready = true;
+    return FEBA_OK;
+}
+
+int feba_cov_diag(feba_handle* h, double* qdiag, size_t u_c) {
+    if (!h || !qdiag) return FEBA_ERR_INVALID;
+    if ((int64_t)u_c != h->P.n_red)
+        return fail(h, FEBA_ERR_INVALID, "qdiag has %zu entries, expected u_c = %d (EOP/IOP part)", u_c, h->P.n_red);
+    int rc = feba_cov_prepare(h);
+    if (rc) return rc;
+    DevProblem& P = h->P;
+    CU(h, launch_cov_diag_cam(P, h->covQ, h->covY, h->covT, h->dvec, h->ywork, h->stream));
+    ++h->launches;
+    CU(h, cudaMemcpyAsync(qdiag, h->ywork, u_c * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return FEBA_OK;
+}
+
+int feba_cov_block(feba_handle* h, const int64_t* idx, int32_t k, double* out) {
+    if (!h || !idx || !out || k < 1) return FEBA_ERR_INVALID;
+    for (int i = 0; i < k; ++i)
+        if (idx[i] < 0 || idx[i] >= h->P.n_red)
+            return fail(h, FEBA_ERR_INVALID, "feba_cov_block: index %lld is not an EOP/IOP unknown", (long long)idx[i]);
+    int rc = feba_cov_prepare(h);
+    if (rc) return rc;
+    long long* didx = nullptr;
+    double* dout = nullptr;
+    CU(h, cudaMalloc((void**)&didx, (size_t)k * sizeof(long long)));
+    cudaError_t e = cudaMalloc((void**)&dout, (size_t)k * k * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(didx, idx, (size_t)k * sizeof(long long), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = launch_cov_block(h->P, h->covQ, h->covY, h->covT, h->dvec, didx, k, dout, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, (size_t)k * k * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(didx);
+    if (dout) cudaFree(dout);
+    ++h->launches;
+    CU(h, e);
     return FEBA_OK;
 }
 

@@ -50,19 +50,22 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // MODE 0: C -= A B'   MODE 1: the same, tiles of the lower block triangle only (SYRK-shaped update)
 // MODE 2: C = A B' (overwrite).  MODE 2 may run in place (C == A, one tile column, K == 64): every
 // global read of the CTA's A rows has landed in shared memory before its first store.
+// MODE 3: C = A B' (overwrite), lower tiles only, for UPPER-triangular A == B (rows bx of A are zero left of
+// column block bx, so the K loop starts there): Q = U U' of the covariance stage.
 template <int MODE>
 __global__ void __launch_bounds__(128) k_gemm_nt(double* __restrict__ C, int ldc, const double* __restrict__ A,
                                                  int lda, const double* __restrict__ B, int ldb, int K) {
     const int bx = blockIdx.x, by = blockIdx.y;
-    if (MODE == 1 && by > bx) return;
+    if ((MODE == 1 || MODE == 3) && by > bx) return;
     extern __shared__ __align__(16) double gsm[];
     double(*As)[GK][GS] = reinterpret_cast<double(*)[GK][GS]>(gsm);
     double(*Bs)[GK][GS] = reinterpret_cast<double(*)[GK][GS]>(gsm + GSTAGES * GK * GS);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp & 1, wn = warp >> 1;
-    const double* Ag = A + (size_t)bx * GT;
-    const double* Bg = B + (size_t)by * GT;
-    const int nk = K / GK;
+    const int k0 = MODE == 3 ? bx * GT : 0;                 // first non-zero column of A's row block
+    const double* Ag = A + (size_t)bx * GT + (size_t)lda * k0;
+    const double* Bg = B + (size_t)by * GT + (size_t)ldb * k0;
+    const int nk = (K - k0) / GK;
 
     auto load_stage = [&](int s, int kt) {
 #pragma unroll
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(128) k_gemm_nt(double* __restrict__ C, int ldc
         for (int j = 0; j < 4; ++j) {
             const int r = wm * 32 + i * 8 + lr;
             const int c = wn * 32 + j * 8 + 2 * lk;
-            if (MODE == 2) {
+            if (MODE == 2 || MODE == 3) {
                 Cg[r + (size_t)ldc * c] = acc[i][j][0];
                 Cg[r + (size_t)ldc * (c + 1)] = acc[i][j][1];
             } else {
@@ -295,8 +298,8 @@ __device__ __forceinline__ void load_tile(double (*dst)[STRIDE], const double* _
 // RM = rows of X per CTA: 64 (one 64-row block per CTA) or 16 (four CTAs per block: more CTAs for the
 // deep levels of the recursion where only a few row blocks exist).
 template <int RM>
-__global__ void __launch_bounds__(256) k_trsm_fused(double* __restrict__ A, int ld, const double* __restrict__ Linv,
-                                                    int r0, int c0, int nt) {
+__global__ void __launch_bounds__(256) k_trsm_fused(double* X, int ldx, const double* A, int ld,
+                                                    const double* __restrict__ Linv, int r0, int c0, int nt) {
     extern __shared__ __align__(16) double fsm[];
     constexpr int XS = RM == 64 ? TS : 20;        // row stride of the X tiles (== 4 mod 16 either way)
     double(*Xs)[64][XS] = reinterpret_cast<double(*)[64][XS]>(fsm);                          // [tile][k][row]
@@ -307,7 +310,8 @@ __global__ void __launch_bounds__(256) k_trsm_fused(double* __restrict__ A, int 
     const int wm = RM == 64 ? (warp & 1) : 0, wn = RM == 64 ? (warp >> 1) : warp;
     const int row0 = wm * 32, col0 = wn * (8 * NF);
     const int lr = lane >> 2, lk = lane & 3;
-    double* Xg = A + (size_t)r0 * kBlk + (size_t)blockIdx.x * RM + (size_t)ld * c0 * kBlk;
+    // X block (r, c) lives at X + r*64 + ldx*c*64 (X == A, ldx == ld inside the factorisation)
+    double* Xg = X + (size_t)r0 * kBlk + (size_t)blockIdx.x * RM + (size_t)ldx * c0 * kBlk;
     auto Btile = [&](int seq, const double*& src, int& bld) {
         // sequence: j = 0: Linv_0 | j = 1: L_10, Linv_1 | j = 2: L_20, L_21, Linv_2 | ...
         int j = 0;
@@ -322,7 +326,7 @@ __global__ void __launch_bounds__(256) k_trsm_fused(double* __restrict__ A, int 
         }
     };
     const int nseq = nt * (nt + 1) / 2;
-    for (int t = 0; t < nt; ++t) load_tile<RM, XS>(Xs[t], Xg + (size_t)ld * t * kBlk, ld, tid);
+    for (int t = 0; t < nt; ++t) load_tile<RM, XS>(Xs[t], Xg + (size_t)ldx * t * kBlk, ldx, tid);
     {
         const double* src;
         int bld;
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(256) k_trsm_fused(double* __restrict__ A, int 
     for (int t = 0; t < nt; ++t)
         for (int q = tid; q < 64 * CH; q += 256) {
             const int k = q / CH, i2 = (q % CH) * 2;
-            *reinterpret_cast<double2*>(Xg + i2 + (size_t)ld * (t * kBlk + k)) =
+            *reinterpret_cast<double2*>(Xg + i2 + (size_t)ldx * (t * kBlk + k)) =
                 *reinterpret_cast<const double2*>(&Xs[t][k][i2]);
         }
 }
@@ -426,15 +430,18 @@ static cudaError_t gemm_nt(double* C, int ldc, const double* A, int lda, const d
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_gemm_nt<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_gemm_nt<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
         configured = true;
     }
     {
-        const long long tiles = (long long)mb * nbk / (mode == 1 ? 2 : 1);
+        const long long tiles = (long long)mb * nbk / (mode == 1 || mode == 3 ? 2 : 1);
         if (chol_skip() & (tiles < 256 ? 4 : 8)) return cudaSuccess;
     }
     dim3 grid(mb, nbk);
     if (mode == 1) k_gemm_nt<1><<<grid, 128, smem, st>>>(C, ldc, A, lda, B, ldb, kb * kBlk);
     else if (mode == 2) k_gemm_nt<2><<<grid, 128, smem, st>>>(C, ldc, A, lda, B, ldb, kb * kBlk);
+    else if (mode == 3) k_gemm_nt<3><<<grid, 128, smem, st>>>(C, ldc, A, lda, B, ldb, kb * kBlk);
     else k_gemm_nt<0><<<grid, 128, smem, st>>>(C, ldc, A, lda, B, ldb, kb * kBlk);
     ++*launches;
     return cudaGetLastError();
@@ -446,8 +453,8 @@ static cudaError_t gemm_nt(double* C, int ldc, const double* A, int lda, const d
 
 // X (mr x n blocks at block (r0, c0)) := X * L^-T with L the n x n block triangle at (c0, c0).
 // Below five blocks the whole solve is one fused launch (k_trsm_fused).
-static cudaError_t rtrsm(double* A, int ld, const double* Linv, int r0, int mr, int c0, int n, cudaStream_t st,
-                         int64_t* launches) {
+static cudaError_t rtrsm(double* X, int ldx, double* A, int ld, const double* Linv, int r0, int mr, int c0, int n,
+                         cudaStream_t st, int64_t* launches) {
     if (n <= TF_MAX) {
         static bool configured = false;
         if (!configured) {
@@ -461,19 +468,19 @@ static cudaError_t rtrsm(double* A, int ld, const double* Linv, int r0, int mr, 
         }
         if (chol_skip() & 2) return cudaSuccess;
         // few row blocks (deep recursion levels): 16-row strips give four times the CTAs
-        if (mr <= 74) k_trsm_fused<16><<<mr * 4, 256, kTrsmFusedSmem16, st>>>(A, ld, Linv, r0, c0, n);
-        else k_trsm_fused<64><<<mr, 256, kTrsmFusedSmem, st>>>(A, ld, Linv, r0, c0, n);
+        if (mr <= 74) k_trsm_fused<16><<<mr * 4, 256, kTrsmFusedSmem16, st>>>(X, ldx, A, ld, Linv, r0, c0, n);
+        else k_trsm_fused<64><<<mr, 256, kTrsmFusedSmem, st>>>(X, ldx, A, ld, Linv, r0, c0, n);
         ++*launches;
         return cudaGetLastError();
     }
     const int n1 = n / 2, n2 = n - n1;
-    cudaError_t e = rtrsm(A, ld, Linv, r0, mr, c0, n1, st, launches);
+    cudaError_t e = rtrsm(X, ldx, A, ld, Linv, r0, mr, c0, n1, st, launches);
     if (e != cudaSuccess) return e;
     // X2 -= X1 * L21'
-    e = gemm_nt(AT(A, ld, r0, c0 + n1), ld, AT(A, ld, r0, c0), ld, AT(A, ld, c0 + n1, c0), ld, mr, n2, n1, 0, st,
+    e = gemm_nt(AT(X, ldx, r0, c0 + n1), ldx, AT(X, ldx, r0, c0), ldx, AT(A, ld, c0 + n1, c0), ld, mr, n2, n1, 0, st,
                 launches);
     if (e != cudaSuccess) return e;
-    return rtrsm(A, ld, Linv, r0, mr, c0 + n1, n2, st, launches);
+    return rtrsm(X, ldx, A, ld, Linv, r0, mr, c0 + n1, n2, st, launches);
 }
 
 // Factor block range [b0, b0+n); the block with index aug_blk (if inside) is not factorised.
@@ -496,7 +503,7 @@ static cudaError_t rchol(double* A, int ld, double* Linv, int b0, int n, int aug
     const int n1 = n / 2, n2 = n - n1;
     cudaError_t e = rchol(A, ld, Linv, b0, n1, aug_blk, info, st, launches);
     if (e != cudaSuccess) return e;
-    e = rtrsm(A, ld, Linv, b0 + n1, n2, b0, n1, st, launches);
+    e = rtrsm(A, ld, A, ld, Linv, b0 + n1, n2, b0, n1, st, launches);
     if (e != cudaSuccess) return e;
     e = gemm_nt(AT(A, ld, b0 + n1, b0 + n1), ld, AT(A, ld, b0 + n1, b0), ld, AT(A, ld, b0 + n1, b0), ld, n2, n2, n1,
                 1, st, launches);
@@ -608,6 +615,101 @@ cudaError_t border_and_backsolve(double* A, int ld, int nb, const double* Linv, 
         if (grid < 1) grid = 1;
         k_backstep<<<grid, 256, 0, st>>>(A, ld, k, LINV(Linv, k), ywork, sol);
         ++*launches;
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Covariance stage (main.m:432-444 keeps Cx = NG^-1(1:u,1:u), main.m:468-480 un-scale
+// its diagonal, main.m:602 multiplies by sigma02).  From the factor M~ = L L' of the last iteration:
+//   U = L^-T (upper; triangular solve on the identity, zero blocks pruned),  Q = M~^-1 = U U'
+//   Y = M~^-1 G~ = U (L^-1 G~)   (the augmented rows 1..7 already hold (L^-1 G~)')
+//   Qxx_cc = D [ Q - Y (G~' M~^-1 G~)^-1 Y' ] D      (top-left block of the bordered inverse; D = Jacobi scaling)
+// Everything reuses the factorisation's kernels (k_trsm_fused, k_gemm_nt); cost ~ u_c^3 flop, once.
+__global__ void k_set_identity(double* __restrict__ U, int n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < (size_t)n * n) U[i] = (i / n == i % n) ? 1.0 : 0.0;
+}
+
+// X rows [r0, r0+mr) x column blocks [c0, c0+n):  X := X L^-T for X = rows of the identity: rows at or
+// beyond the last column block are zero and stay zero.
+static cudaError_t rtrsm_identity(double* X, int ldx, double* A, int ld, const double* Linv, int r0, int mr, int c0,
+                                  int n, cudaStream_t st, int64_t* launches) {
+    if (mr > c0 + n - r0) mr = c0 + n - r0;
+    if (mr <= 0) return cudaSuccess;
+    if (n <= TF_MAX) return rtrsm(X, ldx, A, ld, Linv, r0, mr, c0, n, st, launches);
+    const int n1 = n / 2, n2 = n - n1;
+    cudaError_t e = rtrsm_identity(X, ldx, A, ld, Linv, r0, mr, c0, n1, st, launches);
+    if (e != cudaSuccess) return e;
+    int mr1 = mr;                                   // rows with a non-zero X1
+    if (mr1 > c0 + n1 - r0) mr1 = c0 + n1 - r0;
+    if (mr1 > 0) {
+        e = gemm_nt(AT(X, ldx, r0, c0 + n1), ldx, AT(X, ldx, r0, c0), ldx, AT(A, ld, c0 + n1, c0), ld, mr1, n2, n1, 0,
+                    st, launches);
+        if (e != cudaSuccess) return e;
+    }
+    return rtrsm_identity(X, ldx, A, ld, Linv, r0, mr, c0 + n1, n2, st, launches);
+}
+
+// Y[i][c] = sum_{k >= i} U(i,k) Zg[k][c],  Zg[k][c] = A[(n_pad+1+c) + ld k]  (c = 0..6); Y: n_pad x 8
+__global__ void k_cov_Y(const double* __restrict__ U, int n_pad, const double* __restrict__ A, int ld,
+                        double* __restrict__ Y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int k = i; k < n_pad; ++k) {
+        const double u = U[(size_t)i + (size_t)n_pad * k];
+        const double* z = A + (size_t)(n_pad + 1) + (size_t)ld * k;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) acc[c] += u * z[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 7; ++c) Y[8 * (size_t)i + c] = acc[c];
+    Y[8 * (size_t)i + 7] = 0.0;
+}
+
+// T7inv = (G~' M~^-1 G~)^-1 from the Schur block T = -[g G]' M^-1 [g G] of the factorisation.
+__global__ void k_cov_T7inv(const double* __restrict__ A, int ld, int n_pad, double* __restrict__ T7inv,
+                            int* __restrict__ info) {
+    if (threadIdx.x != 0) return;
+    double Q[7][14];
+    for (int i = 0; i < 7; ++i)
+        for (int j = 0; j < 7; ++j) {
+            const int r = i > j ? i : j, c = i > j ? j : i;
+            Q[i][j] = -A[(size_t)(n_pad + 1 + r) + (size_t)ld * (n_pad + 1 + c)];
+            Q[i][7 + j] = (i == j) ? 1.0 : 0.0;
+        }
+    for (int c = 0; c < 7; ++c) {
+        int p = c;
+        for (int r = c + 1; r < 7; ++r)
+            if (fabs(Q[r][c]) > fabs(Q[p][c])) p = r;
+        if (Q[p][c] == 0.0) { atomicExch(info, 2); return; }
+        if (p != c)
+            for (int j = 0; j < 14; ++j) { const double t = Q[c][j]; Q[c][j] = Q[p][j]; Q[p][j] = t; }
+        for (int r = 0; r < 7; ++r) {
+            if (r == c) continue;
+            const double f = Q[r][c] / Q[c][c];
+            for (int j = c; j < 14; ++j) Q[r][j] -= f * Q[c][j];
+        }
+    }
+    for (int i = 0; i < 7; ++i)
+        for (int j = 0; j < 7; ++j) T7inv[7 * i + j] = Q[i][7 + j] / Q[i][i];
+}
+
+cudaError_t chol_inverse(double* A, int ld, int nb, const double* Linv, int inner, double* U, double* Q, double* Y,
+                         double* T7inv, int* info, cudaStream_t st, int64_t* launches) {
+    const int n_pad = nb * kBlk;
+    const size_t nn = (size_t)n_pad * n_pad;
+    k_set_identity<<<(unsigned)((nn + 255) / 256), 256, 0, st>>>(U, n_pad);
+    ++*launches;
+    cudaError_t e = rtrsm_identity(U, n_pad, A, ld, Linv, 0, nb, 0, nb, st, launches);
+    if (e != cudaSuccess) return e;
+    e = gemm_nt(Q, n_pad, U, n_pad, U, n_pad, nb, nb, nb, 3, st, launches);
+    if (e != cudaSuccess) return e;
+    if (inner) {
+        k_cov_Y<<<(n_pad + 127) / 128, 128, 0, st>>>(U, n_pad, A, ld, Y);
+        k_cov_T7inv<<<1, 32, 0, st>>>(A, ld, n_pad, T7inv, info);
+        *launches += 2;
     }
     return cudaGetLastError();
 }

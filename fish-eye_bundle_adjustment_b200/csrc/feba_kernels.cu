@@ -561,6 +561,61 @@ __global__ void __launch_bounds__(256) k_residuals(DevProblem P, const int* __re
 }
 
 // ------------------------------------------------------------------------------------------
+// Covariance outputs of the EOP/IOP part.  Qxx_cc(i,j) = d_i d_j (Q_ij - Y_i T7inv Y_j')
+// (Q = M~^-1 lower-stored, Y = M~^-1 G~; without inner constraints the second term is absent).
+__device__ __forceinline__ double cov_entry(const DevProblem& P, const double* __restrict__ Q,
+                                            const double* __restrict__ Y, const double* __restrict__ T7inv,
+                                            const double* __restrict__ dvec, int i, int j) {
+    const int a = i > j ? i : j, b = i > j ? j : i;
+    double q = Q[(size_t)a + (size_t)P.n_pad * b];
+    if (P.inner) {
+        const double* yi = Y + 8 * (size_t)i;
+        const double* yj = Y + 8 * (size_t)j;
+        double corr = 0.0;
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+            double t = 0.0;
+#pragma unroll
+            for (int c = 0; c < 7; ++c) t += T7inv[7 * r + c] * yj[c];
+            corr += yi[r] * t;
+        }
+        q -= corr;
+    }
+    return q * dvec[i] * dvec[j];
+}
+
+// diag(Cx)/sigma02 for the EOP/IOP unknowns, distortion entries un-scaled: /r_max^(4j), /r_max^4
+// (main.m:468,477,480 divide Cx(k,k) by dist_scaling^2).
+__global__ void k_cov_diag_cam(DevProblem P, const double* __restrict__ Q, const double* __restrict__ Y,
+                               const double* __restrict__ T7inv, const double* __restrict__ dvec,
+                               double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n_red) return;
+    double q = cov_entry(P, Q, Y, T7inv, dvec, i, i);
+    if (i >= P.off_cam) {
+        const int r = i - P.off_cam;
+        const int cam = r / P.uc, slot = r - cam * P.uc;
+        int p = 0;
+        for (int k = 0; k < P.NC; ++k) if (P.ccol[k] == slot) p = k;
+        const double* ct = P.cam_tab + kCamStride * cam;
+        if (p >= 3 && p < 3 + P.NK) q /= ct[24 + (p - 3)] * ct[24 + (p - 3)];
+        else if (p >= 3 + P.NK) q /= ct[24] * ct[24];
+    }
+    out[i] = q;
+}
+
+// k x k block of Cx/sigma02 BEFORE un-scaling (what main.m:446-456 turns into Correlation): idx are
+// unknown indices of the EOP/IOP part.
+__global__ void k_cov_block(DevProblem P, const double* __restrict__ Q, const double* __restrict__ Y,
+                            const double* __restrict__ T7inv, const double* __restrict__ dvec,
+                            const long long* __restrict__ idx, int k, double* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= k * k) return;
+    const int a = e / k, b = e - a * k;
+    out[e] = cov_entry(P, Q, Y, T7inv, dvec, (int)idx[a], (int)idx[b]);
+}
+
+// ------------------------------------------------------------------------------------------
 // host launchers (dispatch on NK and on whether any camera parameter is estimated)
 
 #define FEBA_NK_DISPATCH(NKV, HASCAM, CALL)                                  \
@@ -659,6 +714,18 @@ cudaError_t launch_xhat_gather(const DevProblem& P, int sm_count, double* xhat, 
 
 cudaError_t launch_delta_gather(const DevProblem& P, int sm_count, double* delta, cudaStream_t st) {
     k_delta_gather<<<stream_grid((int64_t)P.n_red + 3 * (int64_t)P.n_tie, sm_count), 256, 0, st>>>(P, delta);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cov_diag_cam(const DevProblem& P, const double* Q, const double* Y, const double* T7inv,
+                                const double* dvec, double* out, cudaStream_t st) {
+    k_cov_diag_cam<<<(P.n_red + 127) / 128, 128, 0, st>>>(P, Q, Y, T7inv, dvec, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cov_block(const DevProblem& P, const double* Q, const double* Y, const double* T7inv,
+                             const double* dvec, const long long* idx, int k, double* out, cudaStream_t st) {
+    k_cov_block<<<(k * k + 127) / 128, 128, 0, st>>>(P, Q, Y, T7inv, dvec, idx, k, out);
     return cudaGetLastError();
 }
 

@@ -45,4 +45,13 @@ cudaError_t border_and_backsolve(double* A, int ld, int nb, const double* Linv, 
                                  double* ywork, double* sol, int* info, int sm_count, cudaStream_t st,
                                  int64_t* launches);
 
+// Covariance stage: U = L^-T, Q = M~^-1 (n_pad x n_pad, lower valid), Y = M~^-1 G~ (n_pad x 8), T7inv 7x7.
+cudaError_t chol_inverse(double* A, int ld, int nb, const double* Linv, int inner, double* U, double* Q, double* Y,
+                         double* T7inv, int* info, cudaStream_t st, int64_t* launches);
+// cofactor entries of the EOP/IOP part: diag (distortion entries un-scaled, main.m:468-480) and blocks
+cudaError_t launch_cov_diag_cam(const DevProblem& P, const double* Q, const double* Y, const double* T7inv,
+                                const double* dvec, double* out, cudaStream_t st);
+cudaError_t launch_cov_block(const DevProblem& P, const double* Q, const double* Y, const double* T7inv,
+                             const double* dvec, const long long* idx, int k, double* out, cudaStream_t st);
+
 }  // namespace feba

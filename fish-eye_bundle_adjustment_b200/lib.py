@@ -24,7 +24,7 @@ EXPORTS = (
     "feba_create", "feba_destroy", "feba_last_error", "feba_set_stream", "feba_num_unknowns",
     "feba_set_xhat", "feba_get_xhat", "feba_iterate", "feba_iterate_assemble", "feba_reduced_dev",
     "feba_iterate_solve", "feba_get_delta", "feba_residuals", "feba_solve", "feba_last_timing",
-    "feba_launch_count", "feba_debug_reduced", "feba_iterate_async", "feba_iterate_solve_async", "feba_sync",
+    "feba_launch_count", "feba_debug_reduced", "feba_cov_prepare", "feba_cov_diag", "feba_cov_block", "feba_iterate_async", "feba_iterate_solve_async", "feba_sync",
 )
 
 
@@ -87,6 +87,9 @@ def load() -> C.CDLL:
     lib.feba_launch_count.argtypes = [H]
     lib.feba_launch_count.restype = C.c_int64
     lib.feba_debug_reduced.argtypes = [H, _pd, _pd]
+    lib.feba_cov_prepare.argtypes = [H]
+    lib.feba_cov_diag.argtypes = [H, _pd, C.c_size_t]
+    lib.feba_cov_block.argtypes = [H, C.POINTER(C.c_int64), C.c_int32, _pd]
     lib.feba_iterate_async.argtypes = [H]
     lib.feba_iterate_solve_async.argtypes = [H]
     lib.feba_sync.argtypes = [H, _pd]
@@ -239,6 +242,19 @@ class Handle:
         self._check(self._lib.feba_residuals(self._h, _dp(v) if want_v else None,
                                              _dp(rsd) if want_rsd else None, _dp(st)))
         return dict(v=v, RSD=rsd, RMSx=st[0], RMSy=st[1], RMS=st[2], sigma02=st[3], sxx=st[4], syy=st[5])
+
+    def cov_diag(self) -> np.ndarray:
+        """diag(Cx)/sigma02 of the EOP/IOP unknowns (main.m:432-444, un-scaled as main.m:468-480)."""
+        q = np.empty(self.u_c, dtype=np.float64)
+        self._check(self._lib.feba_cov_diag(self._h, _dp(q), q.size))
+        return q
+
+    def cov_block(self, idx) -> np.ndarray:
+        """k x k block of Cx/sigma02 before un-scaling for EOP/IOP unknown indices ``idx``."""
+        ii = np.ascontiguousarray(idx, dtype=np.int64)
+        out = np.empty((ii.size, ii.size), dtype=np.float64)
+        self._check(self._lib.feba_cov_block(self._h, ii.ctypes.data_as(C.POINTER(C.c_int64)), ii.size, _dp(out)))
+        return out
 
     def last_timing(self):
         ms = np.zeros(6, dtype=np.float64)

@@ -26,10 +26,36 @@ from .lib import FebaError, Handle
 from .problem import Buildxhat, Problem, load_problem
 
 
+def covariance_outputs(h: Handle, prob: Problem, sigma02: float, images: Optional[Sequence[int]] = None) -> dict:
+    """What the report stage reads from ``Cx`` / ``Correlation`` for the EOP/IOP unknowns
+    (main.m:602, :728-881): ``Cx_diag`` (variances, distortion entries un-scaled as main.m:468-480),
+    the IOP correlation sub-matrix per camera (main.m:828) and the EOP+IOP correlation block of the
+    requested images (main.m:846-863).  Correlations are taken before un-scaling (main.m:446-456)."""
+    s = prob.settings
+    ui, uc = s.u_perimage, s.u_percam
+    off_cam = ui * prob.numImg
+    out = {"Cx_diag": sigma02 * h.cov_diag()}
+
+    def corr(idx):
+        B = h.cov_block(idx)
+        d = np.sqrt(np.diag(B))
+        return B / np.outer(d, d)
+
+    if uc:
+        out["Correlation_IOP"] = [corr(off_cam + uc * c + np.arange(uc)) for c in range(prob.numCam)]
+    out["Correlation_image"] = {}
+    for j in (images if images is not None else []):
+        cam = int(prob.img_cam[j])
+        idx = np.concatenate([ui * j + np.arange(ui), off_cam + uc * cam + np.arange(uc)])
+        out["Correlation_image"][int(j)] = corr(idx)
+    return out
+
+
 def adjust(prob: Problem, xhat0: Optional[np.ndarray] = None, verbose: bool = True,
-           handle: Optional[Handle] = None) -> dict:
+           handle: Optional[Handle] = None, cov: bool = False) -> dict:
     """main.m:386-602 for an already built ``data``.  Returns xhat, iterations, deltasum trace,
-    v, RSD (n_obs x 5: r vx vy vr vt), RMSx, RMSy, RMS, sigma02, elapsed seconds."""
+    v, RSD (n_obs x 5: r vx vy vr vt), RMSx, RMSy, RMS, sigma02, elapsed seconds; with ``cov`` also
+    the covariance outputs of the EOP/IOP unknowns (``covariance_outputs``)."""
     prob.validate()
     t0 = time.perf_counter()                                              # main.m:386 tic
     if xhat0 is None:
@@ -63,6 +89,8 @@ def adjust(prob: Problem, xhat0: Optional[np.ndarray] = None, verbose: bool = Tr
             print(f"sigma02 = {res['sigma02']:.6g}")                      # main.m:601 (echo)
         res.update(xhat=xhat, iterations=count, deltasum=trace, elapsed=elapsed,
                    delta=h.get_delta(), timing=h.last_timing(), launches=h.launch_count())
+        if cov:
+            res.update(covariance_outputs(h, prob, res["sigma02"], images=range(prob.numImg)))
         return res
     finally:
         if own:

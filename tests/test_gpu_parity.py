@@ -384,3 +384,39 @@ def test_concurrent_batch_equals_one_at_a_time(tmp_path):
         fb.save_problem(prob, str(tmp_path / f"b{k}"), stem="blk")
     assert fb.BatchRun([str(tmp_path)], concurrent=True) == 0
     assert len(fb.BatchRun.last) == 3 and os.path.exists(tmp_path / "b1" / "b1.rsd")
+
+
+@pytest.mark.parametrize("case", ["cam0_pinhole_inner", "cam0_fisheye_free", "synthetic_free", "synthetic_mixed"])
+def test_covariance_outputs_of_the_camera_part(case):
+    """diag(Cx) of the EOP/IOP unknowns (un-scaled distortion variances, sigma02 scaling) and
+    the correlation blocks the report reads, against the literal restatement (explicit inverse of the
+    bordered normal matrix, main.m:432-482, :602; Correlation before un-scaling, main.m:446-456)."""
+    if case == "cam0_pinhole_inner":
+        prob = golden.load_cam0()
+    elif case == "cam0_fisheye_free":
+        prob = golden.load_cam0(type="fisheye", inner=0)
+    elif case == "synthetic_free":
+        prob = synth.make_network(9, 150, 6, 71, mode="free")
+    else:
+        prob = synth.make_network(9, 150, 6, 72, mode="mixed", n_control=20)
+    err, xhat0, _ = fb.Buildxhat(prob)
+    ref = dense.gauss_newton(prob, xhat0)
+    out = fb.adjust(prob, xhat0, verbose=False, cov=True)
+    assert out["iterations"] == ref["iterations"]
+    L = model.layout(prob)
+    u_c = L["off_tie"]
+    dref = np.diag(ref["Cx"])[:u_c]
+    # the explicit inverse is itself accurate to ~cond*eps (1e-5 on the bundled data)
+    tol = 2e-4 if case.startswith("cam0") else 1e-6
+    assert np.max(np.abs(out["Cx_diag"] - dref) / dref) < tol
+    C = ref["Correlation"]
+    off, uc, ui = L["off_cam"], L["u_cam"], L["u_img"]
+    assert np.max(np.abs(out["Correlation_IOP"][0] - C[off:off + uc, off:off + uc])) < tol
+    for j in (0, prob.numImg // 2, prob.numImg - 1):
+        idx = np.concatenate([ui * j + np.arange(ui), off + np.arange(uc)])
+        assert np.max(np.abs(out["Correlation_image"][j] - C[np.ix_(idx, idx)])) < tol
+    # calls in the wrong state are rejected
+    with fb.Handle(prob) as h:
+        with pytest.raises(fb.FebaError) as ei:
+            h.cov_diag()
+        assert ei.value.code == fb.lib.FEBA_ERR_STATE
