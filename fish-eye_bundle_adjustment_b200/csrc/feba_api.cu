@@ -650,16 +650,22 @@ int feba_cov_prepare(feba_handle* h) {
     return FEBA_OK;
 }
 
-int feba_cov_diag(feba_handle* h, double* qdiag, size_t u_c) {
+int feba_cov_diag(feba_handle* h, double* qdiag, size_t u) {
     if (!h || !qdiag) return FEBA_ERR_INVALID;
-    if ((int64_t)u_c != h->P.n_red)
-        return fail(h, FEBA_ERR_INVALID, "qdiag has %zu entries, expected u_c = %d (EOP/IOP part)", u_c, h->P.n_red);
+    if ((int64_t)u != h->u) return fail(h, FEBA_ERR_INVALID, "qdiag has %zu entries, expected %lld", u, (long long)h->u);
     int rc = feba_cov_prepare(h);
     if (rc) return rc;
     DevProblem& P = h->P;
-    CU(h, launch_cov_diag_cam(P, h->covQ, h->covY, h->covT, h->dvec, h->ywork, h->stream));
+    if (!h->delta_out) CU(h, dev_alloc(h, &h->delta_out, (size_t)h->u));
+    // tie entries without observations keep NaN (the reference's N is singular for them)
+    CU(h, cudaMemsetAsync(h->delta_out, 0xff, (size_t)h->u * sizeof(double), h->stream));
+    CU(h, launch_cov_diag_cam(P, h->covQ, h->covY, h->covT, h->dvec, h->delta_out, h->stream));
     ++h->launches;
-    CU(h, cudaMemcpyAsync(qdiag, h->ywork, u_c * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (P.n_tie > 0 && P.n_seg > 0) {
+        CU(h, launch_cov_points(P, h->sm_count, h->covQ, h->covY, h->covT, h->dvec, h->delta_out + P.n_red, h->stream));
+        ++h->launches;
+    }
+    CU(h, cudaMemcpyAsync(qdiag, h->delta_out, (size_t)h->u * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return FEBA_OK;
 }

@@ -615,6 +615,269 @@ __global__ void k_cov_block(DevProblem P, const double* __restrict__ Q, const do
     out[e] = cov_entry(P, Q, Y, T7inv, dvec, (int)idx[a], (int)idx[b]);
 }
 
+// Tie-point variances: Q_pp = V^-1 + V^-1 (W_p' Qxx_cc W_p) V^-1 per tie point, from the
+// cofactors of the EOP/IOP part.  One warp per point, lanes over its observations.  W_p has one 6x3
+// block We_a = Je_a'PJt_a per observation (rows of image i_a) and one NC x 3 block per camera seeing
+// the point (Wc_k = sum_{a in k} Jc_a'PJt_a).  With w'_e = d_e w_e (d = Jacobi scaling) the bilinear
+// form splits as  R = sum_{e,f} w'_e Q(e,f) w'_f'  -  E' T7inv E,  E = sum_e Y_e' w'_e  (7 x 3).
+// Observations beyond one chunk of 32 are handled by re-evaluating the partner chunk (as the
+// Jacobians are never stored).  Output: diag(Q_pp) (3 per tie point), cofactors (x sigma02 -> variances).
+template <int NK, bool HAS_CAM>
+__global__ void __launch_bounds__(128) k_cov_points(DevProblem P, const double* __restrict__ Q,
+                                                    const double* __restrict__ Y, const double* __restrict__ T7inv,
+                                                    const double* __restrict__ dvec, double* __restrict__ out) {
+    constexpr int NC = NK + 5;
+    constexpr int KC = 4;                                   // cameras per point (as in the point pass)
+    __shared__ double sB[4][32][18];                        // partner chunk: w' rows of 32 observations
+    __shared__ int sImg[4][32];
+    __shared__ double sWc[4][KC][NC][3];
+    __shared__ int sCam[4][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int nwarp = gridDim.x * (blockDim.x >> 5);
+    const int gw = blockIdx.x * (blockDim.x >> 5) + wib;
+    const double pw[2] = {P.px, P.py};
+    const int np = P.n_pad;
+    auto Qs = [&](int i, int j) { return i >= j ? Q[(size_t)i + (size_t)np * j] : Q[(size_t)j + (size_t)np * i]; };
+
+    for (int seg = gw; seg < P.n_seg; seg += nwarp) {
+        const int pt = P.seg_pt[seg];
+        const int tie = P.pt_tie[pt];
+        if (tie < 0) continue;
+        const int beg = P.seg_start[seg], end = P.seg_start[seg + 1];
+        // the linearisation point of the last iteration (P.xyz has already been updated)
+        const double X = P.xyz_prev[3 * pt], Yc_ = P.xyz_prev[3 * pt + 1], Z = P.xyz_prev[3 * pt + 2];
+        int cams[KC] = {-1, -1, -1, -1};
+        int ncam = 0;
+        for (int e = lane; e < KC * NC * 3; e += 32) (&sWc[wib][0][0][0])[e] = 0.0;
+        __syncwarp();
+        // ---- pass 1: V, per-camera Wc
+        double V[6] = {0, 0, 0, 0, 0, 0};
+        for (int c0 = beg; c0 < end; c0 += 32) {
+            const int o = c0 + lane;
+            const bool act = o < end;
+            ObsJac<NK> J;
+            int cam = -1;
+            if (act) {
+                const int img = P.oimg[o];
+                cam = P.img_cam[img];
+                observation<NK, HAS_CAM>(P.type, P.ox[o], P.oy[o], P.img_tab + kImgStride * img,
+                                         P.cam_tab + kCamStride * cam, X, Yc_, Z, J);
+                int e = 0;
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int k = 0; k <= i; ++k)
+                        V[e++] += J.Jt[0][i] * pw[0] * J.Jt[0][k] + J.Jt[1][i] * pw[1] * J.Jt[1][k];
+            }
+            sCam[wib][lane] = cam;
+            __syncwarp();
+            const int nrow = min(32, end - c0);
+            for (int l = 0; l < nrow; ++l) {
+                const int c = sCam[wib][l];
+                bool found = false;
+#pragma unroll
+                for (int k = 0; k < KC; ++k) found = found || (k < ncam && cams[k] == c);
+                if (!found && ncam < KC) {
+#pragma unroll
+                    for (int k = 0; k < KC; ++k)
+                        if (k == ncam) cams[k] = c;
+                    ++ncam;
+                }
+            }
+            if (HAS_CAM && act) {
+                int kown = 0;
+#pragma unroll
+                for (int k = 0; k < KC; ++k)
+                    if (cams[k] == cam) kown = k;
+#pragma unroll
+                for (int j = 0; j < NC; ++j)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        atomicAdd(&sWc[wib][kown][j][k], J.Jc[0][j] * pw[0] * J.Jt[0][k] + J.Jc[1][j] * pw[1] * J.Jt[1][k]);
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+#pragma unroll
+            for (int s_ = 16; s_ > 0; s_ >>= 1) V[k] += __shfl_xor_sync(0xffffffffu, V[k], s_);
+        double Vi[6];
+        sym3_inverse(V, Vi);
+        // ---- pass 2: R (3x3, full) and E (7x3)
+        double R[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        double E[7][3];
+#pragma unroll
+        for (int r = 0; r < 7; ++r) E[r][0] = E[r][1] = E[r][2] = 0.0;
+        for (int a0 = beg; a0 < end; a0 += 32) {
+            const int oa = a0 + lane;
+            const bool acta = oa < end;
+            double A_[6][3];
+            int rowa = 0;
+            if (acta) {
+                const int img = P.oimg[oa];
+                rowa = P.ui * img;
+                ObsJac<NK> J;
+                observation<NK, false>(P.type, P.ox[oa], P.oy[oa], P.img_tab + kImgStride * img,
+                                       P.cam_tab + kCamStride * P.img_cam[img], X, Yc_, Z, J);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    const double d = P.ecol[i] >= 0 ? dvec[rowa + P.ecol[i]] : 0.0;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        A_[i][k] = d * (J.Je[0][i] * pw[0] * J.Jt[0][k] + J.Je[1][i] * pw[1] * J.Jt[1][k]);
+                }
+                if (P.inner) {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i)
+                        if (P.ecol[i] >= 0) {
+                            const double* y = Y + 8 * (size_t)(rowa + P.ecol[i]);
+#pragma unroll
+                            for (int r = 0; r < 7; ++r)
+#pragma unroll
+                                for (int k = 0; k < 3; ++k) E[r][k] += y[r] * A_[i][k];
+                        }
+                }
+                // image x camera: A' Q[img rows, cam rows] Wc' + transpose
+                if (HAS_CAM) {
+                    for (int kc = 0; kc < ncam; ++kc) {
+                        const int rc = P.off_cam + P.uc * cams[kc];
+                        for (int j = 0; j < NC; ++j) {
+                            if (P.ccol[j] < 0) continue;
+                            const double dj = dvec[rc + P.ccol[j]];
+                            const double w0 = dj * sWc[wib][kc][j][0], w1 = dj * sWc[wib][kc][j][1], w2 = dj * sWc[wib][kc][j][2];
+                            double t0 = 0, t1 = 0, t2 = 0;           // sum_i A'[i][:] Q(i, j)
+#pragma unroll
+                            for (int i = 0; i < 6; ++i)
+                                if (P.ecol[i] >= 0) {
+                                    const double q = Qs(rc + P.ccol[j], rowa + P.ecol[i]);
+                                    t0 += A_[i][0] * q; t1 += A_[i][1] * q; t2 += A_[i][2] * q;
+                                }
+                            const double t[3] = {t0, t1, t2}, w[3] = {w0, w1, w2};
+#pragma unroll
+                            for (int x = 0; x < 3; ++x)
+#pragma unroll
+                                for (int y2 = 0; y2 < 3; ++y2) R[x][y2] += t[x] * w[y2] + w[x] * t[y2];
+                        }
+                    }
+                }
+            }
+            // image x image over all partner chunks
+            for (int b0 = beg; b0 < end; b0 += 32) {
+                __syncwarp();
+                const int ob = b0 + lane;
+                sImg[wib][lane] = -1;
+                if (b0 == a0) {
+                    if (acta) {
+                        sImg[wib][lane] = rowa;
+#pragma unroll
+                        for (int i = 0; i < 6; ++i)
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) sB[wib][lane][3 * i + k] = A_[i][k];
+                    }
+                } else if (ob < end) {
+                    const int img = P.oimg[ob];
+                    const int rowb = P.ui * img;
+                    ObsJac<NK> Jb;
+                    observation<NK, false>(P.type, P.ox[ob], P.oy[ob], P.img_tab + kImgStride * img,
+                                           P.cam_tab + kCamStride * P.img_cam[img], X, Yc_, Z, Jb);
+                    sImg[wib][lane] = rowb;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        const double d = P.ecol[i] >= 0 ? dvec[rowb + P.ecol[i]] : 0.0;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            sB[wib][lane][3 * i + k] =
+                                d * (Jb.Je[0][i] * pw[0] * Jb.Jt[0][k] + Jb.Je[1][i] * pw[1] * Jb.Jt[1][k]);
+                    }
+                }
+                __syncwarp();
+                if (acta) {
+                    const int nb = min(32, end - b0);
+                    for (int b = 0; b < nb; ++b) {
+                        const int rowb = sImg[wib][b];
+                        // t = A'' Q[rows a, rows b] (3 x 6), then R += t B'  (full double sum over a and b)
+#pragma unroll
+                        for (int jb = 0; jb < 6; ++jb) {
+                            if (P.ecol[jb] < 0) continue;
+                            double t0 = 0, t1 = 0, t2 = 0;
+#pragma unroll
+                            for (int i = 0; i < 6; ++i)
+                                if (P.ecol[i] >= 0) {
+                                    const double q = Qs(rowa + P.ecol[i], rowb + P.ecol[jb]);
+                                    t0 += A_[i][0] * q; t1 += A_[i][1] * q; t2 += A_[i][2] * q;
+                                }
+                            const double b0_ = sB[wib][b][3 * jb], b1_ = sB[wib][b][3 * jb + 1], b2_ = sB[wib][b][3 * jb + 2];
+                            R[0][0] += t0 * b0_; R[0][1] += t0 * b1_; R[0][2] += t0 * b2_;
+                            R[1][0] += t1 * b0_; R[1][1] += t1 * b1_; R[1][2] += t1 * b2_;
+                            R[2][0] += t2 * b0_; R[2][1] += t2 * b1_; R[2][2] += t2 * b2_;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // camera x camera and the camera rows of E: spread over the lanes
+        if (HAS_CAM) {
+            for (int e = lane; e < ncam * NC * ncam * NC; e += 32) {
+                const int e1 = e / (ncam * NC), e2 = e - e1 * (ncam * NC);
+                const int k1 = e1 / NC, j1 = e1 - k1 * NC, k2 = e2 / NC, j2 = e2 - k2 * NC;
+                if (P.ccol[j1] < 0 || P.ccol[j2] < 0) continue;
+                const int i1 = P.off_cam + P.uc * cams[k1] + P.ccol[j1], i2 = P.off_cam + P.uc * cams[k2] + P.ccol[j2];
+                const double q = Qs(i1, i2) * dvec[i1] * dvec[i2];
+#pragma unroll
+                for (int x = 0; x < 3; ++x)
+#pragma unroll
+                    for (int y2 = 0; y2 < 3; ++y2) R[x][y2] += sWc[wib][k1][j1][x] * q * sWc[wib][k2][j2][y2];
+            }
+            if (P.inner)
+                for (int e = lane; e < ncam * NC; e += 32) {
+                    const int k1 = e / NC, j1 = e - k1 * NC;
+                    if (P.ccol[j1] < 0) continue;
+                    const int i1 = P.off_cam + P.uc * cams[k1] + P.ccol[j1];
+                    const double* y = Y + 8 * (size_t)i1;
+#pragma unroll
+                    for (int r = 0; r < 7; ++r)
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) E[r][k] += y[r] * dvec[i1] * sWc[wib][k1][j1][k];
+                }
+        }
+#pragma unroll
+        for (int x = 0; x < 3; ++x)
+#pragma unroll
+            for (int y2 = 0; y2 < 3; ++y2)
+#pragma unroll
+                for (int s_ = 16; s_ > 0; s_ >>= 1) R[x][y2] += __shfl_xor_sync(0xffffffffu, R[x][y2], s_);
+        if (P.inner) {
+#pragma unroll
+            for (int r = 0; r < 7; ++r)
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+#pragma unroll
+                    for (int s_ = 16; s_ > 0; s_ >>= 1) E[r][k] += __shfl_xor_sync(0xffffffffu, E[r][k], s_);
+            // R -= E' T7inv E
+#pragma unroll
+            for (int x = 0; x < 3; ++x)
+#pragma unroll
+                for (int y2 = 0; y2 < 3; ++y2) {
+                    double acc = 0.0;
+                    for (int r = 0; r < 7; ++r)
+                        for (int c = 0; c < 7; ++c) acc += E[r][x] * T7inv[7 * r + c] * E[c][y2];
+                    R[x][y2] -= acc;
+                }
+        }
+        if (lane < 3) {
+            // (V^-1 + V^-1 R V^-1)(lane, lane)
+            double vrow[3] = {sym3(Vi, lane, 0), sym3(Vi, lane, 1), sym3(Vi, lane, 2)};
+            double acc = vrow[lane == 0 ? 0 : (lane == 1 ? 1 : 2)];
+#pragma unroll
+            for (int x = 0; x < 3; ++x)
+#pragma unroll
+                for (int y2 = 0; y2 < 3; ++y2) acc += vrow[x] * R[x][y2] * vrow[y2];
+            out[3 * (size_t)tie + lane] = acc;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // host launchers (dispatch on NK and on whether any camera parameter is estimated)
 
@@ -714,6 +977,16 @@ cudaError_t launch_xhat_gather(const DevProblem& P, int sm_count, double* xhat, 
 
 cudaError_t launch_delta_gather(const DevProblem& P, int sm_count, double* delta, cudaStream_t st) {
     k_delta_gather<<<stream_grid((int64_t)P.n_red + 3 * (int64_t)P.n_tie, sm_count), 256, 0, st>>>(P, delta);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cov_points(const DevProblem& P, int sm_count, const double* Q, const double* Y, const double* T7inv,
+                              const double* dvec, double* out, cudaStream_t st) {
+    const bool hc = P.uc > 0;
+    int grid = (P.n_seg + 3) / 4;
+    if (grid > sm_count * 8) grid = sm_count * 8;
+    if (grid < 1) grid = 1;
+    FEBA_NK_DISPATCH(P.NK, hc, (k_cov_points<NK_, HC_><<<grid, 128, 0, st>>>(P, Q, Y, T7inv, dvec, out)));
     return cudaGetLastError();
 }
 

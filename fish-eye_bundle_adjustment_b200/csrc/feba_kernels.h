@@ -51,6 +51,8 @@ cudaError_t chol_inverse(double* A, int ld, int nb, const double* Linv, int inne
 // cofactor entries of the EOP/IOP part: diag (distortion entries un-scaled, main.m:468-480) and blocks
 cudaError_t launch_cov_diag_cam(const DevProblem& P, const double* Q, const double* Y, const double* T7inv,
                                 const double* dvec, double* out, cudaStream_t st);
+cudaError_t launch_cov_points(const DevProblem& P, int sm_count, const double* Q, const double* Y, const double* T7inv,
+                              const double* dvec, double* out, cudaStream_t st);
 cudaError_t launch_cov_block(const DevProblem& P, const double* Q, const double* Y, const double* T7inv,
                              const double* dvec, const long long* idx, int k, double* out, cudaStream_t st);
 

@@ -244,8 +244,8 @@ class Handle:
         return dict(v=v, RSD=rsd, RMSx=st[0], RMSy=st[1], RMS=st[2], sigma02=st[3], sxx=st[4], syy=st[5])
 
     def cov_diag(self) -> np.ndarray:
-        """diag(Cx)/sigma02 of the EOP/IOP unknowns (main.m:432-444, un-scaled as main.m:468-480)."""
-        q = np.empty(self.u_c, dtype=np.float64)
+        """diag(Cx)/sigma02 of all unknowns (main.m:432-444, un-scaled as main.m:468-480)."""
+        q = np.empty(self.u, dtype=np.float64)
         self._check(self._lib.feba_cov_diag(self._h, _dp(q), q.size))
         return q
 

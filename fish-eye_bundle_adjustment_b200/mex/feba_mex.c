@@ -8,6 +8,7 @@
  *     deltasum = feba_mex('iterate', h);         replaces the while-body main.m:416-487
  *     xhat     = feba_mex('get_xhat', h);
  *     [v, rsd, stats] = feba_mex('residuals', h);   replaces main.m:569-601 (rsd: n_obs x 5 = r vx vy vr vt)
+ *     q = feba_mex('cov_diag', h);  B = feba_mex('cov_block', h, idx);   diag(Cx)/sigma02, Cx/sigma02 blocks
  *                feba_mex('destroy', h);
  * Recoverable errors are NOT raised with mexErrMsgIdAndTxt: like the reference's 0/1 `error` flags
  * (main.m:417-421) the gateway returns the status as the LAST output and prints feba_last_error.
@@ -141,6 +142,18 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         if (nlhs > 1) plhs[1] = rsd;
         if (nlhs > 2) plhs[2] = st;                                        /* RMSx RMSy RMS sigma02 sum_vx2 sum_vy2 */
         status_out(nlhs, plhs, 3, rc, h);
+    } else if (!strcmp(cmd, "cov_diag")) {                                 /* diag(Cx)/sigma02, main.m:432-482 */
+        plhs[0] = mxCreateDoubleMatrix((mwSize)u, 1, mxREAL);
+        status_out(nlhs, plhs, 1, feba_cov_diag(h, mxGetPr(plhs[0]), (size_t)u), h);
+    } else if (!strcmp(cmd, "cov_block")) {                                /* Cx/sigma02 block, 1-based indices */
+        if (nrhs < 3 || !mxIsDouble(prhs[2])) mexErrMsgIdAndTxt("feba:cov", "cov_block needs an index vector");
+        const int32_t k = (int32_t)mxGetNumberOfElements(prhs[2]);
+        int64_t* idx = (int64_t*)mxMalloc(sizeof(int64_t) * (size_t)k);
+        for (int32_t i = 0; i < k; ++i) idx[i] = (int64_t)mxGetPr(prhs[2])[i] - 1;
+        plhs[0] = mxCreateDoubleMatrix((mwSize)k, (mwSize)k, mxREAL);      /* symmetric: layout-agnostic */
+        const int rc = feba_cov_block(h, idx, k, mxGetPr(plhs[0]));
+        mxFree(idx);
+        status_out(nlhs, plhs, 1, rc, h);
     } else {
         mexErrMsgIdAndTxt("feba:cmd", "unknown command %s", cmd);
     }

@@ -138,13 +138,13 @@ int feba_solve(feba_handle *h, int32_t *iterations_out, double *trace_out, size_
 /* Covariance outputs from the normal matrix of the LAST iteration, as the reference
  * keeps Cx = NG^-1(1:u,1:u) of its last loop pass (main.m:432-444).  Values are COFACTORS: multiply
  * by sigma02 for Cx (main.m:602).
- *   feba_cov_diag : diag(Cx)/sigma02 for the first u_c unknowns (EOP + IOP part; tie-point variances are not
- *                   produced yet), distortion entries un-scaled as main.m:468-480.
+ *   feba_cov_diag : diag(Cx)/sigma02 for all u unknowns (tie points: V^-1 + V^-1 W' Qcc W V^-1 per point),
+ *                   distortion entries un-scaled as main.m:468-480.
  *   feba_cov_block: k x k block (row-major) for EOP/IOP unknown indices idx[] (0-based xhat positions),
  *                   BEFORE un-scaling -- the values main.m:446-456 normalises into Correlation.
  * feba_cov_prepare builds the inverse of the reduced system once (~u_c^3 flop); the other two call it. */
 int feba_cov_prepare(feba_handle *h);
-int feba_cov_diag(feba_handle *h, double *qdiag, size_t u_c);
+int feba_cov_diag(feba_handle *h, double *qdiag, size_t u);
 int feba_cov_block(feba_handle *h, const int64_t *idx, int32_t k, double *out);
 
 /* Timing of the last completed iteration in milliseconds (CUDA events on the handle's stream):

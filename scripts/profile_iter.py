@@ -11,6 +11,7 @@ ap.add_argument("--workload", type=int, default=3, help="BASELINE.json configs i
 ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--residuals", action="store_true")
+ap.add_argument("--cov", action="store_true")
 a = ap.parse_args()
 prob = fb.synth.baseline_config(a.workload, scale=a.scale)
 err, x0, _ = fb.Buildxhat(prob)
@@ -27,4 +28,12 @@ with fb.Handle(prob) as h:
     if a.residuals:
         r = h.residuals()
         print("sigma02", r["sigma02"])
+    if a.cov:
+        import time
+        t0 = time.perf_counter()
+        q = h.cov_diag()
+        t1 = time.perf_counter()
+        blk = h.cov_block(list(range(h.u_c - 10, h.u_c)))
+        print(f"covariance stage: diag of all {h.u} unknowns {1e3 * (t1 - t0):.1f} ms (incl. inverse of the reduced "
+              f"system), IOP block {1e3 * (time.perf_counter() - t1):.2f} ms; min/max cofactor {q.min():.3e} {q.max():.3e}")
     print("launches", h.launch_count())

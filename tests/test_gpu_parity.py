@@ -358,12 +358,16 @@ def test_multi_camera_networks(mode, ncams):
         h.iterate_solve()
     sc = np.sqrt(np.abs(np.diag(S_ref)))
     assert np.max(np.abs(S - S_ref) / np.outer(sc, sc)) < 1e-11
-    out = fb.adjust(prob, xhat0, verbose=False)
+    out = fb.adjust(prob, xhat0, verbose=False, cov=True)
     assert out["iterations"] == ref["iterations"]
     assert np.max(np.abs(out["v"] - ref["v"])) < 1e-8 * np.max(np.abs(ref["v"]))
     assert abs(out["sigma02"] - ref["sigma02"]) < 1e-8 * ref["sigma02"]
     assert group_rel(prob, out["xhat"], ref["xhat"]) < 1e-9
     assert np.max(np.abs(out["RSD"] - ref["RSD"])) < 1e-8
+    # variances of every unknown (per-camera IOP blocks, points seen by several cameras)
+    lit = dense.gauss_newton(prob, xhat0)
+    dref = np.diag(lit["Cx"])
+    assert np.max(np.abs(out["Cx_diag"] - dref) / dref) < 1e-6
 
 
 def test_concurrent_batch_equals_one_at_a_time(tmp_path):
@@ -405,10 +409,12 @@ def test_covariance_outputs_of_the_camera_part(case):
     assert out["iterations"] == ref["iterations"]
     L = model.layout(prob)
     u_c = L["off_tie"]
-    dref = np.diag(ref["Cx"])[:u_c]
+    dref = np.diag(ref["Cx"])
     # the explicit inverse is itself accurate to ~cond*eps (1e-5 on the bundled data)
     tol = 2e-4 if case.startswith("cam0") else 1e-6
-    assert np.max(np.abs(out["Cx_diag"] - dref) / dref) < tol
+    assert out["Cx_diag"].shape == dref.shape
+    assert np.max(np.abs(out["Cx_diag"][:u_c] - dref[:u_c]) / dref[:u_c]) < tol          # EOP / IOP
+    assert np.max(np.abs(out["Cx_diag"][u_c:] - dref[u_c:]) / dref[u_c:]) < tol          # tie points
     C = ref["Correlation"]
     off, uc, ui = L["off_cam"], L["u_cam"], L["u_img"]
     assert np.max(np.abs(out["Correlation_IOP"][0] - C[off:off + uc, off:off + uc])) < tol
