@@ -9,6 +9,6 @@ is no CPU fallback for the hot path.
 from .formats import ReadFiles, findSetting, read_string_table          # noqa: F401
 from .problem import Settings, Problem, Buildxhat, load_problem, save_problem  # noqa: F401
 from .lib import Handle, FebaError                                       # noqa: F401
-from .main import main, BatchRun, adjust, findfiles, write_rsd, covariance_outputs  # noqa: F401
+from .main import main, BatchRun, adjust, findfiles, write_rsd, write_par, covariance_outputs  # noqa: F401
 from .batch import adjust_batch                                          # noqa: F401
 from . import synth, lib, build                                          # noqa: F401

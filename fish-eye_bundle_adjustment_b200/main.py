@@ -10,8 +10,7 @@
 The loop body is one ``feba_iterate`` per pass -- the MEX gateway a MATLAB user would call makes
 exactly these calls.  Console lines follow main.m (``Iteration k:``, the echoed
 ``deltasum =``, ``Elapsed time is ...``, ``sigma02 =``).  Report formatting (.out) is out of scope;
-the numeric tables .rsd / .par inputs are returned and the .rsd table is written
-(main.m:957, BuildRSD.m:6,40).
+the numeric tables are written: .rsd (main.m:957, BuildRSD.m:6,40) and .par (main.m:773-823, :958).
 """
 from __future__ import annotations
 
@@ -107,6 +106,38 @@ def write_rsd(path: str, prob: Problem, RSD: np.ndarray) -> None:
             fh.write("\t".join(row) + "\n")
 
 
+def write_par(path: str, prob: Problem, xhat: np.ndarray, Cx_diag: np.ndarray) -> None:
+    """``writecell(PAR, name.par, 'Delimiter','tab')`` (main.m:958).  PAR = three header rows
+    (main.m:773-775), then per camera ``Camera <id>`` and one row ``name value std`` per estimated
+    IOP / distortion term in xhat order (main.m:793-823); std = sqrt(Cx(k,k))."""
+    import datetime
+    s = prob.settings
+    ui, uc = s.u_perimage, s.u_percam
+    rows = [["Created with Fish-eye model Bundle Adjustment version:", "feba_b200", ""],
+            ["Execution date", datetime.date.today().strftime("%d-%b-%Y"), ""], ["", "", ""]]
+    k = ui * prob.numImg
+    for c in range(prob.numCam):
+        rows.append(["Camera", prob.camera_name(c), ""])
+        names = []
+        if s.Estimate_xp:
+            names.append("xp")
+        if s.Estimate_yp:
+            names.append("yp")
+        if s.Estimate_c:
+            names.append("c")
+        if s.Estimate_radial:
+            names += [f"k{j + 1}" for j in range(s.Num_Radial_Distortions)]
+        if s.Estimate_decent:
+            names += ["p1", "p2"]
+        assert len(names) == uc
+        for nm in names:
+            rows.append([nm, repr(float(xhat[k])), repr(float(np.sqrt(Cx_diag[k])))])
+            k += 1
+    with open(path, "w") as fh:
+        for r in rows:
+            fh.write("\t".join(r) + "\n")
+
+
 def main(folder: Optional[str] = None, plot: bool = True, cfg_folder: Optional[str] = None,
          write_files: bool = True, verbose: bool = True):
     """``main_error = main(folder, plot)`` (main.m:10).  ``folder`` None = current directory
@@ -122,14 +153,15 @@ def main(folder: Optional[str] = None, plot: bool = True, cfg_folder: Optional[s
     if prob is None:
         return 1
     try:
-        out = adjust(prob, verbose=verbose)
+        out = adjust(prob, verbose=verbose, cov=write_files)
     except (FebaError, ValueError) as exc:
         print("Error building A and w")                                    # main.m:417-421
         print(str(exc))
         return 1
     if write_files:
         name = os.path.splitext(os.path.basename(prob.settings.Output_Filename))[0]
-        write_rsd(os.path.join(data_dir, name + ".rsd"), prob, out["RSD"])
+        write_rsd(os.path.join(data_dir, name + ".rsd"), prob, out["RSD"])      # main.m:957
+        write_par(os.path.join(data_dir, name + ".par"), prob, out["xhat"], out["Cx_diag"])   # main.m:958
     if verbose:
         print("Done!")
     out["problem"] = prob

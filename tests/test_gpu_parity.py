@@ -283,6 +283,13 @@ def test_main_and_batchrun_over_text_files(tmp_path):
         rsd = [l.split("\t") for l in open(os.path.join(d, os.path.basename(d) + ".rsd")).read().splitlines()]
         assert len(rsd) == prob.n_obs and len(rsd[0]) == 9                       # BuildRSD.m:5-6
         assert abs(float(rsd[3][5]) - out["RSD"][3, 1]) < 1e-12
+        par = [l.split("\t") for l in open(os.path.join(d, os.path.basename(d) + ".par")).read().splitlines()]
+        assert par[3][:2] == ["Camera", "0"] and [r[0] for r in par[4:7]] == ["xp", "yp", "c"]   # main.m:793-808
+        L = model.layout(out["problem"])
+        assert float(par[4][1]) == out["xhat"][L["off_cam"]]
+        assert abs(float(par[6][2]) - np.sqrt(out["Cx_diag"][L["off_cam"] + 2])) < 1e-15
+        lit = dense.gauss_newton(out["problem"], xhat0)
+        assert abs(float(par[6][2]) - np.sqrt(lit["Cx"][L["off_cam"] + 2, L["off_cam"] + 2])) < 1e-6 * float(par[6][2])
     assert fb.BatchRun([str(tmp_path / "root")]) == 0
     # a broken data set stops the batch with error 1 (BatchRun.m:60-64)
     bad = tmp_path / "root" / "set0" / "net0.cfg"
