@@ -623,14 +623,17 @@ __global__ void __launch_bounds__(128) k_image_pass(DevProblem P) {
 #pragma unroll
             for (int k = 0; k < 27; ++k) acc[k] = 0.0;
             for (int t = beg + tid; t < end; t += 128) {
-                const double* r1 = P.rec1 + (size_t)kRec1 * t;
-                const double* r2 = P.rec2 + (size_t)R2 * t;
+                const double2* r1v = reinterpret_cast<const double2*>(P.rec1 + (size_t)kRec1 * t);
+                double r1[kRec1];
+#pragma unroll
+                for (int k = 0; k < kRec1 / 2; ++k) { const double2 v = r1v[k]; r1[2 * k] = v.x; r1[2 * k + 1] = v.y; }
+                const double2 rav = *reinterpret_cast<const double2*>(P.rec2 + (size_t)R2 * t);
                 double Je[2][6], Zm[2][3];
 #pragma unroll
                 for (int k = 0; k < 6; ++k) { Je[0][k] = r1[k]; Je[1][k] = r1[6 + k]; }
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { Zm[0][k] = r1[12 + k]; Zm[1][k] = r1[15 + k]; }
-                const double ra0 = r2[0], ra1 = r2[1];
+                const double ra0 = rav.x, ra1 = rav.y;
                 const double p00 = P.px - (Zm[0][0] * Zm[0][0] + Zm[0][1] * Zm[0][1] + Zm[0][2] * Zm[0][2]);
                 const double p01 = -(Zm[0][0] * Zm[1][0] + Zm[0][1] * Zm[1][1] + Zm[0][2] * Zm[1][2]);
                 const double p11 = P.py - (Zm[1][0] * Zm[1][0] + Zm[1][1] * Zm[1][1] + Zm[1][2] * Zm[1][2]);
@@ -671,14 +674,19 @@ __global__ void __launch_bounds__(128) k_image_pass(DevProblem P) {
 #pragma unroll
             for (int k = 0; k < NC * 6; ++k) acc[k] = 0.0;
             for (int t = beg + tid; t < end; t += 128) {
-                const double* r1 = P.rec1 + (size_t)kRec1 * t;
-                const double* r2 = P.rec2 + (size_t)R2 * t + 2;
+                const double2* r1v = reinterpret_cast<const double2*>(P.rec1 + (size_t)kRec1 * t);
+                const double2* r2v = reinterpret_cast<const double2*>(P.rec2 + (size_t)R2 * t + 2);
                 double Je[2][6];
 #pragma unroll
-                for (int k = 0; k < 6; ++k) { Je[0][k] = r1[k]; Je[1][k] = r1[6 + k]; }
+                for (int k = 0; k < 3; ++k) {
+                    const double2 v0 = r1v[k], v1 = r1v[3 + k];
+                    Je[0][2 * k] = v0.x; Je[0][2 * k + 1] = v0.y;
+                    Je[1][2 * k] = v1.x; Je[1][2 * k + 1] = v1.y;
+                }
 #pragma unroll
                 for (int j = 0; j < NC; ++j) {
-                    const double h0 = r2[2 * j], h1 = r2[2 * j + 1];
+                    const double2 hv = r2v[j];
+                    const double h0 = hv.x, h1 = hv.y;
 #pragma unroll
                     for (int i = 0; i < 6; ++i) acc[6 * j + i] += h0 * Je[0][i] + h1 * Je[1][i];
                 }
@@ -717,27 +725,25 @@ __global__ void __launch_bounds__(128) k_pair_pass(DevProblem P) {
         for (int k = 0; k < 36; ++k) acc[k] = 0.0;
         for (int t = lane; t < b.w; t += 32) {
             const int2 pr = P.pairs[(size_t)b.z + t];
-            const double* ra = P.rec1 + (size_t)kRec1 * pr.x;
-            const double* rb = P.rec1 + (size_t)kRec1 * pr.y;
-            double Za[2][3], Zb[2][3];
+            // 144-byte records, 16-byte aligned: nine 16-byte loads each, all in flight together
+            const double2* ra2 = reinterpret_cast<const double2*>(P.rec1 + (size_t)kRec1 * pr.x);
+            const double2* rb2 = reinterpret_cast<const double2*>(P.rec1 + (size_t)kRec1 * pr.y);
+            double ra[kRec1], rb[kRec1];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                Za[0][k] = ra[12 + k]; Za[1][k] = ra[15 + k];
-                Zb[0][k] = rb[12 + k]; Zb[1][k] = rb[15 + k];
+            for (int k = 0; k < kRec1 / 2; ++k) {
+                const double2 va = ra2[k], vb = rb2[k];
+                ra[2 * k] = va.x; ra[2 * k + 1] = va.y;
+                rb[2 * k] = vb.x; rb[2 * k + 1] = vb.y;
             }
-            const double c00 = Za[0][0] * Zb[0][0] + Za[0][1] * Zb[0][1] + Za[0][2] * Zb[0][2];
-            const double c01 = Za[0][0] * Zb[1][0] + Za[0][1] * Zb[1][1] + Za[0][2] * Zb[1][2];
-            const double c10 = Za[1][0] * Zb[0][0] + Za[1][1] * Zb[0][1] + Za[1][2] * Zb[0][2];
-            const double c11 = Za[1][0] * Zb[1][0] + Za[1][1] * Zb[1][1] + Za[1][2] * Zb[1][2];
-            double Jb[2][6];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) { Jb[0][k] = rb[k]; Jb[1][k] = rb[6 + k]; }
+            const double c00 = ra[12] * rb[12] + ra[13] * rb[13] + ra[14] * rb[14];
+            const double c01 = ra[12] * rb[15] + ra[13] * rb[16] + ra[14] * rb[17];
+            const double c10 = ra[15] * rb[12] + ra[16] * rb[13] + ra[17] * rb[14];
+            const double c11 = ra[15] * rb[15] + ra[16] * rb[16] + ra[17] * rb[17];
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
-                const double ja0 = ra[i], ja1 = ra[6 + i];
-                const double e0 = ja0 * c00 + ja1 * c10, e1 = ja0 * c01 + ja1 * c11;     // (Je_a' C)(i, :)
+                const double e0 = ra[i] * c00 + ra[6 + i] * c10, e1 = ra[i] * c01 + ra[6 + i] * c11;   // (Je_a' C)(i, :)
 #pragma unroll
-                for (int j = 0; j < 6; ++j) acc[6 * i + j] += e0 * Jb[0][j] + e1 * Jb[1][j];
+                for (int j = 0; j < 6; ++j) acc[6 * i + j] += e0 * rb[j] + e1 * rb[6 + j];
             }
         }
 #pragma unroll
