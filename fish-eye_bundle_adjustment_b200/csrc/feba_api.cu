@@ -39,6 +39,9 @@ struct feba_handle {
     double *ywork = nullptr, *Linv = nullptr, *dvec = nullptr;
     double *covU = nullptr, *covQ = nullptr, *covY = nullptr, *covT = nullptr;   // covariance stage (lazy)
     bool cov_ready = false;
+    DagStreams dag;               // task-graph factorisation (large reduced systems)
+    std::vector<cudaEvent_t> dag_events;
+    bool use_dag = false;
     double *scal = nullptr;       // [0] sumabs camera part, [1] sumabs points, [2] sum vx^2, [3] sum vy^2
     double *v_out = nullptr, *rsd_out = nullptr, *delta_out = nullptr;
     int *opt = nullptr, *tie_pt = nullptr, *info = nullptr;
@@ -153,6 +156,13 @@ void feba_destroy(feba_handle* h) {
     if (h->scal_host) cudaFreeHost(h->scal_host);
     if (h->info_host) cudaFreeHost(h->info_host);
     drop_graphs(h);
+    for (int s2 = 0; s2 < h->dag.n_streams; ++s2) {
+        cudaStreamDestroy(h->dag.streams[s2]);
+        if (h->dag.join[s2]) cudaEventDestroy(h->dag.join[s2]);
+    }
+    if (h->dag.fork) cudaEventDestroy(h->dag.fork);
+    for (auto& ev : h->dag_events)
+        if (ev) cudaEventDestroy(ev);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -346,6 +356,42 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
         h->n_partial = a > b ? a : b;
     }
     CU(h, dev_alloc(h, &P.partial, (size_t)h->n_partial));
+    {
+        // task-graph factorisation for large reduced systems (>= 96 blocks, u_c >= 6,144): about 13
+        // supertiles per side (measured on u_c = 12,010: T = 6/8/12/14/16/20/24 blocks -> 48.7/32.6/26.3/
+        // 25.3/25.6/27.7/28.1 ms, recursive form 30.2 ms; 4/8/12/16 streams -> 28.3/25.6/27.6/27.2 ms).
+        // FEBA_DAG_TILE=t forces supertiles of t blocks (0 = recursive form), FEBA_DAG_STREAMS the pool size.
+        const int nb = P.n_pad / kBlk;
+        const char* e_t = std::getenv("FEBA_DAG_TILE");
+        const char* e_s = std::getenv("FEBA_DAG_STREAMS");
+        int T = 0;
+        if (e_t) {
+            T = std::atoi(e_t);
+            if (T > 0 && nb < 2 * T) T = 0;
+        } else if (nb >= 96) {
+            T = (nb + 6) / 13;
+            if (T < 8) T = 8;
+            if (T > 24) T = 24;
+        }
+        const int NS = e_s ? std::atoi(e_s) : 8;
+        if (T > 0 && NS >= 2 && NS <= 16) {
+            h->dag.tile_blocks = T;
+            int lo = 0, hi = 0;
+            CU(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            for (int s2 = 0; s2 < NS; ++s2) {
+                CU(h, cudaStreamCreateWithPriority(&h->dag.streams[s2], cudaStreamNonBlocking, s2 == 0 ? hi : lo));
+                ++h->dag.n_streams;
+                CU(h, cudaEventCreateWithFlags(&h->dag.join[s2], cudaEventDisableTiming));
+            }
+            CU(h, cudaEventCreateWithFlags(&h->dag.fork, cudaEventDisableTiming));
+            const int NT = (nb + T - 1) / T;
+            h->dag_events.assign((size_t)(NT + 1) * (NT + 1), nullptr);
+            for (auto& ev : h->dag_events) CU(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            h->dag.events = h->dag_events.data();
+            h->dag.n_events = (int)h->dag_events.size();
+            h->use_dag = true;
+        }
+    }
     CU(h, dev_alloc(h, &P.cam_part, (size_t)assemble_warps(P, h->sm_count) * kCamPart));
     {
         // image-pair schedule of the Schur blocks: static for the life of the handle
@@ -487,7 +533,8 @@ static int enqueue_solve(feba_handle* h) {
     DevProblem& P = h->P;
     CU(h, launch_border_scale(P, h->eop, h->dvec, h->info, h->stream, &h->launches));
     const int nb = P.n_pad / kBlk;
-    CU(h, chol_augmented(P.S, P.ld, nb, h->Linv, h->info, h->stream, &h->launches));
+    if (h->use_dag) CU(h, chol_dag(P.S, P.ld, nb, h->Linv, h->info, h->dag, h->stream, &h->launches));
+    else CU(h, chol_augmented(P.S, P.ld, nb, h->Linv, h->info, h->stream, &h->launches));
     CU(h, record(h, 3));
     CU(h, border_and_backsolve(P.S, P.ld, nb, h->Linv, P.inner, h->work, h->ywork, h->sol, h->info, h->sm_count,
                                h->stream, &h->launches));

@@ -12,6 +12,7 @@
 // the tensor path for doubles on sm_100a as well.
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "feba_dev.h"
 #include "feba_kernels.h"
@@ -513,6 +514,89 @@ static cudaError_t rchol(double* A, int ld, double* Linv, int b0, int n, int aug
 
 cudaError_t chol_augmented(double* A, int ld, int nb, double* Linv, int* info, cudaStream_t st, int64_t* launches) {
     return rchol(A, ld, Linv, 0, nb + 1, nb, info, st, launches);
+}
+
+// ------------------------------------------------------------------------------------------
+// Task-graph (right-looking, supertile) form of the same factorisation.  The recursive form above is
+// a single chain: its ~190 diagonal 64x64 factorisations, leaves and small products (~12 ms at
+// u_c = 12,010) run with most of the GPU idle.  Here the matrix is cut into supertiles of T 64-blocks;
+//   DIAG(k)      : recursive factorisation of supertile (k,k)                    (the chain above, small)
+//   TRSM(i,k)    : X(i,k) := X(i,k) L_kk^-T                     i > k (incl. the augmented block row)
+//   UPDATE(i,j,k): A(i,j) -= X(i,k) X(j,k)'                     k < j <= i
+// are enqueued on a pool of streams with event dependencies per tile (reads after the tile's last
+// write; every write waits for the previous writer), so that DIAG / TRSM of step k+1 overlap the
+// bulk updates of step k.  Stream 0 has high priority and carries the critical path
+// (DIAG(k), TRSM(k+1,k), UPDATE(k+1,k+1,k)).  Captured into the iteration's CUDA graph like everything
+// else, the events become graph edges.
+cudaError_t chol_dag(double* A, int ld, int nb, double* Linv, int* info, const DagStreams& D, cudaStream_t main,
+                     int64_t* launches) {
+    const int T = D.tile_blocks;
+    const int NT = (nb + T - 1) / T;                  // supertiles of the factorised part
+    const int NR = NT + 1;                            // row supertiles: + the augmented block row
+    auto blk0 = [&](int t) { return t == NT ? nb : t * T; };                     // first 64-block of supertile t
+    auto nblk = [&](int t) { return t == NT ? 1 : (t == NT - 1 ? nb - T * (NT - 1) : T); };
+    if (NR * NR > D.n_events) return cudaErrorInvalidValue;
+    std::vector<int> last(NR * NR, -1);               // stream of the last writer of tile (i,j), -1: none yet
+    auto tid = [&](int i, int j) { return i * NR + j; };
+    auto stream_of = [&](int i, int j) { return 1 + (i * 3 + j * 7) % (D.n_streams - 1); };
+    cudaError_t e = cudaEventRecord(D.fork, main);
+    if (e != cudaSuccess) return e;
+    for (int s = 0; s < D.n_streams; ++s) {
+        e = cudaStreamWaitEvent(D.streams[s], D.fork, 0);
+        if (e != cudaSuccess) return e;
+    }
+    auto acquire = [&](int sid, int i, int j) -> cudaError_t {
+        const int w = last[tid(i, j)];
+        if (w >= 0 && w != sid) return cudaStreamWaitEvent(D.streams[sid], D.events[tid(i, j)], 0);
+        return cudaSuccess;
+    };
+    auto release = [&](int sid, int i, int j) -> cudaError_t {
+        last[tid(i, j)] = sid;
+        return cudaEventRecord(D.events[tid(i, j)], D.streams[sid]);
+    };
+#define DAG_CU(x)                 \
+    do {                          \
+        e = (x);                  \
+        if (e != cudaSuccess) return e; \
+    } while (0)
+    for (int k = 0; k < NT; ++k) {
+        {   // DIAG(k), critical path
+            DAG_CU(acquire(0, k, k));
+            DAG_CU(rchol(A, ld, Linv, blk0(k), nblk(k), -1, info, D.streams[0], launches));
+            DAG_CU(release(0, k, k));
+        }
+        for (int i = k + 1; i < NR; ++i) {
+            const int sid = (i == k + 1) ? 0 : stream_of(i, k);
+            DAG_CU(acquire(sid, k, k));
+            DAG_CU(acquire(sid, i, k));
+            DAG_CU(rtrsm(A, ld, A, ld, Linv, blk0(i), nblk(i), blk0(k), nblk(k), D.streams[sid], launches));
+            DAG_CU(release(sid, i, k));
+        }
+        for (int i = k + 1; i < NR; ++i)
+            for (int j = k + 1; j <= i; ++j) {
+                if (j == NT && i == NT) {
+                    // augmented diagonal block T (never factorised): plain lower update
+                } else if (j >= NT) {
+                    continue;
+                }
+                const int sid = (i == k + 1 && j == k + 1) ? 0 : stream_of(i, j);
+                DAG_CU(acquire(sid, i, k));
+                DAG_CU(acquire(sid, j, k));
+                DAG_CU(acquire(sid, i, j));
+                DAG_CU(gemm_nt(AT(A, ld, blk0(i), blk0(j)), ld, AT(A, ld, blk0(i), blk0(k)), ld,
+                               AT(A, ld, blk0(j), blk0(k)), ld, nblk(i), nblk(j), nblk(k), i == j ? 1 : 0,
+                               D.streams[sid], launches));
+                DAG_CU(release(sid, i, j));
+            }
+    }
+#undef DAG_CU
+    for (int s = 0; s < D.n_streams; ++s) {
+        e = cudaEventRecord(D.join[s], D.streams[s]);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamWaitEvent(main, D.join[s], 0);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -39,6 +39,18 @@ cudaError_t launch_residuals(const DevProblem& P, int sm_count, const int* opt, 
 // Linv: nb blocks of kBlk x kBlk (column-major): inverses of the diagonal factors.
 // info (device int) is set non-zero when a pivot is not positive.
 cudaError_t chol_augmented(double* A, int ld, int nb, double* Linv, int* info, cudaStream_t st, int64_t* launches);
+// Stream pool + events of the task-graph form (owned by the handle).
+struct DagStreams {
+    int tile_blocks = 8;            // supertile size in 64-blocks
+    int n_streams = 0;              // streams[0] has high priority (critical path)
+    cudaStream_t streams[16] = {};
+    cudaEvent_t fork = nullptr;
+    cudaEvent_t join[16] = {};
+    cudaEvent_t* events = nullptr;  // one per tile (row supertile, column supertile)
+    int n_events = 0;
+};
+cudaError_t chol_dag(double* A, int ld, int nb, double* Linv, int* info, const DagStreams& D, cudaStream_t main,
+                     int64_t* launches);
 // ywork (n_pad) := combination of the augmented rows: y = Y'(0,:) + sum_k kvec[k] Y'(1+k,:) where kvec
 // solves the 7x7 border system (inner != 0), else y = Y'(0,:).  Then sol := L^-T y.
 cudaError_t border_and_backsolve(double* A, int ld, int nb, const double* Linv, int inner, double* work,

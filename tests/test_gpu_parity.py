@@ -433,3 +433,26 @@ def test_covariance_outputs_of_the_camera_part(case):
         with pytest.raises(fb.FebaError) as ei:
             h.cov_diag()
         assert ei.value.code == fb.lib.FEBA_ERR_STATE
+
+
+def test_task_graph_factorisation_matches_recursive_form(monkeypatch):
+    """Large reduced systems are factorised as a task graph over supertiles (stream pool + events,
+    csrc/feba_chol.cu::chol_dag); force it on a medium problem (u_c = 1,210, 19 blocks, supertiles of 3
+    blocks, ragged last supertile + augmented row) and compare with the recursive form and the oracle."""
+    from oracle import cport
+    prob = synth.baseline_config(4, scale=1.0)
+    err, xhat0, _ = fb.Buildxhat(prob)
+    monkeypatch.setenv("FEBA_DAG_TILE", "0")
+    a = fb.adjust(prob, xhat0, verbose=False, cov=True)
+    monkeypatch.setenv("FEBA_DAG_TILE", "3")
+    monkeypatch.setenv("FEBA_DAG_STREAMS", "5")
+    b = fb.adjust(prob, xhat0, verbose=False, cov=True)
+    assert a["iterations"] == b["iterations"]
+    assert np.max(np.abs(a["v"] - b["v"])) < 1e-9
+    assert group_rel(prob, b["xhat"], a["xhat"]) < 1e-10
+    assert np.max(np.abs(a["Cx_diag"] - b["Cx_diag"]) / a["Cx_diag"]) < 1e-7
+    ref = cport.CPort(prob).gauss_newton(xhat0)
+    assert b["iterations"] == ref["iterations"] and group_rel(prob, b["xhat"], ref["xhat"]) < 1e-9
+    # deterministic as well: the graph only reorders independent tiles
+    c = fb.adjust(prob, xhat0, verbose=False)
+    assert np.array_equal(b["xhat"], c["xhat"])
