@@ -285,16 +285,18 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end to end through the host-buffer ABI: per step xhat H2D (pinned), iterate, xhat + deltasum D2H
     u_loc = h.u
-    pin_in = torch.empty(u_loc, dtype=torch.float64).pin_memory()
-    pin_out = torch.empty(u_loc, dtype=torch.float64).pin_memory()
-    pin_in.numpy()[:] = h.get_xhat()
-    xin, xout = pin_in.numpy(), pin_out.numpy()
+    pins = [torch.empty(u_loc, dtype=torch.float64).pin_memory() for _ in range(2)]
+    bufs = [p.numpy() for p in pins]
+    bufs[0][:] = h.get_xhat()
+    cur = [0]
 
     def e2e_step():
-        h.set_xhat(xin)
+        # the caller's xhat goes in from pinned host memory, the updated xhat comes back into the
+        # other pinned buffer (main.m:484 keeps xhat on the host between iterations)
+        h.set_xhat(bufs[cur[0]])
         ds = adj.iterate()
-        h.get_xhat(xout)
-        xin[:] = xout
+        h.get_xhat(bufs[1 - cur[0]])
+        cur[0] = 1 - cur[0]
         return ds
 
     for _ in range(2):
