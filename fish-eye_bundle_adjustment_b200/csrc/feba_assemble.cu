@@ -965,13 +965,9 @@ int assemble_warps(const DevProblem& P, int sm_count) { return point_pass_grid(P
 template <int NK, bool HC, int G>
 static cudaError_t launch_point_pass_t(const DevProblem& P, int sm_count, cudaStream_t st) {
     const size_t smem = (128 / G) * sizeof(PtSmem<NK, G>);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_point_pass<NK, HC, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static SmemOptIn opt;
+    cudaError_t e0 = opt.ensure(k_point_pass<NK, HC, G>, smem);
+    if (e0 != cudaSuccess) return e0;
     k_point_pass<NK, HC, G><<<point_pass_grid(P, sm_count), 128, smem, st>>>(P);
     return cudaGetLastError();
 }
@@ -979,13 +975,9 @@ static cudaError_t launch_point_pass_t(const DevProblem& P, int sm_count, cudaSt
 template <int NK, int G>
 static cudaError_t launch_point_pass_mc_t(const DevProblem& P, int sm_count, int* info, cudaStream_t st) {
     const size_t smem = (128 / G) * sizeof(PtSmemMC<NK, G>);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_point_pass_mc<NK, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static SmemOptIn opt;
+    cudaError_t e0 = opt.ensure(k_point_pass_mc<NK, G>, smem);
+    if (e0 != cudaSuccess) return e0;
     k_point_pass_mc<NK, G><<<point_pass_grid(P, sm_count), 128, smem, st>>>(P, info);
     return cudaGetLastError();
 }
@@ -1021,6 +1013,9 @@ cudaError_t launch_assemble(const DevProblem& P, int sm_count, int* info, cudaSt
         }
         if (P.n_blocks > 0) {
             // resident CTAs per SM (measured 1, 2, 4, 8 on config 4: 13.4, 11.3, 12.0, 11.1 ms assembly).
+            // Also tried and rejected: listing the blocks in a locality-preserving (Morton) order of the
+            // camera positions for L2 reuse of the partner records -- no change (8.30 vs 8.22 ms): the
+            // kernel is bound by L1 wavefronts of the record gathers (l1tex 71 % busy), not by DRAM.
             // Tried and rejected: a cooperative gather (nine lanes per 144-byte record, staged through
             // shared memory) -- 19 ms instead of 10.6 ms: the exposed load latency per 32-pair step is
             // not hidden with 12 warps per SM, while the lane-per-record version has all 36 loads of a

@@ -423,18 +423,12 @@ static int chol_skip() {
 static cudaError_t gemm_nt(double* C, int ldc, const double* A, int lda, const double* B, int ldb, int mb,
                            int nbk, int kb, int mode, cudaStream_t st, int64_t* launches) {
     const size_t smem = 2 * GSTAGES * GK * GS * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_nt<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_gemm_nt<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_gemm_nt<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_gemm_nt<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static SmemOptIn o0, o1, o2, o3;
+    cudaError_t e = o0.ensure(k_gemm_nt<0>, smem);
+    if (e == cudaSuccess) e = o1.ensure(k_gemm_nt<1>, smem);
+    if (e == cudaSuccess) e = o2.ensure(k_gemm_nt<2>, smem);
+    if (e == cudaSuccess) e = o3.ensure(k_gemm_nt<3>, smem);
+    if (e != cudaSuccess) return e;
     {
         const long long tiles = (long long)mb * nbk / (mode == 1 || mode == 3 ? 2 : 1);
         if (chol_skip() & (tiles < 256 ? 4 : 8)) return cudaSuccess;
@@ -457,16 +451,10 @@ static cudaError_t gemm_nt(double* C, int ldc, const double* A, int lda, const d
 static cudaError_t rtrsm(double* X, int ldx, double* A, int ld, const double* Linv, int r0, int mr, int c0, int n,
                          cudaStream_t st, int64_t* launches) {
     if (n <= TF_MAX) {
-        static bool configured = false;
-        if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(k_trsm_fused<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)kTrsmFusedSmem);
-            if (e == cudaSuccess)
-                e = cudaFuncSetAttribute(k_trsm_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kTrsmFusedSmem16);
-            if (e != cudaSuccess) return e;
-            configured = true;
-        }
+        static SmemOptIn o64, o16;
+        cudaError_t e0 = o64.ensure(k_trsm_fused<64>, kTrsmFusedSmem);
+        if (e0 == cudaSuccess) e0 = o16.ensure(k_trsm_fused<16>, kTrsmFusedSmem16);
+        if (e0 != cudaSuccess) return e0;
         if (chol_skip() & 2) return cudaSuccess;
         // few row blocks (deep recursion levels): 16-row strips give four times the CTAs
         if (mr <= 74) k_trsm_fused<16><<<mr * 4, 256, kTrsmFusedSmem16, st>>>(X, ldx, A, ld, Linv, r0, c0, n);
@@ -490,12 +478,9 @@ static cudaError_t rchol(double* A, int ld, double* Linv, int b0, int n, int aug
     if (n == 1) {
         if (b0 == aug_blk) return cudaSuccess;
         constexpr size_t psmem = (2 * kBlk * (kBlk + 1) + 3 * 16 * 17 + kBlk) * sizeof(double);
-        static bool configured = false;
-        if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(k_potrf64_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
-            if (e != cudaSuccess) return e;
-            configured = true;
-        }
+        static SmemOptIn opt;
+        cudaError_t e0 = opt.ensure(k_potrf64_inv, psmem);
+        if (e0 != cudaSuccess) return e0;
         if (chol_skip() & 1) return cudaSuccess;
         k_potrf64_inv<<<1, 256, psmem, st>>>(AT(A, ld, b0, b0), ld, LINV(Linv, b0), info);
         ++*launches;

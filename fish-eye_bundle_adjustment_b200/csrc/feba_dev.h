@@ -58,4 +58,21 @@ struct DevProblem {
     double* Gt;                   // inner-constraint rows, compact: (6 n_img) x 8 row-major (col 7 unused)
 };
 
+// Opt-in dynamic shared memory above 48 KB is a per-device function attribute: remember per device
+// (bit i = device i configured) so that handles on several GPUs of one process all work.
+struct SmemOptIn {
+    unsigned long long done = 0;
+    template <typename F>
+    cudaError_t ensure(F func, size_t bytes) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        const unsigned long long bit = 1ull << (dev & 63);
+        if (done & bit) return cudaSuccess;
+        e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e == cudaSuccess) done |= bit;
+        return e;
+    }
+};
+
 }  // namespace feba
