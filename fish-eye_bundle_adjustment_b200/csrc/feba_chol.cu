@@ -129,18 +129,37 @@ __global__ void __launch_bounds__(128) k_gemm_nt(double* __restrict__ C, int ldc
         }
 }
 
+#ifdef FEBA_POTRF_PROF
+__device__ long long g_potrf_prof[32];
+#define POTRF_T(i) do { if (threadIdx.x == 0) g_potrf_prof[i] = clock64(); } while (0)
+#else
+#define POTRF_T(i) do { } while (0)
+#endif
 // ------------------------------------------------------------------------------------------
 // 64x64 Cholesky of a diagonal block (lower) and the inverse of its factor, one CTA of 256 threads,
 // matrix in shared memory, blocked by 16:
-//   for each 16-column panel: (1) 16x16 diagonal factor by half a warp (row per lane, columns
-//   broadcast with shuffles), (2) rows below: X L_kk^-T by substitution, one thread per row,
-//   (3) rank-16 update of the trailing lower triangle spread over the CTA.
+//   for each 16-column panel: (1) 16x16 diagonal factor (row per lane, columns broadcast with
+//   shuffles; every warp does it redundantly so that the shuffles stay in convergent code),
+//   (2) rows below: X L_kk^-T by substitution, one thread per row, (3) rank-16 update of the trailing
+//   lower triangle spread over the CTA.  Phase timings (cycles, scripts/ubench/potrf_bench.cu): load 1.1k,
+//   4 x (diag16 4.9k, panel 0.8k, trailing 2.0/1.8/1.1k), inverse 0.9k + 6.8k, stores 1.5k: 37.8k = 20 us.
 // Then Linv = L^-1: the four 16x16 diagonal blocks by substitution on the identity (one thread per
 // column), the six off-diagonal blocks by block forward substitution
 //   X_ij = -Linv_ii * sum_{k=j}^{i-1} L_ik X_kj      (X_jj = Linv_jj), by block distance 1, 2, 3.
 // Linv (full 64x64, zero upper triangle) lets every later triangular solve with this block run as
 // a DMMA GEMM.  (A thread-per-entry version with predicated register slots needed ~350 SASS
 // instructions per elimination step: 78 us per block, ~15 ms per factorisation at u_c = 12,010.)
+// 1/sqrt(x) for a positive, normally scaled x (the matrix is Jacobi-scaled): single-precision
+// reciprocal square root + two Newton steps in double.  Sits on the pivot-to-pivot dependency chain
+// of the factorisation, where the library rsqrt costs about twice as much.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y = (double)rsqrtf((float)x);
+    const double hx = 0.5 * x;
+    y = y * (1.5 - hx * y * y);
+    y = y * (1.5 - hx * y * y);
+    return y;
+}
+
 __global__ void __launch_bounds__(256) k_potrf64_inv(double* __restrict__ A, int ld, double* __restrict__ Linv,
                                                     int* __restrict__ info) {
     extern __shared__ __align__(16) double psm[];
@@ -149,18 +168,33 @@ __global__ void __launch_bounds__(256) k_potrf64_inv(double* __restrict__ A, int
     double(*sT)[16][17] = reinterpret_cast<double(*)[16][17]>(psm + 2 * kBlk * (kBlk + 1));      // block products
     double* rdiag = psm + 2 * kBlk * (kBlk + 1) + 3 * 16 * 17;                                   // 1 / L_jj
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int q = tid; q < kBlk * kBlk; q += 256) {
-        const int r = q & 63, c = q >> 6;
-        sA[r][c] = (r >= c) ? A[r + (size_t)ld * c] : 0.0;
-        sI[r][c] = 0.0;
+    POTRF_T(0);
+    {
+        // all 16 loads of a thread in flight together (a rolled load->store loop costs one L2 round
+        // trip per iteration: 4.2k of the kernel's 44k cycles)
+        double v[16];
+        const int r = tid & 63, c0 = tid >> 6;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int c = c0 + 4 * t;
+            v[t] = (r >= c) ? A[r + (size_t)ld * c] : 0.0;
+        }
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int c = c0 + 4 * t;
+            sA[r][c] = v[t];
+            sI[r][c] = 0.0;
+        }
     }
     __syncthreads();
+    POTRF_T(1);
     bool bad = false;
 #pragma unroll 1
     for (int kb = 0; kb < 4; ++kb) {
         const int o = 16 * kb;
-        // (1) diagonal block
-        if (warp == 0) {
+        // (1) diagonal block: every warp factorises it redundantly (the shuffles then sit in convergent
+        // code: inside `if (warp == 0)` each one was wrapped in a WARPSYNC.COLLECTIVE sequence), warp 0 stores
+        {
             const int r = lane & 15;
             double d[16];
 #pragma unroll
@@ -169,7 +203,7 @@ __global__ void __launch_bounds__(256) k_potrf64_inv(double* __restrict__ A, int
             for (int j = 0; j < 16; ++j) {
                 const double piv = __shfl_sync(0xffffffffu, d[j], j);
                 if (!(piv > 0.0)) bad = true;
-                const double rs = rsqrt(piv);
+                const double rs = fast_rsqrt(piv);
                 const double l = d[j] * rs;                 // L(r, j) for r >= j
                 d[j] = l;
 #pragma unroll
@@ -178,7 +212,8 @@ __global__ void __launch_bounds__(256) k_potrf64_inv(double* __restrict__ A, int
                     d[c] -= l * lc;                         // rows r < c hold unused values
                 }
             }
-            if (lane < 16) {
+            __syncthreads();                                // every warp has read the block
+            if (warp == 0 && lane < 16) {
 #pragma unroll
                 for (int c = 0; c < 16; ++c)
                     if (c <= r) sA[o + r][o + c] = d[c];
@@ -186,7 +221,9 @@ __global__ void __launch_bounds__(256) k_potrf64_inv(double* __restrict__ A, int
             }
         }
         __syncthreads();
-        // (2) panel below the diagonal block: one thread per row
+        POTRF_T(10 + 3 * kb);
+        // (2) panel below the diagonal block: one thread per row, column-oriented substitution (after
+        // x_j is final the remaining right-hand sides are updated independently: short dependency chain)
         const int nrow = 48 - o;
         if (tid < nrow) {
             const int r = o + 16 + tid;
@@ -195,65 +232,94 @@ __global__ void __launch_bounds__(256) k_potrf64_inv(double* __restrict__ A, int
             for (int c = 0; c < 16; ++c) x[c] = sA[r][o + c];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                double acc = x[j];
+                x[j] *= rdiag[o + j];
 #pragma unroll
-                for (int c = 0; c < j; ++c) acc -= x[c] * sA[o + j][o + c];
-                x[j] = acc * rdiag[o + j];
+                for (int c = j + 1; c < 16; ++c) x[c] -= x[j] * sA[o + c][o + j];
             }
 #pragma unroll
             for (int c = 0; c < 16; ++c) sA[r][o + c] = x[c];
         }
         __syncthreads();
-        // (3) trailing update, lower triangle of the remaining nrow x nrow block
-        const int ntri = nrow * (nrow + 1) / 2;
-        for (int e = tid; e < ntri; e += 256) {
-            int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-            while ((i + 1) * (i + 2) / 2 <= e) ++i;
-            while (i * (i + 1) / 2 > e) --i;
-            const int jj = e - i * (i + 1) / 2;
-            const int r = o + 16 + i, c = o + 16 + jj;
-            double acc = sA[r][c];
+        POTRF_T(11 + 3 * kb);
+        // (3) trailing update, lower triangle of the remaining nrow x nrow block: thread (row i, group g of
+        // 5) keeps its row of the panel in registers and walks the columns jj = g, g+5, ... <= i, two
+        // independent accumulation chains at a time.  (A DMMA version of this update and of the inverse
+        // blocks below was measured slower overall: 42.1k vs 37.8k cycles per block.)
+        if (tid < 5 * nrow) {
+            const int i = tid % nrow, g = tid / nrow;
+            const int r = o + 16 + i;
+            double a[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) acc -= sA[r][o + k] * sA[c][o + k];
-            sA[r][c] = acc;
+            for (int k = 0; k < 16; ++k) a[k] = sA[r][o + k];
+            int jj = g;
+            for (; jj + 5 <= i; jj += 10) {
+                const int c0 = o + 16 + jj, c1 = c0 + 5;
+                double acc0 = sA[r][c0], acc1 = sA[r][c1];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    acc0 -= a[k] * sA[c0][o + k];
+                    acc1 -= a[k] * sA[c1][o + k];
+                }
+                sA[r][c0] = acc0;
+                sA[r][c1] = acc1;
+            }
+            if (jj <= i) {
+                const int c0 = o + 16 + jj;
+                double acc0 = sA[r][c0];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) acc0 -= a[k] * sA[c0][o + k];
+                sA[r][c0] = acc0;
+            }
         }
         __syncthreads();
+        POTRF_T(12 + 3 * kb);
     }
+    POTRF_T(5);
     if (bad && lane == 0) atomicExch(info, 1);
-    for (int q = tid; q < kBlk * kBlk; q += 256) {
-        const int r = q & 63, c = q >> 6;
-        if (r >= c) A[r + (size_t)ld * c] = sA[r][c];
+    {
+        const int r = tid & 63, c0 = tid >> 6;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int c = c0 + 4 * t;
+            if (r >= c) A[r + (size_t)ld * c] = sA[r][c];
+        }
     }
-    // ---- inverse, diagonal blocks: thread (b, c) solves L_bb x = e_c
+    POTRF_T(6);
+    // ---- inverse, diagonal blocks: thread (b, c) solves L_bb x = e_c, column-oriented
     if (tid < 64) {
         const int o = tid & ~15, c = tid & 15;
         double x[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            double acc = (i == c) ? 1.0 : 0.0;
+        for (int i = 0; i < 16; ++i) x[i] = (i == c) ? 1.0 : 0.0;
 #pragma unroll
-            for (int k = 0; k < i; ++k) acc -= sA[o + i][o + k] * x[k];
-            x[i] = (i < c) ? 0.0 : acc * rdiag[o + i];
+        for (int i = 0; i < 16; ++i) {
+            x[i] *= rdiag[o + i];
+#pragma unroll
+            for (int i2 = i + 1; i2 < 16; ++i2) x[i2] -= sA[o + i2][o + i] * x[i];
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) sI[o + i][o + c] = x[i];
     }
     __syncthreads();
-    // ---- off-diagonal blocks by block distance dist = i - j
+    POTRF_T(7);
+    // ---- off-diagonal blocks by block distance dist = i - j (fully unrolled: every bound is static, so
+    // the shared-memory loads of a dot product are issued together instead of one round trip per term)
     const int er = tid >> 4, ec = tid & 15;            // one entry of a 16x16 block per thread
-#pragma unroll 1
+#pragma unroll
     for (int dist = 1; dist <= 3; ++dist) {
-        const int nblk = 4 - dist;
         // T_ij = sum_{k=j}^{i-1} L_ik X_kj
-        for (int bj = 0; bj < nblk; ++bj) {
+#pragma unroll
+        for (int bj = 0; bj < 4 - dist; ++bj) {
             const int bi = bj + dist;
             double acc = 0.0;
+#pragma unroll
             for (int k = 16 * bj; k < 16 * bi; ++k) acc += sA[16 * bi + er][k] * sI[k][16 * bj + ec];
             sT[bj][er][ec] = acc;
         }
         __syncthreads();
         // X_ij = -Linv_ii T_ij
-        for (int bj = 0; bj < nblk; ++bj) {
+#pragma unroll
+        for (int bj = 0; bj < 4 - dist; ++bj) {
             const int bi = bj + dist;
             double acc = 0.0;
 #pragma unroll
@@ -262,10 +328,16 @@ __global__ void __launch_bounds__(256) k_potrf64_inv(double* __restrict__ A, int
         }
         __syncthreads();
     }
-    for (int q = tid; q < kBlk * kBlk; q += 256) {
-        const int r = q & 63, c = q >> 6;
-        Linv[r + (size_t)kBlk * c] = sI[r][c];
+    POTRF_T(8);
+    {
+        const int r = tid & 63, c0 = tid >> 6;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int c = c0 + 4 * t;
+            Linv[r + (size_t)kBlk * c] = sI[r][c];
+        }
     }
+    POTRF_T(9);
 }
 
 // ------------------------------------------------------------------------------------------
