@@ -456,3 +456,46 @@ def test_task_graph_factorisation_matches_recursive_form(monkeypatch):
     # deterministic as well: the graph only reorders independent tiles
     c = fb.adjust(prob, xhat0, verbose=False)
     assert np.array_equal(b["xhat"], c["xhat"])
+
+
+@pytest.mark.parametrize("variant", ["sigma_y", "y_dir_plus", "NK1", "NK8"])
+def test_setting_variants(variant):
+    """Settings the reference reads that the other tests leave at their defaults: Meas_std_y (weights,
+    main.m:397-402), y_dir = +1 (main.m:331-337), Num_Radial_Distortions 1 and 8."""
+    NK = {"NK1": 1, "NK8": 8}.get(variant, 5)
+    prob = synth.make_network(12, 500, 7, 808, NK=min(NK, 5), mode="mixed", n_control=40)
+    if NK == 8:      # three more (zero) radial terms than the generator's truth
+        prob.settings.Num_Radial_Distortions = 8
+        prob.iop0 = np.concatenate([prob.iop0[:, :8], np.zeros((1, 3)), prob.iop0[:, 8:]], axis=1)
+    if variant == "sigma_y":
+        prob.settings.Meas_std_y = 0.45
+    if variant == "y_dir_plus":
+        # mirror the image y axis about yp: y_dir = +1 with y -> 2 yp - y is the same geometry
+        prob.cam_box = prob.cam_box.copy()
+        prob.cam_box[:, 0] = 1.0
+        prob.obs_y = 2 * prob.iop0[0, 1] - prob.obs_y
+    err, xhat0, _ = fb.Buildxhat(prob)
+    ref = sparse.gauss_newton(prob, xhat0)
+    assert ref["iterations"] < prob.settings.Iteration_Cap
+    out = fb.adjust(prob, xhat0, verbose=False)
+    assert out["iterations"] == ref["iterations"], variant
+    assert np.max(np.abs(out["v"] - ref["v"])) < 1e-8 * np.max(np.abs(ref["v"])), variant
+    assert abs(out["sigma02"] - ref["sigma02"]) < 1e-8 * ref["sigma02"], variant
+    assert group_rel(prob, out["xhat"], ref["xhat"]) < 1e-9, variant
+    assert abs(out["RMSx"] - ref["RMSx"]) < 1e-9 and abs(out["RMSy"] - ref["RMSy"]) < 1e-9
+
+
+@pytest.mark.parametrize("typ", ["equisolid", "orthographic", "stereographic"])
+def test_other_projection_types_full_run_with_inner_constraints(typ):
+    """The three remaining projection models (BuildAwG.m:196-207) through the whole loop with inner
+    constraints and tie points, on the bundled data."""
+    prob = golden.load_cam0(type=typ, inner=1)
+    err, xhat0, _ = fb.Buildxhat(prob)
+    ref = sparse.gauss_newton(prob, xhat0)
+    out = fb.adjust(prob, xhat0, verbose=False)
+    assert out["iterations"] == ref["iterations"]
+    assert np.max(np.abs(out["v"] - ref["v"])) < 1e-8 * np.max(np.abs(ref["v"]))
+    assert abs(out["sigma02"] - ref["sigma02"]) < 1e-8 * ref["sigma02"]
+    L = model.layout(prob)
+    iop = slice(L["off_cam"], L["off_cam"] + 3)
+    assert np.max(np.abs(out["xhat"][iop] - ref["xhat"][iop]) / np.abs(ref["xhat"][iop])) < 1e-9
