@@ -15,7 +15,11 @@ ap.add_argument("--cov", action="store_true")
 a = ap.parse_args()
 prob = fb.synth.baseline_config(a.workload, scale=a.scale)
 err, x0, _ = fb.Buildxhat(prob)
-with fb.Handle(prob) as h:
+import time as _t
+_t0 = _t.perf_counter()
+_h = fb.Handle(prob)
+print(f"feba_create (sort by point, uploads, pair schedule): {1e3 * (_t.perf_counter() - _t0):.1f} ms", flush=True)
+with _h as h:
     h.set_xhat(x0)
     for i in range(a.iters):
         try:
