@@ -323,6 +323,7 @@ def run_ours(args, rank, world, local_rank):
     st = prob.settings
     sigma02 = float((ss[0] / st.sigma_x ** 2 + ss[1] / st.sigma_y ** 2).item()) / (2 * prob.n_obs - prob.u)
 
+    h.close()                                   # every rank: the handle may hold a communicator
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -362,7 +363,10 @@ def run_ours(args, rank, world, local_rank):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "desc": desc, "n_obs": prob.n_obs, "n_img": prob.numImg,
                    "n_pts": prob.numPts, "u": prob.u, "u_c": prob.u_c, "inner_constraints": prob.settings.Inner_Constraints,
-                   "type": prob.settings.type, "parallelism": f"point-sharded x{world}" if world > 1 else "single GPU",
+                   "type": prob.settings.type, "parallelism": (f"point-sharded assembly x{world}, all-reduce of the reduced system, "
+                                   + ("replicated factorisation" if os.environ.get("FEBA_DIST_CHOL", "1") == "0"
+                                      else "column-cyclic shared factorisation (panel broadcasts)"))
+                   if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (observations + reduced system > 126 MB); no flush needed"},
         "e2e": {"value": e2e_val, "unit": "obs/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(8 * u_loc),
                 "d2h_bytes_per_step": int(8 * u_loc + 16)},
@@ -372,7 +376,6 @@ def run_ours(args, rank, world, local_rank):
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
-    h.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -495,6 +498,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: libraries that print there on their own (NCCL's version
+    # banner at communicator creation) are sent to stderr; print() keeps the real stdout
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args, rank)
         return

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfeba.so")
-SOURCES = ("feba_api.cu", "feba_kernels.cu", "feba_assemble.cu", "feba_chol.cu")
+SOURCES = ("feba_api.cu", "feba_kernels.cu", "feba_assemble.cu", "feba_chol.cu", "feba_dist.cu", "feba_green.cu")
 HEADERS = ("feba_dev.h", "feba_kernels.h", "feba_model.cuh", os.path.join("..", "..", "include", "feba.h"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall", "--use_fast_math=false"]
@@ -50,7 +50,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     for cmd, pr in procs:
         if pr.wait() != 0:
             raise subprocess.CalledProcessError(pr.returncode, cmd)
-    subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart"],
+    subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"],
                    check=True)
     return LIB
 

@@ -42,6 +42,9 @@ struct feba_handle {
     DagStreams dag;               // task-graph factorisation (large reduced systems)
     std::vector<cudaEvent_t> dag_events;
     bool use_dag = false;
+    DistCtx dist;                 // group of GPUs factorising together (feba_dist_init)
+    GreenPair green;              // SM partitions of the task graph (chain | bulk), optional
+    bool dist_active = false;
     double *scal = nullptr;       // [0] sumabs camera part, [1] sumabs points, [2] sum vx^2, [3] sum vy^2
     double *v_out = nullptr, *rsd_out = nullptr, *delta_out = nullptr;
     int *opt = nullptr, *tie_pt = nullptr, *info = nullptr;
@@ -122,6 +125,16 @@ cudaError_t upload(feba_handle* h, T** p, const T* src, size_t count) {
     return e;
 }
 
+// Stream of the task-graph pool: slot 0 (panel chain) lives in the chain partition when the device
+// is split, all others in the bulk partition.
+cudaError_t pool_stream(feba_handle* h, int slot, int priority, cudaStream_t* out) {
+    if (h->green.chain) {
+        if (green_stream(slot == 0 ? h->green.chain : h->green.bulk, priority, out) == 0) return cudaSuccess;
+        return cudaErrorNotSupported;
+    }
+    return cudaStreamCreateWithPriority(out, cudaStreamNonBlocking, priority);
+}
+
 int check_settings(const feba_problem* pr) {
     const feba_settings& s = pr->settings;
     if (s.type < 0 || s.type > 4)
@@ -160,7 +173,11 @@ void feba_destroy(feba_handle* h) {
         cudaStreamDestroy(h->dag.streams[s2]);
         if (h->dag.join[s2]) cudaEventDestroy(h->dag.join[s2]);
     }
+    if (h->dag.join[h->dag.n_streams]) cudaEventDestroy(h->dag.join[h->dag.n_streams]);
     if (h->dag.fork) cudaEventDestroy(h->dag.fork);
+    green_destroy(&h->green);
+    if (h->dist.comm) dist_comm_destroy(&h->dist);
+    if (h->dist.stream) cudaStreamDestroy(h->dist.stream);
     for (auto& ev : h->dag_events)
         if (ev) cudaEventDestroy(ev);
     for (auto& e : h->ev)
@@ -378,8 +395,18 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
             h->dag.tile_blocks = T;
             int lo = 0, hi = 0;
             CU(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            // FEBA_GREEN_SMS=r: r SMs (multiple of 8) are set aside for the panel chain, 0 = shared GPU
+            const char* e_g = std::getenv("FEBA_GREEN_SMS");
+            const int reserve = e_g ? std::atoi(e_g) : 0;
+            if (reserve > 0) {
+                char why[128];
+                if (green_create(h->device, reserve, &h->green, why, sizeof(why)) != 0 && std::getenv("FEBA_VERBOSE"))
+                    fprintf(stderr, "[feba] %s; the task graph shares the whole GPU\n", why);
+                else if (std::getenv("FEBA_VERBOSE"))
+                    fprintf(stderr, "[feba] SM partitions: chain %d, bulk %d\n", h->green.chain_sms, h->green.bulk_sms);
+            }
             for (int s2 = 0; s2 < NS; ++s2) {
-                CU(h, cudaStreamCreateWithPriority(&h->dag.streams[s2], cudaStreamNonBlocking, s2 == 0 ? hi : lo));
+                CU(h, pool_stream(h, s2, s2 == 0 ? hi : lo, &h->dag.streams[s2]));
                 ++h->dag.n_streams;
                 CU(h, cudaEventCreateWithFlags(&h->dag.join[s2], cudaEventDisableTiming));
             }
@@ -420,6 +447,37 @@ int feba_set_stream(feba_handle* h, void* stream) {
     h->own_stream = false;
     // stream capture is not permitted on the legacy default stream: run eagerly there
     if (h->stream == nullptr || h->stream == cudaStreamLegacy) h->use_graph = false;
+    return FEBA_OK;
+}
+
+int feba_dist_unique_id(void* id, size_t bytes) {
+    if (!id || bytes != FEBA_DIST_ID_BYTES) return fail(nullptr, FEBA_ERR_INVALID, "id buffer must be %d bytes", FEBA_DIST_ID_BYTES);
+    if (dist_unique_id(id)) return fail(nullptr, FEBA_ERR_CUDA, "%s", dist_load_error());
+    return FEBA_OK;
+}
+
+int feba_dist_init(feba_handle* h, int32_t rank, int32_t world, const void* id, size_t bytes) {
+    if (!h || !id || bytes != FEBA_DIST_ID_BYTES || world < 1 || rank < 0 || rank >= world)
+        return fail(h, FEBA_ERR_INVALID, "feba_dist_init: bad arguments");
+    if (h->dist.comm) return fail(h, FEBA_ERR_STATE, "feba_dist_init called twice");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    // the communicator is created by every rank even when this problem keeps the replicated solve
+    if (dist_comm_init(&h->dist, rank, world, id)) return fail(h, FEBA_ERR_CUDA, "%s", h->dist.err);
+    if (!h->use_dag || world == 1 || h->dag.n_streams < 6) return FEBA_OK;
+    drop_graphs(h);
+    int lo = 0, hi = 0;
+    CU(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    for (int s2 = 1; s2 <= 3; ++s2) {            // panel streams: high priority like the critical-path stream
+        CU(h, cudaStreamDestroy(h->dag.streams[s2]));
+        CU(h, pool_stream(h, s2, hi, &h->dag.streams[s2]));
+    }
+    CU(h, cudaStreamCreateWithPriority(&h->dist.stream, cudaStreamNonBlocking, hi));
+    CU(h, cudaEventCreateWithFlags(&h->dag.join[h->dag.n_streams], cudaEventDisableTiming));
+    const size_t tile = (size_t)h->dag.tile_blocks * kBlk;
+    CU(h, dev_alloc(h, &h->dist.staging, tile * tile));
+    h->dist.staging_count = tile * tile;
+    h->dist_active = true;
     return FEBA_OK;
 }
 
@@ -533,7 +591,11 @@ static int enqueue_solve(feba_handle* h) {
     DevProblem& P = h->P;
     CU(h, launch_border_scale(P, h->eop, h->dvec, h->info, h->stream, &h->launches));
     const int nb = P.n_pad / kBlk;
-    if (h->use_dag) CU(h, chol_dag(P.S, P.ld, nb, h->Linv, h->info, h->dag, h->stream, &h->launches));
+    if (h->dist_active) {
+        const cudaError_t ed = chol_dag_dist(P.S, P.ld, nb, h->Linv, h->info, h->dag, h->dist, h->stream, &h->launches);
+        if (ed == cudaErrorUnknown && h->dist.err[0]) return fail(h, FEBA_ERR_CUDA, "%s", h->dist.err);
+        CU(h, ed);
+    } else if (h->use_dag) CU(h, chol_dag(P.S, P.ld, nb, h->Linv, h->info, h->dag, h->stream, &h->launches));
     else CU(h, chol_augmented(P.S, P.ld, nb, h->Linv, h->info, h->stream, &h->launches));
     CU(h, record(h, 3));
     CU(h, border_and_backsolve(P.S, P.ld, nb, h->Linv, P.inner, h->work, h->ywork, h->sol, h->info, h->sm_count,

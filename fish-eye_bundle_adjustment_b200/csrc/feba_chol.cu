@@ -585,6 +585,13 @@ cudaError_t chol_augmented(double* A, int ld, int nb, double* Linv, int* info, c
 // bulk updates of step k.  Stream 0 has high priority and carries the critical path
 // (DIAG(k), TRSM(k+1,k), UPDATE(k+1,k+1,k)).  Captured into the iteration's CUDA graph like everything
 // else, the events become graph edges.
+// FEBA_UPD1_BULK=1: the first update of the next diagonal tile runs with the bulk updates (same CTA
+// footprint, so stream priority is effective there) instead of on the chain stream.
+static bool upd1_bulk() {
+    static const bool v = std::getenv("FEBA_UPD1_BULK") != nullptr;
+    return v;
+}
+
 cudaError_t chol_dag(double* A, int ld, int nb, double* Linv, int* info, const DagStreams& D, cudaStream_t main,
                      int64_t* launches) {
     const int T = D.tile_blocks;
@@ -636,7 +643,7 @@ cudaError_t chol_dag(double* A, int ld, int nb, double* Linv, int* info, const D
                 } else if (j >= NT) {
                     continue;
                 }
-                const int sid = (i == k + 1 && j == k + 1) ? 0 : stream_of(i, j);
+                const int sid = (i == k + 1 && j == k + 1 && !upd1_bulk()) ? 0 : stream_of(i, j);
                 DAG_CU(acquire(sid, i, k));
                 DAG_CU(acquire(sid, j, k));
                 DAG_CU(acquire(sid, i, j));
@@ -652,6 +659,166 @@ cudaError_t chol_dag(double* A, int ld, int nb, double* Linv, int* info, const D
         if (e != cudaSuccess) return e;
         e = cudaStreamWaitEvent(main, D.join[s], 0);
         if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// ------------------------------------------------------------------------------------------
+// The same task graph over a group of GPUs (one process each).  Supertile column k
+// belongs to rank k % world (1-D block-cyclic): its owner runs DIAG(k) and TRSM(.,k) and broadcasts
+// each finished tile; every rank applies UPDATE(i,j,k) to the columns j it owns (the 64-row augmented
+// diagonal block is updated by everybody -- it is tiny and all ranks need it).  Collectives need
+// contiguous buffers and one issue order per communicator: all of them go through dist.stream in
+// program order, a tile is packed into dist.staging by a strided device copy, broadcast, and unpacked
+// on the receivers.  Streams 0..3 of the pool have high priority: 0 carries the critical path, 1..3
+// the rest of the panel (TRSM and the look-ahead updates of the next panel); 4.. the bulk updates.
+cudaError_t chol_dag_dist(double* A, int ld, int nb, double* Linv, int* info, const DagStreams& D, DistCtx& dist,
+                          cudaStream_t main, int64_t* launches) {
+    const int T = D.tile_blocks;
+    const int NT = (nb + T - 1) / T;
+    const int NR = NT + 1;
+    auto blk0 = [&](int t) { return t == NT ? nb : t * T; };
+    auto nblk = [&](int t) { return t == NT ? 1 : (t == NT - 1 ? nb - T * (NT - 1) : T); };
+    if (NR * NR > D.n_events || D.n_streams < 6 || !dist.comm) return cudaErrorInvalidValue;
+    const int COMM = D.n_streams;                     // pseudo stream id of dist.stream
+    auto S = [&](int sid) { return sid == COMM ? dist.stream : D.streams[sid]; };
+    std::vector<int> last(NR * NR, -1);
+    auto tid = [&](int i, int j) { return i * NR + j; };
+    auto panel_stream = [&](int i) { return 1 + i % 3; };
+    auto bulk_stream = [&](int i, int j) { return 4 + (i * 3 + j * 7) % (D.n_streams - 4); };
+    auto owner = [&](int k) { return k % dist.world; };
+    // FEBA_DIST_PROF=1 (eager runs only): time stamps of the panel chain and of the collectives
+    static const bool prof_env = std::getenv("FEBA_DIST_PROF") != nullptr;
+    static int prof_calls = 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(main, &cap);
+    const bool prof = prof_env && cap == cudaStreamCaptureStatusNone && ++prof_calls == 3;
+    std::vector<cudaEvent_t> pev;
+    auto mark = [&](int sid) -> int {
+        if (!prof) return -1;
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        cudaEventRecord(ev, sid < 0 ? main : S(sid));
+        pev.push_back(ev);
+        return (int)pev.size() - 1;
+    };
+    std::vector<int> pm((size_t)NT * 6, -1);
+    const int m_fork = mark(-1);
+    cudaError_t e = cudaEventRecord(D.fork, main);
+    if (e != cudaSuccess) return e;
+    for (int s = 0; s <= COMM; ++s) {
+        e = cudaStreamWaitEvent(S(s), D.fork, 0);
+        if (e != cudaSuccess) return e;
+    }
+    auto acquire = [&](int sid, int i, int j) -> cudaError_t {
+        const int w = last[tid(i, j)];
+        if (w >= 0 && w != sid) return cudaStreamWaitEvent(S(sid), D.events[tid(i, j)], 0);
+        return cudaSuccess;
+    };
+    auto release = [&](int sid, int i, int j) -> cudaError_t {
+        last[tid(i, j)] = sid;
+        return cudaEventRecord(D.events[tid(i, j)], S(sid));
+    };
+#define DAG_CU(x)                 \
+    do {                          \
+        e = (x);                  \
+        if (e != cudaSuccess) return e; \
+    } while (0)
+    // finished tile (i,k): owner -> everybody
+    auto share_tile = [&](int i, int k) -> cudaError_t {
+        const size_t rows = (size_t)nblk(i) * kBlk, cols = (size_t)nblk(k) * kBlk;
+        double* tile = AT(A, ld, blk0(i), blk0(k));
+        const bool root = owner(k) == dist.rank;
+        if (rows * cols > dist.staging_count) return cudaErrorInvalidValue;
+        if (root) {
+            DAG_CU(acquire(COMM, i, k));
+            DAG_CU(cudaMemcpy2DAsync(dist.staging, rows * sizeof(double), tile, (size_t)ld * sizeof(double),
+                                     rows * sizeof(double), cols, cudaMemcpyDeviceToDevice, dist.stream));
+        }
+        if (dist_bcast_f64(&dist, dist.staging, rows * cols, owner(k), dist.stream)) return cudaErrorUnknown;
+        if (!root) {
+            DAG_CU(cudaMemcpy2DAsync(tile, (size_t)ld * sizeof(double), dist.staging, rows * sizeof(double),
+                                     rows * sizeof(double), cols, cudaMemcpyDeviceToDevice, dist.stream));
+            DAG_CU(release(COMM, i, k));
+        }
+        return cudaSuccess;
+    };
+    auto share_diag = [&](int k) -> cudaError_t {
+        DAG_CU(share_tile(k, k));
+        if (dist_bcast_f64(&dist, LINV(Linv, blk0(k)), (size_t)nblk(k) * kBlk * kBlk, owner(k), dist.stream))
+            return cudaErrorUnknown;
+        return cudaSuccess;
+    };
+    static const int diag_order = std::getenv("FEBA_DIST_DIAG") ? std::atoi(std::getenv("FEBA_DIST_DIAG")) : 0;
+    for (int k = 0; k < NT; ++k) {
+        const bool mine = owner(k) == dist.rank;
+        if (mine) {
+            DAG_CU(acquire(0, k, k));
+            pm[k * 6 + 0] = mark(0);
+            DAG_CU(rchol(A, ld, Linv, blk0(k), nblk(k), -1, info, D.streams[0], launches));
+            DAG_CU(release(0, k, k));
+            pm[k * 6 + 1] = mark(0);
+            for (int i = k + 1; i < NR; ++i) {
+                const int sid = (i == k + 1) ? 0 : panel_stream(i);
+                DAG_CU(acquire(sid, k, k));
+                DAG_CU(acquire(sid, i, k));
+                DAG_CU(rtrsm(A, ld, A, ld, Linv, blk0(i), nblk(i), blk0(k), nblk(k), D.streams[sid], launches));
+                DAG_CU(release(sid, i, k));
+                if (i == k + 1) pm[k * 6 + 2] = mark(0);
+            }
+        }
+        // the tile the next panel waits for goes first; the diagonal tiles and the inverted diagonal
+        // factors are only read by the backward solve and follow after the last panel
+        for (int i = k + 1; i < NR; ++i) {
+            if (i == k + 1) pm[k * 6 + 3] = mark(COMM);
+            DAG_CU(share_tile(i, k));
+            if (i == k + 1) pm[k * 6 + 4] = mark(COMM);
+            if (i == k + 1 && diag_order == 1) DAG_CU(share_diag(k));
+        }
+        if (diag_order == 0) DAG_CU(share_diag(k));
+        pm[k * 6 + 5] = mark(COMM);
+        for (int j = k + 1; j < NR; ++j) {
+            if (j < NT && owner(j) != dist.rank) continue;
+            for (int i = j; i < NR; ++i) {
+                if (j == NT && i != NT) continue;
+                const int sid = (i == k + 1 && j == k + 1) ? (upd1_bulk() ? 1 : 0)
+                                                           : (j == k + 1 && j < NT ? panel_stream(i) : bulk_stream(i, j));
+                DAG_CU(acquire(sid, i, k));
+                DAG_CU(acquire(sid, j, k));
+                DAG_CU(acquire(sid, i, j));
+                DAG_CU(gemm_nt(AT(A, ld, blk0(i), blk0(j)), ld, AT(A, ld, blk0(i), blk0(k)), ld,
+                               AT(A, ld, blk0(j), blk0(k)), ld, nblk(i), nblk(j), nblk(k), i == j ? 1 : 0,
+                               D.streams[sid], launches));
+                DAG_CU(release(sid, i, j));
+            }
+        }
+    }
+    if (diag_order == 2)
+        for (int k = 0; k < NT; ++k) DAG_CU(share_diag(k));
+#undef DAG_CU
+    for (int s = 0; s <= COMM; ++s) {
+        e = cudaEventRecord(D.join[s], S(s));
+        if (e != cudaSuccess) return e;
+        e = cudaStreamWaitEvent(main, D.join[s], 0);
+        if (e != cudaSuccess) return e;
+    }
+    // a failed pivot is only seen by the owner of that column
+    if (dist_allreduce_max_i32(&dist, info, 1, main)) return cudaErrorUnknown;
+    if (prof) {
+        const int m_end = mark(-1);
+        cudaStreamSynchronize(main);
+        auto at = [&](int m) {
+            float ms = -1.f;
+            if (m >= 0) cudaEventElapsedTime(&ms, pev[m_fork], pev[m]);
+            return ms;
+        };
+        fprintf(stderr, "[feba dist prof] rank %d/%d T=%d NT=%d total %.3f ms\n", dist.rank, dist.world, T, NT, at(m_end));
+        fprintf(stderr, "[feba dist prof] rank k owner | diag_start diag_end trsm1_end | first_tile_in first_tile_out column_out (ms after fork)\n");
+        for (int k = 0; k < NT; ++k)
+            fprintf(stderr, "[feba dist prof] %d %2d %d | %8.3f %8.3f %8.3f | %8.3f %8.3f %8.3f\n", dist.rank, k, owner(k),
+                    at(pm[k * 6 + 0]), at(pm[k * 6 + 1]), at(pm[k * 6 + 2]), at(pm[k * 6 + 3]), at(pm[k * 6 + 4]),
+                    at(pm[k * 6 + 5]));
+        for (cudaEvent_t ev : pev) cudaEventDestroy(ev);
     }
     return cudaSuccess;
 }

@@ -45,12 +45,48 @@ struct DagStreams {
     int n_streams = 0;              // streams[0] has high priority (critical path)
     cudaStream_t streams[16] = {};
     cudaEvent_t fork = nullptr;
-    cudaEvent_t join[16] = {};
+    cudaEvent_t join[17] = {};         // [n_streams] belongs to the collective stream of a group run
     cudaEvent_t* events = nullptr;  // one per tile (row supertile, column supertile)
     int n_events = 0;
 };
 cudaError_t chol_dag(double* A, int ld, int nb, double* Linv, int* info, const DagStreams& D, cudaStream_t main,
                      int64_t* launches);
+
+// feba_green.cu -- two disjoint SM partitions of one device (green contexts): `chain` for the panel
+// chain of the factorisation, `bulk` for its trailing updates.  -1 when the driver cannot provide them.
+struct GreenPair {
+    void* chain = nullptr;
+    void* bulk = nullptr;
+    int chain_sms = 0, bulk_sms = 0;
+};
+int green_create(int device, int reserve_sms, GreenPair* out, char* err, size_t errlen);
+int green_stream(void* gctx, int priority, cudaStream_t* out);
+void green_destroy(GreenPair* g);
+
+// feba_dist.cu -- one rank of a group of GPUs that factorise the reduced system together.
+struct DistCtx {
+    int rank = 0, world = 1;
+    void* comm = nullptr;            // ncclComm_t
+    cudaStream_t stream = nullptr;   // every collective of the factorisation is issued here, in program order
+    double* staging = nullptr;       // one supertile, contiguous (collectives need contiguous buffers)
+    size_t staging_count = 0;
+    char err[256] = {0};
+};
+const char* dist_load_error();
+int dist_unique_id(void* id128);
+int dist_comm_init(DistCtx* D, int rank, int world, const void* id128);
+void dist_comm_destroy(DistCtx* D);
+int dist_bcast_f64(DistCtx* D, double* buf, size_t count, int root, cudaStream_t st);
+int dist_reduce_f64(DistCtx* D, double* buf, size_t count, int root, cudaStream_t st);
+int dist_allreduce_f64(DistCtx* D, double* buf, size_t count, cudaStream_t st);
+int dist_allreduce_max_i32(DistCtx* D, int* buf, size_t count, cudaStream_t st);
+int dist_group_start();
+int dist_group_end(DistCtx* D);
+// Column-cyclic distributed form of chol_dag: supertile column k belongs to rank k % world, which
+// factorises it (DIAG, TRSM) and broadcasts the finished tiles; every rank applies the updates of its
+// own columns.  On return every rank holds the whole factor.  cudaErrorUnknown: see dist.err.
+cudaError_t chol_dag_dist(double* A, int ld, int nb, double* Linv, int* info, const DagStreams& D, DistCtx& dist,
+                          cudaStream_t main, int64_t* launches);
 // ywork (n_pad) := combination of the augmented rows: y = Y'(0,:) + sum_k kvec[k] Y'(1+k,:) where kvec
 // solves the 7x7 border system (inner != 0), else y = Y'(0,:).  Then sol := L^-T y.
 cudaError_t border_and_backsolve(double* A, int ld, int nb, const double* Linv, int inner, double* work,

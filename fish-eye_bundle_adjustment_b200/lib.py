@@ -25,7 +25,20 @@ EXPORTS = (
     "feba_set_xhat", "feba_get_xhat", "feba_iterate", "feba_iterate_assemble", "feba_reduced_dev",
     "feba_iterate_solve", "feba_get_delta", "feba_residuals", "feba_solve", "feba_last_timing",
     "feba_launch_count", "feba_debug_reduced", "feba_cov_prepare", "feba_cov_diag", "feba_cov_block", "feba_iterate_async", "feba_iterate_solve_async", "feba_sync",
+    "feba_dist_unique_id", "feba_dist_init",
 )
+
+
+DIST_ID_BYTES = 128
+
+
+def dist_unique_id() -> bytes:
+    """feba_dist_unique_id: the token one rank creates and every rank passes to ``Handle.dist_init``."""
+    lib = load()
+    buf = C.create_string_buffer(DIST_ID_BYTES)
+    if lib.feba_dist_unique_id(buf, DIST_ID_BYTES) != 0:
+        raise FebaError(3, (lib.feba_last_error(None) or b"").decode())
+    return buf.raw
 
 
 class FebaSettings(C.Structure):
@@ -93,6 +106,8 @@ def load() -> C.CDLL:
     lib.feba_iterate_async.argtypes = [H]
     lib.feba_iterate_solve_async.argtypes = [H]
     lib.feba_sync.argtypes = [H, _pd]
+    lib.feba_dist_unique_id.argtypes = [C.c_void_p, C.c_size_t]
+    lib.feba_dist_init.argtypes = [H, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t]
     _lib = lib
     return lib
 
@@ -214,6 +229,12 @@ class Handle:
         p, n = C.c_void_p(), C.c_size_t()
         self._check(self._lib.feba_reduced_dev(self._h, C.byref(p), C.byref(n)))
         return int(p.value), int(n.value)
+
+    def dist_init(self, rank: int, world: int, unique_id: bytes):
+        """Join a group of handles (one per GPU/process) that factorise the reduced system together
+        (feba_dist_init; collective).  ``unique_id`` comes from ``dist_unique_id()`` on one rank."""
+        buf = C.create_string_buffer(bytes(unique_id), DIST_ID_BYTES)
+        self._check(self._lib.feba_dist_init(self._h, rank, world, buf, DIST_ID_BYTES))
 
     def iterate_solve(self):
         a, b = C.c_double(), C.c_double()

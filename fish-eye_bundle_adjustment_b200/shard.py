@@ -7,6 +7,8 @@ Schur contribution local; the camera-block sums are additive.  Per iteration:
     rank r:  feba_iterate_assemble()            partial S_r, g_r of its points
     all   :  all_reduce(sum) of the reduced-system buffer (NCCL over NVLink; gloo in CPU tests)
     rank r:  feba_iterate_solve()               identical EOP/IOP update everywhere, own points
+             (with feba_dist_init the factorisation inside is shared: supertile columns are dealt
+              out over the ranks, finished panels are broadcast; see csrc/feba_chol.cu)
     all   :  all_reduce(sum) of sum|delta_points|  -> deltasum of main.m:487
 
 No other exchange exists on the path.  ``shard_problem`` is host-side index bookkeeping only.
@@ -14,6 +16,7 @@ No other exchange exists on the path.  ``shard_problem`` is host-side index book
 from __future__ import annotations
 
 import copy
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -105,6 +108,15 @@ class ShardedAdjustment:
             ptr, count = handle.reduced_dev()
             self._red = torch.as_tensor(DeviceBuffer(ptr, count), device=torch.device("cuda", torch.cuda.current_device()))
             self._scal = torch.zeros(1, dtype=torch.float64, device=self._red.device)
+            # factorise the summed system together (feba_dist_init) instead of once per rank;
+            # FEBA_DIST_CHOL=0 keeps the replicated solve
+            if os.environ.get("FEBA_DIST_CHOL", "1") != "0" and dist.get_backend(group) == "nccl":
+                from .lib import dist_unique_id
+                rank = dist.get_rank(group)
+                src = dist.get_global_rank(group, 0) if group is not None else 0
+                ids = [dist_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(ids, src=src, group=group)
+                handle.dist_init(rank, self.world, ids[0])
 
     def iterate(self) -> float:
         """One pass of main.m:412-494 over all ranks; returns the global deltasum."""

@@ -121,6 +121,19 @@ int feba_iterate_assemble(feba_handle *h);
 int feba_reduced_dev(feba_handle *h, double **dev_ptr, size_t *count);
 int feba_iterate_solve(feba_handle *h, double *deltasum_cam, double *deltasum_pts);
 
+/* Optional: let the ranks factorise the summed reduced system TOGETHER instead of each rank
+ * repeating it (the factorisation is ~70 % of an iteration at u_c = 12,010 and does not shrink with
+ * the point shards).  Rank 0 obtains an id, the caller ships the FEBA_DIST_ID_BYTES bytes to every
+ * rank (MPI_Bcast, torch.distributed.broadcast, a file ...), then every rank calls feba_dist_init on
+ * its handle -- collectively, like ncclCommInitRank, which it wraps.  After that feba_iterate_solve
+ * is collective too: supertile columns of the reduced matrix are dealt out cyclically, each owner
+ * factorises its panel and broadcasts it (NCCL, loaded at run time from libnccl.so.2 or
+ * $FEBA_NCCL_LIB), all ranks end with the same factor and the same EOP/IOP update.  Results are the
+ * ones of the replicated solve; small reduced systems (< 96 blocks of 64) keep the replicated solve. */
+#define FEBA_DIST_ID_BYTES 128
+int feba_dist_unique_id(void *id, size_t bytes);
+int feba_dist_init(feba_handle *h, int32_t rank, int32_t world, const void *id, size_t bytes);
+
 /* Last increment delta (un-scaled, main.m:458-482), length u. */
 int feba_get_delta(feba_handle *h, double *delta, size_t u);
 
