@@ -45,6 +45,8 @@ struct feba_handle {
     DistCtx dist;                 // group of GPUs factorising together (feba_dist_init)
     GreenPair green;              // SM partitions of the task graph (chain | bulk), optional
     bool dist_active = false;
+    bool dag_cols = false;        // column form of the task graph (chol_cols), issued eagerly unless solve_graph
+    bool solve_graph = true;      // capture the solve half into a CUDA graph
     double *scal = nullptr;       // [0] sumabs camera part, [1] sumabs points, [2] sum vx^2, [3] sum vy^2
     double *v_out = nullptr, *rsd_out = nullptr, *delta_out = nullptr;
     int *opt = nullptr, *tie_pt = nullptr, *info = nullptr;
@@ -133,6 +135,80 @@ cudaError_t pool_stream(feba_handle* h, int slot, int priority, cudaStream_t* ou
         return cudaErrorNotSupported;
     }
     return cudaStreamCreateWithPriority(out, cudaStreamNonBlocking, priority);
+}
+
+// Stream pool, events and SM partitions of the task-graph factorisation (large reduced systems,
+// >= 96 blocks, u_c >= 6,144).  Single GPU: about 13 supertiles per side, captured tile graph, whole GPU
+// shared (measured on u_c = 12,010: T = 6/8/12/14/16/20/24 blocks -> 48.7/32.6/26.3/25.3/25.6/27.7/
+// 28.1 ms, recursive form 30.2 ms; 4/8/12/16 streams -> 28.3/25.6/27.6/27.2 ms; a chain partition of
+// 8/16/24/32 SMs -> 30.1/28.0/27.9/28.4 ms: one GPU is bound by the bulk updates, not by the chain).
+// Group (feba_dist_init): about 19 supertiles, column form issued eagerly, 32 SMs for the panel chain
+// (2 GPUs, whole iteration: tile graph 32.2 ms; column form T=14 33.6, +32 SMs 31.2, T=10 30.6 ms).
+// FEBA_DAG_TILE=t (0 = recursive form), FEBA_DAG_STREAMS, FEBA_GREEN_SMS=r (multiple of 8, 0 = shared),
+// FEBA_DAG_FORM=cols|tiles, FEBA_SOLVE_GRAPH=0|1 override.
+int setup_pool(feba_handle* h, bool group) {
+    // tear down what an earlier call built
+    for (int s2 = 0; s2 < h->dag.n_streams; ++s2) {
+        cudaStreamDestroy(h->dag.streams[s2]);
+        if (h->dag.join[s2]) cudaEventDestroy(h->dag.join[s2]);
+        h->dag.streams[s2] = nullptr;
+        h->dag.join[s2] = nullptr;
+    }
+    h->dag.n_streams = 0;
+    if (h->dag.fork) cudaEventDestroy(h->dag.fork);
+    h->dag.fork = nullptr;
+    for (auto& ev : h->dag_events)
+        if (ev) cudaEventDestroy(ev);
+    h->dag_events.clear();
+    green_destroy(&h->green);
+    h->use_dag = false;
+
+    const int nb = h->P.n_pad / kBlk;
+    const char* e_t = std::getenv("FEBA_DAG_TILE");
+    const char* e_s = std::getenv("FEBA_DAG_STREAMS");
+    int T = 0;
+    if (e_t) {
+        T = std::atoi(e_t);
+        if (T > 0 && nb < 2 * T) T = 0;
+    } else if (nb >= 96) {
+        T = group ? (nb + 9) / 19 : (nb + 6) / 13;
+        if (T < 8) T = 8;
+        if (T > 24) T = 24;
+    }
+    const int NS = e_s ? std::atoi(e_s) : 8;
+    if (T <= 0 || NS < 2 || NS > 16) return FEBA_OK;
+    h->dag.tile_blocks = T;
+    const char* e_f = std::getenv("FEBA_DAG_FORM");
+    h->dag_cols = e_f ? std::strcmp(e_f, "cols") == 0 : group;
+    const char* e_sg = std::getenv("FEBA_SOLVE_GRAPH");
+    h->solve_graph = e_sg ? std::atoi(e_sg) != 0 : !h->dag_cols;
+    int lo = 0, hi = 0;
+    CU(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    const char* e_g = std::getenv("FEBA_GREEN_SMS");
+    const int reserve = e_g ? std::atoi(e_g) : (group && h->dag_cols ? 32 : 0);
+    if (reserve > 0) {
+        char why[128];
+        const int rc = green_create(h->device, reserve, &h->green, why, sizeof(why));
+        if (std::getenv("FEBA_VERBOSE")) {
+            if (rc) fprintf(stderr, "[feba] %s; the task graph shares the whole GPU\n", why);
+            else fprintf(stderr, "[feba] SM partitions: chain %d, bulk %d\n", h->green.chain_sms, h->green.bulk_sms);
+        }
+    }
+    // priorities: stream 0 is the chain; in a group the panel streams (1..2 column form, 1..3 tile form) too
+    const int n_hi = group ? (h->dag_cols ? 3 : 4) : 1;
+    for (int s2 = 0; s2 < NS; ++s2) {
+        CU(h, pool_stream(h, s2, s2 < n_hi ? hi : lo, &h->dag.streams[s2]));
+        ++h->dag.n_streams;
+        CU(h, cudaEventCreateWithFlags(&h->dag.join[s2], cudaEventDisableTiming));
+    }
+    CU(h, cudaEventCreateWithFlags(&h->dag.fork, cudaEventDisableTiming));
+    const int NT = (nb + T - 1) / T;
+    h->dag_events.assign((size_t)(NT + 1) * (NT + 1), nullptr);
+    for (auto& ev : h->dag_events) CU(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    h->dag.events = h->dag_events.data();
+    h->dag.n_events = (int)h->dag_events.size();
+    h->use_dag = true;
+    return FEBA_OK;
 }
 
 int check_settings(const feba_problem* pr) {
@@ -374,50 +450,8 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
     }
     CU(h, dev_alloc(h, &P.partial, (size_t)h->n_partial));
     {
-        // task-graph factorisation for large reduced systems (>= 96 blocks, u_c >= 6,144): about 13
-        // supertiles per side (measured on u_c = 12,010: T = 6/8/12/14/16/20/24 blocks -> 48.7/32.6/26.3/
-        // 25.3/25.6/27.7/28.1 ms, recursive form 30.2 ms; 4/8/12/16 streams -> 28.3/25.6/27.6/27.2 ms).
-        // FEBA_DAG_TILE=t forces supertiles of t blocks (0 = recursive form), FEBA_DAG_STREAMS the pool size.
-        const int nb = P.n_pad / kBlk;
-        const char* e_t = std::getenv("FEBA_DAG_TILE");
-        const char* e_s = std::getenv("FEBA_DAG_STREAMS");
-        int T = 0;
-        if (e_t) {
-            T = std::atoi(e_t);
-            if (T > 0 && nb < 2 * T) T = 0;
-        } else if (nb >= 96) {
-            T = (nb + 6) / 13;
-            if (T < 8) T = 8;
-            if (T > 24) T = 24;
-        }
-        const int NS = e_s ? std::atoi(e_s) : 8;
-        if (T > 0 && NS >= 2 && NS <= 16) {
-            h->dag.tile_blocks = T;
-            int lo = 0, hi = 0;
-            CU(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            // FEBA_GREEN_SMS=r: r SMs (multiple of 8) are set aside for the panel chain, 0 = shared GPU
-            const char* e_g = std::getenv("FEBA_GREEN_SMS");
-            const int reserve = e_g ? std::atoi(e_g) : 0;
-            if (reserve > 0) {
-                char why[128];
-                if (green_create(h->device, reserve, &h->green, why, sizeof(why)) != 0 && std::getenv("FEBA_VERBOSE"))
-                    fprintf(stderr, "[feba] %s; the task graph shares the whole GPU\n", why);
-                else if (std::getenv("FEBA_VERBOSE"))
-                    fprintf(stderr, "[feba] SM partitions: chain %d, bulk %d\n", h->green.chain_sms, h->green.bulk_sms);
-            }
-            for (int s2 = 0; s2 < NS; ++s2) {
-                CU(h, pool_stream(h, s2, s2 == 0 ? hi : lo, &h->dag.streams[s2]));
-                ++h->dag.n_streams;
-                CU(h, cudaEventCreateWithFlags(&h->dag.join[s2], cudaEventDisableTiming));
-            }
-            CU(h, cudaEventCreateWithFlags(&h->dag.fork, cudaEventDisableTiming));
-            const int NT = (nb + T - 1) / T;
-            h->dag_events.assign((size_t)(NT + 1) * (NT + 1), nullptr);
-            for (auto& ev : h->dag_events) CU(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-            h->dag.events = h->dag_events.data();
-            h->dag.n_events = (int)h->dag_events.size();
-            h->use_dag = true;
-        }
+        const int rc_pool = setup_pool(h, false);
+        if (rc_pool) return rc_pool;
     }
     CU(h, dev_alloc(h, &P.cam_part, (size_t)assemble_warps(P, h->sm_count) * kCamPart));
     {
@@ -464,19 +498,20 @@ int feba_dist_init(feba_handle* h, int32_t rank, int32_t world, const void* id, 
     CU(h, cudaStreamSynchronize(h->stream));
     // the communicator is created by every rank even when this problem keeps the replicated solve
     if (dist_comm_init(&h->dist, rank, world, id)) return fail(h, FEBA_ERR_CUDA, "%s", h->dist.err);
-    if (!h->use_dag || world == 1 || h->dag.n_streams < 6) return FEBA_OK;
+    if (!h->use_dag || world == 1) return FEBA_OK;
     drop_graphs(h);
+    {
+        const int rc_pool = setup_pool(h, true);
+        if (rc_pool) return rc_pool;
+    }
+    if (!h->use_dag || h->dag.n_streams < 6) return FEBA_OK;
     int lo = 0, hi = 0;
     CU(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    for (int s2 = 1; s2 <= 3; ++s2) {            // panel streams: high priority like the critical-path stream
-        CU(h, cudaStreamDestroy(h->dag.streams[s2]));
-        CU(h, pool_stream(h, s2, hi, &h->dag.streams[s2]));
-    }
     CU(h, cudaStreamCreateWithPriority(&h->dist.stream, cudaStreamNonBlocking, hi));
     CU(h, cudaEventCreateWithFlags(&h->dag.join[h->dag.n_streams], cudaEventDisableTiming));
     const size_t tile = (size_t)h->dag.tile_blocks * kBlk;
-    CU(h, dev_alloc(h, &h->dist.staging, tile * tile));
-    h->dist.staging_count = tile * tile;
+    h->dist.staging_count = tile * (size_t)(h->P.n_pad + kBlk);      // up to one supertile column
+    CU(h, dev_alloc(h, &h->dist.staging, h->dist.staging_count));
     h->dist_active = true;
     return FEBA_OK;
 }
@@ -541,9 +576,9 @@ static int enqueue_assemble(feba_handle* h) {
 
 // Run one phase eagerly (first call: kernels set their attributes), capture it (second call) or
 // replay its graph.
-static int run_phase(feba_handle* h, feba_handle::GraphSlot& g, int (*fn)(feba_handle*)) {
+static int run_phase(feba_handle* h, feba_handle::GraphSlot& g, int (*fn)(feba_handle*), bool allow_graph = true) {
     const int call = g.calls++;
-    if (!h->use_graph || call == 0) return fn(h);
+    if (!h->use_graph || !allow_graph || call == 0) return fn(h);
     if (!g.exec) {
         const int64_t before = h->launches;
         CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -591,7 +626,12 @@ static int enqueue_solve(feba_handle* h) {
     DevProblem& P = h->P;
     CU(h, launch_border_scale(P, h->eop, h->dvec, h->info, h->stream, &h->launches));
     const int nb = P.n_pad / kBlk;
-    if (h->dist_active) {
+    if (h->use_dag && h->dag_cols) {
+        const cudaError_t ed = chol_cols(P.S, P.ld, nb, h->Linv, h->info, h->dag, h->dist_active ? &h->dist : nullptr,
+                                         h->stream, &h->launches);
+        if (ed == cudaErrorUnknown && h->dist.err[0]) return fail(h, FEBA_ERR_CUDA, "%s", h->dist.err);
+        CU(h, ed);
+    } else if (h->dist_active) {
         const cudaError_t ed = chol_dag_dist(P.S, P.ld, nb, h->Linv, h->info, h->dag, h->dist, h->stream, &h->launches);
         if (ed == cudaErrorUnknown && h->dist.err[0]) return fail(h, FEBA_ERR_CUDA, "%s", h->dist.err);
         CU(h, ed);
@@ -616,7 +656,7 @@ static int enqueue_solve(feba_handle* h) {
 
 static int solve_async(feba_handle* h) {
     if (h->phase != 1) return fail(h, FEBA_ERR_STATE, "feba_iterate_solve without feba_iterate_assemble");
-    const int rc = run_phase(h, h->g_solve, enqueue_solve);
+    const int rc = run_phase(h, h->g_solve, enqueue_solve, h->solve_graph);
     if (rc) return rc;
     h->phase = 0;
     ++h->iterations;
@@ -637,6 +677,7 @@ static int finish_iteration(feba_handle* h, double* dcam_sum, double* dpts_sum) 
     }
     if (ok) h->timing[5] = tot;
     h->timing_valid = ok;
+    if (h->dist_active && !h->dag_cols && h->g_solve.exec && h->g_solve.calls >= 5) dist_prof_report();
     if (dcam_sum) *dcam_sum = h->scal_host[0];
     if (dpts_sum) *dpts_sum = h->scal_host[1];
     if (*h->info_host == 1)

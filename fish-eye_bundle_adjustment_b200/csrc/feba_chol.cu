@@ -672,6 +672,40 @@ cudaError_t chol_dag(double* A, int ld, int nb, double* Linv, int* info, const D
 // program order, a tile is packed into dist.staging by a strided device copy, broadcast, and unpacked
 // on the receivers.  Streams 0..3 of the pool have high priority: 0 carries the critical path, 1..3
 // the rest of the panel (TRSM and the look-ahead updates of the next panel); 4.. the bulk updates.
+struct DistProf {
+    static constexpr int kCols = 12;
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> pm, join;
+    int m_fork = -1, m_end = -1, NT = 0, T = 0, rank = 0, world = 1;
+    bool printed = false;
+};
+static DistProf g_prof;
+
+void dist_prof_report() {
+    if (g_prof.ev.empty() || g_prof.printed) return;
+    g_prof.printed = true;
+    auto at = [&](int m) {
+        float ms = -1.f;
+        if (m >= 0 && cudaEventElapsedTime(&ms, g_prof.ev[g_prof.m_fork], g_prof.ev[m]) != cudaSuccess) {
+            cudaGetLastError();
+            ms = -2.f;
+        }
+        return ms;
+    };
+    const int r = g_prof.rank;
+    fprintf(stderr, "[feba dist prof] rank %d/%d T=%d NT=%d total %.3f ms; stream ends:", r, g_prof.world, g_prof.T,
+            g_prof.NT, at(g_prof.m_end));
+    for (int m : g_prof.join) fprintf(stderr, " %.2f", at(m));
+    fprintf(stderr, "\n[feba dist prof] rank k | diag_start diag_end trsm1_end trsm2_end trsmN_end | comm_in tile1_out "
+                    "tile2_out col_out | upd1_end upd21_end last_upd_end (ms after fork)\n");
+    for (int k = 0; k < g_prof.NT; ++k) {
+        const int* m = &g_prof.pm[(size_t)k * DistProf::kCols];
+        fprintf(stderr, "[feba dist prof] %d %2d | %7.3f %7.3f %7.3f %7.3f %7.3f | %7.3f %7.3f %7.3f %7.3f | %7.3f %7.3f %7.3f\n",
+                r, k, at(m[0]), at(m[1]), at(m[2]), at(m[3]), at(m[4]), at(m[5]), at(m[6]), at(m[7]), at(m[8]), at(m[9]),
+                at(m[10]), at(m[11]));
+    }
+}
+
 cudaError_t chol_dag_dist(double* A, int ld, int nb, double* Linv, int* info, const DagStreams& D, DistCtx& dist,
                           cudaStream_t main, int64_t* launches) {
     const int T = D.tile_blocks;
@@ -687,22 +721,22 @@ cudaError_t chol_dag_dist(double* A, int ld, int nb, double* Linv, int* info, co
     auto panel_stream = [&](int i) { return 1 + i % 3; };
     auto bulk_stream = [&](int i, int j) { return 4 + (i * 3 + j * 7) % (D.n_streams - 4); };
     auto owner = [&](int k) { return k % dist.world; };
-    // FEBA_DIST_PROF=1 (eager runs only): time stamps of the panel chain and of the collectives
+    // FEBA_DIST_PROF=1: time stamps of the panel chain, the collectives and the updates, recorded as
+    // external event nodes of the captured graph and printed by dist_prof_report() after a replay
     static const bool prof_env = std::getenv("FEBA_DIST_PROF") != nullptr;
-    static int prof_calls = 0;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(main, &cap);
-    const bool prof = prof_env && cap == cudaStreamCaptureStatusNone && ++prof_calls == 3;
-    std::vector<cudaEvent_t> pev;
+    const bool prof = prof_env && cap == cudaStreamCaptureStatusActive && g_prof.ev.empty();
     auto mark = [&](int sid) -> int {
         if (!prof) return -1;
         cudaEvent_t ev;
         cudaEventCreate(&ev);
-        cudaEventRecord(ev, sid < 0 ? main : S(sid));
-        pev.push_back(ev);
-        return (int)pev.size() - 1;
+        cudaEventRecordWithFlags(ev, sid < 0 ? main : S(sid), cudaEventRecordExternal);
+        g_prof.ev.push_back(ev);
+        return (int)g_prof.ev.size() - 1;
     };
-    std::vector<int> pm((size_t)NT * 6, -1);
+    constexpr int PC = DistProf::kCols;
+    std::vector<int> pm((size_t)NT * PC, -1);
     const int m_fork = mark(-1);
     cudaError_t e = cudaEventRecord(D.fork, main);
     if (e != cudaSuccess) return e;
@@ -754,29 +788,33 @@ cudaError_t chol_dag_dist(double* A, int ld, int nb, double* Linv, int* info, co
         const bool mine = owner(k) == dist.rank;
         if (mine) {
             DAG_CU(acquire(0, k, k));
-            pm[k * 6 + 0] = mark(0);
+            pm[k * PC + 0] = mark(0);
             DAG_CU(rchol(A, ld, Linv, blk0(k), nblk(k), -1, info, D.streams[0], launches));
             DAG_CU(release(0, k, k));
-            pm[k * 6 + 1] = mark(0);
+            pm[k * PC + 1] = mark(0);
             for (int i = k + 1; i < NR; ++i) {
                 const int sid = (i == k + 1) ? 0 : panel_stream(i);
                 DAG_CU(acquire(sid, k, k));
                 DAG_CU(acquire(sid, i, k));
                 DAG_CU(rtrsm(A, ld, A, ld, Linv, blk0(i), nblk(i), blk0(k), nblk(k), D.streams[sid], launches));
                 DAG_CU(release(sid, i, k));
-                if (i == k + 1) pm[k * 6 + 2] = mark(0);
+                if (i == k + 1) pm[k * PC + 2] = mark(0);
+                if (i == k + 2) pm[k * PC + 3] = mark(sid);
+                if (i == NR - 1) pm[k * PC + 4] = mark(sid);
             }
         }
         // the tile the next panel waits for goes first; the diagonal tiles and the inverted diagonal
         // factors are only read by the backward solve and follow after the last panel
         for (int i = k + 1; i < NR; ++i) {
-            if (i == k + 1) pm[k * 6 + 3] = mark(COMM);
+            if (i == k + 1) pm[k * PC + 5] = mark(COMM);
             DAG_CU(share_tile(i, k));
-            if (i == k + 1) pm[k * 6 + 4] = mark(COMM);
+            if (i == k + 1) pm[k * PC + 6] = mark(COMM);
+            if (i == k + 2) pm[k * PC + 7] = mark(COMM);
             if (i == k + 1 && diag_order == 1) DAG_CU(share_diag(k));
         }
         if (diag_order == 0) DAG_CU(share_diag(k));
-        pm[k * 6 + 5] = mark(COMM);
+        pm[k * PC + 8] = mark(COMM);
+        int last_sid = -1;
         for (int j = k + 1; j < NR; ++j) {
             if (j < NT && owner(j) != dist.rank) continue;
             for (int i = j; i < NR; ++i) {
@@ -790,13 +828,18 @@ cudaError_t chol_dag_dist(double* A, int ld, int nb, double* Linv, int* info, co
                                AT(A, ld, blk0(j), blk0(k)), ld, nblk(i), nblk(j), nblk(k), i == j ? 1 : 0,
                                D.streams[sid], launches));
                 DAG_CU(release(sid, i, j));
+                if (i == k + 1 && j == k + 1) pm[k * PC + 9] = mark(sid);
+                if (i == k + 2 && j == k + 1) pm[k * PC + 10] = mark(sid);
+                last_sid = sid;
             }
         }
+        if (last_sid >= 0) pm[k * PC + 11] = mark(last_sid);
     }
     if (diag_order == 2)
         for (int k = 0; k < NT; ++k) DAG_CU(share_diag(k));
 #undef DAG_CU
     for (int s = 0; s <= COMM; ++s) {
+        if (prof) g_prof.join.push_back(mark(s));
         e = cudaEventRecord(D.join[s], S(s));
         if (e != cudaSuccess) return e;
         e = cudaStreamWaitEvent(main, D.join[s], 0);
@@ -805,21 +848,196 @@ cudaError_t chol_dag_dist(double* A, int ld, int nb, double* Linv, int* info, co
     // a failed pivot is only seen by the owner of that column
     if (dist_allreduce_max_i32(&dist, info, 1, main)) return cudaErrorUnknown;
     if (prof) {
-        const int m_end = mark(-1);
-        cudaStreamSynchronize(main);
-        auto at = [&](int m) {
-            float ms = -1.f;
-            if (m >= 0) cudaEventElapsedTime(&ms, pev[m_fork], pev[m]);
-            return ms;
-        };
-        fprintf(stderr, "[feba dist prof] rank %d/%d T=%d NT=%d total %.3f ms\n", dist.rank, dist.world, T, NT, at(m_end));
-        fprintf(stderr, "[feba dist prof] rank k owner | diag_start diag_end trsm1_end | first_tile_in first_tile_out column_out (ms after fork)\n");
-        for (int k = 0; k < NT; ++k)
-            fprintf(stderr, "[feba dist prof] %d %2d %d | %8.3f %8.3f %8.3f | %8.3f %8.3f %8.3f\n", dist.rank, k, owner(k),
-                    at(pm[k * 6 + 0]), at(pm[k * 6 + 1]), at(pm[k * 6 + 2]), at(pm[k * 6 + 3]), at(pm[k * 6 + 4]),
-                    at(pm[k * 6 + 5]));
-        for (cudaEvent_t ev : pev) cudaEventDestroy(ev);
+        g_prof.m_fork = m_fork;
+        g_prof.m_end = mark(-1);
+        g_prof.pm = pm;
+        g_prof.NT = NT;
+        g_prof.T = T;
+        g_prof.rank = dist.rank;
+        g_prof.world = dist.world;
     }
+    return cudaSuccess;
+}
+
+// ------------------------------------------------------------------------------------------
+// Column form of the task graph, for eager (not captured) execution by one GPU or by a group.
+// Per supertile column j the matrix is cut into three parts: D(j) the diagonal tile, S(j) the tile
+// below it (the next panel's input) and R(j) the rest of the column down to the augmented block row,
+// R(j) in up to three row chunks.  Step k:
+//   chain stream (own SM partition when the device is split):   DIAG(k), TRSM of S(k), update of D(k+1)
+//   panel streams (high priority):   TRSM of the chunks of R(k); look-ahead update of S(k+1), R(k+1)
+//   bulk streams:   one tall lower-trapezoid product per remaining column j >= k+2 (rows j..end)
+// so a step is ~10 large launches instead of ~100 tile launches, few enough to be issued eagerly while
+// the GPU works (the captured tile graph loses its priorities: ready chain nodes queue behind nodes
+// that wait for later tiles).  In a group, column k belongs to rank k % world: the owner factorises
+// it and broadcasts S(k), the chunks of R(k), then D(k) and the inverted diagonal factors, through
+// dist->stream in program order (packed into dist->staging: collectives need contiguous buffers);
+// every rank updates the columns it owns, and the 64-row augmented diagonal block.
+cudaError_t chol_cols(double* A, int ld, int nb, double* Linv, int* info, const DagStreams& D, DistCtx* dist,
+                      cudaStream_t main, int64_t* launches) {
+    const int T = D.tile_blocks;
+    const int NT = (nb + T - 1) / T;
+    const int NR = NT + 1;
+    auto blk0 = [&](int t) { return t >= NT ? nb : t * T; };
+    auto nblk = [&](int t) { return t == NT ? 1 : (t == NT - 1 ? nb - T * (NT - 1) : T); };
+    const bool group = dist && dist->comm && dist->world > 1;
+    const int world = group ? dist->world : 1, rank = group ? dist->rank : 0;
+    if (NR * NR > D.n_events || D.n_streams < 5) return cudaErrorInvalidValue;
+    const int CH = 0, COMM = D.n_streams;
+    auto S = [&](int sid) { return sid == COMM ? dist->stream : D.streams[sid]; };
+    auto bulk_stream = [&](int j) { return 3 + j % (D.n_streams - 3); };
+    auto owner = [&](int k) { return k % world; };
+    std::vector<int> last(NR * NR, -1);
+    // resources -> event slots
+    auto rD = [&](int j) { return j * NR + j; };
+    auto rS = [&](int j) { return (j + 1) * NR + j; };
+    struct Chunk { int a, b; };                       // supertile rows [a, b) of the rest of a column
+    auto chunks = [&](int j) {
+        std::vector<Chunk> v;
+        const int first = j + 2, n = NR - first;
+        if (n <= 0) return v;
+        // chunk 0 is the single supertile row the next panel's S part depends on; the remainder in two
+        v.push_back({first, first + 1});
+        const int m = n - 1, nc = m < 2 ? m : 2;
+        for (int c = 0; c < nc; ++c) v.push_back({first + 1 + m * c / nc, first + 1 + m * (c + 1) / nc});
+        return v;
+    };
+    auto rC = [&](int j, const Chunk& c) { return c.a * NR + j; };
+    cudaError_t e = cudaEventRecord(D.fork, main);
+    if (e != cudaSuccess) return e;
+    const int n_used = group ? COMM : COMM - 1;
+    for (int s = 0; s <= n_used; ++s) {
+        e = cudaStreamWaitEvent(S(s), D.fork, 0);
+        if (e != cudaSuccess) return e;
+    }
+    auto acquire = [&](int sid, int res) -> cudaError_t {
+        const int w = last[res];
+        if (w >= 0 && w != sid) return cudaStreamWaitEvent(S(sid), D.events[res], 0);
+        return cudaSuccess;
+    };
+    auto release = [&](int sid, int res) -> cudaError_t {
+        last[res] = sid;
+        return cudaEventRecord(D.events[res], S(sid));
+    };
+#define DAG_CU(x)                 \
+    do {                          \
+        e = (x);                  \
+        if (e != cudaSuccess) return e; \
+    } while (0)
+    // finished rows [r0, r0 + mr) (64-blocks) of column k: owner -> everybody
+    auto share = [&](int res, int r0, int mr, int k) -> cudaError_t {
+        const size_t rows = (size_t)mr * kBlk, cols = (size_t)nblk(k) * kBlk;
+        double* src = AT(A, ld, r0, blk0(k));
+        const bool root = owner(k) == rank;
+        if (rows * cols > dist->staging_count) return cudaErrorInvalidValue;
+        if (root) {
+            DAG_CU(acquire(COMM, res));
+            DAG_CU(cudaMemcpy2DAsync(dist->staging, rows * sizeof(double), src, (size_t)ld * sizeof(double),
+                                     rows * sizeof(double), cols, cudaMemcpyDeviceToDevice, dist->stream));
+        }
+        if (dist_bcast_f64(dist, dist->staging, rows * cols, owner(k), dist->stream)) return cudaErrorUnknown;
+        if (!root) {
+            DAG_CU(cudaMemcpy2DAsync(src, (size_t)ld * sizeof(double), dist->staging, rows * sizeof(double),
+                                     rows * sizeof(double), cols, cudaMemcpyDeviceToDevice, dist->stream));
+            DAG_CU(release(COMM, res));
+        }
+        return cudaSuccess;
+    };
+    for (int k = 0; k < NT; ++k) {
+        const bool mine = owner(k) == rank;
+        const std::vector<Chunk> ck = chunks(k);
+        if (mine) {
+            DAG_CU(acquire(CH, rD(k)));
+            DAG_CU(rchol(A, ld, Linv, blk0(k), nblk(k), -1, info, D.streams[CH], launches));
+            DAG_CU(release(CH, rD(k)));
+            DAG_CU(acquire(CH, rS(k)));
+            DAG_CU(rtrsm(A, ld, A, ld, Linv, blk0(k + 1), nblk(k + 1), blk0(k), nblk(k), D.streams[CH], launches));
+            DAG_CU(release(CH, rS(k)));
+            for (size_t c = 0; c < ck.size(); ++c) {
+                const int sid = c == 0 ? CH : 1 + (int)(c & 1);
+                const int r0 = blk0(ck[c].a), mr = (ck[c].b >= NR ? nb + 1 : blk0(ck[c].b)) - r0;
+                DAG_CU(acquire(sid, rD(k)));
+                DAG_CU(acquire(sid, rC(k, ck[c])));
+                DAG_CU(rtrsm(A, ld, A, ld, Linv, r0, mr, blk0(k), nblk(k), D.streams[sid], launches));
+                DAG_CU(release(sid, rC(k, ck[c])));
+            }
+        }
+        if (group) {
+            DAG_CU(share(rS(k), blk0(k + 1), nblk(k + 1), k));
+            for (const Chunk& c : ck) {
+                const int r0 = blk0(c.a), mr = (c.b >= NR ? nb + 1 : blk0(c.b)) - r0;
+                DAG_CU(share(rC(k, c), r0, mr, k));
+            }
+            DAG_CU(share(rD(k), blk0(k), nblk(k), k));
+            if (dist_bcast_f64(dist, LINV(Linv, blk0(k)), (size_t)nblk(k) * kBlk * kBlk, owner(k), dist->stream))
+                return cudaErrorUnknown;
+        }
+        // D(k+1) -= S(k) S(k)'   (k+1 == NT: the augmented diagonal block, kept by every rank)
+        if (k + 1 == NT || owner(k + 1) == rank) {
+            DAG_CU(acquire(CH, rS(k)));
+            DAG_CU(acquire(CH, rD(k + 1)));
+            DAG_CU(gemm_nt(AT(A, ld, blk0(k + 1), blk0(k + 1)), ld, AT(A, ld, blk0(k + 1), blk0(k)), ld,
+                           AT(A, ld, blk0(k + 1), blk0(k)), ld, nblk(k + 1), nblk(k + 1), nblk(k), 1, D.streams[CH],
+                           launches));
+            DAG_CU(release(CH, rD(k + 1)));
+        }
+        if (ck.empty()) continue;
+        const int r2 = blk0(k + 2);                         // first row below S(k)
+        // look-ahead on column k+1: its S part (one tile, needs only chunk 0 of R(k)), and the rest
+        // -= R(k)[rows k+3..] S(k)', on the two panel streams
+        if (k + 1 < NT && owner(k + 1) == rank) {
+            const int ls = 2;       // not the chain stream: DIAG(k+1) must not queue behind the wait for chunk 0
+            DAG_CU(acquire(ls, rS(k)));
+            DAG_CU(acquire(ls, rC(k, ck[0])));
+            DAG_CU(acquire(ls, rS(k + 1)));
+            DAG_CU(gemm_nt(AT(A, ld, r2, blk0(k + 1)), ld, AT(A, ld, r2, blk0(k)), ld, AT(A, ld, blk0(k + 1), blk0(k)), ld,
+                           nblk(k + 2), nblk(k + 1), nblk(k), 0, D.streams[ls], launches));
+            DAG_CU(release(ls, rS(k + 1)));
+            const std::vector<Chunk> cn = chunks(k + 1);
+            if (!cn.empty()) {
+                const int sid = 1;
+                const int r3 = blk0(k + 3), m3 = nb + 1 - r3;
+                DAG_CU(acquire(sid, rS(k)));
+                for (size_t c = 1; c < ck.size(); ++c) DAG_CU(acquire(sid, rC(k, ck[c])));
+                for (const Chunk& c : cn) DAG_CU(acquire(sid, rC(k + 1, c)));
+                DAG_CU(gemm_nt(AT(A, ld, r3, blk0(k + 1)), ld, AT(A, ld, r3, blk0(k)), ld, AT(A, ld, blk0(k + 1), blk0(k)),
+                               ld, m3, nblk(k + 1), nblk(k), 0, D.streams[sid], launches));
+                for (const Chunk& c : cn) DAG_CU(release(sid, rC(k + 1, c)));
+            }
+        }
+        // bulk: column j (rows j..end, lower trapezoid) -= R(k)[rows j..] R(k)[rows of j]'
+        for (int j = k + 2; j < NT; ++j) {
+            if (owner(j) != rank) continue;
+            const int sid = bulk_stream(j);
+            const std::vector<Chunk> cj = chunks(j);
+            for (const Chunk& c : ck) DAG_CU(acquire(sid, rC(k, c)));
+            DAG_CU(acquire(sid, rD(j)));
+            DAG_CU(acquire(sid, rS(j)));
+            for (const Chunk& c : cj) DAG_CU(acquire(sid, rC(j, c)));
+            DAG_CU(gemm_nt(AT(A, ld, blk0(j), blk0(j)), ld, AT(A, ld, blk0(j), blk0(k)), ld, AT(A, ld, blk0(j), blk0(k)),
+                           ld, nb + 1 - blk0(j), nblk(j), nblk(k), 1, D.streams[sid], launches));
+            DAG_CU(release(sid, rD(j)));
+            DAG_CU(release(sid, rS(j)));
+            for (const Chunk& c : cj) DAG_CU(release(sid, rC(j, c)));
+        }
+        {   // augmented diagonal block -= (augmented row of R(k)) (...)'
+            const int sid = bulk_stream(NT);
+            DAG_CU(acquire(sid, rC(k, ck.back())));
+            DAG_CU(acquire(sid, rD(NT)));
+            DAG_CU(gemm_nt(AT(A, ld, nb, nb), ld, AT(A, ld, nb, blk0(k)), ld, AT(A, ld, nb, blk0(k)), ld, 1, 1, nblk(k), 1,
+                           D.streams[sid], launches));
+            DAG_CU(release(sid, rD(NT)));
+        }
+    }
+#undef DAG_CU
+    for (int s = 0; s <= n_used; ++s) {
+        e = cudaEventRecord(D.join[s], S(s));
+        if (e != cudaSuccess) return e;
+        e = cudaStreamWaitEvent(main, D.join[s], 0);
+        if (e != cudaSuccess) return e;
+    }
+    // a failed pivot is only seen by the owner of that column
+    if (group && dist_allreduce_max_i32(dist, info, 1, main)) return cudaErrorUnknown;
     return cudaSuccess;
 }
 

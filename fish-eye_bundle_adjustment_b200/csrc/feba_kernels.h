@@ -87,6 +87,11 @@ int dist_group_end(DistCtx* D);
 // own columns.  On return every rank holds the whole factor.  cudaErrorUnknown: see dist.err.
 cudaError_t chol_dag_dist(double* A, int ld, int nb, double* Linv, int* info, const DagStreams& D, DistCtx& dist,
                           cudaStream_t main, int64_t* launches);
+// Column form (D / S / R parts per supertile column, ~10 large launches per step), for eager issue;
+// dist == nullptr: one GPU.
+cudaError_t chol_cols(double* A, int ld, int nb, double* Linv, int* info, const DagStreams& D, DistCtx* dist,
+                      cudaStream_t main, int64_t* launches);
+void dist_prof_report();   // FEBA_DIST_PROF=1: prints the time stamps of the last replay once
 // ywork (n_pad) := combination of the augmented rows: y = Y'(0,:) + sum_k kvec[k] Y'(1+k,:) where kvec
 // solves the 7x7 border system (inner != 0), else y = Y'(0,:).  Then sol := L^-T y.
 cudaError_t border_and_backsolve(double* A, int ld, int nb, const double* Linv, int inner, double* work,

@@ -435,10 +435,14 @@ def test_covariance_outputs_of_the_camera_part(case):
         assert ei.value.code == fb.lib.FEBA_ERR_STATE
 
 
-def test_task_graph_factorisation_matches_recursive_form(monkeypatch):
+@pytest.mark.parametrize("form,graph", [("tiles", "1"), ("cols", "0"), ("cols", "1")])
+def test_task_graph_factorisation_matches_recursive_form(monkeypatch, form, graph):
     """Large reduced systems are factorised as a task graph over supertiles (stream pool + events,
-    csrc/feba_chol.cu::chol_dag); force it on a medium problem (u_c = 1,210, 19 blocks, supertiles of 3
+    csrc/feba_chol.cu::chol_dag, tile form captured in a CUDA graph; chol_cols, column form, issued
+    eagerly or captured); force it on a medium problem (u_c = 1,210, 19 blocks, supertiles of 3
     blocks, ragged last supertile + augmented row) and compare with the recursive form and the oracle."""
+    monkeypatch.setenv("FEBA_DAG_FORM", form)
+    monkeypatch.setenv("FEBA_SOLVE_GRAPH", graph)
     from oracle import cport
     prob = synth.baseline_config(4, scale=1.0)
     err, xhat0, _ = fb.Buildxhat(prob)
@@ -499,3 +503,21 @@ def test_other_projection_types_full_run_with_inner_constraints(typ):
     L = model.layout(prob)
     iop = slice(L["off_cam"], L["off_cam"] + 3)
     assert np.max(np.abs(out["xhat"][iop] - ref["xhat"][iop]) / np.abs(ref["xhat"][iop])) < 1e-9
+
+
+def test_shared_factorisation_over_two_gpus():
+    """with feba_dist_init the ranks factorise the summed reduced system together
+    (panel broadcasts over NCCL).  Same shards, same ranks, same xhat as the replicated solve:
+    scripts/dist_check.py runs both in every rank and compares (also covers CUDA-graph replay of
+    the collectives: iteration 1 runs eagerly, 2 is captured, 3 replays)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "scripts", "dist_check.py"),
+           "--workload", "config3", "--tile", "6", "--iters", "3", "--tol", "1e-12"]
+    out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
