@@ -11,4 +11,5 @@ from .problem import Settings, Problem, Buildxhat, load_problem, save_problem  #
 from .lib import Handle, FebaError                                       # noqa: F401
 from .main import main, BatchRun, adjust, findfiles, write_rsd, write_par, covariance_outputs  # noqa: F401
 from .batch import adjust_batch                                          # noqa: F401
-from . import synth, lib, build                                          # noqa: F401
+from .pack import load_problem_native, pack_files, PackError            # noqa: F401
+from . import synth, lib, build, pack, report                                    # noqa: F401

@@ -13,10 +13,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfeba.so")
-SOURCES = ("feba_api.cu", "feba_kernels.cu", "feba_assemble.cu", "feba_chol.cu", "feba_dist.cu", "feba_green.cu")
-HEADERS = ("feba_dev.h", "feba_kernels.h", "feba_model.cuh", os.path.join("..", "..", "include", "feba.h"))
+SOURCES = ("feba_api.cu", "feba_kernels.cu", "feba_assemble.cu", "feba_chol.cu", "feba_dist.cu", "feba_green.cu",
+           "feba_pack.cpp")            # the last one is host-only C++ (problem build, include/feba_pack.h)
+HEADERS = ("feba_dev.h", "feba_kernels.h", "feba_model.cuh", os.path.join("..", "..", "include", "feba.h"),
+           os.path.join("..", "..", "include", "feba_pack.h"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-O3,-Wall", "--use_fast_math=false"]
+              "-Xcompiler", "-fPIC,-O3,-Wall,-pthread", "--use_fast_math=false"]
 
 
 def _nvcc() -> str:
@@ -41,7 +43,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     objs, procs = [], []
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
     for src in SOURCES:                      # translation units compile concurrently
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
         cmd = [_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -50,7 +52,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     for cmd, pr in procs:
         if pr.wait() != 0:
             raise subprocess.CalledProcessError(pr.returncode, cmd)
-    subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"],
+    subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart", "-ldl", "-lpthread"],
                    check=True)
     return LIB
 

@@ -9,8 +9,10 @@
 
 The loop body is one ``feba_iterate`` per pass -- the MEX gateway a MATLAB user would call makes
 exactly these calls.  Console lines follow main.m (``Iteration k:``, the echoed
-``deltasum =``, ``Elapsed time is ...``, ``sigma02 =``).  Report formatting (.out) is out of scope;
-the numeric tables are written: .rsd (main.m:957, BuildRSD.m:6,40) and .par (main.m:773-823, :958).
+``deltasum =``, ``Elapsed time is ...``, ``sigma02 =``).  Output files: .out (``report.write_out``, main.m:629-950),
+.rsd (main.m:957, BuildRSD.m:6,40) and .par (main.m:773-823, :958).  Files are read and IDs resolved
+by the native packer (``pack.load_problem_native``, include/feba_pack.h); ``native=False`` keeps the
+interpreted mirror of main.m:196-384.
 """
 from __future__ import annotations
 
@@ -20,8 +22,9 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-from . import formats
+from . import formats, report
 from .lib import FebaError, Handle
+from .pack import load_problem_native
 from .problem import Buildxhat, Problem, load_problem
 
 
@@ -139,19 +142,26 @@ def write_par(path: str, prob: Problem, xhat: np.ndarray, Cx_diag: np.ndarray) -
 
 
 def main(folder: Optional[str] = None, plot: bool = True, cfg_folder: Optional[str] = None,
-         write_files: bool = True, verbose: bool = True):
+         write_files: bool = True, verbose: bool = True, native: bool = True):
     """``main_error = main(folder, plot)`` (main.m:10).  ``folder`` None = current directory
     (non-batch mode, main.m:24-31).  Returns 0/1; the results of the last run are in
     ``main.last`` (MATLAB keeps them in the workspace / output files)."""
     main.last = None
     data_dir = os.getcwd() if folder is None else folder
     try:
-        prob = load_problem(data_dir, cfg_folder=cfg_folder)               # main.m:60-384
+        prob = (load_problem_native if native else load_problem)(data_dir, cfg_folder=cfg_folder)   # main.m:60-384
     except (OSError, IndexError, ValueError) as exc:
         print(f"Error reading files ({exc})")
         return 1
     if prob is None:
         return 1
+    CZE = None
+    if prob.settings.Check_Points:                                         # main.m:266-275
+        term, files = formats.ReadFiles([".cze"], data_dir)
+        if term:
+            print("Error reading files")
+            return 1
+        CZE = files[0]
     try:
         out = adjust(prob, verbose=verbose, cov=write_files)
     except (FebaError, ValueError) as exc:
@@ -162,6 +172,10 @@ def main(folder: Optional[str] = None, plot: bool = True, cfg_folder: Optional[s
         name = os.path.splitext(os.path.basename(prob.settings.Output_Filename))[0]
         write_rsd(os.path.join(data_dir, name + ".rsd"), prob, out["RSD"])      # main.m:957
         write_par(os.path.join(data_dir, name + ".par"), prob, out["xhat"], out["Cx_diag"])   # main.m:958
+        cp = report.check_point_differences(prob, out["xhat"], CZE) if CZE is not None else None  # main.m:604-627
+        if verbose:
+            print("Writing output file...")                                # main.m:631
+        report.write_out(os.path.join(data_dir, prob.settings.Output_Filename), prob, out, cp=cp)
     if verbose:
         print("Done!")
     out["problem"] = prob

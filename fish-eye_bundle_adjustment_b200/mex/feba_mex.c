@@ -10,6 +10,9 @@
  *     [v, rsd, stats] = feba_mex('residuals', h);   replaces main.m:569-601 (rsd: n_obs x 5 = r vx vy vr vt)
  *     q = feba_mex('cov_diag', h);  B = feba_mex('cov_block', h, idx);   diag(Cx)/sigma02, Cx/sigma02 blocks
  *                feba_mex('destroy', h);
+ *     [S, err] = feba_mex('pack', pho, ext, cnt, int, tie, NK, allgcp);   native problem build (feba_pack.h):
+ *                the numeric arrays of S straight from the five text files, instead of main.m:196-384
+ *                (tie = '' when there is no .tie file); add the settings fields and pass S to 'create'
  * Recoverable errors are NOT raised with mexErrMsgIdAndTxt: like the reference's 0/1 `error` flags
  * (main.m:417-421) the gateway returns the status as the LAST output and prints feba_last_error.
  * The handle travels as a uint64 scalar; all arrays stay owned by MATLAB.
@@ -17,6 +20,7 @@
 #include <string.h>
 
 #include "feba.h"
+#include "feba_pack.h"
 #include "mex.h"
 
 static feba_handle* get_handle(const mxArray* a) {
@@ -100,6 +104,52 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
         *(uint64_t*)mxGetData(plhs[0]) = (uint64_t)(uintptr_t)h;
         status_out(nlhs, plhs, 1, rc, NULL);
+        return;
+    }
+    if (!strcmp(cmd, "pack")) {
+        /* main.m:196-384 in one call: tokenise the files, str2double, resolve image / camera / target /
+         * tie IDs (first match wins).  Index fields are 0-based int32 as 'create' expects them. */
+        char path[5][1024];
+        if (nrhs < 8) mexErrMsgIdAndTxt("feba:pack", "pack needs pho, ext, cnt, int, tie, NK, allgcp");
+        for (int k = 0; k < 5; ++k)
+            if (mxGetString(prhs[1 + k], path[k], sizeof(path[k]))) mexErrMsgIdAndTxt("feba:pack", "file names must be char");
+        feba_pack* pk = NULL;
+        const int rc = feba_pack_read(path[0], path[1], path[2], path[3], path[4][0] ? path[4] : NULL,
+                                      (int32_t)mxGetScalar(prhs[6]), (int32_t)mxGetScalar(prhs[7]), 0, &pk);
+        if (rc) {
+            mexPrintf("%s\n", feba_pack_last_error());       /* the text of main.m's errordlg (main.m:293,316,352) */
+            plhs[0] = mxCreateDoubleMatrix(0, 0, mxREAL);
+            if (nlhs > 1) plhs[1] = mxCreateDoubleScalar(1.0);
+            return;
+        }
+        feba_pack_view v;
+        feba_pack_get(pk, &v);
+        static const char* names[] = {"n_obs", "n_img", "n_cam", "n_pts", "n_tie", "obs_x", "obs_y", "obs_img", "obs_pt",
+                                      "img_cam", "pt_tie", "tie_pt", "eop0", "iop0", "cam_box", "xyz0"};
+        mxArray* S = mxCreateStructMatrix(1, 1, 16, names);
+        const double counts[5] = {(double)v.n_obs, v.n_img, v.n_cam, v.n_pts, v.n_tie};
+        for (int k = 0; k < 5; ++k) mxSetField(S, 0, names[k], mxCreateDoubleScalar(counts[k]));
+        const struct { const char* name; const double* src; size_t rows, cols; } dd[] = {
+            {"obs_x", v.obs_x, (size_t)v.n_obs, 1}, {"obs_y", v.obs_y, (size_t)v.n_obs, 1},
+            {"eop0", v.eop0, 6, (size_t)v.n_img}, {"iop0", v.iop0, (size_t)v.n_iop_cols, (size_t)v.n_cam},
+            {"cam_box", v.cam_box, 5, (size_t)v.n_cam}, {"xyz0", v.xyz0, 3, (size_t)v.n_pts}};
+        for (size_t k = 0; k < sizeof(dd) / sizeof(dd[0]); ++k) {    /* row-major C = column-major MATLAB transposed */
+            mxArray* a = mxCreateDoubleMatrix((mwSize)dd[k].rows, (mwSize)dd[k].cols, mxREAL);
+            if (dd[k].rows && dd[k].cols) memcpy(mxGetPr(a), dd[k].src, dd[k].rows * dd[k].cols * sizeof(double));
+            mxSetField(S, 0, dd[k].name, a);
+        }
+        const struct { const char* name; const int32_t* src; size_t count; } ii[] = {
+            {"obs_img", v.obs_img, (size_t)v.n_obs}, {"obs_pt", v.obs_pt, (size_t)v.n_obs},
+            {"img_cam", v.img_cam, (size_t)v.n_img}, {"pt_tie", v.pt_tie, (size_t)v.n_pts},
+            {"tie_pt", v.tie_pt, (size_t)v.n_tie}};
+        for (size_t k = 0; k < sizeof(ii) / sizeof(ii[0]); ++k) {
+            mxArray* a = mxCreateNumericMatrix((mwSize)ii[k].count, 1, mxINT32_CLASS, mxREAL);
+            if (ii[k].count) memcpy(mxGetData(a), ii[k].src, ii[k].count * sizeof(int32_t));
+            mxSetField(S, 0, ii[k].name, a);
+        }
+        feba_pack_free(pk);
+        plhs[0] = S;
+        if (nlhs > 1) plhs[1] = mxCreateDoubleScalar(0.0);
         return;
     }
     if (nrhs < 2) mexErrMsgIdAndTxt("feba:cmd", "%s needs a handle", cmd);

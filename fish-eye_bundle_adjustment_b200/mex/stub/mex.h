@@ -22,6 +22,8 @@ int mxGetString(const mxArray*, char*, mwSize);
 mxArray* mxCreateDoubleMatrix(mwSize, mwSize, mxComplexity);
 mxArray* mxCreateDoubleScalar(double);
 mxArray* mxCreateNumericMatrix(mwSize, mwSize, mxClassID, mxComplexity);
+mxArray* mxCreateStructMatrix(mwSize, mwSize, int, const char**);
+void mxSetField(mxArray*, mwSize, const char*, mxArray*);
 void* mxMalloc(size_t);
 void mxFree(void*);
 void mexErrMsgIdAndTxt(const char*, const char*, ...);

@@ -290,6 +290,12 @@ def test_main_and_batchrun_over_text_files(tmp_path):
         assert abs(float(par[6][2]) - np.sqrt(out["Cx_diag"][L["off_cam"] + 2])) < 1e-15
         lit = dense.gauss_newton(out["problem"], xhat0)
         assert abs(float(par[6][2]) - np.sqrt(lit["Cx"][L["off_cam"] + 2, L["off_cam"] + 2])) < 1e-6 * float(par[6][2])
+        # .out report (main.m:629-950) from the covariance outputs of the CUDA path
+        rep = open(os.path.join(d, os.path.basename(d) + ".out")).read()
+        import re
+        assert re.search(r"^Total Unknowns \.+ %d$" % out["problem"].u, rep, flags=re.M)
+        assert ("%-14.5s%-14.5f%-14.5f" % ("Xc", out["xhat"][0], np.sqrt(out["Cx_diag"][0]))) in rep.split("\n")
+        assert "Absolute (positive) mean correlation coefficients between EOPs and IOPs" in rep
     assert fb.BatchRun([str(tmp_path / "root")]) == 0
     # a broken data set stops the batch with error 1 (BatchRun.m:60-64)
     bad = tmp_path / "root" / "set0" / "net0.cfg"

@@ -1,0 +1,149 @@
+"""Report stage: .out writer and check-point differences, fed here by the dense
+oracle (literal main.m) so the test runs without a GPU; on the GPU the same writer is fed by the
+covariance outputs of the CUDA path (tests/test_gpu_parity.py::test_main_and_batchrun_over_text_files)."""
+import re
+
+import numpy as np
+
+import feba_b200 as fb
+from feba_b200 import report
+from oracle import dense
+from tests import golden
+
+
+def oracle_outputs(prob):
+    """What ``adjust(..., cov=True)`` returns, taken from the literal restatement of main.m."""
+    err, x0, _ = fb.Buildxhat(prob)
+    o = dense.gauss_newton(prob, x0)
+    s = prob.settings
+    ui, uc, off = s.u_perimage, s.u_percam, s.u_perimage * prob.numImg
+    C = o["Correlation"]
+    o["Cx_diag"] = np.diag(o["Cx"]).copy()
+    o["Correlation_IOP"] = [C[off + uc * c: off + uc * (c + 1), off + uc * c: off + uc * (c + 1)]
+                            for c in range(prob.numCam)]
+    o["Correlation_image"] = {}
+    for j in range(prob.numImg):
+        cam = int(prob.img_cam[j])
+        idx = np.concatenate([ui * j + np.arange(ui), off + uc * cam + np.arange(uc)])
+        o["Correlation_image"][j] = C[np.ix_(idx, idx)]
+    o["elapsed"] = 1.25
+    return o
+
+
+def test_num2str_and_print_cell():
+    assert report.num2str(42) == "42" and report.num2str(0.3) == "0.3" and report.num2str(1e-6) == "1e-06"
+    assert report.num2str(0.618691873512, 10) == "0.6186918735"
+    txt = report.print_cell([["ab", 1], ["\\line", ""], ["abcd", "x"], ["\\n", ""]], ">", 2)
+    # the longest first-column entry counts '\\line' (5 characters) too, as printCell.m:3-8 does
+    assert txt == ">ab ..... 1\n" + "-" * 13 + "\n>abcd ... x\n\n"
+
+
+def test_out_file_of_cam0(tmp_path):
+    prob = golden.load_cam0()                                   # shipped config: pinhole, IOP + distortions
+    out = oracle_outputs(prob)
+    path = tmp_path / "cam0.out"
+    report.write_out(str(path), prob, out, version="v-test", when="01-Jan-2020 00:00:00")
+    text = path.read_text()
+    lines = text.split("\n")
+    s = prob.settings
+    assert lines[0] == "Version: v-test" and report.LINE in text and len(report.LINE) == 109
+    assert f"Iterations:\t\t{out['iterations']}" in text and "Model Used:\t\tpinhole" in text
+    # summary block (main.m:655-684)
+    def field(name):
+        m = re.search(r"^" + re.escape(name) + r" \.+ (\S+)$", text, flags=re.M)
+        assert m, name
+        return m.group(1)
+    assert int(field("Number of Photos")) == 42 and int(field("Number of image points")) == 1029
+    assert int(field("Total Unknowns")) == prob.u == 580
+    assert int(field("Total Degrees of Freedom")) == 2 * 1029 + 7 * s.Inner_Constraints - 580
+    assert field("A-Posteriori") == "%.10g" % out["sigma02"]
+    assert field("RMS") == "%.10g" % out["RMS"]
+    # EOP table: first image, widths and degrees (main.m:723-777, printEOP)
+    W = report.column_width(prob)
+    assert W == 14
+    k0 = lines.index("Estimated EOPs")
+    blk = lines[k0:k0 + 14]
+    assert blk[3].startswith("Image ") and blk[3].endswith(" " + prob.image_name(0))
+    xc = [ln for ln in blk if ln.startswith("Xc")][0]
+    assert xc == "%-14.5s%-14.5f%-14.5f" % ("Xc", out["xhat"][0], np.sqrt(out["Cx"][0, 0]))
+    om = [ln for ln in blk if ln.startswith("Omega")][0]
+    assert om == "%-14.5s%-14.5f%-14.5f" % ("Omega", np.degrees(out["xhat"][3]), np.degrees(np.sqrt(out["Cx"][3, 3])))
+    # IOP block (printEOP for xp yp c, printDist for k*, p*), IOP correlation lower triangle
+    off = s.u_perimage * prob.numImg
+    names = report.iop_names(s)
+    for q, nm in enumerate(names):
+        fmt = "%-14.5s%-14.5e%-14.5e" if nm[0] in "kp" else "%-14.5s%-14.5f%-14.5f"
+        assert fmt % (nm, out["xhat"][off + q], np.sqrt(out["Cx"][off + q, off + q])) in lines, nm
+    k1 = lines.index("IOP Correlation sub-matrix")
+    assert lines[k1 + 2] == "".join("%-6.2s" % n for n in [""] + names)
+    assert lines[k1 + 3] == "%-6.2s%-+6.2f" % (names[0], 1.0)
+    assert len(lines[k1 + 2 + len(names)]) == 6 * (len(names) + 1)
+    # ground coordinates: one row per TIE entry + mean std (main.m:866-888)
+    k2 = lines.index("Estimated Ground Coordinates of targets")
+    rows = lines[k2 + 3:k2 + 3 + prob.numtie]
+    t = 5
+    p = int(prob.tie_pt[t])
+    u0 = prob.u_c + 3 * t
+    expect = ("%-14s%-14.0d" + "%-14.5f" * 6) % ((prob.point_name(p), int(np.sum(prob.obs_pt == p)))
+                                                  + tuple(out["xhat"][u0:u0 + 3])
+                                                  + tuple(np.sqrt(np.diag(out["Cx"])[u0:u0 + 3])))
+    assert rows[t] == expect
+    var = np.diag(out["Cx"])[prob.u_c:].reshape(-1, 3)
+    assert ("\t\t" + "%-14.5f" * 3) % tuple(np.sqrt(var.mean(axis=0))) in lines
+    # corrected measurements (main.m:587-590, :891-895): one row per observation, PHO order
+    k3 = lines.index("Corrected Image Measurements")
+    rows = lines[k3 + 3:k3 + 3 + prob.n_obs]
+    i = 777
+    assert rows[i] == "%-14s%-14s%-14.5f%-14.5f" % (prob.point_name(int(prob.obs_pt[i])),
+                                                    prob.image_name(int(prob.obs_img[i])),
+                                                    prob.obs_x[i] + out["RSD"][i, 1], prob.obs_y[i] + out["RSD"][i, 2])
+    # mean |correlation| table: one camera, (6 + gap + IOP) labels, entries are means over 42 images
+    k4 = lines.index("Absolute (positive) mean correlation coefficients between EOPs and IOPs")
+    assert lines[k4 + 2] == "Camera " + prob.camera_name(0)
+    mean = sum(np.abs(out["Correlation_image"][j]) for j in range(42)) / 42
+    assert lines[k4 + 4] == "%-6.2s%-+6.2f" % ("Xc", 1.0)
+    assert lines[k4 + 5] == "%-6.2s%-+6.2f%-+6.2f" % ("Yc", mean[1, 0], 1.0)
+    assert lines[k4 + 4 + 6].startswith("      ")               # the reference's empty label before the IOP names
+
+
+def test_check_point_differences(capsys):
+    prob = golden.load_cam0()
+    err, x0, _ = fb.Buildxhat(prob)
+    t = 3
+    p = int(prob.tie_pt[t])
+    xyz = x0[prob.u_c + 3 * t: prob.u_c + 3 * t + 3]
+    CZE = [[prob.point_name(p), repr(float(xyz[0]) - 1.0), repr(float(xyz[1]) + 2.0), repr(float(xyz[2]))], ["nope", "0", "0", "0"]]
+    cp = report.check_point_differences(prob, x0, CZE)
+    assert "Check point not found in xhat -> nope" in capsys.readouterr().out
+    assert cp["names"] == [prob.point_name(p)]
+    assert np.allclose(cp["diff"], [[1.0, -2.0, 0.0]], atol=1e-9)
+    assert np.allclose(cp["rms"], [1.0, 2.0, 0.0], atol=1e-9)
+
+
+def test_main_writes_out_rsd_par_from_text_files(tmp_path, monkeypatch):
+    """File-level flow of main.m on the CPU: native problem build -> (adjust replaced by the literal
+    oracle, the GPU is absent here) -> .out/.rsd/.par + check points from a .cze file."""
+    import sys
+    prob = fb.synth.make_network(8, 150, 6, 77, mode="mixed", n_control=20)
+    prob.settings.Check_Points = 1
+    d = tmp_path / "blockA"
+    fb.save_problem(prob, str(d), "net")
+    with open(d / "net.cfg", "a") as fh:
+        fh.write("Check_Points\t1\n")
+    t = 2
+    p = int(prob.tie_pt[t])
+    fb.formats.write_cnt(str(d / "net.cze"), [prob.point_name(p)], prob.xyz0[p:p + 1] + 0.5)
+    mod = sys.modules["feba_b200.main"]
+    monkeypatch.setattr(mod, "adjust", lambda pr, verbose=True, cov=False: oracle_outputs(pr))
+    assert fb.main(str(d), False, verbose=False) == 0
+    out = fb.main.last
+    text = (d / "blockA.out").read_text()                        # Output_Filename defaults to <folder>.out (main.m:116-120)
+    assert "Check point differences" in text and "Estimated Ground Coordinates of targets" in text
+    u0 = prob.u_c + 3 * t
+    diff = out["xhat"][u0:u0 + 3] - (prob.xyz0[p] + 0.5)
+    W = report.column_width(out["problem"])
+    assert (f"%-{W}s" + f"%-{W}.5f" * 3) % ((prob.point_name(p),) + tuple(diff)) in text.split("\n")
+    assert (d / "blockA.rsd").exists() and (d / "blockA.par").exists()
+    # a missing .cze with Check_Points = 1 is a read error (main.m:266-275)
+    (d / "net.cze").unlink()
+    assert fb.main(str(d), False, verbose=False) == 1
