@@ -215,7 +215,7 @@ def BatchRun(selpath: Sequence[str], cfg_folder: Optional[str] = None, verbose: 
     probs = []
     for folder in allfolders:
         try:
-            prob = load_problem(folder, cfg_folder=cfg_folder)
+            prob = load_problem_native(folder, cfg_folder=cfg_folder)
             if prob is not None:
                 prob.validate()
         except (OSError, IndexError, ValueError) as exc:
