@@ -527,3 +527,19 @@ def test_shared_factorisation_over_two_gpus():
            "--workload", "config3", "--tile", "6", "--iters", "3", "--tol", "1e-12"]
     out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_known_answer_shipped_int_file_cuda_path():
+    """The only output of the reference program that ships with it: cam0.int:2 is the converged IOP
+    solution of the shipped configuration.  Same bound as the oracle's test
+    (tests/test_oracle.py: 1e-4 relative, xp yp c to the printed millipixel)."""
+    from tests.test_oracle import KNOWN_ANSWER_RTOL, SHIPPED_INT_ROW2
+    prob = golden.load_cam0()
+    err, x0, _ = fb.Buildxhat(prob)
+    out = fb.adjust(prob, x0, verbose=False)
+    off = prob.settings.u_perimage * prob.numImg
+    got = out["xhat"][off:off + 10]
+    rel = np.abs(got - SHIPPED_INT_ROW2) / np.abs(SHIPPED_INT_ROW2)
+    assert out["iterations"] == 5 and rel.max() < KNOWN_ANSWER_RTOL, rel
+    assert ["%.3f" % v for v in got[:3]] == ["1207.903", "1013.724", "1234.758"]

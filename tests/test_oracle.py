@@ -115,6 +115,30 @@ def test_dense_oracle_reproduces_frozen_run(name):
         assert abs(out["deltasum"][0] - 0.1430413) < 1e-6
 
 
+# The one output of the reference program itself that ships with it: cam0.int:2
+# holds the IOPs / distortion terms a previous run of main.m with the shipped config.cfg (Type 'pinhole')
+# converged to, printed with '%.3f' (xp yp c) and 5 significant digits (k1..k5 p1 p2).  The inputs of that
+# run are not the shipped ones to the last digit (cam0.ext / cam0.cnt are themselves rounded output), so
+# the restart moves the values a little: the oracle must come back to the shipped numbers within
+# 1e-4 relative (observed: 9e-8 .. 4.7e-5, i.e. at most 1.5 units of the last printed digit).
+SHIPPED_INT_ROW2 = (1207.903, 1013.724, 1234.758, -2.2408e-07, -5.2142e-14, -3.0190e-20, 9.5835e-27,
+                    -6.0954e-33, 2.2184e-07, 5.9616e-07)
+KNOWN_ANSWER_RTOL = 1e-4
+
+
+def test_known_answer_shipped_int_file_is_the_converged_pinhole_solution():
+    prob = golden.load_cam0()                                  # shipped config: pinhole, everything estimated
+    assert prob.settings.type == "pinhole" and prob.settings.u_percam == 10
+    assert tuple(prob.iop0[0]) == SHIPPED_INT_ROW2             # the fixture is that file
+    err, x0, _ = fb.Buildxhat(prob)
+    off = prob.settings.u_perimage * prob.numImg
+    for run in (dense.gauss_newton(prob, x0), sparse.gauss_newton(prob, x0)):
+        got = run["xhat"][off:off + 10]
+        rel = np.abs(got - SHIPPED_INT_ROW2) / np.abs(SHIPPED_INT_ROW2)
+        assert run["iterations"] == 5 and rel.max() < KNOWN_ANSWER_RTOL, rel
+        assert ["%.3f" % v for v in got[:3]] == ["1207.903", "1013.724", "1234.758"]   # to the printed digits
+
+
 def test_sparse_schur_path_agrees_with_dense():
     prob = golden.load_cam0()
     err, xhat0, _ = fb.Buildxhat(prob)
