@@ -91,3 +91,40 @@ def test_two_rank_point_sharded_iteration(tmp_path, mode):
     assert not np.isnan(x_glob).any() and not np.isnan(v_glob).any()    # every unknown / row owned once
     assert np.linalg.norm(x_glob - x_ref) < 1e-10 * np.linalg.norm(x_ref)
     assert np.max(np.abs(v_glob - res_ref["v"])) < 1e-8
+
+
+@pytest.mark.parametrize("world", [3, 4, 8])
+def test_partition_covers_every_point_and_observation_once(world):
+    """shard_problem for the bench's group sizes (no process group needed): points, observations and
+    tie unknowns are split without overlap, the shards are balanced by observation count, local slots
+    are consistent, and local <-> global xhat maps invert each other."""
+    prob = synth.make_network(16, 1200, 7, 99, mode="mixed", n_control=60)
+    err, xhat0, _ = fb.Buildxhat(prob)
+    owner = sh.point_owner(prob, world)
+    assert owner.shape == (prob.numPts,) and set(np.unique(owner)) == set(range(world))
+    assert np.all(np.diff(owner) >= 0)                                   # contiguous CNT ranges
+    seen_rows = np.zeros(prob.n_obs, dtype=int)
+    seen_pts = np.zeros(prob.numPts, dtype=int)
+    seen_tie = np.zeros(prob.numtie, dtype=int)
+    x_glob = np.full(prob.u, np.nan)
+    counts = []
+    for r in range(world):
+        shd = sh.shard_problem(prob, r, world)
+        loc = shd.prob
+        loc.validate()
+        seen_rows[shd.obs_rows] += 1
+        seen_pts[shd.pts] += 1
+        seen_tie[shd.tie_global] += 1
+        counts.append(loc.n_obs)
+        assert loc.numImg == prob.numImg and loc.numCam == prob.numCam    # full image / camera tables
+        assert np.array_equal(shd.pts[loc.obs_pt], prob.obs_pt[shd.obs_rows])
+        assert np.array_equal(loc.obs_x, prob.obs_x[shd.obs_rows])
+        # local tie slots keep the global TIE order
+        assert np.all(np.diff(shd.tie_global) > 0)
+        assert np.array_equal(shd.pts[loc.tie_pt], prob.tie_pt[shd.tie_global])
+        x_loc = shd.local_xhat(xhat0)
+        assert x_loc.size == loc.u and np.array_equal(x_loc[:prob.u_c], xhat0[:prob.u_c])
+        shd.scatter_xhat(x_loc, x_glob)
+    assert np.all(seen_rows == 1) and np.all(seen_pts == 1) and np.all(seen_tie == 1)
+    assert np.array_equal(x_glob, xhat0)
+    assert max(counts) - min(counts) < 0.25 * prob.n_obs / world + 50
