@@ -53,6 +53,8 @@ struct feba_handle {
     double* scal_host = nullptr;  // pinned mirror of scal
     int* info_host = nullptr;
     size_t S_count = 0;
+    double* packed = nullptr;     // lower trapezoids of S, contiguous (feba_reduced_pack)
+    size_t packed_count = 0;
     long long n_pairs = 0;
     int64_t u = 0;
     int n_partial = 0;
@@ -618,6 +620,54 @@ int feba_reduced_dev(feba_handle* h, double** dev_ptr, size_t* count) {
     if (!h || !dev_ptr || !count) return FEBA_ERR_INVALID;
     *dev_ptr = h->P.S;
     *count = h->S_count;
+    return FEBA_OK;
+}
+
+// Packed form of the exchange buffer (opt-in, FEBA_PACKED_REDUCE=1 in shard.py): the solve half reads the
+// lower triangle and the augmented block row only, so per group of kPackCols 64-column blocks the rows from
+// the group's first row down to the end of the buffer are copied (strided device copies, no kernel) into
+// one contiguous buffer of ~(1/2 + 1/(2 groups)) of the square; the caller sums THAT across ranks and
+// feba_reduced_unpack copies it back.  Entries above a group's first row keep this rank's partial sums:
+// nothing reads them.
+static constexpr int kPackCols = 8;
+
+int feba_reduced_pack(feba_handle* h, double** dev_ptr, size_t* count) {
+    if (!h || !dev_ptr || !count) return FEBA_ERR_INVALID;
+    if (h->phase != 1) return fail(h, FEBA_ERR_STATE, "feba_reduced_pack needs a pending feba_iterate_assemble");
+    CU(h, cudaSetDevice(h->device));
+    const DevProblem& P = h->P;
+    const size_t ld = (size_t)P.ld, w = (size_t)kPackCols * kBlk;
+    if (!h->packed) {
+        size_t total = 0;
+        for (size_t c0 = 0; c0 < ld; c0 += w) total += (ld - c0) * std::min(w, ld - c0);
+        h->packed_count = total;
+        CU(h, dev_alloc(h, &h->packed, total));
+    }
+    size_t off = 0;
+    for (size_t c0 = 0; c0 < ld; c0 += w) {
+        const size_t rows = ld - c0, cols = std::min(w, ld - c0);
+        CU(h, cudaMemcpy2DAsync(h->packed + off, rows * sizeof(double), P.S + c0 + ld * c0, ld * sizeof(double),
+                                rows * sizeof(double), cols, cudaMemcpyDeviceToDevice, h->stream));
+        off += rows * cols;
+    }
+    *dev_ptr = h->packed;
+    *count = h->packed_count;
+    return FEBA_OK;
+}
+
+int feba_reduced_unpack(feba_handle* h) {
+    if (!h) return FEBA_ERR_INVALID;
+    if (h->phase != 1 || !h->packed) return fail(h, FEBA_ERR_STATE, "feba_reduced_unpack without feba_reduced_pack");
+    CU(h, cudaSetDevice(h->device));
+    const DevProblem& P = h->P;
+    const size_t ld = (size_t)P.ld, w = (size_t)kPackCols * kBlk;
+    size_t off = 0;
+    for (size_t c0 = 0; c0 < ld; c0 += w) {
+        const size_t rows = ld - c0, cols = std::min(w, ld - c0);
+        CU(h, cudaMemcpy2DAsync(P.S + c0 + ld * c0, ld * sizeof(double), h->packed + off, rows * sizeof(double),
+                                rows * sizeof(double), cols, cudaMemcpyDeviceToDevice, h->stream));
+        off += rows * cols;
+    }
     return FEBA_OK;
 }
 

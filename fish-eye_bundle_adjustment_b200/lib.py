@@ -25,7 +25,7 @@ EXPORTS = (
     "feba_set_xhat", "feba_get_xhat", "feba_iterate", "feba_iterate_assemble", "feba_reduced_dev",
     "feba_iterate_solve", "feba_get_delta", "feba_residuals", "feba_solve", "feba_last_timing",
     "feba_launch_count", "feba_debug_reduced", "feba_cov_prepare", "feba_cov_diag", "feba_cov_block", "feba_iterate_async", "feba_iterate_solve_async", "feba_sync",
-    "feba_dist_unique_id", "feba_dist_init",
+    "feba_dist_unique_id", "feba_dist_init", "feba_reduced_pack", "feba_reduced_unpack",
 )
 
 
@@ -94,6 +94,8 @@ def load() -> C.CDLL:
     lib.feba_iterate_assemble.argtypes = [H]
     lib.feba_reduced_dev.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     lib.feba_iterate_solve.argtypes = [H, _pd, _pd]
+    lib.feba_reduced_pack.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    lib.feba_reduced_unpack.argtypes = [H]
     lib.feba_residuals.argtypes = [H, _pd, _pd, _pd]
     lib.feba_solve.argtypes = [H, _pi, _pd, C.c_size_t]
     lib.feba_last_timing.argtypes = [H, _pd]
@@ -229,6 +231,16 @@ class Handle:
         p, n = C.c_void_p(), C.c_size_t()
         self._check(self._lib.feba_reduced_dev(self._h, C.byref(p), C.byref(n)))
         return int(p.value), int(n.value)
+
+    def reduced_pack(self):
+        """feba_reduced_pack: copy what the solve half reads of the reduced system into one contiguous
+        device buffer; returns (device pointer, number of doubles).  Pair with ``reduced_unpack``."""
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self._lib.feba_reduced_pack(self._h, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def reduced_unpack(self):
+        self._check(self._lib.feba_reduced_unpack(self._h))
 
     def dist_init(self, rank: int, world: int, unique_id: bytes):
         """Join a group of handles (one per GPU/process) that factorise the reduced system together

@@ -120,6 +120,13 @@ int feba_iterate(feba_handle *h, double *deltasum_out);
 int feba_iterate_assemble(feba_handle *h);
 int feba_reduced_dev(feba_handle *h, double **dev_ptr, size_t *count);
 int feba_iterate_solve(feba_handle *h, double *deltasum_cam, double *deltasum_pts);
+/* Optional, smaller exchange: only the lower triangle and the augmented block row of the reduced
+ * system are read by the solve half.  _pack copies those (per group of 512 columns: the rows from the
+ * group's first row down) into one contiguous device buffer of about half the size and returns it;
+ * the caller sums THAT buffer across ranks instead of feba_reduced_dev() and calls _unpack before
+ * feba_iterate_solve.  Device copies on the handle's stream, asynchronous like the caller's collective. */
+int feba_reduced_pack(feba_handle *h, double **dev_ptr, size_t *count);
+int feba_reduced_unpack(feba_handle *h);
 
 /* Optional: let the ranks factorise the summed reduced system TOGETHER instead of each rank
  * repeating it (the factorisation is ~70 % of an iteration at u_c = 12,010 and does not shrink with

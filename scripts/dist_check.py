@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--tile", type=int, default=6)
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--tol", type=float, default=1e-9)
+    ap.add_argument("--packed", action="store_true",
+                    help="also run the shared factorisation with the packed exchange (FEBA_PACKED_REDUCE=1)")
     args = ap.parse_args()
     if args.tile:
         os.environ["FEBA_DAG_TILE"] = str(args.tile)
@@ -41,8 +43,9 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     out = {}
-    for mode in ("0", "1"):
-        os.environ["FEBA_DIST_CHOL"] = mode
+    for mode in ("0", "1") + (("1p",) if args.packed else ()):
+        os.environ["FEBA_DIST_CHOL"] = mode[0]
+        os.environ["FEBA_PACKED_REDUCE"] = "1" if mode.endswith("p") else "0"
         h = fb.Handle(shard.prob)
         h.set_stream(stream.cuda_stream)
         adj = sh.ShardedAdjustment(h, shard)
@@ -58,11 +61,19 @@ def main():
     errs = torch.tensor([err_cam, err_pts], dtype=torch.float64, device="cuda")
     dist.all_reduce(errs, op=dist.ReduceOp.MAX)
     ok = bool((errs <= args.tol).all().item())
+    extra = {}
+    if args.packed:
+        xp = out["1p"][0]
+        ep = torch.tensor([float(np.max(np.abs(xp - xb) / (np.abs(xb) + 1e-3)))], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ep, op=dist.ReduceOp.MAX)
+        # same numbers, same collective; with more than two ranks the order of the sum may differ per element
+        ok = ok and float(ep.item()) <= args.tol
+        extra = {"packed_rel_diff_vs_shared": float(ep.item()), "factor_ms_shared_packed": out["1p"][2]["factor_ms"]}
     if rank == 0:
         print(json.dumps({"world": world, "workload": args.workload, "tile": args.tile, "u_c": int(u_c),
                           "err_cam": float(errs[0]), "err_pts": float(errs[1]), "ok": ok,
                           "deltasum_replicated": out["0"][1], "deltasum_shared": out["1"][1],
-                          "factor_ms_replicated": out["0"][2]["factor_ms"], "factor_ms_shared": out["1"][2]["factor_ms"]}),
+                          "factor_ms_replicated": out["0"][2]["factor_ms"], "factor_ms_shared": out["1"][2]["factor_ms"], **extra}),
               flush=True)
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
