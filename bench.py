@@ -365,7 +365,8 @@ def run_ours(args, rank, world, local_rank):
                    "n_pts": prob.numPts, "u": prob.u, "u_c": prob.u_c, "inner_constraints": prob.settings.Inner_Constraints,
                    "type": prob.settings.type, "parallelism": (f"point-sharded assembly x{world}, all-reduce of the reduced system, "
                                    + ("replicated factorisation" if os.environ.get("FEBA_DIST_CHOL", "1") == "0"
-                                      else "column-cyclic shared factorisation (panel broadcasts)"))
+                                      else "column-cyclic shared factorisation (panel broadcasts)")
+                                   + (", packed exchange" if os.environ.get("FEBA_PACKED_REDUCE", "0") == "1" else ""))
                    if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (observations + reduced system > 126 MB); no flush needed"},
         "e2e": {"value": e2e_val, "unit": "obs/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(8 * u_loc),
