@@ -364,7 +364,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": args.workload, "desc": desc, "n_obs": prob.n_obs, "n_img": prob.numImg,
                    "n_pts": prob.numPts, "u": prob.u, "u_c": prob.u_c, "inner_constraints": prob.settings.Inner_Constraints,
                    "type": prob.settings.type, "parallelism": (f"point-sharded assembly x{world}, all-reduce of the reduced system, "
-                                   + ("replicated factorisation" if os.environ.get("FEBA_DIST_CHOL", "1") == "0"
+                                   + ("replicated factorisation" if not (adj.shared_factorisation and prob.u_c > 95 * 64)
                                       else "column-cyclic shared factorisation (panel broadcasts)")
                                    + (", packed exchange" if os.environ.get("FEBA_PACKED_REDUCE", "0") == "1" else ""))
                    if world > 1 else "single GPU",

@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import copy
 import os
+import sys
 from dataclasses import dataclass
 from typing import Optional
 
@@ -102,6 +103,7 @@ class ShardedAdjustment:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._red = None
         self._pk, self._pk_key = None, None
+        self.shared_factorisation = False
         # opt-in until it has been timed on the 8-GPU box: exchange the packed lower trapezoids only
         self._packed = os.environ.get("FEBA_PACKED_REDUCE", "0") == "1"
         if self.world > 1:
@@ -114,12 +116,27 @@ class ShardedAdjustment:
             # factorise the summed system together (feba_dist_init) instead of once per rank;
             # FEBA_DIST_CHOL=0 keeps the replicated solve
             if os.environ.get("FEBA_DIST_CHOL", "1") != "0" and dist.get_backend(group) == "nccl":
-                from .lib import dist_unique_id
+                from .lib import FebaError, dist_unique_id
                 rank = dist.get_rank(group)
                 src = dist.get_global_rank(group, 0) if group is not None else 0
-                ids = [dist_unique_id() if rank == 0 else None]
-                dist.broadcast_object_list(ids, src=src, group=group)
-                handle.dist_init(rank, self.world, ids[0])
+                # feba_dist_init is collective (ncclCommInitRank): make sure EVERY rank can bind NCCL
+                # before any rank enters it, otherwise the others would wait for ever
+                try:
+                    my_id, ok = dist_unique_id(), 1.0
+                except FebaError as exc:
+                    my_id, ok = None, 0.0
+                    print(f"[feba] rank {rank}: {exc.text}", file=sys.stderr)
+                flag = torch.tensor([ok], dtype=torch.float64, device=self._red.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+                if float(flag.item()) < 1.0:
+                    if rank == 0:
+                        print("[feba] NCCL could not be bound on every rank: keeping the replicated solve",
+                              file=sys.stderr)
+                else:
+                    ids = [my_id if rank == 0 else None]
+                    dist.broadcast_object_list(ids, src=src, group=group)
+                    handle.dist_init(rank, self.world, ids[0])
+                    self.shared_factorisation = True
 
     def _exchange(self):
         """Sum the partial reduced systems over the ranks (between the two halves of an iteration)."""
