@@ -543,3 +543,34 @@ def test_known_answer_shipped_int_file_cuda_path():
     rel = np.abs(got - SHIPPED_INT_ROW2) / np.abs(SHIPPED_INT_ROW2)
     assert out["iterations"] == 5 and rel.max() < KNOWN_ANSWER_RTOL, rel
     assert ["%.3f" % v for v in got[:3]] == ["1207.903", "1013.724", "1234.758"]
+
+
+@pytest.mark.parametrize("name", ["cam0_refrun_pinhole", "syn_refrun_mixed", "cam0_refrun_fisheye"])
+def test_cuda_path_against_executed_reference(name):
+    """The CUDA path against outputs of the reference's OWN source (Buildxhat.m, BuildAwG.m, main.m:396-494,
+    :569, BuildRSD.m, main.m:592-602) executed by the MATLAB-subset interpreter and frozen in
+    tests/golden/*_refrun_*.npz (tests/golden/make_refrun.py; tests/test_reference_source_run.py checks the
+    oracles against the same files).  North-star tolerances: xhat 1e-9 (group-normalised), v 1e-8 max|v|,
+    sigma02 / RMS 1e-8, same iteration count.  cam0 + Type 'fisheye' (first sum|delta| = 509 at cond 2e13) is
+    limited by the reference's explicit inverse, which does not reproduce ITSELF better than 4e-7 there
+    (DESIGN.md section 5): that case is compared at 1e-5 / 2e-5 like the oracle is."""
+    from tests.test_reference_source_run import CASES
+    z = np.load(golden.path(name + ".npz"))
+    prob = CASES[name]()
+    loose = name == "cam0_refrun_fisheye"
+    err, x0, names = fb.Buildxhat(prob)
+    assert np.array_equal(x0, z["xhat0"])
+    out = fb.adjust(prob, x0, verbose=False)
+    assert out["iterations"] == int(z["iterations"])
+    assert np.allclose(out["deltasum"][:2], z["deltasum"][:2], rtol=1e-5 if loose else 1e-6)
+    tol_v = 1e-5 if loose else 1e-8
+    vmax = np.max(np.abs(z["v"]))
+    assert np.max(np.abs(out["v"] - z["v"])) < tol_v * vmax
+    assert np.max(np.abs(out["RSD"] - z["RSD"])) < tol_v * max(1.0, vmax)
+    for k in ("RMSx", "RMSy", "RMS", "sigma02"):
+        assert abs(out[k] - float(z[k])) < tol_v * float(z[k]), k
+    if loose:
+        d = np.abs(out["xhat"] - z["xhat"]) / (np.abs(z["xhat"]) + 1e-3)
+        assert d.max() < 2e-5
+    else:
+        assert group_rel(prob, out["xhat"], z["xhat"]) < 1e-9
