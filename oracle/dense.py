@@ -7,8 +7,9 @@ section 8a-Q.  Dense n x u design matrix and explicit inverse, exactly like the 
 it is for the bundled cam0 data and small synthetic networks only.  P is kept as its diagonal
 (the reference stores the same diagonal densely, main.m:398-405).
 
-Parity status: see ``oracle/model.py`` (expression-level pin against the reference source;
-no MATLAB run available => loop-level parity unpinned).
+Parity status: see ``oracle/model.py``.  Loop level: checked against the reference's own loop
+statements executed by ``oracle/refrun.py`` (xhat 7e-12, v 3e-12 px, sigma02 5e-14 on cam0;
+``tests/test_reference_source_run.py``); no MATLAB process is available.
 """
 from __future__ import annotations
 

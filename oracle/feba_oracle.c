@@ -17,8 +17,8 @@
  *   main.m:569                    v = A delta + w with the scaled distortion columns of A
  * The Jacobian is the chain rule through (U,V,W), written independently of
  * oracle/model.py and of the CUDA kernels; tests/test_oracle.py checks it against the frozen outputs
- * of the reference's own generated expressions.  Parity status: see oracle/model.py (unpinned by
- * MATLAB runs; pinned at expression level against the reference source).
+ * of the reference's own generated expressions.  Parity status: see oracle/model.py (pinned against
+ * the reference's source executed by oracle/mlab.py and at expression level; no MATLAB process).
  *
  * Build: oracle/Makefile -> oracle/_build/libfeba_oracle.so   (gcc -O2 -fopenmp)
  */

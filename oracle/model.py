@@ -8,13 +8,16 @@ CPU-baseline / ``--impl reference`` legs may import this package; the product pa
 (``fish-eye_bundle_adjustment_b200``) never does.
 
 Parity status: the reference is MATLAB and neither MATLAB nor Octave exists in the build
-container, and the reference ships no tests or golden outputs, so end-to-end parity is
-**unpinned by reference-run outputs**.  What *is* pinned: every generated Jacobian
-expression of ``BuildAwG.m:223-495`` (100 expressions, 5 models) and the projection /
-IOP / G-row statements are executed from the reference's own source text by
-``oracle/refexpr.py`` (MATLAB arithmetic -> Python arithmetic, nothing copied into this
-repo) and compared with this module in ``tests/test_oracle_vs_reference_source.py``; the
-vectors so produced on the bundled cam0 data are committed under ``tests/golden/``.
+container, and the reference ships no tests or golden outputs.  What this oracle is pinned to:
+(1) the reference's own source EXECUTED -- ``oracle/mlab.py`` / ``oracle/refrun.py`` run the whole
+``BuildAwG.m`` (and ``Buildxhat.m``, ``BuildRSD.m``, ``sumabs.m``, the loop / residual / statistics
+statements of ``main.m``) from ``/root/reference`` with a MATLAB-subset interpreter; this module's
+``A``, ``w``, ``G``, ``dist_scaling`` match to 3e-16 / 5e-13 px / 9e-16, the loops built on it to 1e-11
+(``tests/test_reference_source_run.py``, frozen in ``tests/golden/*_refrun_*.npz``); (2) expression
+level, ``oracle/refexpr.py`` (``tests/test_oracle.py``, ``tests/golden/cam0_refsrc_t*.npz``); (3) the one
+shipped output of the reference, ``cam0.int:2`` (``tests/test_oracle.py::test_known_answer_...``).
+Not pinned: a MATLAB process (libm / LAPACK differences of a few ulp, amplified by cond(N) after the
+explicit inverse).
 
 The Jacobian here is *not* a transcription of the generated expressions: it is the chain
 rule through (U,V,W) of the same function, which is what the

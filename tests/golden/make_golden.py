@@ -8,7 +8,7 @@ container:  python tests/golden/make_golden.py
 * cam0_gn_<type>.npz      -- one full run of the literal dense restatement (oracle/dense.py) of
                              main.m:412-494 + 569-602 for the shipped config (pinhole) and for
                              Type 'fisheye': xhat, deltasum trace, v, RSD, sigma02, RMSx, RMSy
-                             (oracle output, NOT MATLAB output -- loop-level parity is unpinned)
+                             (oracle output; the reference's own loop, executed, is frozen by make_refrun.py)
 * cam0_gn_fisheye_exact.npz -- the same loop with every step solved to extended precision
                              (oracle/exact.py).  cond(N) ~ 2e13 on this case: the explicit-inverse
                              run above deviates from this one by 4.3e-7 px in v (its own round-off),
