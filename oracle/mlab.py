@@ -59,7 +59,21 @@ COLON = _Colon()
 
 
 class _End:
-    pass
+    """``end`` inside a subscript, with ``end-1`` / ``end+k`` arithmetic."""
+
+    def __init__(self, off: int = 0):
+        self.off = off
+
+    def __sub__(self, k):
+        return _End(self.off - int(round(float(k))))
+
+    def __add__(self, k):
+        return _End(self.off + int(round(float(k))))
+
+    __radd__ = __add__
+
+    def at(self, n: int) -> int:
+        return n + self.off
 
 
 END = _End()
@@ -72,12 +86,12 @@ class Rng:
         self.a, self.s, self.b = (a, 1, b) if c is None else (a, b, c)
 
     def resolve(self, n: int) -> np.ndarray:
-        b = n if self.b is END else self.b
-        a = n if self.a is END else self.a
+        b = self.b.at(n) if isinstance(self.b, _End) else self.b
+        a = self.a.at(n) if isinstance(self.a, _End) else self.a
         return np.arange(int(round(a)), int(round(b)) + (1 if self.s > 0 else -1), int(round(self.s)))
 
     def __iter__(self):
-        if self.b is END or self.a is END:
+        if isinstance(self.b, _End) or isinstance(self.a, _End):
             raise MlabError("'end' outside an index")
         return iter(int(v) for v in self.resolve(0))
 
@@ -99,8 +113,8 @@ def _index(i, n: int):
         return np.arange(n)
     if isinstance(i, Rng):
         return i.resolve(n) - 1
-    if i is END:
-        return n - 1
+    if isinstance(i, _End):
+        return i.at(n) - 1
     if isinstance(i, Mat):
         return np.rint(i.a.ravel(order="F")).astype(int) - 1
     k = int(round(float(i)))
@@ -234,6 +248,49 @@ class Mat:
     __hash__ = None
 
 
+class Char(str):
+    """char row vector: indexable with ``s(1)``, ``s(2:end-1)``."""
+
+    def __call__(self, *idx):
+        if len(idx) != 1:
+            raise MlabError("char arrays take one subscript here")
+        k = _index(idx[0], len(self))
+        if isinstance(k, (int, np.integer)):
+            return Char(self[k])
+        return Char("".join(self[j] for j in k))
+
+    @property
+    def T(self):
+        return self
+
+
+class StrMat:
+    """MATLAB string matrix (``readmatrix(...,'OutputType','string')``); ``None`` is ``<missing>``."""
+
+    def __init__(self, rows):
+        r = len(rows)
+        c = max((len(x) for x in rows), default=0)
+        self.a = np.empty((r, c), dtype=object)
+        for i, row in enumerate(rows):
+            for j in range(c):
+                v = row[j] if j < len(row) else None
+                self.a[i, j] = None if v is None else Char(v)
+
+    def _get(self, idx):
+        if len(idx) == 1:
+            k = _index(idx[0], self.a.size)
+            return self.a.ravel(order="F")[k]
+        return self.a[_index(idx[0], self.a.shape[0]), _index(idx[1], self.a.shape[1])]
+
+    def __call__(self, *idx):
+        v = self._get(idx)
+        if isinstance(v, np.ndarray):
+            raise MlabError("string-matrix slices are not in the subset")
+        return v
+
+    brace = __call__
+
+
 class EW:
     """Exponent of ``.^`` (element-wise power)."""
 
@@ -304,6 +361,11 @@ class Cell:
             rr, cc = np.atleast_1d(r), np.atleast_1d(c)
             if len(vals) != rr.size * cc.size:
                 raise MlabError("cell assignment size mismatch")
+            nr, nc = max(self.a.shape[0], int(rr.max()) + 1), max(self.a.shape[1], int(cc.max()) + 1)
+            if (nr, nc) != self.a.shape:                       # MATLAB grows the cell, new slots hold []
+                big = Cell(nr, nc)
+                big.a[:self.a.shape[0], :self.a.shape[1]] = self.a
+                self.a = big.a
             k = 0
             for j in cc:
                 for i in rr:
@@ -343,7 +405,12 @@ class StructArray:
         self.items = items
 
     def __call__(self, i):
-        return self.items[_index(i, len(self.items))]
+        if i is COLON:
+            return self
+        k = _index(i, len(self.items))
+        if k == len(self.items):                               # data.points(i).x = ... creates element i
+            self.items.append(Struct())
+        return self.items[k]
 
     def __getattr__(self, name):                              # data.points.x -> comma-separated list
         if name == "items":
@@ -361,7 +428,7 @@ class StrCol(list):
 # ------------------------------------------------------------------------------------ built-ins
 
 def _size(x, d=None):
-    if isinstance(x, (Mat, Cell)):
+    if isinstance(x, (Mat, Cell, StrMat)):
         shp = x.a.shape
     elif isinstance(x, StructArray):
         shp = (1, len(x.items))
@@ -410,7 +477,7 @@ def _mat(rows):
     if all(isinstance(e, str) for e in flat):
         if len(rows) != 1:
             raise MlabError("multi-row char literal")
-        return "".join(flat)
+        return Char("".join(flat))
     if any(isinstance(e, str) for e in flat):
         raise MlabError("mixed char / numeric literal")
 
@@ -468,17 +535,55 @@ def _power(x, e):
     return _num(x) ** _num(e)
 
 
+def _unwrap1(x):
+    """1 x 1 cell -> its content (strcmp(CNT(j,1), id) compares a 1x1 cell with a char)."""
+    if isinstance(x, Cell) and x.a.size == 1:
+        return x.a.flat[0]
+    return x
+
+
 def _strcmp(a, b):
-    return isinstance(a, str) and isinstance(b, str) and a == b
+    a, b = _unwrap1(a), _unwrap1(b)
+    return isinstance(a, str) and isinstance(b, str) and str(a) == str(b)
 
 
 def _strcat(*parts):
-    return "".join(str(p) for p in parts)
+    return Char("".join(str(p) for p in parts))
 
 
 def _num2str(v, *_):
     v = _num(v)
-    return "%d" % int(v) if v == int(v) else "%.5g" % v
+    return Char("%d" % int(v) if v == int(v) else "%.5g" % v)
+
+
+def _str2double(x):
+    """MATLAB str2double for the plain decimal forms the data files use; NaN otherwise."""
+    x = _unwrap1(x)
+    if not isinstance(x, str) or "_" in x:
+        return math.nan
+    try:
+        return float(x)
+    except ValueError:
+        return math.nan
+
+
+def _isnan(x):
+    return isinstance(x, float) and math.isnan(x)
+
+
+def _unique(x):
+    if isinstance(x, Cell):
+        vals = sorted({str(v) for v in x.a.ravel(order="F")})
+        return Cell.of([[Char(v)] for v in vals])
+    if isinstance(x, Mat):
+        return Mat(np.unique(x.a).reshape(1, -1) if x.a.shape[0] == 1 else np.unique(x.a).reshape(-1, 1))
+    raise MlabError("unique: unsupported argument")
+
+
+def _fileparts(path):
+    d, base = os.path.split(str(path).rstrip("/"))
+    stem, ext = os.path.splitext(base)
+    return Char(d), Char(stem), Char(ext)
 
 
 def _rmfield(s: Struct, name: str):
@@ -497,12 +602,16 @@ BUILTINS = {
     "atan": _elementwise(math.atan), "atan2": lambda y, x: math.atan2(_num(y), _num(x)),
     "sec": _elementwise(lambda t: 1.0 / math.cos(t)), "abs": _elementwise(abs), "strcmp": _strcmp,
     "strcat": _strcat, "num2str": _num2str, "diag": _diag, "repmat": _repmat, "sum": _sum, "rmfield": _rmfield,
-    "isempty": _isempty, "pi": lambda: math.pi,
+    "isempty": _isempty, "pi": lambda: math.pi, "str2double": _str2double, "isnan": _isnan, "unique": _unique,
+    "char": lambda x: Char(_unwrap1(x)), "ismissing": lambda x: x is None, "fileparts": _fileparts,
+    "true": True, "false": False, "__chr": Char,
     "__mat": _mat, "__rng": Rng, "__COLON": COLON, "__END": END, "__power": _power, "__Cell": Cell,
     "__cellwrap": lambda v: Cell.of([list(v.items)]) if isinstance(v, CsList) else Cell.of([[v]]),
     "__ew": EW,
 }
 DROPPED = ("disp", "errordlg", "waitfor", "tic", "fprintf", "warning", "clear", "close", "figure")
+for _name in DROPPED:                                           # `h = errordlg(...)`: the call survives as a no-op
+    BUILTINS[_name] = lambda *a: 0.0
 
 # ------------------------------------------------------------------------------------ tokeniser
 
@@ -696,7 +805,7 @@ def expr(toks: List[Tok], indexing: bool = False) -> str:
         if t.kind == "num":
             out.append(t.text if any(c in t.text for c in ".eE") else t.text + ".0")
         elif t.kind == "str":
-            out.append(repr(t.text))
+            out.append("__chr(" + repr(t.text) + ")")
         elif t.kind == "id":
             if t.text == "end" and indexing:
                 out.append("__END")
@@ -950,7 +1059,9 @@ class Program:
             if only is not None and name not in only:
                 continue
             ret = "return " + (("(" + ", ".join(outs) + ",)") if len(outs) > 1 else (outs[0] if outs else "None"))
-            lines = [f"def {name}({', '.join(args)}):"] + self._emit(body, outs, 1) + ["    " + ret]
+            lines = [f"def {name}({', '.join(a + '=None' for a in args)}):",
+                     f"    nargin = float(len([__a for __a in ({' '.join(a + ',' for a in args)}) if __a is not None]))"] \
+                + self._emit(body, outs, 1) + ["    " + ret]
             code = "\n".join(lines)
             self.sources[name] = code
             exec(compile(code, f"<mlab:{name}>", "exec"), self.env)

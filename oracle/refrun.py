@@ -14,6 +14,7 @@ files under ``/root/reference``:
 * ``functions/BuildRSD.m``    (whole function)            |
 * ``main.m:592-602`` + local ``rms`` (main.m:997-1002)    |
 * ``functions/sumabs.m``      (whole function)
+* ``main.m:105-384`` + ``functions/findSetting.m``: settings and the problem build -> ``ReferenceProblemBuild``
 
 The only statements left out are the ones that talk to the user (dropped by the interpreter) and
 ``tic`` / plotting.  Nothing of the reference is stored in this repository; see ``mlab.py`` for what the
@@ -27,7 +28,7 @@ from typing import Optional
 import numpy as np
 
 from . import mlab
-from .mlab import Cell, Mat, StrCol, Struct, StructArray
+from .mlab import Cell, Char, Mat, StrCol, StrMat, Struct, StructArray
 
 
 def _settings(prob) -> Struct:
@@ -139,10 +140,60 @@ class Reference:
         return out
 
 
+class ReferenceProblemBuild:
+    """main.m:105-384 executed: files{1..4} -> PHO/EXT/CNT/INT (:105-110), settings through the
+    reference's ``findSetting.m`` (:112-177), the .tie read (:179-188), string -> numeric cells
+    (:196-258), ``Estimate_AllGCP`` (:260-264) and the ``data.points`` build with its linear ``strcmp``
+    scans (:277-384).  ``ReadFiles.m`` itself cannot run (``dir``, ``readmatrix``, dialogs): its stand-in
+    hands the interpreter the string tables ``formats.read_string_table`` produces, i.e. the statement of
+    ``readmatrix``'s options at ReadFiles.m:49 -- that one built-in stays unexecuted."""
+
+    def __init__(self):
+        if not mlab.available():
+            raise RuntimeError("reference tree not mounted")
+        self.prog = mlab.Program()
+        assert self.prog.add_functions(mlab.read_file("functions/findSetting.m")) == ["findSetting"]
+        self.src = (mlab.read_lines("main.m", 105, 110) + mlab.read_lines("main.m", 112, 177)
+                    + mlab.read_lines("main.m", 179, 188) + mlab.read_lines("main.m", 196, 264)
+                    + mlab.read_lines("main.m", 277, 384))
+
+    def run(self, folder: str, cfg_folder: Optional[str] = None) -> Optional[dict]:
+        import glob
+        import os
+        from feba_b200 import formats
+
+        def table(ext, where=folder):
+            hits = sorted(glob.glob(os.path.join(where, "*" + ext)))
+            if len(hits) != 1:
+                return None
+            return StrMat(formats.read_string_table(hits[0]))
+
+        def ReadFiles(exts):                                     # stand-in, see the class docstring
+            out = Cell(exts.a.size, 1)
+            for k, e in enumerate(exts.a.ravel(order="F")):
+                t = table(str(e))
+                if t is None:
+                    return 1.0, out
+                out.a[k, 0] = t
+            return 0.0, out
+
+        cfg_dir = folder if glob.glob(os.path.join(folder, "*.cfg")) else (cfg_folder or folder)
+        files = Cell(4, 1)
+        for k, e in enumerate((".pho", ".ext", ".cnt", ".int")):
+            files.a[k, 0] = table(e)
+        self.prog.env["ReadFiles"] = ReadFiles
+        ws = dict(files=files, CFG=table(".cfg", cfg_dir), data=Struct(settings=Struct(), points=StructArray([])),
+                  pwd=Char(os.path.abspath(folder)), main_error=0.0)
+        ws = self.prog.run(self.src, ws, "problem_build")
+        if "EXT" not in ws or not hasattr(ws["data"], "numImg"):   # a `return` ended the script early
+            return None
+        return ws
+
+
 def sparse_rows(A: np.ndarray):
     """Non-zeros of a design matrix (for compact fixtures)."""
     r, c = np.nonzero(A)
     return r.astype(np.int32), c.astype(np.int32), A[r, c]
 
 
-__all__ = ["Reference", "workspace", "sparse_rows", "math"]
+__all__ = ["Reference", "ReferenceProblemBuild", "workspace", "sparse_rows", "math"]

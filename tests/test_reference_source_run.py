@@ -168,3 +168,90 @@ def test_oracle_against_frozen_reference_run(name):
         for j in (0, 16):
             idx = np.concatenate([ui * j + np.arange(ui), off + np.arange(uc)])
             assert np.max(np.abs(C[np.ix_(idx, idx)] - z[f"corr_img{j}"])) < 1e-6
+
+
+# ------------------------------------------------------------------ live: the problem build (main.m:105-384)
+
+def _cmp_build(ws, prob):
+    """Workspace left by the executed main.m:105-384 vs the Problem of load_problem / the native packer."""
+    d, s = ws["data"], prob.settings
+    st = d.settings
+    assert str(st.type) == s.type and str(st.Output_Filename) == s.Output_Filename
+    assert st.Meas_std == s.Meas_std and bool(st.no_std_y) == (s.Meas_std_y is None)
+    for k in ("Iteration_Cap", "threshold", "Inner_Constraints", "Estimate_Xc", "Estimate_Yc", "Estimate_Zc",
+              "Estimate_w", "Estimate_p", "Estimate_k", "Estimate_c", "Estimate_xp", "Estimate_yp", "Estimate_radial",
+              "Num_Radial_Distortions", "Estimate_decent", "Estimate_tie", "Estimate_AllGCP", "Check_Points"):
+        assert float(getattr(st, k)) == float(getattr(s, k)), k
+    assert (d.numImg, d.numCam, d.n, d.numtie) == (prob.numImg, prob.numCam, 2 * prob.n_obs, prob.numtie)
+    assert d.numGCP == np.unique(prob.obs_pt).size
+    NK = s.Num_Radial_Distortions
+    same = lambda a, b: (a == b) or (np.isnan(a) and np.isnan(b))
+    for i in range(prob.n_obs):
+        p = d.points(i + 1)
+        j, q = int(prob.obs_img[i]), int(prob.obs_pt[i])
+        c = int(prob.img_cam[j])
+        assert same(p.x, prob.obs_x[i]) and same(p.y, prob.obs_y[i])
+        assert (p.ext_index - 1, p.cnt_index - 1, p.cam_num - 1) == (j, q, c)
+        assert str(p.targetID) == prob.point_name(q) and str(p.imageID) == prob.image_name(j)
+        assert [p.Xc, p.Yc, p.Zc, p.w, p.p, p.k] == list(prob.eop0[j])           # bit-exact, degrees -> radians
+        assert [p.xp, p.yp, p.c] == list(prob.iop0[c, :3])
+        assert list(p.K.a.ravel()) == list(prob.iop0[c, 3:3 + NK]) and list(p.P.a.ravel()) == list(prob.iop0[c, 3 + NK:])
+        assert [p.y_dir, p.xmin, p.ymin, p.xmax, p.ymax] == list(prob.cam_box[c])
+        assert all(same(a, b) for a, b in zip([p.X, p.Y, p.Z], prob.xyz0[q]))
+        assert p.tieIndex - 1 == prob.pt_tie[q] if p.isTie else (p.tieIndex == -1 and prob.pt_tie[q] == -1)
+    TIE = ws["TIE"]
+    ids = [str(v) for v in TIE.a.ravel(order="F")] if hasattr(TIE, "a") else []
+    assert ids == [prob.point_name(int(q)) if q >= 0 else ids[t] for t, q in enumerate(prob.tie_pt)]
+
+
+@live
+@pytest.mark.parametrize("case", ["cam0", "free_allgcp", "mixed_tie_file", "ragged"])
+def test_problem_build_executed_reference(tmp_path, case):
+    """main.m:105-384 (findSetting.m, str2double conversion, Estimate_AllGCP, the strcmp scans that build
+    data.points) executed on the same files vs the interpreted mirror and the native packer."""
+    from oracle import refrun
+    from tests.test_pack import _write, same_problem
+    if case == "cam0":
+        folder = mlab.REFERENCE_ROOT
+    else:
+        folder = str(tmp_path / "data9")
+        if case == "ragged":
+            import os
+            os.makedirs(folder)
+            _write(folder)
+        else:
+            prob = fb.synth.make_network(9, 120, 5, 31, mode="free" if case == "free_allgcp" else "mixed",
+                                         **({} if case == "free_allgcp" else dict(n_control=15)))
+            fb.save_problem(prob, folder, "net")
+    ws = refrun.ReferenceProblemBuild().run(folder)
+    assert ws is not None
+    py, nat = fb.load_problem(folder), fb.load_problem_native(folder)
+    same_problem(py, nat)
+    _cmp_build(ws, nat)
+
+
+@live
+@pytest.mark.parametrize("what", ["image", "target", "camera"])
+def test_problem_build_errors_executed_reference(tmp_path, what):
+    """Unknown image / target ID: the executed main.m stops (errordlg + return, main.m:293-297, :352-356)
+    and so do the mirror and the native packer.  Unknown camera ID: the reference's scan runs
+    ``for j = 1:2:length(INT)`` over a cell that is wider than it is tall, so with one camera MATLAB
+    indexes past the last row before it can reach its own error dialog (main.m:310-320; ``length`` is the
+    LARGEST dimension) -- the interpreter reproduces that as an IndexError; ours reports the missing ID."""
+    from oracle import refrun
+    prob = fb.synth.make_network(9, 120, 5, 31, mode="mixed", n_control=15)
+    folder = str(tmp_path / "data9")
+    fb.save_problem(prob, folder, "net")
+    name = {"image": "net.pho", "target": "net.pho", "camera": "net.ext"}[what]
+    lines = open(f"{folder}/{name}").read().split("\n")
+    cols = lines[5].split("\t")
+    cols[{"image": 1, "target": 0, "camera": 1}[what]] = "NOSUCH"
+    lines[5] = "\t".join(cols)
+    open(f"{folder}/{name}", "w").write("\n".join(lines))
+    B = refrun.ReferenceProblemBuild()
+    if what == "camera":
+        with pytest.raises(IndexError):
+            B.run(folder)
+    else:
+        assert B.run(folder) is None
+    assert fb.load_problem(folder) is None and fb.load_problem_native(folder) is None
