@@ -170,6 +170,10 @@ class Mat:
                 float(v.flat[0]) if isinstance(v, np.ndarray) else v)
             return
         r, c = _index(idx[0], self.a.shape[0]), _index(idx[1], self.a.shape[1])
+        if np.size(r) == 0 or np.size(c) == 0:                  # A(1:2, 5:4) = zeros(2,0): nothing to store
+            if isinstance(v, np.ndarray) and v.size:
+                raise MlabError("non-empty value into an empty selection")
+            return
         if np.max(r) >= self.a.shape[0] or np.max(c) >= self.a.shape[1]:
             raise MlabError("assignment would grow the array (not supported)")
         if isinstance(r, (int, np.integer)) and isinstance(c, (int, np.integer)):

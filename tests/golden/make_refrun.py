@@ -12,6 +12,10 @@ Needs /root/reference; run in the build container:  python tests/golden/make_ref
 * syn_refrun_mixed.npz    -- synthetic 8-image network (synth.make_network(8, 150, 6, 4242, mode='mixed',
                              n_control=30, NK=3)), Estimate_Yc = 0, Estimate_Phi = 0, no decentering terms, no inner
                              constraints, control + tie points: exercises the flag compaction of the xhat layout
+* syn_refrun_2cam.npz     -- synthetic free network (inner constraints, Estimate_AllGCP, IOP + 5 radial + decentering),
+                             8 images dealt round-robin to TWO cameras: per-camera IOP blocks (cam_num, main.m:322;
+                             BuildAwG.m:110-155,448)
+* syn_refrun_eop.npz      -- synthetic EOP-only adjustment with fixed control points (the shape of BASELINE configs[1])
 These are outputs of the reference's statements run on NumPy / libm, not of MATLAB (see oracle/mlab.py).
 """
 import os
@@ -35,6 +39,23 @@ def synthetic_mixed():
     s = prob.settings
     s.Estimate_Yc, s.Estimate_p, s.Estimate_decent, s.Inner_Constraints = 0, 0, 0, 0
     return prob
+
+
+def synthetic_two_cameras():
+    import copy
+    base = fb.synth.make_network(8, 150, 6, 777, mode="free")
+    prob = copy.copy(base)
+    prob.settings = copy.copy(base.settings)
+    prob.img_cam = (np.arange(base.numImg) % 2).astype(np.int32)
+    prob.iop0 = np.repeat(base.iop0, 2, axis=0)
+    prob.iop0[1, :3] += np.array([0.6, -0.4, 1.1])
+    prob.cam_box = np.repeat(base.cam_box, 2, axis=0)
+    prob.camera_ids = ["0", "1"]
+    return prob
+
+
+def synthetic_eop_only():
+    return fb.synth.make_network(8, 150, 6, 778, mode="eop")
 
 
 def freeze(R, prob, name, correlation=False, blocks=()):
@@ -69,6 +90,8 @@ def main():
     freeze(R, golden.load_cam0(), "cam0_refrun_pinhole.npz", correlation=True, blocks=(0, 16))
     freeze(R, golden.load_cam0(type="fisheye"), "cam0_refrun_fisheye.npz")
     freeze(R, synthetic_mixed(), "syn_refrun_mixed.npz")
+    freeze(R, synthetic_two_cameras(), "syn_refrun_2cam.npz")
+    freeze(R, synthetic_eop_only(), "syn_refrun_eop.npz")
 
 
 if __name__ == "__main__":

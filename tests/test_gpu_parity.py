@@ -545,7 +545,8 @@ def test_known_answer_shipped_int_file_cuda_path():
     assert ["%.3f" % v for v in got[:3]] == ["1207.903", "1013.724", "1234.758"]
 
 
-@pytest.mark.parametrize("name", ["cam0_refrun_pinhole", "syn_refrun_mixed", "cam0_refrun_fisheye"])
+@pytest.mark.parametrize("name", ["cam0_refrun_pinhole", "syn_refrun_mixed", "syn_refrun_2cam", "syn_refrun_eop",
+                                  "cam0_refrun_fisheye"])
 def test_cuda_path_against_executed_reference(name):
     """The CUDA path against outputs of the reference's OWN source (Buildxhat.m, BuildAwG.m, main.m:396-494,
     :569, BuildRSD.m, main.m:592-602) executed by the MATLAB-subset interpreter and frozen in
