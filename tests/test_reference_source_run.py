@@ -112,7 +112,9 @@ def test_buildawg_executed_reference_flag_compaction(ref):
 
 def _cmp_run(prob, run, out, tol_x=1e-9, tol_v=1e-8, tol_d=1e-6):
     assert out["iterations"] == int(run["iterations"])
-    assert np.allclose(out["deltasum"], run["deltasum"], rtol=1e-3, atol=1e-9)   # last entries are ~1e-8 of noise
+    # the tail of the trace (values below the 1e-6 threshold) is round-off of the explicit inverse; the
+    # stop decision itself is covered by the iteration count above
+    assert np.allclose(out["deltasum"], run["deltasum"], rtol=1e-3, atol=5e-8)
     assert np.allclose(out["deltasum"][:2], run["deltasum"][:2], rtol=tol_d)
     vmax = np.max(np.abs(run["v"]))
     assert np.max(np.abs(out["v"] - run["v"])) < tol_v * vmax
