@@ -18,7 +18,7 @@ SOURCES = ("feba_api.cu", "feba_kernels.cu", "feba_assemble.cu", "feba_chol.cu",
 HEADERS = ("feba_dev.h", "feba_kernels.h", "feba_model.cuh", os.path.join("..", "..", "include", "feba.h"),
            os.path.join("..", "..", "include", "feba_pack.h"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-O3,-Wall,-pthread", "--use_fast_math=false"]
+              "-Xcompiler", "-fPIC,-O3,-Wall,-pthread,-Wno-unknown-pragmas", "--use_fast_math=false"]
 
 
 def _nvcc() -> str:

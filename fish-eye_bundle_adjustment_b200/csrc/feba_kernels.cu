@@ -19,37 +19,8 @@ __global__ void k_tables(int n_img, int n_cam, int NK, const double* __restrict_
                          const double* __restrict__ iop, const double* __restrict__ cam_box,
                          double* __restrict__ img_tab, double* __restrict__ cam_tab) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_img) {
-        const double* e = eop + 6 * i;
-        double sw, cw, sp, cp, sk, ck;
-        sincos(e[3], &sw, &cw);
-        sincos(e[4], &sp, &cp);
-        sincos(e[5], &sk, &ck);
-        double* t = img_tab + kImgStride * i;
-        t[0] = e[0]; t[1] = e[1]; t[2] = e[2];
-        t[3] = ck * cp;  t[4] = cw * sk + ck * sp * sw;  t[5] = sk * sw - ck * cw * sp;
-        t[6] = -cp * sk; t[7] = ck * cw - sk * sp * sw;  t[8] = ck * sw + cw * sk * sp;
-        t[9] = sp;       t[10] = -cp * sw;               t[11] = cp * cw;
-        t[12] = ck; t[13] = sk; t[14] = 0.0; t[15] = 0.0;
-    }
-    if (i < n_cam) {
-        const int NC = NK + 5;
-        const double* p = iop + NC * i;
-        const double* b = cam_box + 5 * i;
-        double* t = cam_tab + kCamStride * i;
-        for (int k = 0; k < kCamStride; ++k) t[k] = 0.0;
-        t[0] = p[0]; t[1] = p[1]; t[2] = p[2]; t[3] = b[0];
-        t[4] = p[3 + NK]; t[5] = p[4 + NK];
-        for (int j = 0; j < NK; ++j) t[6 + j] = p[3 + j];
-        const double hx = (b[3] - b[1]) * 0.5, hy = (b[4] - b[2]) * 0.5;
-        const double rmax2 = hx * hx + hy * hy;          // r_max^2  (BuildAwG.m:422)
-        double s = 1.0;
-        for (int j = 0; j < NK; ++j) {
-            s *= rmax2;                                  // r_max^(2j) (BuildAwG.m:424-426)
-            t[16 + j] = 1.0 / s;
-            t[24 + j] = s;
-        }
-    }
+    if (i < n_img) image_table_row(eop + 6 * i, img_tab + kImgStride * i);
+    if (i < n_cam) camera_table_row(NK, iop + (NK + 5) * i, cam_box + 5 * i, cam_tab + kCamStride * i);
 }
 
 // Inner-constraint rows per image from the CURRENT EOPs (BuildAwG.m:514-527), written as the

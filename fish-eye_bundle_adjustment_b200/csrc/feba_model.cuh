@@ -10,8 +10,19 @@
 //   fx = -c   (U/R) g(theta) + xp + dr*xb + P1 (yb^2+3xb^2) + 2 P2 xb yb         BuildAwG.m:168-208
 //   fy = -c yd(V/R) g(theta) + yp + dr*yb + P2 (xb^2+3yb^2) + 2 P1 xb yb
 //   xb = x-xp, yb = y-yp (OBSERVED coordinates), dr = sum_j K_j r^(2j)
+//
+// The functions here are plain scalar C++ (FEBA_HD = __host__ __device__): the kernels inline them, and
+// tests/host_model compiles THIS FILE with g++ to check the same source on the CPU against the reference's
+// own BuildAwG.m (tests/test_cuda_model_source_on_host.py) -- a check of the arithmetic, not a CPU path of
+// the product (nothing in the library calls the host instantiation).
 #pragma once
+#ifdef __CUDACC__
 #include <cuda_runtime.h>
+#define FEBA_HD __host__ __device__ __forceinline__
+#else
+#include <math.h>
+#define FEBA_HD inline
+#endif
 #include <stdint.h>
 
 namespace feba {
@@ -24,6 +35,37 @@ constexpr int kCamStride = 32;   // doubles per camera-table row
 // camera table row: [0] xp [1] yp [2] c [3] y_dir [4] P1 [5] P2 [6..6+NK) K_j
 //                   [16..16+NK) 1/r_max^(2j)   (BuildAwG.m:422-426; columns are pre-divided)
 
+// Image-table row from the EOPs of one image.  M = R3(kappa) R2(phi) R1(omega) as written in
+// BuildAwG.m:163-165.
+FEBA_HD void image_table_row(const double* __restrict__ e, double* __restrict__ t) {
+    double sw, cw, sp, cp, sk, ck;
+    sincos(e[3], &sw, &cw);
+    sincos(e[4], &sp, &cp);
+    sincos(e[5], &sk, &ck);
+    t[0] = e[0]; t[1] = e[1]; t[2] = e[2];
+    t[3] = ck * cp;  t[4] = cw * sk + ck * sp * sw;  t[5] = sk * sw - ck * cw * sp;
+    t[6] = -cp * sk; t[7] = ck * cw - sk * sp * sw;  t[8] = ck * sw + cw * sk * sp;
+    t[9] = sp;       t[10] = -cp * sw;               t[11] = cp * cw;
+    t[12] = ck; t[13] = sk; t[14] = 0.0; t[15] = 0.0;
+}
+
+// Camera-table row from xp yp c k1..kNK p1 p2 (p) and y_dir xmin ymin xmax ymax (b).
+FEBA_HD void camera_table_row(int NK, const double* __restrict__ p, const double* __restrict__ b,
+                              double* __restrict__ t) {
+    for (int k = 0; k < kCamStride; ++k) t[k] = 0.0;
+    t[0] = p[0]; t[1] = p[1]; t[2] = p[2]; t[3] = b[0];
+    t[4] = p[3 + NK]; t[5] = p[4 + NK];
+    for (int j = 0; j < NK; ++j) t[6 + j] = p[3 + j];
+    const double hx = (b[3] - b[1]) * 0.5, hy = (b[4] - b[2]) * 0.5;
+    const double rmax2 = hx * hx + hy * hy;          // r_max^2  (BuildAwG.m:422)
+    double s = 1.0;
+    for (int j = 0; j < NK; ++j) {
+        s *= rmax2;                                  // r_max^(2j) (BuildAwG.m:424-426)
+        t[16 + j] = 1.0 / s;
+        t[24 + j] = s;
+    }
+}
+
 template <int NK>
 struct ObsJac {
     double Je[2][6];        // d(fx,fy)/d(Xc,Yc,Zc,omega,phi,kappa)         BuildAwG.m:217-352
@@ -32,7 +74,7 @@ struct ObsJac {
     double w[2];            // misclosure fx-x, fy-y                         BuildAwG.m:505-512
 };
 
-__device__ __forceinline__ void g_and_dg(int type, double R, double W, double& g, double& dg) {
+FEBA_HD void g_and_dg(int type, double R, double W, double& g, double& dg) {
     // g(theta), g'(theta), theta = atan(R/W)  (BuildAwG.m:184-208)
     const double t = R / W;
     if (type == 0) {            // equidistant fish-eye: r = c*theta
@@ -58,10 +100,10 @@ __device__ __forceinline__ void g_and_dg(int type, double R, double W, double& g
 
 // WANT_J = false computes only the misclosure (fx-x, fy-y).
 template <int NK, bool WANT_CAM>
-__device__ __forceinline__ void observation(int type, double x, double y,
-                                            const double* __restrict__ it,   // image row
-                                            const double* __restrict__ ct,   // camera row
-                                            double X, double Y, double Z, ObsJac<NK>& o) {
+FEBA_HD void observation(int type, double x, double y,
+                         const double* __restrict__ it,   // image row
+                         const double* __restrict__ ct,   // camera row
+                         double X, double Y, double Z, ObsJac<NK>& o) {
     const double dX = X - it[0], dY = Y - it[1], dZ = Z - it[2];
     const double m00 = it[3], m01 = it[4], m02 = it[5];
     const double m10 = it[6], m11 = it[7], m12 = it[8];

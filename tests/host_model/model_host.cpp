@@ -1,0 +1,45 @@
+// TEST INFRASTRUCTURE: the CUDA path's per-observation source (csrc/feba_model.cuh: table rows,
+// projection, distortion, analytic Jacobian, misclosure) compiled for the HOST with g++, so that the very
+// statements the kernels inline can be checked in a container without a GPU against the reference's own
+// BuildAwG.m (tests/test_cuda_model_source_on_host.py).  Nothing in the product links or calls this.
+#include "../../fish-eye_bundle_adjustment_b200/csrc/feba_model.cuh"
+
+namespace {
+
+template <int NK>
+void run(int type, double x, double y, const double* it, const double* ct, const double* xyz, double* Je, double* Jc,
+         double* Jt, double* w) {
+    feba::ObsJac<NK> o;
+    feba::observation<NK, true>(type, x, y, it, ct, xyz[0], xyz[1], xyz[2], o);
+    for (int r = 0; r < 2; ++r) {
+        for (int k = 0; k < 6; ++k) Je[6 * r + k] = o.Je[r][k];
+        for (int k = 0; k < NK + 5; ++k) Jc[(NK + 5) * r + k] = o.Jc[r][k];
+        for (int k = 0; k < 3; ++k) Jt[3 * r + k] = o.Jt[r][k];
+        w[r] = o.w[r];
+    }
+}
+
+}  // namespace
+
+// eop[6] (angles in radians), iop[NK+5] = xp yp c k1..kNK p1 p2, box[5] = y_dir xmin ymin xmax ymax.
+// Outputs row-major: Je[2][6], Jc[2][NK+5] (columns xp yp c k1..kNK p1 p2, distortion columns divided by
+// r_max^(2j) / r_max^2 as BuildAwG.m:428-445), Jt[2][3], w[2].  Returns 0, or 1 for an unsupported NK.
+extern "C" int feba_host_observation(int type, int NK, double x, double y, const double* eop, const double* iop,
+                                     const double* box, const double* xyz, double* Je, double* Jc, double* Jt,
+                                     double* w) {
+    double it[feba::kImgStride], ct[feba::kCamStride];
+    feba::image_table_row(eop, it);
+    feba::camera_table_row(NK, iop, box, ct);
+    switch (NK) {
+        case 1: run<1>(type, x, y, it, ct, xyz, Je, Jc, Jt, w); break;
+        case 2: run<2>(type, x, y, it, ct, xyz, Je, Jc, Jt, w); break;
+        case 3: run<3>(type, x, y, it, ct, xyz, Je, Jc, Jt, w); break;
+        case 4: run<4>(type, x, y, it, ct, xyz, Je, Jc, Jt, w); break;
+        case 5: run<5>(type, x, y, it, ct, xyz, Je, Jc, Jt, w); break;
+        case 6: run<6>(type, x, y, it, ct, xyz, Je, Jc, Jt, w); break;
+        case 7: run<7>(type, x, y, it, ct, xyz, Je, Jc, Jt, w); break;
+        case 8: run<8>(type, x, y, it, ct, xyz, Je, Jc, Jt, w); break;
+        default: return 1;
+    }
+    return 0;
+}
