@@ -6,13 +6,14 @@ Host code that runs once after the loop.  Everything numeric comes from the devi
 sub-matrix per camera and the EOP+IOP correlation block per image (``feba_cov_block``, normalised as
 main.m:446-456), ``RSD`` (corrected measurements x + vx, y + vy, main.m:587-590), RMS and sigma02.
 Formats follow the reference's ``fprintf`` patterns (``printEOP`` / ``printDist`` / ``printTIE`` at
-main.m:969-977, ``printCell.m``) so that a file written here can be diffed against a MATLAB run.
+main.m:972-980, ``printCell.m``) so that a file written here can be diffed against a MATLAB run.
 
 Known quirks of the reference that are kept (they shape the file): the column width looks at image IDs
 only when they are longer than the longest target ID (main.m:711-717); the labels of the
 EOP/IOP mean-correlation table carry an empty entry between the EOP and IOP names
 (main.m:841-850: ``names`` already starts with the padding cell when it is appended).
-``num2str`` is approximated by ``%d`` for integers and ``%.{floor(log10|x|)+5}g`` otherwise.
+``num2str(x)`` is ``%d`` for integers and ``%.Ng`` with N = max(floor(log10|x|)+5, 5) otherwise (MATLAB's rule
+for scalars: four digits after the leading ones).
 """
 from __future__ import annotations
 
@@ -40,7 +41,7 @@ def num2str(v, digits: Optional[int] = None) -> str:
         return "%d" % int(v)
     if not math.isfinite(v) or v == 0:
         return "%g" % v
-    return "%.*g" % (max(int(math.floor(math.log10(abs(v)))) + 5, 1), v)
+    return "%.*g" % (min(max(int(math.floor(math.log10(abs(v)))) + 5, 5), 16), v)
 
 
 def print_cell(rows: Sequence[Sequence], prefix: str = "", padding: int = 4) -> str:
@@ -137,9 +138,9 @@ def write_out(path: str, prob: Problem, out: dict, version: str = "feba_b200", c
     xhat, std = out["xhat"], np.sqrt(out["Cx_diag"])
     W = column_width(prob)
     dec = 5                                                                  # main.m:698
-    fs = f"%-{W}.{dec}s%-{W}.{dec}f%-{W}.{dec}f\n"                           # printEOP   main.m:969-971
-    fe = f"%-{W}.{dec}s%-{W}.{dec}e%-{W}.{dec}e\n"                           # printDist  main.m:972-974
-    ft = f"%-{W}s%-{W}.0d" + f"%-{W}.{dec}f" * 6 + "\n"                      # printTIE   main.m:975-977
+    fs = f"%-{W}.{dec}s%-{W}.{dec}f%-{W}.{dec}f\n"                           # printEOP   main.m:972-974
+    fe = f"%-{W}.{dec}s%-{W}.{dec}e%-{W}.{dec}e\n"                           # printDist  main.m:975-977
+    ft = f"%-{W}s%-{W}.0d" + f"%-{W}.{dec}f" * 6 + "\n"                      # printTIE   main.m:978-980
     when = when or datetime.datetime.now().strftime("%d-%b-%Y %H:%M:%S")
     ui, uc = s.u_perimage, s.u_percam
     n = prob.n
@@ -173,7 +174,7 @@ def write_out(path: str, prob: Problem, out: dict, version: str = "feba_b200", c
 
     # ---- EOPs per image (main.m:723-777); angles in degrees
     w("Estimated EOPs\nEOP Name\tValue\tStandard Deviation\n")
-    per_image = np.bincount(prob.obs_img, minlength=prob.numImg)             # countImagePoints, main.m:978-985
+    per_image = np.bincount(prob.obs_img, minlength=prob.numImg)             # countImagePoints, main.m:981-988
     k = 0
     for j in range(prob.numImg):
         w("\n")
@@ -205,7 +206,7 @@ def write_out(path: str, prob: Problem, out: dict, version: str = "feba_b200", c
     # ---- ground coordinates (main.m:866-888)
     if s.Estimate_tie:
         w("\n" + LINE + "\n\nEstimated Ground Coordinates of targets\nTargetID\tnumImages\tX\tY\tZ\tstdX\tstdY\tstdZ\n\n")
-        per_point = np.bincount(prob.obs_pt, minlength=prob.numPts)          # countTargetImages, main.m:986-993
+        per_point = np.bincount(prob.obs_pt, minlength=prob.numPts)          # countTargetImages, main.m:989-996
         var = np.zeros((prob.numtie, 3))
         for t in range(prob.numtie):
             p = int(prob.tie_pt[t])

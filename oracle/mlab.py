@@ -27,7 +27,8 @@ values are Python floats (scalars), ``Mat`` (2-D double), ``str``, ``Cell``, ``S
 power or ``^-1`` = inverse; ``'`` transposes; indexing is 1-based, column-major for one subscript,
 with ``:``, ``a:b``, ``a:s:b`` and ``end``; matrix literals split elements on blanks the way MATLAB
 does (``[1 -x]`` is two elements, ``[1 - x]`` one); statements that only talk to the user
-(``disp``, ``errordlg``, ``waitfor``, ``tic``, ``fprintf``) are dropped.
+(``disp``, ``errordlg``, ``waitfor``, ``tic``) are dropped; ``fprintf`` writes into a ``FileSink``
+(escapes, positional ``%N$`` conversions, cyclic reuse of the format).
 """
 from __future__ import annotations
 
@@ -555,9 +556,89 @@ def _strcat(*parts):
     return Char("".join(str(p) for p in parts))
 
 
-def _num2str(v, *_):
+def _num2str(v, prec=None):
+    """num2str for scalars: '%d' for integers, else '%.Ng' with N = max(floor(log10|x|) + 5, 5) (<= 16);
+    num2str(x, n) = '%.ng'."""
+    if isinstance(v, str):
+        return Char(v)
     v = _num(v)
-    return Char("%d" % int(v) if v == int(v) else "%.5g" % v)
+    if prec is not None:
+        return Char("%.*g" % (int(_num(prec)), v))
+    if math.isfinite(v) and v == int(v):
+        return Char("%d" % int(v))
+    if not math.isfinite(v):
+        return Char("NaN" if math.isnan(v) else ("Inf" if v > 0 else "-Inf"))
+    n = min(max(int(math.floor(math.log10(abs(v)))) + 5, 5), 16)
+    return Char("%.*g" % (n, v))
+
+
+_CONV = re.compile(r"%(?:(\d+)\$)?([-+ 0#]*)(\d+)?(?:\.(\d+))?([sdifeEgGc%])")
+
+
+def _fprintf_text(fmt, args):
+    """MATLAB fprintf semantics on a char format: escapes, positional %N$, cyclic reuse of the format."""
+    fmt = str(fmt).replace("\\n", "\n").replace("\\t", "\t").replace("\\\\", "\\")
+    flat = []
+    for a in args:
+        if isinstance(a, CsList):
+            flat += list(a.items)
+        elif isinstance(a, Mat):
+            flat += [float(x) for x in a.a.ravel(order="F")]
+        else:
+            flat.append(a)
+    convs = [m for m in _CONV.finditer(fmt) if m.group(5) != "%"]
+    if not convs:
+        return fmt.replace("%%", "%")
+    positional = any(m.group(1) for m in convs)
+    per = max(int(m.group(1)) for m in convs) if positional else len(convs)
+
+    def once(vals):
+        out, pos, k = [], 0, 0
+        for m in _CONV.finditer(fmt):
+            out.append(fmt[pos:m.start()])
+            pos = m.end()
+            if m.group(5) == "%":
+                out.append("%")
+                continue
+            idx = int(m.group(1)) - 1 if m.group(1) else k
+            k += 1
+            if idx >= len(vals):
+                break                                            # MATLAB stops at the first conversion without data
+            v = vals[idx]
+            conv = "d" if m.group(5) == "i" else m.group(5)
+            spec = "%" + m.group(2) + (m.group(3) or "") + ("." + m.group(4) if m.group(4) is not None else "") + conv
+            if conv in "di" and not isinstance(v, str):
+                spec = spec if float(v) == int(float(v)) else spec[:-1] + "e"
+                v = int(float(v)) if float(v) == int(float(v)) else float(v)
+            elif conv in "feEgG":
+                v = float(v)
+            elif conv in "sc":
+                v = str(v) if isinstance(v, str) else _num2str(v)
+            out.append(spec % v)
+        else:
+            out.append(fmt[pos:])
+        return "".join(out)
+
+    if not flat:
+        return once([])
+    return "".join(once(flat[i:i + per]) for i in range(0, len(flat), per))
+
+
+class FileSink:
+    """fopen/fprintf/fclose target that keeps the text."""
+
+    def __init__(self):
+        self.parts = []
+
+    def text(self):
+        return "".join(self.parts)
+
+
+def _fprintf(fid, fmt, *args):
+    if not isinstance(fid, FileSink):
+        raise MlabError("fprintf needs a FileSink as its first argument here")
+    fid.parts.append(_fprintf_text(fmt, args))
+    return 0.0
 
 
 def _str2double(x):
@@ -608,14 +689,16 @@ BUILTINS = {
     "strcat": _strcat, "num2str": _num2str, "diag": _diag, "repmat": _repmat, "sum": _sum, "rmfield": _rmfield,
     "isempty": _isempty, "pi": lambda: math.pi, "str2double": _str2double, "isnan": _isnan, "unique": _unique,
     "char": lambda x: Char(_unwrap1(x)), "ismissing": lambda x: x is None, "fileparts": _fileparts,
-    "true": True, "false": False, "__chr": Char,
+    "true": True, "false": False, "__chr": Char, "ischar": lambda x: isinstance(x, str),
+    "isa": lambda x, cls: (str(cls) == "double" and isinstance(x, (float, int, Mat)) and not isinstance(x, bool)),
     "__mat": _mat, "__rng": Rng, "__COLON": COLON, "__END": END, "__power": _power, "__Cell": Cell,
     "__cellwrap": lambda v: Cell.of([list(v.items)]) if isinstance(v, CsList) else Cell.of([[v]]),
     "__ew": EW,
 }
-DROPPED = ("disp", "errordlg", "waitfor", "tic", "fprintf", "warning", "clear", "close", "figure")
+DROPPED = ("disp", "errordlg", "waitfor", "tic", "warning", "clear", "close", "figure")
 for _name in DROPPED:                                           # `h = errordlg(...)`: the call survives as a no-op
     BUILTINS[_name] = lambda *a: 0.0
+BUILTINS["fprintf"] = _fprintf
 
 # ------------------------------------------------------------------------------------ tokeniser
 

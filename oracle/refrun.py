@@ -12,7 +12,7 @@ files under ``/root/reference``:
 * ``main.m:446-456``          ``Correlation`` (optional: a u^2 interpreted loop, minutes at u = 580)
 * ``main.m:569``              ``v = A*delta + w``         |
 * ``functions/BuildRSD.m``    (whole function)            |
-* ``main.m:592-602`` + local ``rms`` (main.m:997-1002)    |
+* ``main.m:592-602`` + local ``rms`` (main.m:998-1002)    |
 * ``functions/sumabs.m``      (whole function)
 * ``main.m:105-384`` + ``functions/findSetting.m``: settings and the problem build -> ``ReferenceProblemBuild``
 

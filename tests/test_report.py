@@ -3,6 +3,8 @@ oracle (literal main.m) so the test runs without a GPU; on the GPU the same writ
 covariance outputs of the CUDA path (tests/test_gpu_parity.py::test_main_and_batchrun_over_text_files)."""
 import re
 
+import pytest
+
 import numpy as np
 
 import feba_b200 as fb
@@ -147,3 +149,43 @@ def test_main_writes_out_rsd_par_from_text_files(tmp_path, monkeypatch):
     # a missing .cze with Check_Points = 1 is a read error (main.m:266-275)
     (d / "net.cze").unlink()
     assert fb.main(str(d), False, verbose=False) == 1
+
+
+# ------------------------------------------------------------------ formatting primitives vs the reference's source
+
+@pytest.mark.skipif(not __import__("oracle.mlab", fromlist=["x"]).available(), reason="reference tree not mounted")
+def test_formatting_primitives_against_executed_reference():
+    """functions/printCell.m and the local printEOP / printDist / printTIE of main.m (:972-980), executed by
+    the MATLAB-subset interpreter (fprintf with positional conversions into a text sink), produce the same
+    text as report.print_cell and the format strings of report.write_out."""
+    from oracle import mlab
+    from oracle.mlab import Cell, Char, FileSink
+    P = mlab.Program()
+    assert P.add_functions(mlab.read_file("functions/printCell.m")) == ["printCell"]
+    assert P.add_functions(mlab.read_lines("main.m", 972, 980)) == ["printEOP", "printDist", "printTIE"]
+    prob = golden.load_cam0()
+    tables = [
+        (report.settings_rows(prob.settings), "\t\t", 4),
+        ([["Number of Photos", "42"], ["Total EOP unknowns", "252"], ["\\line", ""], ["Total Unknowns", "580"],
+          ["\\n", ""], ["A-Posteriori", report.num2str(0.618691873512, 10)]], "", 4),
+        ([["Image", "101"], ["Camera", "0"], ["Number of image points", "27"], ["\\line", ""]], "", 4),
+    ]
+    for rows, prefix, padding in tables:
+        sink = FileSink()
+        cell = Cell.of([[Char(r[0]), Char(r[1]) if isinstance(r[1], str) else float(r[1])] for r in rows])
+        P.env["printCell"](sink, cell, Char(prefix.replace("\t", "\\t")), float(padding))
+        assert sink.text() == report.print_cell(rows, prefix, padding)
+    W, dec = 14, 5
+    for name, val, std in (("Xc", 4264.5531234, 0.4123456), ("Omega", -90.04123, 0.0101), ("c", 1234.75756, 0.25)):
+        sink = FileSink()
+        P.env["printEOP"](sink, Char(name), val, std, Char(str(W)), Char(str(dec)))
+        assert sink.text() == f"%-{W}.{dec}s%-{W}.{dec}f%-{W}.{dec}f\n" % (name, val, std)
+    for name, val, std in (("k1", -2.2407864e-07, 1.3e-09), ("p2", 5.96155801e-07, 2.2e-08)):
+        sink = FileSink()
+        P.env["printDist"](sink, Char(name), val, std, Char(str(W)), Char(str(dec)))
+        assert sink.text() == f"%-{W}.{dec}s%-{W}.{dec}e%-{W}.{dec}e\n" % (name, val, std)
+    sink = FileSink()
+    XYZ, sd = mlab.Mat([[2.018], [2574.346], [3519.11]]), mlab.Mat([[0.11], [0.22], [0.33]])
+    P.env["printTIE"](sink, Char("AL01"), 17.0, XYZ, sd, Char(str(W)), Char(str(dec)))
+    assert sink.text() == (f"%-{W}s%-{W}.0d" + f"%-{W}.{dec}f" * 6 + "\n") % ("AL01", 17, 2.018, 2574.346, 3519.11,
+                                                                          0.11, 0.22, 0.33)
