@@ -76,7 +76,7 @@ def settings_rows(s) -> List[list]:
     if s.Meas_std_y is not None:
         rows += [["Meas_std_y", s.Meas_std_y], ["no_std_y", 0]]
     else:
-        rows += [["Meas_std_y", -1], ["no_std_y", 1]]
+        rows += [["no_std_y", 1]]                     # main.m:400 removes the Meas_std_y field (rmfield)
     rows += [["type", s.type], ["Check_Points", s.Check_Points], ["Iteration_Cap", s.Iteration_Cap],
              ["threshold", s.threshold], ["Inner_Constraints", s.Inner_Constraints]]
     for k in ("Estimate_Xc", "Estimate_Yc", "Estimate_Zc", "Estimate_w", "Estimate_p", "Estimate_k", "Estimate_c",

@@ -383,9 +383,43 @@ class Cell:
             for i, j, v in zip(rr, cc, vals):
                 self.a[i, j] = v
 
+    def _grow_for(self, idx):
+        """c{end+1} = v / c{i,j} = v beyond the current size: MATLAB grows the cell."""
+        if len(idx) == 1:
+            i = idx[0]
+            k = (i.at(self.a.size) if isinstance(i, _End) else int(round(float(i)))) - 1
+            if k >= self.a.size:
+                if self.a.size and self.a.shape[0] != 1:
+                    raise MlabError("linear growth of a non-row cell")
+                big = Cell(1, k + 1)
+                big.a[0, :self.a.size] = self.a.ravel(order="F")
+                self.a = big.a
+            return
+        need = []
+        for i, n in zip(idx, self.a.shape):
+            need.append(max(n, i.at(n) if isinstance(i, _End) else int(round(float(i)))))
+        if tuple(need) != self.a.shape:
+            big = Cell(*need)
+            big.a[:self.a.shape[0], :self.a.shape[1]] = self.a
+            self.a = big.a
+
     def brace_set(self, idx, val):
+        # 'end' refers to the size BEFORE the assignment grows the cell
+        dims = (self.a.size,) if len(idx) == 1 else self.a.shape
+        idx = tuple(float(i.at(n)) if isinstance(i, _End) else i for i, n in zip(idx, dims))
+        self._grow_for(idx)
         r, c, _ = self._rc(idx)
         self.a[r, c] = val
+
+    def brace_ref(self, *idx):
+        """``c{i,j}`` as the base of a nested assignment (``c{i,j}{end+1} = v``): an empty slot
+        becomes a cell, as MATLAB does."""
+        r, c, _ = self._rc(idx)
+        v = self.a[r, c]
+        if isinstance(v, Mat) and v.a.size == 0:
+            v = Cell(0, 0)
+            self.a[r, c] = v
+        return v
 
 
 class CsList:
@@ -427,7 +461,9 @@ class StrCol(list):
     """n x 1 string array (``TIE``): ``TIE(i)`` is the i-th string."""
 
     def __call__(self, i):
-        return self[_index(i, len(self))]
+        return Char(self[_index(i, len(self))])
+
+    brace = __call__
 
 
 # ------------------------------------------------------------------------------------ built-ins
@@ -473,9 +509,11 @@ def _mat(rows):
     if any(isinstance(e, Cell) for e in flat):
         blocks = []
         for r in rows:
-            if not all(isinstance(e, Cell) for e in r):
-                raise MlabError("mixed cell / non-cell literal")
-            blocks.append(np.concatenate([e.a for e in r], axis=1))
+            # [c, 'a', 'b'] : non-cell elements are wrapped; empty cells vanish
+            parts = [(e if isinstance(e, Cell) else Cell.of([[e]])) for e in r]
+            parts = [e.a for e in parts if e.a.size] or [np.empty((0, 0), dtype=object)]
+            blocks.append(np.concatenate(parts, axis=1))
+        blocks = [b for b in blocks if b.size] or [np.empty((0, 0), dtype=object)]
         out = Cell(0, 0)
         out.a = np.concatenate(blocks, axis=0)
         return out
@@ -665,6 +703,34 @@ def _unique(x):
     raise MlabError("unique: unsupported argument")
 
 
+def _mean(x):
+    if not isinstance(x, Mat):
+        return float(x)
+    if 1 in x.a.shape:
+        return _sum(x) / x.a.size
+    return Mat(x.a.mean(axis=0, keepdims=True))
+
+
+def _max(x):
+    return float(np.max(x.a)) if isinstance(x, Mat) else float(x)
+
+
+def _fieldnames(s):
+    return Cell.of([[Char(k)] for k in s.__dict__])
+
+
+def _struct2cell(s):
+    return Cell.of([[Char(v) if isinstance(v, str) else v] for v in s.__dict__.values()])
+
+
+def _sortrows(c, col):
+    j = int(_num(col)) - 1
+    order = sorted(range(c.a.shape[0]), key=lambda i: str(c.a[i, j]))     # stable, like sortrows
+    out = Cell(0, 0)
+    out.a = c.a[order, :].copy()
+    return out
+
+
 def _fileparts(path):
     d, base = os.path.split(str(path).rstrip("/"))
     stem, ext = os.path.splitext(base)
@@ -689,6 +755,8 @@ BUILTINS = {
     "strcat": _strcat, "num2str": _num2str, "diag": _diag, "repmat": _repmat, "sum": _sum, "rmfield": _rmfield,
     "isempty": _isempty, "pi": lambda: math.pi, "str2double": _str2double, "isnan": _isnan, "unique": _unique,
     "char": lambda x: Char(_unwrap1(x)), "ismissing": lambda x: x is None, "fileparts": _fileparts,
+    "mean": _mean, "max": _max, "fieldnames": _fieldnames, "struct2cell": _struct2cell, "sortrows": _sortrows,
+    "fopen": lambda *a: FileSink(), "fclose": lambda *a: 0.0,
     "true": True, "false": False, "__chr": Char, "ischar": lambda x: isinstance(x, str),
     "isa": lambda x, cls: (str(cls) == "double" and isinstance(x, (float, int, Mat)) and not isinstance(x, bool)),
     "__mat": _mat, "__rng": Rng, "__COLON": COLON, "__END": END, "__power": _power, "__Cell": Cell,
@@ -944,8 +1012,13 @@ def expr(toks: List[Tok], indexing: bool = False) -> str:
                     out.append("(" + expr(inner, indexing) + ")")
             elif t.text == "[":
                 rows = _split(toks[i + 1:j], ("semi", "nl"))
+                def element(e):
+                    parts = _split(e, ("colon",))
+                    if len(parts) > 1:                          # [a b:c] : a range as an element
+                        return "__rng(" + ", ".join(expr(p_, indexing) for p_ in parts) + ").mat()"
+                    return expr(e, indexing)
                 out.append("__mat([" + ", ".join(
-                    "[" + ", ".join(expr(e, indexing) for e in _elements(r)) + "]" for r in rows if r) + "])")
+                    "[" + ", ".join(element(e) for e in _elements(r)) + "]" for r in rows if r) + "])")
             else:  # {
                 if attached:
                     args = _split(inner, ("comma",))
@@ -1101,6 +1174,9 @@ class Program:
                 args = _split(lhs[last_open + 1:-1], ("comma",))
                 a = ", ".join(_arg(x, True) for x in args)
                 meth = "brace_set" if lhs[last_open].text == "{" else "set"
+                if meth == "brace_set" and ".brace(" in base and base.rstrip().endswith(")"):
+                    k2 = base.rindex(".brace(")                # c{i,j}{end+1} = v : the inner slot becomes a cell
+                    base = base[:k2] + ".brace_ref(" + base[k2 + len(".brace("):]
                 put(f"{base}.{meth}(({a},), {expr(rhs)})")
                 continue
             put(f"{expr(lhs)} = {expr(rhs)}")

@@ -104,6 +104,11 @@ class Reference:
         self.src_loop_tail = mlab.read_lines("main.m", 458, 494)        # un-scaling ... end of while
         self.src_resid = mlab.read_lines("main.m", 569, 571)
         self.src_stats = mlab.read_lines("main.m", 592, 602)
+        self.src_xcorr = mlab.read_lines("main.m", 587, 590)
+        self.src_report = mlab.read_lines("main.m", 631, 950)           # the .out writer (check points off)
+        assert self.prog.add_functions(mlab.read_file("functions/printCell.m")) == ["printCell"]
+        names = self.prog.add_functions(mlab.read_lines("main.m", 972, 996))
+        assert names == ["printEOP", "printDist", "printTIE", "countImagePoints", "countTargetImages"], names
 
     # ---- single functions
     def buildxhat(self, prob):
@@ -190,10 +195,27 @@ class ReferenceProblemBuild:
         return ws
 
 
+def report_text(R: "Reference", prob, xhat0, version: str = "v-test\n", date: str = "01-Jan-2020 00:00:00",
+                time: str = "1.25") -> str:
+    """main.m:396-602 and then the .out writer main.m:631-950 executed (fopen/fprintf go to a text sink):
+    the text of the reference's report for this problem.  ``Check_Points`` must be 0 (main.m:604-627 needs the
+    .cze table and ``find``)."""
+    assert not prob.settings.Check_Points
+    ws = workspace(prob)
+    ws["xhat"] = Mat(np.asarray(xhat0, float).reshape(-1, 1))
+    ws["xhatnames"] = None
+    ws = R.prog.run(R.src_weights, ws, "weights")
+    ws = R.prog.run(R.src_init + R.src_loop_head + R.src_corr + R.src_loop_tail, ws, "loop")
+    ws = R.prog.run(R.src_resid + R.src_xcorr + R.src_stats, ws, "residuals")
+    ws.update(version=Char(version), date=Char(date), time=Char(time), mfiles=Char(""))
+    ws = R.prog.run(R.src_report, ws, "report")
+    return ws["fileID"].text()
+
+
 def sparse_rows(A: np.ndarray):
     """Non-zeros of a design matrix (for compact fixtures)."""
     r, c = np.nonzero(A)
     return r.astype(np.int32), c.astype(np.int32), A[r, c]
 
 
-__all__ = ["Reference", "ReferenceProblemBuild", "workspace", "sparse_rows", "math"]
+__all__ = ["Reference", "ReferenceProblemBuild", "workspace", "report_text", "sparse_rows", "math"]

@@ -94,5 +94,26 @@ def main():
     freeze(R, synthetic_eop_only(), "syn_refrun_eop.npz")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--report" not in sys.argv:
     main()
+
+
+def report_case():
+    """Small mixed network (control + tie points, IOP + 2 radial + decentering terms, no inner constraints)."""
+    return fb.synth.make_network(8, 60, 6, 4242, mode="mixed", n_control=15, NK=2)
+
+
+def freeze_report():
+    """syn_refrun_report.out -- the text the reference's OWN report writer (main.m:631-950, printCell.m,
+    printEOP/Dist/TIE, countImagePoints/TargetImages) produces for report_case() after its own loop
+    (main.m:396-602), with fopen/fprintf redirected to a text sink; version / date / time fixed."""
+    R = refrun.Reference()
+    prob = report_case()
+    txt = refrun.report_text(R, prob, fb.Buildxhat(prob)[1])
+    with open(os.path.join(OUT, "syn_refrun_report.out"), "w") as fh:
+        fh.write(txt)
+    print("syn_refrun_report.out:", len(txt), "bytes")
+
+
+if __name__ == "__main__" and "--report" in sys.argv:
+    freeze_report()

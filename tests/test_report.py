@@ -189,3 +189,46 @@ def test_formatting_primitives_against_executed_reference():
     P.env["printTIE"](sink, Char("AL01"), 17.0, XYZ, sd, Char(str(W)), Char(str(dec)))
     assert sink.text() == (f"%-{W}s%-{W}.0d" + f"%-{W}.{dec}f" * 6 + "\n") % ("AL01", 17, 2.018, 2574.346, 3519.11,
                                                                           0.11, 0.22, 0.33)
+
+
+# ------------------------------------------------------------------ the whole .out against the reference's own writer
+
+def _our_report(prob, tmp_path):
+    out = oracle_outputs(prob)
+    out["elapsed"] = "1.25"
+    path = tmp_path / "ours.out"
+    report.write_out(str(path), prob, out, version="v-test", when="01-Jan-2020 00:00:00")
+    return path.read_text()
+
+
+def test_out_file_equals_frozen_report_of_the_reference_writer(tmp_path):
+    """tests/golden/syn_refrun_report.out is the text the reference's OWN report writer (main.m:631-950 with
+    printCell.m and its local print functions, executed by the MATLAB-subset interpreter after the reference's
+    own loop) produced for a small mixed network: report.write_out, fed by the oracle, must give the same file,
+    character for character (625 lines: settings, summary, EOP / IOP / correlation / ground-coordinate / corrected-
+    measurement / mean-correlation tables)."""
+    from tests.golden.make_refrun import report_case
+    ours = _our_report(report_case(), tmp_path)
+    ref = open(golden.path("syn_refrun_report.out")).read()
+    assert ours.split("\n") == ref.split("\n")
+
+
+@pytest.mark.skipif(not __import__("oracle.mlab", fromlist=["x"]).available(), reason="reference tree not mounted")
+def test_out_file_equals_live_report_two_cameras_inner_constraints(tmp_path):
+    """Live: free network (inner constraints, every point a tie point) with two cameras -> per-camera IOP
+    tables, IOP correlation sub-matrices and mean EOP x IOP correlations, through the reference's writer."""
+    from oracle import refrun
+    from tests.golden.make_refrun import synthetic_two_cameras
+    import copy
+    base = synthetic_two_cameras()
+    # smaller than the loop fixture: the reference's Correlation is a u^2 interpreted loop per iteration
+    prob = fb.synth.make_network(8, 40, 6, 779, mode="free", NK=2)
+    prob.img_cam = base.img_cam.copy()
+    prob.iop0 = np.repeat(prob.iop0, 2, axis=0)
+    prob.iop0[1, :3] += np.array([0.6, -0.4, 1.1])
+    prob.cam_box = np.repeat(prob.cam_box, 2, axis=0)
+    prob.camera_ids = ["0", "1"]
+    x0 = fb.Buildxhat(prob)[1]
+    ref = refrun.report_text(refrun.Reference(), prob, x0)
+    ours = _our_report(prob, tmp_path)
+    assert ours.split("\n") == ref.split("\n")
