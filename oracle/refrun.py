@@ -196,7 +196,7 @@ class ReferenceProblemBuild:
 
 
 def report_text(R: "Reference", prob, xhat0, version: str = "v-test\n", date: str = "01-Jan-2020 00:00:00",
-                time: str = "1.25") -> str:
+                time: str = "1.25", want_workspace: bool = False):
     """main.m:396-602 and then the .out writer main.m:631-950 executed (fopen/fprintf go to a text sink):
     the text of the reference's report for this problem.  ``Check_Points`` must be 0 (main.m:604-627 needs the
     .cze table and ``find``)."""
@@ -209,7 +209,7 @@ def report_text(R: "Reference", prob, xhat0, version: str = "v-test\n", date: st
     ws = R.prog.run(R.src_resid + R.src_xcorr + R.src_stats, ws, "residuals")
     ws.update(version=Char(version), date=Char(date), time=Char(time), mfiles=Char(""))
     ws = R.prog.run(R.src_report, ws, "report")
-    return ws["fileID"].text()
+    return (ws["fileID"].text(), ws) if want_workspace else ws["fileID"].text()
 
 
 def sparse_rows(A: np.ndarray):

@@ -229,6 +229,27 @@ def test_out_file_equals_live_report_two_cameras_inner_constraints(tmp_path):
     prob.cam_box = np.repeat(prob.cam_box, 2, axis=0)
     prob.camera_ids = ["0", "1"]
     x0 = fb.Buildxhat(prob)[1]
-    ref = refrun.report_text(refrun.Reference(), prob, x0)
+    ref, ws = refrun.report_text(refrun.Reference(), prob, x0, want_workspace=True)
     ours = _our_report(prob, tmp_path)
     assert ours.split("\n") == ref.split("\n")
+    # the cells the reference hands to writecell (main.m:957-958): PAR rows and RSD rows vs write_par / write_rsd
+    out = oracle_outputs(prob)
+    fb.write_par(str(tmp_path / "o.par"), prob, out["xhat"], out["Cx_diag"])
+    fb.write_rsd(str(tmp_path / "o.rsd"), prob, out["RSD"])
+    par = [ln.split("\t") for ln in (tmp_path / "o.par").read_text().splitlines()]
+    PAR = ws["PAR"].a
+    assert PAR.shape[0] == len(par) and PAR.shape[1] == 3
+    for i in range(3, len(par)):                                     # rows 1-3 are the version / date header
+        assert str(PAR[i, 0]) == par[i][0]
+        if par[i][0] == "Camera":
+            assert str(PAR[i, 1]) == par[i][1]
+        else:
+            assert abs(float(PAR[i, 1]) - float(par[i][1])) <= 1e-9 * abs(float(par[i][1]))
+            assert abs(float(PAR[i, 2]) - float(par[i][2])) <= 1e-6 * abs(float(par[i][2]))
+    rsd = [ln.split("\t") for ln in (tmp_path / "o.rsd").read_text().splitlines()]
+    RSD = ws["RSD"].a
+    assert RSD.shape == (len(rsd), 9)
+    for i in (0, 7, len(rsd) - 1):
+        assert [str(RSD[i, 0]), str(RSD[i, 1])] == rsd[i][:2]
+        assert [float(RSD[i, k]) for k in (2, 3)] == [float(rsd[i][k]) for k in (2, 3)]
+        assert np.allclose([float(RSD[i, k]) for k in range(4, 9)], [float(v) for v in rsd[i][4:]], rtol=0, atol=1e-8)
