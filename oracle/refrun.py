@@ -129,7 +129,6 @@ class Reference:
         ws["xhat"] = Mat(np.asarray(xhat0, float).reshape(-1, 1))
         ws = self.prog.run(self.src_weights, ws, "weights")
         src = self.src_init + self.src_loop_head + (self.src_corr if correlation else "") + self.src_loop_tail
-        trace_hook = {}
         ws = self.prog.run(src, ws, "loop")
         ws = self.prog.run(self.src_resid + self.src_stats, ws, "residuals")
         RSD = ws["RSD"]
@@ -141,7 +140,6 @@ class Reference:
                    Cx_diag=np.diag(ws["Cx"].a).copy(), w=ws["w"].a.ravel().copy())
         if correlation:
             out["Correlation"] = ws["Correlation"].a.copy()
-        del trace_hook
         return out
 
 
