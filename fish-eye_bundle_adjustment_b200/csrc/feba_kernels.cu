@@ -457,7 +457,6 @@ __global__ void __launch_bounds__(256) k_residuals(DevProblem P, const int* __re
                                                    const double* __restrict__ xyz_prev,
                                                    const double* __restrict__ iop_new,
                                                    double* __restrict__ v_out, double* __restrict__ rsd_out) {
-    constexpr int NC = NK + 5;
     __shared__ double red[2][256];
     double sx = 0.0, sy = 0.0;
     for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < P.n_obs;
@@ -469,33 +468,9 @@ __global__ void __launch_bounds__(256) k_residuals(DevProblem P, const int* __re
         const int cam = P.img_cam[img];
         observation<NK, HAS_CAM>(P.type, x, y, P.img_tab + kImgStride * img, P.cam_tab + kCamStride * cam,
                                  xyz_prev[3 * pt], xyz_prev[3 * pt + 1], xyz_prev[3 * pt + 2], J);
-        double v[2] = {J.w[0], J.w[1]};
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            if (P.ecol[i] >= 0) {
-                const double d = P.dcam_unscaled[P.ui * img + P.ecol[i]];
-                v[0] += J.Je[0][i] * d;
-                v[1] += J.Je[1][i] * d;
-            }
-        }
-        if (HAS_CAM) {
-#pragma unroll
-            for (int j = 0; j < NC; ++j) {
-                if (P.ccol[j] >= 0) {
-                    const double d = P.dcam_unscaled[P.off_cam + P.uc * cam + P.ccol[j]];
-                    v[0] += J.Jc[0][j] * d;
-                    v[1] += J.Jc[1][j] * d;
-                }
-            }
-        }
-        if (tie >= 0) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const double d = P.dpts[3 * tie + k];
-                v[0] += J.Jt[0][k] * d;
-                v[1] += J.Jt[1][k] * d;
-            }
-        }
+        double v[2];
+        residual_of<NK, HAS_CAM>(J, P.ecol, P.ccol, P.dcam_unscaled + P.ui * img,
+                                 P.dcam_unscaled + P.off_cam + P.uc * cam, tie >= 0 ? P.dpts + 3 * tie : nullptr, v);
         sx += v[0] * v[0];
         sy += v[1] * v[1];
         const int row = P.operm[o];
@@ -503,17 +478,8 @@ __global__ void __launch_bounds__(256) k_residuals(DevProblem P, const int* __re
             v_out[2 * (size_t)row] = v[0];
             v_out[2 * (size_t)row + 1] = v[1];
         }
-        if (rsd_out) {
-            const double xb = x - iop_new[P.NC * cam], yb = y - iop_new[P.NC * cam + 1];
-            const double theta = atan2(yb, xb), Phi = atan2(v[1], v[0]);
-            const double vd = sqrt(v[0] * v[0] + v[1] * v[1]);
-            double* r = rsd_out + 5 * (size_t)row;
-            r[0] = sqrt(xb * xb + yb * yb);
-            r[1] = v[0];
-            r[2] = v[1];
-            r[3] = vd * cos(theta - Phi);
-            r[4] = vd * sin(theta - Phi);
-        }
+        if (rsd_out)
+            rsd_row(x, y, iop_new[P.NC * cam], iop_new[P.NC * cam + 1], v, rsd_out + 5 * (size_t)row);
     }
     red[0][threadIdx.x] = sx;
     red[1][threadIdx.x] = sy;

@@ -188,4 +188,54 @@ FEBA_HD void observation(int type, double x, double y,
     }
 }
 
+// v = A*delta + w for one observation (main.m:569) from its Jacobian blocks at the LAST linearisation point:
+// d_img / d_cam = this image's / this camera's slice of the UN-scaled increment (main.m:458-482) -- applied
+// to the SCALED distortion columns of Jc, as the reference codes it -- d_pt = increment of the tie point or
+// nullptr for a control point.  ecol[6] / ccol[NK+5]: slot of each parameter inside its block or -1.
+template <int NK, bool HAS_CAM>
+FEBA_HD void residual_of(const ObsJac<NK>& J, const int* __restrict__ ecol, const int* __restrict__ ccol,
+                         const double* __restrict__ d_img, const double* __restrict__ d_cam,
+                         const double* __restrict__ d_pt, double v[2]) {
+    v[0] = J.w[0];
+    v[1] = J.w[1];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        if (ecol[i] >= 0) {
+            const double d = d_img[ecol[i]];
+            v[0] += J.Je[0][i] * d;
+            v[1] += J.Je[1][i] * d;
+        }
+    }
+    if (HAS_CAM) {
+#pragma unroll
+        for (int j = 0; j < NK + 5; ++j) {
+            if (ccol[j] >= 0) {
+                const double d = d_cam[ccol[j]];
+                v[0] += J.Jc[0][j] * d;
+                v[1] += J.Jc[1][j] * d;
+            }
+        }
+    }
+    if (d_pt) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double d = d_pt[k];
+            v[0] += J.Jt[0][k] * d;
+            v[1] += J.Jt[1][k] * d;
+        }
+    }
+}
+
+// BuildRSD.m:29-40: r, vx, vy, vr, vt of one observation; xp, yp are the POST-update values (BuildRSD.m:14-27).
+FEBA_HD void rsd_row(double x, double y, double xp, double yp, const double v[2], double* __restrict__ r) {
+    const double xb = x - xp, yb = y - yp;
+    const double theta = atan2(yb, xb), Phi = atan2(v[1], v[0]);
+    const double vd = sqrt(v[0] * v[0] + v[1] * v[1]);
+    r[0] = sqrt(xb * xb + yb * yb);
+    r[1] = v[0];
+    r[2] = v[1];
+    r[3] = vd * cos(theta - Phi);
+    r[4] = vd * sin(theta - Phi);
+}
+
 }  // namespace feba

@@ -43,3 +43,41 @@ extern "C" int feba_host_observation(int type, int NK, double x, double y, const
     }
     return 0;
 }
+
+namespace {
+
+template <int NK>
+void run_residual(int type, bool has_cam, double x, double y, const double* it, const double* ct, const double* xyz,
+                  const int* ecol, const int* ccol, const double* d_img, const double* d_cam, const double* d_pt,
+                  double xp_new, double yp_new, double* v, double* rsd) {
+    feba::ObsJac<NK> o;
+    if (has_cam) {
+        feba::observation<NK, true>(type, x, y, it, ct, xyz[0], xyz[1], xyz[2], o);
+        feba::residual_of<NK, true>(o, ecol, ccol, d_img, d_cam, d_pt, v);
+    } else {
+        feba::observation<NK, false>(type, x, y, it, ct, xyz[0], xyz[1], xyz[2], o);
+        feba::residual_of<NK, false>(o, ecol, ccol, d_img, d_cam, d_pt, v);
+    }
+    feba::rsd_row(x, y, xp_new, yp_new, v, rsd);
+}
+
+}  // namespace
+
+// What k_residuals does for one observation: Jacobian blocks at the last linearisation point (eop, iop, xyz
+// BEFORE the last update), v = w + J * (un-scaled last increment), then the BuildRSD row with the post-update
+// xp, yp.  d_img / d_cam: the image's / camera's slice of the increment in xhat order; d_pt may be NULL.
+extern "C" int feba_host_residual(int type, int NK, int has_cam, double x, double y, const double* eop,
+                                  const double* iop, const double* box, const double* xyz, const int* ecol,
+                                  const int* ccol, const double* d_img, const double* d_cam, const double* d_pt,
+                                  double xp_new, double yp_new, double* v, double* rsd) {
+    double it[feba::kImgStride], ct[feba::kCamStride];
+    feba::image_table_row(eop, it);
+    feba::camera_table_row(NK, iop, box, ct);
+#define FEBA_CASE(N) case N: run_residual<N>(type, has_cam != 0, x, y, it, ct, xyz, ecol, ccol, d_img, d_cam, d_pt, xp_new, yp_new, v, rsd); break;
+    switch (NK) {
+        FEBA_CASE(1) FEBA_CASE(2) FEBA_CASE(3) FEBA_CASE(4) FEBA_CASE(5) FEBA_CASE(6) FEBA_CASE(7) FEBA_CASE(8)
+        default: return 1;
+    }
+#undef FEBA_CASE
+    return 0;
+}

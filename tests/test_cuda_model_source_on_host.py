@@ -43,6 +43,9 @@ def host():
                         "-Wno-unknown-pragmas", SRC, "-o", LIB], check=True)
     lib = C.CDLL(LIB)
     lib.feba_host_observation.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double] + [_pd] * 8
+    _pi = C.POINTER(C.c_int)
+    lib.feba_host_residual.argtypes = ([C.c_int, C.c_int, C.c_int, C.c_double, C.c_double] + [_pd] * 4 + [_pi, _pi]
+                                       + [_pd] * 3 + [C.c_double, C.c_double, _pd, _pd])
     return lib
 
 
@@ -116,3 +119,43 @@ def test_cuda_model_source_against_numpy_oracle_after_an_update(host):
         err, A_ref, w_ref, G, ds = dense.BuildAwG(prob, x1)
         A, w = design_matrix_from_cuda_source(host, prob, x1)
         compare(prob, A, w, A_ref, w_ref)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cuda_residual_source_against_frozen_executed_reference(host, name):
+    """What k_residuals computes per observation (csrc/feba_model.cuh: residual_of, rsd_row) against the
+    reference's own v = A*delta + w (main.m:569, scaled distortion columns x un-scaled increment) and BuildRSD.m,
+    as executed and frozen: linearisation point = xhat before the last update, increment = the last delta,
+    xp / yp of the RSD columns from the final xhat."""
+    z = np.load(golden.path(name + ".npz"))
+    prob = CASES[name]()
+    s = prob.settings
+    L = model.layout(prob)
+    NK = s.NK
+    x_prev, x_fin, delta = z["xhat_arr"][-2], z["xhat"], z["delta"]
+    assert np.allclose(x_prev + delta, x_fin, rtol=0, atol=1e-9 * np.max(np.abs(x_fin)))
+    eop, iop, xyz = model.gather_params(prob, x_prev)
+    _, iop_fin, _ = model.gather_params(prob, x_fin)
+    ecol = np.ascontiguousarray(L["ecols"], dtype=np.int32)
+    ccol = np.ascontiguousarray(L["ccols"][:NK + 5], dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(_pd)
+    pi = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    v, rsd = np.zeros(2), np.zeros(5)
+    V, RSD = np.zeros(2 * prob.n_obs), np.zeros((prob.n_obs, 5))
+    for i in range(prob.n_obs):
+        j, q = int(prob.obs_img[i]), int(prob.obs_pt[i])
+        c = int(prob.img_cam[j])
+        t = int(prob.pt_tie[q])
+        e, io, bx, X = (np.ascontiguousarray(a, dtype=np.float64) for a in (eop[j], iop[c], prob.cam_box[c], xyz[q]))
+        d_img = np.ascontiguousarray(delta[L["u_img"] * j: L["u_img"] * (j + 1)])
+        d_cam = np.ascontiguousarray(delta[L["off_cam"] + L["u_cam"] * c: L["off_cam"] + L["u_cam"] * (c + 1)])
+        d_pt = np.ascontiguousarray(delta[L["off_tie"] + 3 * t: L["off_tie"] + 3 * t + 3]) if t >= 0 else None
+        assert host.feba_host_residual(s.typeint, NK, int(L["u_cam"] > 0), float(prob.obs_x[i]), float(prob.obs_y[i]),
+                                       p(e), p(io), p(bx), p(X), pi(ecol), pi(ccol), p(d_img), p(d_cam),
+                                       p(d_pt) if d_pt is not None else None, float(iop_fin[c, 0]),
+                                       float(iop_fin[c, 1]), p(v), p(rsd)) == 0
+        V[2 * i: 2 * i + 2] = v
+        RSD[i] = rsd
+    vmax = np.max(np.abs(z["v"]))
+    assert np.max(np.abs(V - z["v"])) < 1e-10 * vmax
+    assert np.max(np.abs(RSD - z["RSD"])) < 1e-10 * max(1.0, vmax)
