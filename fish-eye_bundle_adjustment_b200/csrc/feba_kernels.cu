@@ -28,17 +28,8 @@ __global__ void k_tables(int n_img, int n_cam, int NK, const double* __restrict_
 __global__ void k_G_rows(DevProblem P, const double* __restrict__ eop) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_img) return;
-    const double* e = eop + 6 * i;
-    const double Xc = e[0], Yc = e[1], Zc = e[2];
-    double sw, cw;
-    sincos(e[3], &sw, &cw);
-    const double tp = tan(e[4]), secp = 1.0 / cos(e[4]);
-    double G[6][7] = {{1, 0, 0, 0, -Zc, Yc, Xc},
-                      {0, 1, 0, Zc, 0, -Xc, Yc},
-                      {0, 0, 1, -Yc, Xc, 0, Zc},
-                      {0, 0, 0, -1, -sw * tp, cw * tp, 0},
-                      {0, 0, 0, 0, -cw, -sw, 0},
-                      {0, 0, 0, 0, sw * secp, -cw * secp, 0}};
+    double G[6][7];
+    inner_constraint_rows(eop + 6 * i, G);
     for (int q = 0; q < 6; ++q) {
         for (int c = 0; c < 7; ++c) {
             P.S[(size_t)(P.n_pad + 1 + c) + (size_t)P.ld * (6 * i + q)] = G[q][c];

@@ -66,6 +66,23 @@ FEBA_HD void camera_table_row(int NK, const double* __restrict__ p, const double
     }
 }
 
+// Inner-constraint rows of one image from its CURRENT EOPs (Gblock of BuildAwG.m:514-527): rows = the six
+// EOPs, columns = translation X Y Z, rotation omega phi kappa, scale.
+FEBA_HD void inner_constraint_rows(const double* __restrict__ e, double G[6][7]) {
+    const double Xc = e[0], Yc = e[1], Zc = e[2];
+    double sw, cw;
+    sincos(e[3], &sw, &cw);
+    const double tp = tan(e[4]), secp = 1.0 / cos(e[4]);
+    const double rows[6][7] = {{1, 0, 0, 0, -Zc, Yc, Xc},
+                               {0, 1, 0, Zc, 0, -Xc, Yc},
+                               {0, 0, 1, -Yc, Xc, 0, Zc},
+                               {0, 0, 0, -1, -sw * tp, cw * tp, 0},
+                               {0, 0, 0, 0, -cw, -sw, 0},
+                               {0, 0, 0, 0, sw * secp, -cw * secp, 0}};
+    for (int q = 0; q < 6; ++q)
+        for (int c = 0; c < 7; ++c) G[q][c] = rows[q][c];
+}
+
 template <int NK>
 struct ObsJac {
     double Je[2][6];        // d(fx,fy)/d(Xc,Yc,Zc,omega,phi,kappa)         BuildAwG.m:217-352

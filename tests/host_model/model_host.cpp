@@ -81,3 +81,11 @@ extern "C" int feba_host_residual(int type, int NK, int has_cam, double x, doubl
 #undef FEBA_CASE
     return 0;
 }
+
+// Gblock of one image (k_G_rows): G[6][7] row-major from eop[6].
+extern "C" void feba_host_inner_constraint_rows(const double* eop, double* G42) {
+    double G[6][7];
+    feba::inner_constraint_rows(eop, G);
+    for (int q = 0; q < 6; ++q)
+        for (int c = 0; c < 7; ++c) G42[7 * q + c] = G[q][c];
+}

@@ -159,3 +159,21 @@ def test_cuda_residual_source_against_frozen_executed_reference(host, name):
     vmax = np.max(np.abs(z["v"]))
     assert np.max(np.abs(V - z["v"])) < 1e-10 * vmax
     assert np.max(np.abs(RSD - z["RSD"])) < 1e-10 * max(1.0, vmax)
+
+
+@pytest.mark.parametrize("name", ["cam0_refrun_pinhole", "cam0_refrun_fisheye", "syn_refrun_2cam"])
+def test_cuda_inner_constraint_rows_against_frozen_executed_reference(host, name):
+    """k_G_rows' per-image block (inner_constraint_rows) against the G the executed BuildAwG.m:514-527 built."""
+    z = np.load(golden.path(name + ".npz"))
+    prob = CASES[name]()
+    assert prob.settings.Inner_Constraints and prob.settings.u_perimage == 6
+    eop, _, _ = model.gather_params(prob, z["xhat0"])
+    host.feba_host_inner_constraint_rows.argtypes = [_pd, _pd]
+    G = np.zeros((prob.u, 7))
+    blk = np.zeros(42)
+    for j in range(prob.numImg):
+        e = np.ascontiguousarray(eop[j], dtype=np.float64)
+        host.feba_host_inner_constraint_rows(e.ctypes.data_as(_pd), blk.ctypes.data_as(_pd))
+        G[6 * j: 6 * j + 6] = blk.reshape(6, 7)
+    assert np.array_equal(G != 0, z["G0"] != 0)
+    assert np.max(np.abs(G - z["G0"])) < 1e-13 * np.max(np.abs(z["G0"]))
