@@ -19,6 +19,7 @@
 #include "feba_dev.h"
 #include "feba_kernels.h"
 #include "feba_model.cuh"
+#include "feba_sparse.h"
 
 using namespace feba;
 
@@ -45,6 +46,12 @@ struct feba_handle {
     DistCtx dist;                 // group of GPUs factorising together (feba_dist_init)
     GreenPair green;              // SM partitions of the task graph (chain | bulk), optional
     bool dist_active = false;
+    // block-sparse form of the reduced system (FEBA_SPARSE=1, feba_sparse.h): supertile pattern incl. fill
+    // for chol_dag, datum-image flags on the device
+    bool sparse = false;
+    std::vector<unsigned char> nzmask;
+    unsigned char* datum_dev = nullptr;
+    int sparse_nz = 0, sparse_all = 0;   // non-zero / all lower supertiles of the factorised part
     bool dag_cols = false;        // column form of the task graph (chol_cols), issued eagerly unless solve_graph
     bool solve_graph = true;      // capture the solve half into a CUDA graph
     double *scal = nullptr;       // [0] sumabs camera part, [1] sumabs points, [2] sum vx^2, [3] sum vy^2
@@ -213,6 +220,57 @@ int setup_pool(feba_handle* h, bool group) {
     return FEBA_OK;
 }
 
+// FEBA_SPARSE=1: supertile pattern of the reduced system from the pair schedule (+ symbolic fill) and, for
+// free networks, the datum images of the sparse-datum form (feba_sparse.h).  Single GPU, tile task graph only;
+// anything else keeps the dense form.  Called once the pair schedule and the stream pool exist.
+int setup_sparse(feba_handle* h) {
+    h->sparse = false;
+    h->nzmask.clear();
+    DevProblem& P = h->P;
+    P.aug_rows = kAugRows;
+    P.datum = nullptr;
+    const char* e = std::getenv("FEBA_SPARSE");
+    if (!e || std::atoi(e) == 0 || !h->use_dag || h->dag_cols || h->dist_active) return FEBA_OK;
+    if (P.inner && P.ui != 6) return FEBA_OK;
+    const int nb = P.n_pad / kBlk, T = h->dag.tile_blocks;
+    std::vector<int> ab;
+    if (P.n_blocks > 0) {
+        std::vector<int4> blk((size_t)P.n_blocks);
+        CU(h, cudaMemcpyAsync(blk.data(), P.blocks, blk.size() * sizeof(int4), cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        ab.resize(2 * blk.size());
+        for (size_t i = 0; i < blk.size(); ++i) {
+            ab[2 * i] = blk[i].x;
+            ab[2 * i + 1] = blk[i].y;
+        }
+    }
+    std::vector<int> datum;
+    if (P.inner) datum = sparse_datum_images(P.n_img, P.ui, nb, T);
+    const SparsePattern pat = sparse_supertile_pattern(nb, T, P.ui, P.n_img, P.off_cam, P.n_red, P.n_blocks,
+                                                       ab.data(), datum);
+    h->nzmask = pat.nz;
+    h->sparse_nz = h->sparse_all = 0;
+    for (int i = 0; i < pat.NT; ++i)
+        for (int j = 0; j <= i; ++j) {
+            ++h->sparse_all;
+            if (pat.at(i, j)) ++h->sparse_nz;
+        }
+    if (P.inner) {
+        std::vector<unsigned char> flags((size_t)P.n_img, 0);
+        for (int im : datum) flags[(size_t)im] = 1;
+        if (!h->datum_dev) CU(h, dev_alloc(h, &h->datum_dev, flags.size()));
+        CU(h, cudaMemcpyAsync(h->datum_dev, flags.data(), flags.size(), cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        P.datum = h->datum_dev;
+        P.aug_rows = kSparseAugRows;
+    }
+    h->sparse = true;
+    if (std::getenv("FEBA_VERBOSE"))
+        fprintf(stderr, "[feba] sparse reduced system: %d of %d lower supertiles (T = %d blocks), %zu datum images\n",
+                h->sparse_nz, h->sparse_all, T, datum.size());
+    return FEBA_OK;
+}
+
 int check_settings(const feba_problem* pr) {
     const feba_settings& s = pr->settings;
     if (s.type < 0 || s.type > 4)
@@ -303,6 +361,8 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
     P.NK = s.num_radial;
     P.NC = P.NK + 5;
     P.inner = s.inner_constraints ? 1 : 0;
+    P.aug_rows = kAugRows;
+    P.datum = nullptr;
     P.px = 1.0 / (s.sigma_x * s.sigma_x);      // main.m:396-405
     P.py = 1.0 / (s.sigma_y * s.sigma_y);
     // slots of the estimated parameters (BuildAwG.m:24-25, :52-93, :110-155)
@@ -463,6 +523,10 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
         if (kp) h->allocs.push_back(kp);
         if (kb) h->allocs.push_back(kb);
     }
+    {
+        const int rc_sp = setup_sparse(h);
+        if (rc_sp) return rc_sp;
+    }
     // xhat = Buildxhat of the uploaded tables (Buildxhat.m:22-135)
     CU(h, cudaMemsetAsync(h->xhat, 0, (size_t)h->u * sizeof(double), h->stream));
     CU(h, launch_xhat_gather(P, h->sm_count, h->xhat, h->eop, h->iop, h->tie_pt, h->stream));
@@ -502,6 +566,12 @@ int feba_dist_init(feba_handle* h, int32_t rank, int32_t world, const void* id, 
     if (dist_comm_init(&h->dist, rank, world, id)) return fail(h, FEBA_ERR_CUDA, "%s", h->dist.err);
     if (!h->use_dag || world == 1) return FEBA_OK;
     drop_graphs(h);
+    if (h->sparse) {                      // the block-sparse form is single-GPU: a group keeps the dense factorisation
+        h->sparse = false;
+        h->nzmask.clear();
+        h->P.aug_rows = kAugRows;
+        h->P.datum = nullptr;
+    }
     {
         const int rc_pool = setup_pool(h, true);
         if (rc_pool) return rc_pool;
@@ -685,11 +755,13 @@ static int enqueue_solve(feba_handle* h) {
         const cudaError_t ed = chol_dag_dist(P.S, P.ld, nb, h->Linv, h->info, h->dag, h->dist, h->stream, &h->launches);
         if (ed == cudaErrorUnknown && h->dist.err[0]) return fail(h, FEBA_ERR_CUDA, "%s", h->dist.err);
         CU(h, ed);
-    } else if (h->use_dag) CU(h, chol_dag(P.S, P.ld, nb, h->Linv, h->info, h->dag, h->stream, &h->launches));
+    } else if (h->use_dag)
+        CU(h, chol_dag(P.S, P.ld, nb, h->Linv, h->info, h->dag, h->stream, &h->launches,
+                       h->sparse ? h->nzmask.data() : nullptr));
     else CU(h, chol_augmented(P.S, P.ld, nb, h->Linv, h->info, h->stream, &h->launches));
     CU(h, record(h, 3));
     CU(h, border_and_backsolve(P.S, P.ld, nb, h->Linv, P.inner, h->work, h->ywork, h->sol, h->info, h->sm_count,
-                               h->stream, &h->launches));
+                               h->stream, &h->launches, P.datum != nullptr));
     CU(h, record(h, 4));
     CU(h, launch_update_cam(P, h->sol, h->dvec, h->dcam, h->dcam_unscaled, h->eop, h->iop, h->scal, h->stream));
     ++h->launches;
@@ -832,6 +904,9 @@ int feba_cov_prepare(feba_handle* h) {
     if (h->iterations < 1 || h->phase != 0)
         return fail(h, FEBA_ERR_STATE, "feba_cov_prepare needs a completed iteration (Cx comes from the last N, main.m:432-444)");
     if (h->cov_ready) return FEBA_OK;
+    if (h->P.datum)
+        return fail(h, FEBA_ERR_STATE, "the covariance stage needs the dense datum form: not available with FEBA_SPARSE=1 "
+                                       "on a free network");
     CU(h, cudaSetDevice(h->device));
     DevProblem& P = h->P;
     const size_t nn = (size_t)P.n_pad * (size_t)P.n_pad;
@@ -900,6 +975,19 @@ int feba_last_timing(const feba_handle* h, double ms[6]) {
 }
 
 int64_t feba_launch_count(const feba_handle* h) { return h ? h->launches : 0; }
+
+int feba_sparse_info(const feba_handle* h, int32_t info[4]) {
+    if (!h || !info) return FEBA_ERR_INVALID;
+    info[0] = h->sparse ? 1 : 0;
+    info[1] = h->sparse ? h->sparse_nz : 0;
+    info[2] = h->sparse ? h->sparse_all : 0;
+    info[3] = 0;
+    if (h->sparse && h->P.datum) {
+        const std::vector<int> d = sparse_datum_images(h->P.n_img, h->P.ui, h->P.n_pad / kBlk, h->dag.tile_blocks);
+        info[3] = (int32_t)d.size();
+    }
+    return FEBA_OK;
+}
 
 // Diagnostic: the reduced camera system as assembled by the last feba_iterate_assemble (before the
 // inner-constraint border is added): S_out n_red x n_red column-major, full symmetric; g_out n_red.

@@ -16,6 +16,7 @@
 
 #include "feba_dev.h"
 #include "feba_kernels.h"
+#include "feba_sparse.h"
 
 namespace feba {
 
@@ -592,11 +593,14 @@ static bool upd1_bulk() {
     return v;
 }
 
+// nz (optional): (NT+1) x (NT+1) row-major pattern of the structurally non-zero supertiles INCLUDING fill
+// (feba_sparse.h::sparse_supertile_pattern); TRSM / UPDATE tasks on zero supertiles are not issued.
 cudaError_t chol_dag(double* A, int ld, int nb, double* Linv, int* info, const DagStreams& D, cudaStream_t main,
-                     int64_t* launches) {
+                     int64_t* launches, const unsigned char* nz) {
     const int T = D.tile_blocks;
     const int NT = (nb + T - 1) / T;                  // supertiles of the factorised part
     const int NR = NT + 1;                            // row supertiles: + the augmented block row
+    auto on = [&](int i, int j) { return nz == nullptr || nz[(size_t)i * NR + j] != 0; };
     auto blk0 = [&](int t) { return t == NT ? nb : t * T; };                     // first 64-block of supertile t
     auto nblk = [&](int t) { return t == NT ? 1 : (t == NT - 1 ? nb - T * (NT - 1) : T); };
     if (NR * NR > D.n_events) return cudaErrorInvalidValue;
@@ -630,6 +634,7 @@ cudaError_t chol_dag(double* A, int ld, int nb, double* Linv, int* info, const D
             DAG_CU(release(0, k, k));
         }
         for (int i = k + 1; i < NR; ++i) {
+            if (!on(i, k)) continue;
             const int sid = (i == k + 1) ? 0 : stream_of(i, k);
             DAG_CU(acquire(sid, k, k));
             DAG_CU(acquire(sid, i, k));
@@ -638,6 +643,7 @@ cudaError_t chol_dag(double* A, int ld, int nb, double* Linv, int* info, const D
         }
         for (int i = k + 1; i < NR; ++i)
             for (int j = k + 1; j <= i; ++j) {
+                if (!on(i, k) || !on(j, k)) continue;
                 if (j == NT && i == NT) {
                     // augmented diagonal block T (never factorised): plain lower update
                 } else if (j >= NT) {
@@ -1074,17 +1080,30 @@ __global__ void k_border_solve(const double* __restrict__ A, int ld, int n_pad, 
     }
 }
 
-// y[j] = Y'(0,j) + sum_k kvec[k] Y'(1+k,j)
-__global__ void k_combine(const double* __restrict__ A, int ld, int n_pad, int inner,
+// Sparse-datum form (feba_sparse.h): B = [g G~ E], T = -B' M_s^-1 B (15 x 15, lower triangle stored);
+// work[0..13] = coefficients of the augmented rows 1..14 (k, -t).
+__global__ void k_border_solve_sparse(const double* __restrict__ A, int ld, int n_pad, double* __restrict__ work,
+                                      int* __restrict__ info) {
+    if (threadIdx.x != 0) return;
+    double T[kSparseAugRows][kSparseAugRows];
+    for (int i = 0; i < kSparseAugRows; ++i)
+        for (int j = 0; j <= i; ++j) T[i][j] = T[j][i] = A[(size_t)(n_pad + i) + (size_t)ld * (n_pad + j)];
+    double coef[2 * kDatumCols];
+    if (!sparse_border_solve(T, coef)) {
+        atomicExch(info, 2);
+        return;
+    }
+    for (int m = 0; m < 2 * kDatumCols; ++m) work[m] = coef[m];
+}
+
+// y[j] = Y'(0,j) + sum_k kvec[k] Y'(1+k,j),  k < ncoef (0: no border, 7: dense datum, 14: sparse datum)
+__global__ void k_combine(const double* __restrict__ A, int ld, int n_pad, int ncoef,
                           const double* __restrict__ kvec, double* __restrict__ y) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_pad) return;
     const double* col = A + (size_t)n_pad + (size_t)ld * j;
     double t = col[0];
-    if (inner) {
-#pragma unroll
-        for (int k = 0; k < 7; ++k) t += kvec[k] * col[1 + k];
-    }
+    for (int k = 0; k < ncoef; ++k) t += kvec[k] * col[1 + k];
     y[j] = t;
 }
 
@@ -1127,13 +1146,15 @@ __global__ void __launch_bounds__(256) k_backstep(const double* __restrict__ A, 
 
 cudaError_t border_and_backsolve(double* A, int ld, int nb, const double* Linv, int inner, double* work,
                                  double* ywork, double* sol, int* info, int sm_count, cudaStream_t st,
-                                 int64_t* launches) {
+                                 int64_t* launches, int sparse_datum) {
     const int n_pad = nb * kBlk;
     if (inner) {
-        k_border_solve<<<1, 32, 0, st>>>(A, ld, n_pad, work, info);
+        if (sparse_datum) k_border_solve_sparse<<<1, 32, 0, st>>>(A, ld, n_pad, work, info);
+        else k_border_solve<<<1, 32, 0, st>>>(A, ld, n_pad, work, info);
         ++*launches;
     }
-    k_combine<<<(n_pad + 255) / 256, 256, 0, st>>>(A, ld, n_pad, inner, work, ywork);
+    const int ncoef = inner ? (sparse_datum ? 2 * kDatumCols : kDatumCols) : 0;
+    k_combine<<<(n_pad + 255) / 256, 256, 0, st>>>(A, ld, n_pad, ncoef, work, ywork);
     ++*launches;
     for (int k = nb - 1; k >= 0; --k) {
         int grid = (k * kBlk + 7) / 8;

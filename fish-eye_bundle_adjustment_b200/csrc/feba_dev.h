@@ -6,7 +6,7 @@
 namespace feba {
 
 constexpr int kBlk = 64;          // dense linear-algebra tile; reduced system is padded to it
-constexpr int kAugRows = 8;       // rows of the augmented block in use: [g ; G(:,1..7)]
+constexpr int kAugRows = 8;       // rows of the augmented block in use: [g ; G(:,1..7)]  (15 in the sparse-datum form)
 constexpr int kRec1 = 18;         // per-observation record 1: Je (2x6), Z (2x3)
 constexpr int kCamPart = 104;     // per-warp camera partial: packed NC(NC+1)/2 block + NC rhs (NC <= 13)
 
@@ -56,6 +56,9 @@ struct DevProblem {
     int n_blocks;
     double* cam_part;             // per-warp camera-camera partial sums
     double* Gt;                   // inner-constraint rows, compact: (6 n_img) x 8 row-major (col 7 unused)
+    // sparse-datum form (feba_sparse.h, FEBA_SPARSE=1): flags of the datum images, or null (dense M = S + G G')
+    int aug_rows;                 // rows of the augmented block in use: kAugRows, or kSparseAugRows
+    const unsigned char* datum;   // n_img flags
 };
 
 // Opt-in dynamic shared memory above 48 KB is a per-device function attribute: remember per device

@@ -157,6 +157,23 @@ __global__ void __launch_bounds__(256) k_G_condition(DevProblem P, int* __restri
     }
 }
 
+// Sparse-datum form (feba_sparse.h): after the conditioning G -> G C, the rows of the datum images are
+// copied into the augmented rows 8..14 (E = G~ restricted to those images; the rows of all other images
+// stay zero there) and the compact copy Gt keeps the datum rows only, so that k_diag_scale and
+// k_border_scale form M_s = S + E E' instead of the dense S + G~ G~'.  Augmented rows 1..7 keep all of G~.
+__global__ void k_datum_split(DevProblem P) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P.off_cam) return;
+    const bool is_datum = P.datum[r / 6] != 0;
+    double* g = P.Gt + 8 * (size_t)r;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const double v = is_datum ? g[k] : 0.0;
+        P.S[(size_t)(P.n_pad + 8 + k) + (size_t)P.ld * r] = v;
+        g[k] = v;
+    }
+}
+
 // Unit diagonal on the padding rows so the padded matrix stays positive definite.
 __global__ void k_pad_diag(DevProblem P) {
     const int i = P.n_red + blockIdx.x * blockDim.x + threadIdx.x;
@@ -203,7 +220,7 @@ __global__ void __launch_bounds__(256) k_border_scale(DevProblem P, const double
             }
             P.S[(size_t)r + (size_t)P.ld * c] = v * dvec[r] * dc;
         }
-    } else if (r < P.n_pad + kAugRows) {
+    } else if (r < P.n_pad + P.aug_rows) {
         P.S[(size_t)r + (size_t)P.ld * c] *= dc;
     }
 }
@@ -835,13 +852,17 @@ cudaError_t launch_border_scale(const DevProblem& P, const double* eop, double* 
         k_G_rows<<<(P.n_img + 127) / 128, 128, 0, st>>>(P, eop);
         k_G_condition<<<1, 256, 0, st>>>(P, info);
         *launches += 2;
+        if (P.datum) {
+            k_datum_split<<<(P.off_cam + 255) / 256, 256, 0, st>>>(P);
+            ++*launches;
+        }
     }
     if (P.n_pad > P.n_red) {
         k_pad_diag<<<1, 64, 0, st>>>(P);
         ++*launches;
     }
     k_diag_scale<<<(P.n_pad + 255) / 256, 256, 0, st>>>(P, dvec, info);
-    dim3 blk(32, 8), grd((P.n_pad + kAugRows + 31) / 32, (P.n_pad + 7) / 8);
+    dim3 blk(32, 8), grd((P.n_pad + P.aug_rows + 31) / 32, (P.n_pad + 7) / 8);
     k_border_scale<<<grd, blk, 0, st>>>(P, dvec);
     *launches += 2;
     return cudaGetLastError();

@@ -49,8 +49,9 @@ struct DagStreams {
     cudaEvent_t* events = nullptr;  // one per tile (row supertile, column supertile)
     int n_events = 0;
 };
+// nz: optional supertile pattern incl. fill (feba_sparse.h), (NT+1) x (NT+1) row-major; null = dense
 cudaError_t chol_dag(double* A, int ld, int nb, double* Linv, int* info, const DagStreams& D, cudaStream_t main,
-                     int64_t* launches);
+                     int64_t* launches, const unsigned char* nz = nullptr);
 
 // feba_green.cu -- two disjoint SM partitions of one device (green contexts): `chain` for the panel
 // chain of the factorisation, `bulk` for its trailing updates.  -1 when the driver cannot provide them.
@@ -94,9 +95,10 @@ cudaError_t chol_cols(double* A, int ld, int nb, double* Linv, int* info, const 
 void dist_prof_report();   // FEBA_DIST_PROF=1: prints the time stamps of the last replay once
 // ywork (n_pad) := combination of the augmented rows: y = Y'(0,:) + sum_k kvec[k] Y'(1+k,:) where kvec
 // solves the 7x7 border system (inner != 0), else y = Y'(0,:).  Then sol := L^-T y.
+// sparse_datum != 0: 14 coefficients from the border of the sparse-datum form (feba_sparse.h).
 cudaError_t border_and_backsolve(double* A, int ld, int nb, const double* Linv, int inner, double* work,
                                  double* ywork, double* sol, int* info, int sm_count, cudaStream_t st,
-                                 int64_t* launches);
+                                 int64_t* launches, int sparse_datum = 0);
 
 // Covariance stage: U = L^-T, Q = M~^-1 (n_pad x n_pad, lower valid), Y = M~^-1 G~ (n_pad x 8), T7inv 7x7.
 cudaError_t chol_inverse(double* A, int ld, int nb, const double* Linv, int inner, double* U, double* Q, double* Y,

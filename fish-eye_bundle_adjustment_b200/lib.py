@@ -24,7 +24,7 @@ EXPORTS = (
     "feba_create", "feba_destroy", "feba_last_error", "feba_set_stream", "feba_num_unknowns",
     "feba_set_xhat", "feba_get_xhat", "feba_iterate", "feba_iterate_assemble", "feba_reduced_dev",
     "feba_iterate_solve", "feba_get_delta", "feba_residuals", "feba_solve", "feba_last_timing",
-    "feba_launch_count", "feba_debug_reduced", "feba_cov_prepare", "feba_cov_diag", "feba_cov_block", "feba_iterate_async", "feba_iterate_solve_async", "feba_sync",
+    "feba_launch_count", "feba_sparse_info", "feba_debug_reduced", "feba_cov_prepare", "feba_cov_diag", "feba_cov_block", "feba_iterate_async", "feba_iterate_solve_async", "feba_sync",
     "feba_dist_unique_id", "feba_dist_init", "feba_reduced_pack", "feba_reduced_unpack",
 )
 
@@ -100,6 +100,7 @@ def load() -> C.CDLL:
     lib.feba_solve.argtypes = [H, _pi, _pd, C.c_size_t]
     lib.feba_last_timing.argtypes = [H, _pd]
     lib.feba_launch_count.argtypes = [H]
+    lib.feba_sparse_info.argtypes = [H, C.POINTER(C.c_int32)]
     lib.feba_launch_count.restype = C.c_int64
     lib.feba_debug_reduced.argtypes = [H, _pd, _pd]
     lib.feba_cov_prepare.argtypes = [H]
@@ -297,3 +298,10 @@ class Handle:
 
     def launch_count(self) -> int:
         return int(self._lib.feba_launch_count(self._h))
+
+    def sparse_info(self) -> dict:
+        """Block-sparse form of the reduced system (FEBA_SPARSE=1 at creation): active, non-zero / all lower
+        supertiles (fill included), datum images."""
+        v = (C.c_int32 * 4)()
+        self._check(self._lib.feba_sparse_info(self._h, v))
+        return dict(active=bool(v[0]), nonzero_supertiles=int(v[1]), lower_supertiles=int(v[2]), datum_images=int(v[3]))

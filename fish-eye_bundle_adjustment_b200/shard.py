@@ -106,6 +106,10 @@ class ShardedAdjustment:
         self.shared_factorisation = False
         # opt-in until it has been timed on the 8-GPU box: exchange the packed lower trapezoids only
         self._packed = os.environ.get("FEBA_PACKED_REDUCE", "0") == "1"
+        if self.world > 1 and handle.sparse_info()["active"]:
+            # the supertile pattern of FEBA_SPARSE=1 comes from THIS shard's pair schedule; the summed system
+            # has the union of all shards' patterns
+            raise RuntimeError("FEBA_SPARSE=1 (block-sparse reduced system) is single-GPU: unset it for sharded runs")
         if self.world > 1:
             # kernels, copies and the collective are all ordered on torch's current stream (callers
             # should make a non-default stream current: the library captures CUDA graphs on it)

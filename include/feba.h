@@ -176,6 +176,13 @@ int feba_last_timing(const feba_handle *h, double ms[6]);
 /* Kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
 int64_t feba_launch_count(const feba_handle *h);
 
+/* Block-sparse form of the reduced system (opt-in: environment FEBA_SPARSE=1 when the handle is created;
+ * one GPU, reduced systems of 96 blocks or more; csrc/feba_sparse.h).  info[0] = 1 when active, info[1] /
+ * info[2] = structurally non-zero / all lower supertiles of the factorised part (symbolic fill included),
+ * info[3] = number of datum images of the sparse-datum form (0: no inner constraints).  The reference has no
+ * counterpart: main.m:432,442 invert the dense bordered matrix. */
+int feba_sparse_info(const feba_handle *h, int32_t info[4]);
+
 /* Diagnostic for parity tests: the point-eliminated camera system left by a pending
  * feba_iterate_assemble() (S = N_cc - W V^-1 W', g = u_c - W V^-1 u_p; main.m:424-425 reduced),
  * S_out [u_c*u_c] column-major full symmetric, g_out [u_c]; either may be NULL. */

@@ -89,3 +89,31 @@ extern "C" void feba_host_inner_constraint_rows(const double* eop, double* G42) 
     for (int q = 0; q < 6; ++q)
         for (int c = 0; c < 7; ++c) G42[7 * q + c] = G[q][c];
 }
+
+// ---- block-sparse reduced system (csrc/feba_sparse.h, opt-in FEBA_SPARSE=1): the 14x14 border of the
+// sparse-datum form and the supertile pattern with symbolic fill, as the library computes them.
+#include "../../fish-eye_bundle_adjustment_b200/csrc/feba_sparse.h"
+
+// T225: 15x15 row-major (symmetric).  coef14 out.  Returns 1 when singular.
+extern "C" int feba_host_sparse_border(const double* T225, double* coef14) {
+    double T[feba::kSparseAugRows][feba::kSparseAugRows];
+    for (int i = 0; i < feba::kSparseAugRows; ++i)
+        for (int j = 0; j < feba::kSparseAugRows; ++j) T[i][j] = T225[feba::kSparseAugRows * i + j];
+    return feba::sparse_border_solve(T, coef14) ? 0 : 1;
+}
+
+// datum_out: up to 4 image indices, returns their number.
+extern "C" int feba_host_sparse_datum(int n_img, int ui, int nb, int T, int* datum_out) {
+    const std::vector<int> d = feba::sparse_datum_images(n_img, ui, nb, T);
+    for (size_t i = 0; i < d.size(); ++i) datum_out[i] = d[i];
+    return (int)d.size();
+}
+
+// nz_out: (NT+1) x (NT+1) row-major; returns NT.
+extern "C" int feba_host_sparse_pattern(int nb, int T, int ui, int n_img, int off_cam, int n_red, int n_blocks,
+                                        const int* blocks_ab, int n_datum, const int* datum, unsigned char* nz_out) {
+    const std::vector<int> d(datum, datum + n_datum);
+    const feba::SparsePattern P = feba::sparse_supertile_pattern(nb, T, ui, n_img, off_cam, n_red, n_blocks, blocks_ab, d);
+    for (size_t i = 0; i < P.nz.size(); ++i) nz_out[i] = P.nz[i];
+    return P.NT;
+}
