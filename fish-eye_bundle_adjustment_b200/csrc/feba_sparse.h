@@ -6,7 +6,7 @@
 // instead of 5.3e11 flop).  The free-network datum as the dense path applies it, M = S + G~ G~'
 // (k_border_scale), fills every tile.  Here the factorised matrix is
 //     M_s = S + E E',   E = G~ restricted to the rows of a few datum images
-// (two at each end of the image order: their supertiles are coupled through the dense last block row
+// (four at each end of the image order: their supertiles are coupled through the dense last block row
 // anyway, so E E' adds no fill).  M_s is positive definite (a similarity transform that leaves two images
 // in place is the identity) and, with the datum images at opposite ends of the block, as well conditioned
 // as M (tests/research/sparse_reduced_prototype.py: cond 7e10 vs 8e10 at 400 images, step error 1e-9 ..
@@ -92,25 +92,26 @@ struct SparsePattern {
     }
 };
 
-// Datum images: two at each end of the image order (fewer when the block is tiny), the inner two as far
-// inside as the first / last supertile reaches.
+// Datum images: four at each end of the image order (all of them when the block is tiny), spread from the
+// first image to the last one entirely inside supertile 0, and from the first one entirely inside the last
+// supertile to the last image.  (Step error against extended precision with the conditioned G~, 900 images:
+// 4 images 1e-11, 8 images 2e-12, 16 images 5e-13; tests/research/sparse_reduced_prototype.py.)
+constexpr int kDatumImages = 8;
 inline std::vector<int> sparse_datum_images(int n_img, int ui, int nb, int T) {
     std::vector<int> v;
-    if (n_img <= 4) {
+    if (n_img <= kDatumImages) {
         for (int i = 0; i < n_img; ++i) v.push_back(i);
         return v;
     }
-    const int NT = (nb + T - 1) / T;
+    const int NT = (nb + T - 1) / T, h = kDatumImages / 2;
     int b = (64 * T) / ui - 1;                              // last image entirely inside supertile 0
-    if (b < 1) b = 1;
+    if (b < h - 1) b = h - 1;
     if (b > n_img / 2 - 1) b = n_img / 2 - 1;
     int c = ((NT - 1) * 64 * T + ui - 1) / ui;              // first image entirely inside the last supertile
-    if (c > n_img - 2) c = n_img - 2;
+    if (c > n_img - h) c = n_img - h;
     if (c <= b) c = b + 1;
-    v.push_back(0);
-    v.push_back(b);
-    v.push_back(c);
-    v.push_back(n_img - 1);
+    for (int i = 0; i < h; ++i) v.push_back((int)((long long)b * i / (h - 1)));
+    for (int i = 0; i < h; ++i) v.push_back(c + (int)((long long)(n_img - 1 - c) * i / (h - 1)));
     return v;
 }
 

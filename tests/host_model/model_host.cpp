@@ -102,7 +102,7 @@ extern "C" int feba_host_sparse_border(const double* T225, double* coef14) {
     return feba::sparse_border_solve(T, coef14) ? 0 : 1;
 }
 
-// datum_out: up to 4 image indices, returns their number.
+// datum_out: up to feba::kDatumImages (8) image indices, returns their number.
 extern "C" int feba_host_sparse_datum(int n_img, int ui, int nb, int T, int* datum_out) {
     const std::vector<int> d = feba::sparse_datum_images(n_img, ui, nb, T);
     for (size_t i = 0; i < d.size(); ++i) datum_out[i] = d[i];

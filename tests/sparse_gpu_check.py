@@ -60,7 +60,7 @@ def main():
               f"{ref['iterations']})   v vs oracle {e_v:.2e}   sigma02 {e_s:.2e}   xhat vs dense form {e_x:.2e}")
         good = (e_step < 1e-7 and sp["it"] == ref["iterations"] and e_v < 1e-8 and e_s < 1e-8)
         if mode == "free":
-            good = good and sp["info"]["datum_images"] == 4
+            good = good and sp["info"]["datum_images"] == 8
         if not good:
             print(f"[{mode}] FAIL")
             ok = False

@@ -53,7 +53,7 @@ def image_pairs(prob):
 def pattern(lib, prob, n_red, nb, T):
     ui = prob.settings.u_perimage
     off_cam = ui * prob.numImg
-    datum = np.zeros(4, dtype=np.int32)
+    datum = np.zeros(8, dtype=np.int32)
     nd = lib.feba_host_sparse_datum(prob.numImg, ui, nb, T, datum.ctypes.data_as(_pi))
     datum = datum[:nd]
     blocks = image_pairs(prob)
@@ -161,7 +161,8 @@ def test_pattern_of_a_banded_block_is_sparse(host):
         frac = nz[:NT, :NT][lower].sum() / lower.sum()
         assert frac <= frac_max, (T, frac)
         assert nz[NT].all() and nz[NT - 1, :NT].all()          # augmented and camera rows are dense
-        assert len(datum) == 4 and datum[0] == 0 and datum[-1] == prob.numImg - 1
+        assert len(datum) == 8 and datum[0] == 0 and datum[-1] == prob.numImg - 1
+        assert np.all(np.diff(datum) > 0)
 
 
 def test_sparse_border_reports_a_singular_system(host):
