@@ -50,6 +50,7 @@ struct feba_handle {
     // for chol_dag, datum-image flags on the device
     bool sparse = false;
     std::vector<unsigned char> nzmask;
+    std::vector<int> row_first;          // envelope of the pattern per 64-block row (backward substitution)
     unsigned char* datum_dev = nullptr;
     int sparse_nz = 0, sparse_all = 0;   // non-zero / all lower supertiles of the factorised part
     bool dag_cols = false;        // column form of the task graph (chol_cols), issued eagerly unless solve_graph
@@ -249,6 +250,7 @@ int setup_sparse(feba_handle* h) {
     const SparsePattern pat = sparse_supertile_pattern(nb, T, P.ui, P.n_img, P.off_cam, P.n_red, P.n_blocks,
                                                        ab.data(), datum);
     h->nzmask = pat.nz;
+    h->row_first = pat.row_first_block(nb);
     h->sparse_nz = h->sparse_all = 0;
     for (int i = 0; i < pat.NT; ++i)
         for (int j = 0; j <= i; ++j) {
@@ -761,7 +763,8 @@ static int enqueue_solve(feba_handle* h) {
     else CU(h, chol_augmented(P.S, P.ld, nb, h->Linv, h->info, h->stream, &h->launches));
     CU(h, record(h, 3));
     CU(h, border_and_backsolve(P.S, P.ld, nb, h->Linv, P.inner, h->work, h->ywork, h->sol, h->info, h->sm_count,
-                               h->stream, &h->launches, P.datum != nullptr));
+                               h->stream, &h->launches, P.datum != nullptr,
+                               h->sparse ? h->row_first.data() : nullptr));
     CU(h, record(h, 4));
     CU(h, launch_update_cam(P, h->sol, h->dvec, h->dcam, h->dcam_unscaled, h->eop, h->iop, h->scal, h->stream));
     ++h->launches;

@@ -1111,9 +1111,11 @@ __global__ void k_combine(const double* __restrict__ A, int ld, int n_pad, int n
 //   x_k = L_kk^-T y_k (every CTA recomputes it from the inverted diagonal factor -- 4096 FMAs -- so
 //   no second launch is needed), CTA 0 stores it, then y_c -= sum_r L[k*64+r][c] x_k[r] for the
 //   columns c < k*64, one warp per column.
+// c_begin: first column that can be non-zero in block row k (0 = dense; sparse form: the envelope of the
+// supertile pattern -- supertiles left of it were never written and are exactly zero).
 __global__ void __launch_bounds__(256) k_backstep(const double* __restrict__ A, int ld, int k,
                                                   const double* __restrict__ Linv_k, double* __restrict__ y,
-                                                  double* __restrict__ x_out) {
+                                                  double* __restrict__ x_out, int c_begin) {
     __shared__ double sx[kBlk];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double* yk = y + (size_t)k * kBlk;
@@ -1133,7 +1135,7 @@ __global__ void __launch_bounds__(256) k_backstep(const double* __restrict__ A, 
     __syncthreads();
     const int ncols = k * kBlk;
     const double x0 = sx[lane], x1 = sx[lane + 32];
-    for (int c = blockIdx.x * 8 + warp; c < ncols; c += gridDim.x * 8) {
+    for (int c = c_begin + blockIdx.x * 8 + warp; c < ncols; c += gridDim.x * 8) {
         const double* colp = A + (size_t)k * kBlk + (size_t)ld * c;
         double acc = colp[lane] * x0 + colp[lane + 32] * x1;
 #pragma unroll
@@ -1146,7 +1148,7 @@ __global__ void __launch_bounds__(256) k_backstep(const double* __restrict__ A, 
 
 cudaError_t border_and_backsolve(double* A, int ld, int nb, const double* Linv, int inner, double* work,
                                  double* ywork, double* sol, int* info, int sm_count, cudaStream_t st,
-                                 int64_t* launches, int sparse_datum) {
+                                 int64_t* launches, int sparse_datum, const int* row_first_block) {
     const int n_pad = nb * kBlk;
     if (inner) {
         if (sparse_datum) k_border_solve_sparse<<<1, 32, 0, st>>>(A, ld, n_pad, work, info);
@@ -1157,10 +1159,12 @@ cudaError_t border_and_backsolve(double* A, int ld, int nb, const double* Linv, 
     k_combine<<<(n_pad + 255) / 256, 256, 0, st>>>(A, ld, n_pad, ncoef, work, ywork);
     ++*launches;
     for (int k = nb - 1; k >= 0; --k) {
-        int grid = (k * kBlk + 7) / 8;
+        int c_begin = row_first_block ? row_first_block[k] * kBlk : 0;
+        if (c_begin > k * kBlk) c_begin = k * kBlk;
+        int grid = (k * kBlk - c_begin + 7) / 8;
         if (grid > 2 * sm_count) grid = 2 * sm_count;
         if (grid < 1) grid = 1;
-        k_backstep<<<grid, 256, 0, st>>>(A, ld, k, LINV(Linv, k), ywork, sol);
+        k_backstep<<<grid, 256, 0, st>>>(A, ld, k, LINV(Linv, k), ywork, sol, c_begin);
         ++*launches;
     }
     return cudaGetLastError();

@@ -85,6 +85,17 @@ struct SparsePattern {
         const int s = row / (64 * T);
         return s < NT ? s : NT - 1;
     }
+    // envelope: first 64-block column that can be non-zero in 64-block row k (nb block rows)
+    std::vector<int> row_first_block(int nb) const {
+        std::vector<int> v((size_t)nb, 0);
+        for (int k = 0; k < nb; ++k) {
+            const int I = k / T < NT ? k / T : NT - 1;
+            int J = 0;
+            while (J < I && !at(I, J)) ++J;
+            v[(size_t)k] = J * T;
+        }
+        return v;
+    }
     // couple the unknowns [a0, a1] with [b0, b1] (inclusive row ranges of the reduced system)
     void couple(int a0, int a1, int b0, int b1) {
         for (int i = supertile_of_row(a0); i <= supertile_of_row(a1); ++i)

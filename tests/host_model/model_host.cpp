@@ -117,3 +117,13 @@ extern "C" int feba_host_sparse_pattern(int nb, int T, int ui, int n_img, int of
     for (size_t i = 0; i < P.nz.size(); ++i) nz_out[i] = P.nz[i];
     return P.NT;
 }
+
+// Envelope of a pattern (backward substitution): first 64-block column that can be non-zero per 64-block row.
+extern "C" void feba_host_sparse_row_first(int nb, int T, const unsigned char* nz, int* out_nb) {
+    feba::SparsePattern P;
+    P.T = T;
+    P.NT = (nb + T - 1) / T;
+    P.nz.assign(nz, nz + (size_t)(P.NT + 1) * (P.NT + 1));
+    const std::vector<int> v = P.row_first_block(nb);
+    for (int k = 0; k < nb; ++k) out_nb[k] = v[(size_t)k];
+}

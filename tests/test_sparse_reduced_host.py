@@ -38,6 +38,7 @@ def host():
     lib.feba_host_sparse_border.argtypes = [_pd, _pd]
     lib.feba_host_sparse_datum.argtypes = [C.c_int] * 4 + [_pi]
     lib.feba_host_sparse_pattern.argtypes = [C.c_int] * 7 + [_pi, C.c_int, _pi, C.POINTER(C.c_ubyte)]
+    lib.feba_host_sparse_row_first.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_ubyte), _pi]
     return lib
 
 
@@ -126,6 +127,15 @@ def test_sparse_datum_form_matches_bordered_solution(host, n_img, n_pts, T):
             if not nz[i, j]:
                 blk = Lm[i * T * 64:min(nb, (i + 1) * T) * 64, j * T * 64:(j + 1) * T * 64]
                 assert not np.any(blk), (i, j)
+    # the envelope the backward substitution starts from (k_backstep's c_begin): nothing left of it
+    first = np.zeros(nb, dtype=np.int32)
+    nz8 = np.ascontiguousarray(nz.astype(np.uint8))
+    host.feba_host_sparse_row_first(nb, T, nz8.ctypes.data_as(C.POINTER(C.c_ubyte)), first.ctypes.data_as(_pi))
+    for k in range(nb):
+        assert 0 <= first[k] <= k
+        assert not np.any(Lm[64 * k:64 * k + 64, :64 * first[k]]), k
+    if n_img >= 150 and T == 2:
+        assert first.max() > 0                                  # the envelope actually cuts something
     # --- border (k_border_solve in its sparse form) and combination (k_combine), backward substitution
     Tm = Lm[n_pad:n_pad + 15, n_pad:n_pad + 15]
     Tm = np.tril(Tm) + np.tril(Tm, -1).T
