@@ -423,6 +423,28 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
     }
     for (int sg = 0; sg < P.n_seg; ++sg)
         for (int o = seg_start[sg]; o < seg_start[sg + 1]; ++o) oseg[o] = sg;
+    // the multi-camera point pass keeps the per-camera blocks of a point in shared memory for at most
+    // kMaxCamPt (4) different cameras: refuse the problem HERE, before any state exists (the reference has no
+    // such limit, BuildAwG.m:110-155; documented in feba.h)
+    if (P.uc > 0 && pr->n_cam > 4) {
+        for (int j = 0; j < pr->n_img; ++j)
+            if (pr->img_cam[j] < 0 || pr->img_cam[j] >= pr->n_cam)
+                return fail(h, FEBA_ERR_INVALID, "img_cam[%d] out of range", j);
+        for (int sg = 0; sg < P.n_seg; ++sg) {
+            int cams[4], nc = 0;
+            for (int o = seg_start[sg]; o < seg_start[sg + 1]; ++o) {
+                const int c = pr->img_cam[simg[o]];
+                bool found = false;
+                for (int k = 0; k < nc; ++k) found = found || cams[k] == c;
+                if (found) continue;
+                if (nc == 4)
+                    return fail(h, FEBA_ERR_INVALID,
+                                "object point %d (CNT row, 0-based) is observed by images of more than 4 different "
+                                "cameras while camera parameters are estimated: unsupported (feba.h)", seg_pt[sg]);
+                cams[nc++] = c;
+            }
+        }
+    }
     // image-major record positions (stable: point-major order is kept inside an image)
     std::vector<int> img_start((size_t)pr->n_img + 1, 0), ipos((size_t)n);
     for (int64_t o = 0; o < n; ++o) ++img_start[(size_t)simg[o] + 1];
@@ -596,6 +618,8 @@ int feba_num_unknowns(const feba_handle* h, int64_t* u, int64_t* u_c) {
     if (u_c) *u_c = h->P.n_red;
     return FEBA_OK;
 }
+
+int64_t feba_num_obs(const feba_handle* h) { return h ? h->P.n_obs : -1; }
 
 int feba_set_xhat(feba_handle* h, const double* xhat, size_t u) {
     if (!h || !xhat) return FEBA_ERR_INVALID;
@@ -872,6 +896,9 @@ int feba_solve(feba_handle* h, int32_t* iterations_out, double* trace_out, size_
 int feba_residuals(feba_handle* h, double* v, double* rsd, double stats[6]) {
     if (!h) return FEBA_ERR_INVALID;
     if (h->iterations < 1) return fail(h, FEBA_ERR_STATE, "feba_residuals before any iteration (main.m:569 uses the last A, w, delta)");
+    if (h->phase != 0)
+        return fail(h, FEBA_ERR_STATE, "feba_residuals between feba_iterate_assemble and feba_iterate_solve: the tables "
+                                       "already belong to the next linearisation point");
     CU(h, cudaSetDevice(h->device));
     DevProblem& P = h->P;
     const size_t n = (size_t)P.n_obs;

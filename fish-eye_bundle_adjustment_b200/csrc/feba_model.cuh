@@ -131,11 +131,29 @@ FEBA_HD void observation(int type, double x, double y,
     const double W = m20 * dX + m21 * dY + m22 * dZ;
     const double R2 = U * U + V * V;
     const double R = sqrt(R2);
-    double g, dg;
-    g_and_dg(type, R, W, g, dg);
-    const double invR = 1.0 / R;
-    const double s = g * invR;
-    const double invD = 1.0 / (R2 + W * W);
+    // s = g(theta)/R and its derivatives with respect to (U,V,W).  The pinhole model is s = 1/W exactly
+    // (the reference writes it -c*U/W, BuildAwG.m:190-193): no 1/R, so a point on the optical axis
+    // (U = V = 0) stays finite as it does in the reference; the other four models divide by R there too.
+    double s, dsU, dsV, dsW;
+    if (type == 1) {
+        const double invW = 1.0 / W;
+        s = invW;
+        dsU = 0.0;
+        dsV = 0.0;
+        dsW = -invW * invW;
+    } else {
+        double g, dg;
+        g_and_dg(type, R, W, g, dg);
+        const double invR = 1.0 / R;
+        const double invD = 1.0 / (R2 + W * W);
+        s = g * invR;
+        const double a = dg * invR;
+        const double b = s * invR * invR;
+        const double thU = U * W * invR * invD, thV = V * W * invR * invD, thW = -R * invD;
+        dsU = a * thU - b * U;
+        dsV = a * thV - b * V;
+        dsW = a * thW;
+    }
     const double xp = ct[0], yp = ct[1], c = ct[2], yd = ct[3], P1 = ct[4], P2 = ct[5];
     const double xb = x - xp, yb = y - yp;
     const double r2 = xb * xb + yb * yb;
@@ -155,11 +173,6 @@ FEBA_HD void observation(int type, double x, double y,
     o.w[0] = fx - x;
     o.w[1] = fy - y;
 
-    // d s / d(U,V,W),  s = g(theta)/R
-    const double a = dg * invR;
-    const double b = s * invR * invR;
-    const double thU = U * W * invR * invD, thV = V * W * invR * invD, thW = -R * invD;
-    const double dsU = a * thU - b * U, dsV = a * thV - b * V, dsW = a * thW;
     const double cy = c * yd;
     const double JxU = -c * (s + U * dsU), JxV = -c * U * dsV, JxW = -c * U * dsW;
     const double JyU = -cy * V * dsU, JyV = -cy * (s + V * dsV), JyW = -cy * V * dsW;

@@ -21,7 +21,7 @@ FEBA_OK, FEBA_ERR_INVALID, FEBA_ERR_CUDA, FEBA_ERR_NUMERIC, FEBA_ERR_STATE = 0, 
 
 # every symbol include/feba.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = (
-    "feba_create", "feba_destroy", "feba_last_error", "feba_set_stream", "feba_num_unknowns",
+    "feba_create", "feba_destroy", "feba_last_error", "feba_set_stream", "feba_num_unknowns", "feba_num_obs",
     "feba_set_xhat", "feba_get_xhat", "feba_iterate", "feba_iterate_assemble", "feba_reduced_dev",
     "feba_iterate_solve", "feba_get_delta", "feba_residuals", "feba_solve", "feba_last_timing",
     "feba_launch_count", "feba_sparse_info", "feba_debug_reduced", "feba_cov_prepare", "feba_cov_diag", "feba_cov_block", "feba_iterate_async", "feba_iterate_solve_async", "feba_sync",
@@ -87,6 +87,8 @@ def load() -> C.CDLL:
     lib.feba_last_error.restype = C.c_char_p
     lib.feba_set_stream.argtypes = [H, C.c_void_p]
     lib.feba_num_unknowns.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.feba_num_obs.argtypes = [H]
+    lib.feba_num_obs.restype = C.c_int64
     lib.feba_set_xhat.argtypes = [H, _pd, C.c_size_t]
     lib.feba_get_xhat.argtypes = [H, _pd, C.c_size_t]
     lib.feba_get_delta.argtypes = [H, _pd, C.c_size_t]
@@ -166,7 +168,8 @@ class Handle:
         u, uc = C.c_int64(), C.c_int64()
         self._lib.feba_num_unknowns(self._h, C.byref(u), C.byref(uc))
         self.u, self.u_c = int(u.value), int(uc.value)
-        self.n_obs = prob.n_obs
+        self.n_obs = int(self._lib.feba_num_obs(self._h))
+        assert self.n_obs == prob.n_obs
 
     # -- lifetime
     def close(self):

@@ -52,6 +52,6 @@ while deltasum > s.threshold                                      % main.m:412
     end
 end
 xhat = feba_mex('get_xhat', h);
-[v, rsd, stats, err] = feba_mex('residuals', h, S.n_obs);         % main.m:569-601
+[v, rsd, stats, err] = feba_mex('residuals', h);                % main.m:569-601
 RSDnum = rsd'; RMSx = stats(1); RMSy = stats(2); RMS = stats(3); sigma02 = stats(4);
 end

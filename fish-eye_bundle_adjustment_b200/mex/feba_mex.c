@@ -63,10 +63,10 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         /* S: n_obs n_img n_cam n_pts n_tie | obs_x obs_y (double) obs_img obs_pt (int32, 0-based) img_cam
          * pt_tie (int32) | eop0 (6 x n_img) iop0 ((3+NK+2) x n_cam) cam_box (5 x n_cam) xyz0 (3 x n_pts),
          * column-major = the row-major layout of feba.h | settings fields */
+        if (nrhs < 2 || !mxIsStruct(prhs[1])) mexErrMsgIdAndTxt("feba:create", "create needs the packed problem struct");
         const mxArray* S = prhs[1];
         feba_problem p;
         memset(&p, 0, sizeof(p));
-        if (nrhs < 2 || !mxIsStruct(S)) mexErrMsgIdAndTxt("feba:create", "create needs the packed problem struct");
         p.n_obs = (int64_t)sfield(S, "n_obs");
         p.n_img = (int32_t)sfield(S, "n_img");
         p.n_cam = (int32_t)sfield(S, "n_cam");
@@ -184,7 +184,9 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         mxFree(trace);
         status_out(nlhs, plhs, 2, rc, h);
     } else if (!strcmp(cmd, "residuals")) {
-        const size_t n = (size_t)mxGetScalar(prhs[2]);                     /* n_obs */
+        const int64_t n_obs = feba_num_obs(h);                             /* the handle's own count, never the caller's */
+        if (n_obs < 0) mexErrMsgIdAndTxt("feba:handle", "residuals: invalid handle");
+        const size_t n = (size_t)n_obs;
         plhs[0] = mxCreateDoubleMatrix((mwSize)(2 * n), 1, mxREAL);        /* v, main.m:569 */
         mxArray* rsd = mxCreateDoubleMatrix(5, (mwSize)n, mxREAL);         /* 5 x n_obs column-major = n_obs x 5 row-major */
         mxArray* st = mxCreateDoubleMatrix(1, 6, mxREAL);

@@ -33,6 +33,13 @@ extern "C" {
 
 #define FEBA_VERSION 100
 #define FEBA_MAX_NK 8 /* largest Num_Radial_Distortions supported by the kernels */
+/* Limits the reference does not have (BuildAwG.m:110-155): Num_Radial_Distortions <= FEBA_MAX_NK, and, when
+ * camera parameters are estimated for more than one camera, an object point may be seen by images of at most
+ * FEBA_MAX_CAMS_PER_POINT different cameras.  Both are checked by feba_create (FEBA_ERR_INVALID) before any
+ * device state exists.  With several cameras AND camera unknowns the point pass adds the cross-camera terms
+ * with FP64 atomics: results are then reproducible to rounding only, not bit for bit (one camera: bit-identical
+ * reruns). */
+#define FEBA_MAX_CAMS_PER_POINT 4
 
 enum feba_status {
     FEBA_OK = 0,
@@ -100,6 +107,9 @@ const char *feba_last_error(const feba_handle *h); /* h may be NULL: last create
 
 /* Number of unknowns u, and the split u_c (EOP+IOP part) / 3*n_tie (Buildxhat.m:5-15). */
 int feba_num_unknowns(const feba_handle *h, int64_t *u, int64_t *u_c);
+/* Number of image observations of the handle (data.n / 2, main.m:381): feba_residuals writes 2*n_obs (v)
+ * and 5*n_obs (rsd) doubles -- size the outputs from THIS, not from a caller-side count.  -1: null handle. */
+int64_t feba_num_obs(const feba_handle *h);
 
 /* xhat in the layout of Buildxhat.m:22-135 (length u). */
 int feba_set_xhat(feba_handle *h, const double *xhat, size_t u);

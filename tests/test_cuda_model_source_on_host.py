@@ -177,3 +177,49 @@ def test_cuda_inner_constraint_rows_against_frozen_executed_reference(host, name
         G[6 * j: 6 * j + 6] = blk.reshape(6, 7)
     assert np.array_equal(G != 0, z["G0"] != 0)
     assert np.max(np.abs(G - z["G0"])) < 1e-13 * np.max(np.abs(z["G0"]))
+
+
+def test_pinhole_point_on_the_optical_axis_is_finite(host):
+    """Type 'pinhole' is fx = -c*U/W in the reference (BuildAwG.m:190-193): a point on the optical axis
+    (U = V = 0, R = 0) has finite fx and finite typeint==1 Jacobians there.  The CUDA source must not go
+    through g(theta)/R for that model.  Checked against central differences of its own misclosure."""
+    NK = 2
+    eop = np.array([100.0, 200.0, 1500.0, 0.03, -0.02, 0.7])
+    iop = np.array([1207.9, 1013.7, 1234.7, -4.5e-9, 1.3e-15, 1.2e-7, 3.7e-7])
+    box = np.array([-1.0, 0.0, 0.0, 2448.0, 2048.0])
+    # the object point straight down the optical axis: (X - Xc) = -d * M(3,:)'  =>  U = V = 0, W = -d
+    w_, p_, k_ = eop[3:6]
+    M = fb.synth._rotation(np.array([w_]), np.array([p_]), np.array([k_]))[0]
+    xyz = eop[0:3] - 900.0 * M[2]
+    p = lambda a: a.ctypes.data_as(_pd)
+
+    def run(e, io, X):
+        Je, Jc, Jt, ww = np.zeros(12), np.zeros(2 * (NK + 5)), np.zeros(6), np.zeros(2)
+        assert host.feba_host_observation(1, NK, 1300.0, 900.0, p(np.ascontiguousarray(e)), p(np.ascontiguousarray(io)),
+                                          p(box), p(np.ascontiguousarray(X)), p(Je), p(Jc), p(Jt), p(ww)) == 0
+        return Je.reshape(2, 6), Jc.reshape(2, NK + 5), Jt.reshape(2, 3), ww.copy()
+
+    Je, Jc, Jt, w0 = run(eop, iop, xyz)
+    for blk in (Je, Jc, Jt, w0):
+        assert np.all(np.isfinite(blk))
+    # on the axis the projection term vanishes: fx = xp + distortion(x, y)
+    for k in range(3):                                   # d/dX, d/dY, d/dZ by central differences
+        h = 1e-3
+        dp, dm = xyz.copy(), xyz.copy()
+        dp[k] += h; dm[k] -= h
+        num = (run(eop, iop, dp)[3] - run(eop, iop, dm)[3]) / (2 * h)
+        assert np.allclose(Jt[:, k], num, rtol=1e-6, atol=1e-9)
+    for k in range(6):
+        h = 1e-3 if k < 3 else 1e-7
+        ep, em = eop.copy(), eop.copy()
+        ep[k] += h; em[k] -= h
+        num = (run(ep, iop, xyz)[3] - run(em, iop, xyz)[3]) / (2 * h)
+        assert np.allclose(Je[:, k], num, rtol=1e-5, atol=1e-6)
+    # U = V = 0 exactly (nadir image, point straight below): everything finite, Jt(:, Z) = 0
+    nadir = np.array([100.0, 200.0, 1500.0, 0.0, 0.0, 0.0])
+    below = np.array([100.0, 200.0, 600.0])
+    Je, Jc, Jt, w0 = run(nadir, iop, below)
+    for blk in (Je, Jc, Jt, w0):
+        assert np.all(np.isfinite(blk))
+    assert Jt[0, 2] == 0.0 and Jt[1, 2] == 0.0
+    assert np.isclose(Jt[0, 0], -iop[2] / -900.0) and np.isclose(Jt[1, 1], iop[2] / -900.0)   # -c/W, -c*y_dir/W
