@@ -130,16 +130,30 @@ def make_workload(name: str, scale: float):
 
 # --------------------------------------------------------------------------- CPU baseline
 
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_port(prob):
+    """The C/OpenMP + LAPACK restatement of the reference algorithm (oracle/cport.py) on ALL host cores, also
+    under a launcher that exported OMP_NUM_THREADS=1 (torchrun does)."""
+    from oracle import cport
+    threads = cport.set_threads(host_cores())
+    return cport.CPort(prob), threads
+
+
 def cpu_iteration_seconds(prob, fraction: float = 1.0):
     """Time of ONE Gauss-Newton iteration of the CPU restatement of the reference algorithm
     (oracle/cport.py: C + OpenMP block normal equations and Schur complement on all host cores,
     LAPACK dpotrf/dpotrs for the bordered reduced solve, C back-substitution).
-    fraction = 1: the full workload.  fraction < 1 (bounded sample for the multi-step reference arm):
-    assembly and back-substitution run on the first ``fraction`` of the object points with all their
-    observations and are scaled by the observation ratio (their cost is linear in observations); the
-    dense reduced solve is always timed at the FULL reduced size u_c.  Returns (seconds, parts)."""
+    fraction = 1: the full workload.  fraction < 1 (opt-in bounded sample): assembly and back-substitution run
+    on the first ``fraction`` of the object points with all their observations and are scaled by the observation
+    ratio (their cost is linear in observations); the dense reduced solve is always timed at the FULL reduced
+    size u_c.  Returns (seconds, parts)."""
     import copy
-    from oracle import cport
     import feba_b200 as fb
     nP = prob.numPts
     k = nP if fraction >= 1.0 else max(int(nP * fraction), min(nP, 1000))
@@ -158,14 +172,13 @@ def cpu_iteration_seconds(prob, fraction: float = 1.0):
     else:
         sub = prob
     err, x0, _ = fb.Buildxhat(sub)
-    cp = cport.CPort(sub)
+    cp, threads = cpu_port(sub)
     tm = {}
     cp.iterate(x0, tm, diag_shift=0.0 if k == nP else 1e-3)
     ratio = prob.n_obs / max(sub.n_obs, 1)
     total = (tm["assemble_s"] + tm["backsub_s"]) * ratio + tm["solve_s"]
     return total, dict(sample_obs=int(sub.n_obs), sample_points=int(k), assemble_schur_s=tm["assemble_s"],
-                       solve_s=tm["solve_s"], backsub_s=tm["backsub_s"], scale=ratio,
-                       threads=int(cport.lib().feba_oracle_threads()))
+                       solve_s=tm["solve_s"], backsub_s=tm["backsub_s"], scale=ratio, threads=threads)
 
 
 def cpu_sample_text(prob, parts):
@@ -177,9 +190,17 @@ def cpu_sample_text(prob, parts):
             f"{parts['backsub_s']:.2f} s measured); LAPACK bordered solve at full u_c={prob.u_c} {parts['solve_s']:.2f} s")
 
 
+def workload_config(args, prob, desc):
+    """The keys BOTH arms print under ``config`` (the driver compares them)."""
+    return {"workload": args.workload, "desc": desc, "n_obs": int(prob.n_obs), "n_img": int(prob.numImg),
+            "n_pts": int(prob.numPts), "u": int(prob.u), "u_c": int(prob.u_c),
+            "inner_constraints": int(prob.settings.Inner_Constraints), "type": prob.settings.type}
+
+
 def run_reference(args, rank):
     """--impl reference: the CPU restatement of the reference algorithm on the host cores (MATLAB /
-    Octave do not exist in this image, and literal main.m cannot hold these sizes: SURVEY.md 8d)."""
+    Octave do not exist in this image, and literal main.m cannot hold these sizes: SURVEY.md 8d).  Every step is
+    one FULL Gauss-Newton iteration of the workload (no sampling unless --cpu-fraction < 1 is given)."""
     if rank != 0:
         return
     prob, desc = make_workload(args.workload, args.scale)
@@ -194,8 +215,7 @@ def run_reference(args, rank):
             "unit": "obs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "desc": desc, "n_obs": prob.n_obs, "n_img": prob.numImg,
-                       "n_pts": prob.numPts, "u": prob.u, "u_c": prob.u_c},
+            "config": workload_config(args, prob, desc),
             "cpu_baseline": {"value": val, "unit": "obs/s", "cores": parts["threads"], "kind": "port",
                              "sample": cpu_sample_text(prob, parts)},
             "e2e": {"value": val, "unit": "obs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -224,6 +244,22 @@ def fp64_tensor_peak(torch):
     return best
 
 
+def ncu_traffic(kernel_substr: str):
+    """dram read+write bytes per launch of a kernel from the committed ncu summary of THIS round
+    (profiles/r2_ncu_traffic.json, written by scripts/ncu_extract.py), or None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    try:
+        d = json.load(open(p))
+    except ValueError:
+        return None, None
+    for k, v in d.get("kernels", {}).items():
+        if kernel_substr in k:
+            return float(v["dram_bytes_per_launch"]), d.get("source")
+    return None, None
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -235,17 +271,40 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     prob, desc = make_workload(args.workload, args.scale)
     counts = algorithmic_counts(prob)
-    shard = sh.shard_problem(prob, rank, world)
-    err, x0 = fb.Buildxhat(shard.prob)[:2]
+    err, x0 = fb.Buildxhat(prob)[:2]
     assert err == 0
-    h = fb.Handle(shard.prob)
     # one non-default torch stream carries the library's kernels (graph capture is not allowed on the
-    # legacy default stream), the NCCL all-reduce and the timing events
+    # legacy default stream), its NCCL collectives and the timing events
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    h.set_stream(stream.cuda_stream)
-    adj = sh.ShardedAdjustment(h, shard)
-    h.set_xhat(x0)
+    mode, shard, t_create = "single GPU", None, time.perf_counter()
+    if world == 1:
+        h = fb.Handle(prob, plan=args.plan)
+        h.set_stream(stream.cuda_stream)
+        adj = None
+    else:
+        adj = None
+        if not args.replicated:
+            try:
+                adj = sh.GroupAdjustment(prob, plan=args.plan)
+                h = adj.h
+                mode = "group"
+            except fb.FebaError as exc:
+                if exc.code != fb.lib.FEBA_ERR_INVALID:
+                    raise
+                if rank == 0:
+                    print(f"[bench] {exc.text}; falling back to the replicated form", file=sys.stderr)
+        if adj is None:
+            shard = sh.shard_problem(prob, rank, world)
+            h = fb.Handle(shard.prob, plan=-1)
+            h.set_stream(stream.cuda_stream)
+            adj = sh.ShardedAdjustment(h, shard)
+            mode = "replicated"
+    t_create = time.perf_counter() - t_create
+    x_start = x0 if shard is None else fb.Buildxhat(shard.prob)[1]
+    h.set_xhat(x_start)
+    step_async = h.iterate_async if adj is None else adj.iterate_async
+    step_sync = h.iterate if adj is None else adj.iterate
 
     def barrier():
         if world > 1:
@@ -254,7 +313,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- device-resident timing: inputs already in HBM, nothing read back inside the region
     for _ in range(max(args.warmup, 3)):
-        adj.iterate_async()
+        step_async()
     h.sync()
     sampler = ClockSampler(local_rank)
     launches0 = h.launch_count()
@@ -262,18 +321,18 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    phase_ms = np.zeros(6)
     e0.record()
     for _ in range(args.steps):
-        adj.iterate_async()
+        step_async()
     e1.record()
     torch.cuda.synchronize()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = h.launch_count() - launches0
     h.sync()
-    t = h.last_timing()
-    phase_ms = np.array([t["prep_ms"], t["assemble_ms"], t["factor_ms"], t["solve_ms"], t["update_ms"], t["total_ms"]])
+    t = h.last_timing_ex()
+    phase_ms = np.array([t["prep_ms"], t["assemble_ms"], t["factor_ms"], t["solve_ms"], t["update_ms"], t["total_ms"],
+                         t["exchange_ms"]])
     ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
@@ -294,7 +353,7 @@ def run_ours(args, rank, world, local_rank):
         # the caller's xhat goes in from pinned host memory, the updated xhat comes back into the
         # other pinned buffer (main.m:484 keeps xhat on the host between iterations)
         h.set_xhat(bufs[cur[0]])
-        ds = adj.iterate()
+        ds = step_sync()
         h.get_xhat(bufs[1 - cur[0]])
         cur[0] = 1 - cur[0]
         return ds
@@ -312,18 +371,60 @@ def run_ours(args, rank, world, local_rank):
     e2e_ms = float(t_e2e.item()) * 1e3 / args.steps
     e2e_val = prob.n_obs / (e2e_ms * 1e-3)
 
-    # ---- residual stage (main.m:569-602), once, device time + D2H of v and RSD
+    # ---- the whole adjustment from the initial values (main.m:407-494) + residual stage (main.m:569-602): the
+    # numbers the parity object compares, and the residual-stage timing.  v / RSD go into page-locked arrays of the
+    # caller (one DMA each); the same call into pageable arrays is timed next to it.
+    n_rows = h.n_obs
+    v_pin = torch.empty(2 * n_rows, dtype=torch.float64).pin_memory()
+    r_pin = torch.empty((n_rows, 5), dtype=torch.float64).pin_memory()
+    h.set_xhat(x_start)
+    if adj is None or mode == "group":
+        its, trace = h.solve()
+    else:
+        its, trace, ds = 0, [], 100.0
+        while ds > prob.settings.threshold and its < prob.settings.Iteration_Cap:
+            ds = adj.iterate()
+            trace.append(ds)
+            its += 1
+    barrier()
     t0 = time.perf_counter()
-    res = h.residuals()
+    res = h.residuals(v_out=v_pin.numpy(), rsd_out=r_pin.numpy())
     rsd_ms = (time.perf_counter() - t0) * 1e3
-    # variance factor over ALL ranks (main.m:601): sum the squared residuals of the shards
-    ss = torch.tensor([res["sxx"], res["syy"]], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ss, op=dist.ReduceOp.SUM)
+    rsd_kernel_ms = h.last_timing_ex()["residual_kernel_ms"]
+    rsd_pageable_ms = None
+    if world == 1:
+        t0 = time.perf_counter()
+        h.residuals()
+        rsd_pageable_ms = (time.perf_counter() - t0) * 1e3
+    xhat_end = h.get_xhat()
     st = prob.settings
-    sigma02 = float((ss[0] / st.sigma_x ** 2 + ss[1] / st.sigma_y ** 2).item()) / (2 * prob.n_obs - prob.u)
+    if mode == "replicated":
+        # variance factor over ALL ranks (main.m:601): sum the squared residuals of the shards
+        ss = torch.tensor([res["sxx"], res["syy"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ss, op=dist.ReduceOp.SUM)
+        sigma02 = float((ss[0] / st.sigma_x ** 2 + ss[1] / st.sigma_y ** 2).item()) / (2 * prob.n_obs - prob.u)
+    else:
+        sigma02 = float(res["sigma02"])
 
-    sp_info = h.sparse_info()                   # FEBA_SPARSE=1 (opt-in): block-sparse reduced system
+    # ---- group vs one GPU (driver-visible multi-GPU parity): rank 0 repeats the FIRST step alone on the complete
+    # problem and compares the increment of the group with it
+    group_check = None
+    if world > 1 and mode == "group" and not args.no_group_check:
+        h.set_xhat(x_start)
+        h.iterate()
+        d_group = h.get_delta()
+        if rank == 0:
+            with fb.Handle(prob, plan=args.plan) as h1:
+                h1.set_xhat(x_start)
+                h1.iterate()
+                d_one = h1.get_delta()
+            from oracle.compare import group_rel
+            group_check = {"first_step_delta_rel_vs_one_gpu": float(group_rel(prob, d_group, d_one)),
+                           "tolerance": 1e-9}
+        barrier()
+
+    sp_info = h.sparse_info()
+    plan_info = h.plan_info()
     h.close()                                   # every rank: the handle may hold a communicator
     if rank != 0:
         if world > 1:
@@ -331,56 +432,100 @@ def run_ours(args, rank, world, local_rank):
         return
     hbm_peak, peak_src = measured_peaks()
     dgemm_peak = fp64_tensor_peak(torch)
+    fact_flop = plan_info["flop"] if plan_info["nested_dissection"] else counts["F_chol"]
     kernels = {
         "assemble_schur": {"ms": float(phase_ms[1]), "GBps": counts["B_asm"] / world / (phase_ms[1] * 1e-3) / 1e9,
                            "TFLOPs": (counts["F_asm"] + counts["F_schur"]) / world / (phase_ms[1] * 1e-3) / 1e12},
-        "cholesky": {"ms": float(phase_ms[2]), "TFLOPs": counts["F_chol"] / (phase_ms[2] * 1e-3) / 1e12},
+        "cholesky": {"ms": float(phase_ms[2]), "TFLOPs": fact_flop / (phase_ms[2] * 1e-3) / 1e12,
+                     "flop": fact_flop, "flop_dense": counts["F_chol"], "chain_blocks": plan_info["chain_blocks"],
+                     "exchange_ms": float(phase_ms[6])},
         "prep_clear": {"ms": float(phase_ms[0])}, "triangular_solve": {"ms": float(phase_ms[3])},
         "update_backsub": {"ms": float(phase_ms[4])},
+        "residuals": {"ms": float(rsd_kernel_ms), "GBps": counts["B_rsd"] / world / (max(rsd_kernel_ms, 1e-6) * 1e-3) / 1e9,
+                      "frac_of_hbm_peak": counts["B_rsd"] / world / (max(rsd_kernel_ms, 1e-6) * 1e-3) / 1e9 / hbm_peak},
     }
     if phase_ms[2] >= phase_ms[1]:
-        roof = {"kernel": "k_gemm_nt (FP64 DMMA products of the blocked Cholesky; achieved = u_c^3/3 flop over the "
-                          "WHOLE factorisation phase incl. its latency-bound leaves)", "bound": "tensor",
-                "achieved": kernels["cholesky"]["TFLOPs"], "peak": dgemm_peak, "unit": "TFLOP/s",
+        tr, tr_src = ncu_traffic("k_gemm_nt")
+        roof = {"kernel": "k_gemm_nt (FP64 DMMA products of the blocked Cholesky; achieved = flop EXECUTED by the plan's "
+                          "task graph over the WHOLE factorisation phase incl. its latency-bound chain of diagonal blocks)",
+                "bound": "tensor", "achieved": kernels["cholesky"]["TFLOPs"], "peak": dgemm_peak, "unit": "TFLOP/s",
                 "frac": kernels["cholesky"]["TFLOPs"] / dgemm_peak if dgemm_peak else None,
-                "traffic": 6.02e9 if args.workload == "config4" else None,
-                "traffic_note": "dram read+write of the top-level trailing-update launch (2.25e11 flop, 6.62 ms, "
-                                "33.9 TFLOP/s, DMMA pipe 92 % active): ncu --set full, profiles/r1e_end_state_config4.md",
+                "traffic": tr, "traffic_source": tr_src,
                 "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run (FP64 is not in MEASURED_PEAKS.json); "
                                "DMMA issue peak by microbenchmark 37.1 TFLOP/s (profiles/r1_dmma_rate_microbench.txt)"}
     else:
-        roof = {"kernel": "k_assemble (fused BuildAwG + normal blocks + Schur)", "bound": "hbm",
-                "achieved": kernels["assemble_schur"]["GBps"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": kernels["assemble_schur"]["GBps"] / hbm_peak, "traffic": None, "peak_source": peak_src}
-    if sp_info["active"] and roof.get("bound") == "tensor":
-        roof["note"] = ("block-sparse factorisation: 'achieved' still counts the DENSE u_c^3/3 flop over the phase time "
-                        "(an effective rate for comparison with the dense form), not the flop executed")
-    # CPU baseline: bounded sample on the host cores (rank 0, N=1 only)
-    cpu = None
+        tr, tr_src = ncu_traffic("assembly")
+        roof = {"kernel": "k_point_pass + k_image_pass + k_pair_pass (fused BuildAwG + normal blocks + Schur); achieved = "
+                          "algorithmic bytes of SURVEY 8(d) over the assembly phase",
+                "bound": "hbm", "achieved": kernels["assemble_schur"]["GBps"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": kernels["assemble_schur"]["GBps"] / hbm_peak, "traffic": tr, "traffic_source": tr_src,
+                "peak_source": peak_src}
+    # CPU baseline + parity at the benchmark's own size (rank 0, N=1 only): the CPU port runs the WHOLE adjustment
+    # from the same initial values; its mean iteration time is the baseline, its results are the oracle
+    cpu, parity = None, None
     if world == 1 and not args.no_cpu:
-        sec, parts = cpu_iteration_seconds(prob, 1.0)
-        cpu = {"value": prob.n_obs / sec, "unit": "obs/s", "cores": parts["threads"], "kind": "port",
-               "ms_per_step": sec * 1e3, "sample": cpu_sample_text(prob, parts)}
+        from oracle.compare import group_rel
+        cp, threads = cpu_port(prob)
+        xh, ds_c, n_it, tms, state = np.array(x0, dtype=np.float64), 100.0, 0, [], None
+        trace_c = []
+        while ds_c > st.threshold and n_it < st.Iteration_Cap and n_it < args.cpu_iterations:
+            tm = {}
+            xh, ds_c, state = cp.iterate(xh, tm)
+            tms.append(tm)
+            trace_c.append(ds_c)
+            n_it += 1
+        sec = float(np.mean([m["total_s"] for m in tms]))
+        cpu = {"value": prob.n_obs / sec, "unit": "obs/s", "cores": threads, "kind": "port", "ms_per_step": sec * 1e3,
+               "sample": (f"full workload, mean of {n_it} measured iterations of the whole adjustment: assembly+Schur "
+                          f"{np.mean([m['assemble_s'] for m in tms]):.2f} s, LAPACK bordered solve at u_c={prob.u_c} "
+                          f"{np.mean([m['solve_s'] for m in tms]):.2f} s, back-substitution "
+                          f"{np.mean([m['backsub_s'] for m in tms]):.2f} s")}
+        converged = ds_c <= st.threshold
+        parity = {"against": "oracle/cport.py (C/OpenMP + LAPACK restatement), whole adjustment from the same xhat0",
+                  "iterations": [int(its), int(n_it)], "cpu_converged": bool(converged),
+                  "deltasum_first_rel": float(abs(trace[0] - trace_c[0]) / trace_c[0])}
+        if converged and n_it == its:
+            ref = cp.residuals(state, xh)
+            vmax = float(np.max(np.abs(ref["v"])))
+            parity.update({"xhat_group_rel": float(group_rel(prob, xhat_end, xh)), "xhat_tol": 1e-9,
+                           "v_max_abs_over_max_v": float(np.max(np.abs(v_pin.numpy() - ref["v"])) / vmax), "v_tol": 1e-8,
+                           "sigma02_rel": float(abs(sigma02 - ref["sigma02"]) / ref["sigma02"]), "sigma02_tol": 1e-8,
+                           "sigma02_cpu": float(ref["sigma02"])})
+            parity["ok"] = bool(parity["xhat_group_rel"] < 1e-9 and parity["v_max_abs_over_max_v"] < 1e-8
+                                and parity["sigma02_rel"] < 1e-8)
+        else:
+            parity["ok"] = False
+    cfg = workload_config(args, prob, desc)
+    cfg.update({
+        "parallelism": ("single GPU" if world == 1 else
+                        (f"nested-dissection group x{world}: one subtree of the image block per rank, local elimination, "
+                         f"shared top part ({plan_info['rows'] - plan_info['top_row0']} of {plan_info['rows']} rows) summed "
+                         "over NVLink inside feba_iterate (3 small + 1 large ncclAllReduce)" if mode == "group" else
+                         f"point-sharded assembly x{world}, all-reduce of the whole reduced system, "
+                         + ("column-cyclic shared factorisation (panel broadcasts)"
+                            if (adj.shared_factorisation and prob.u_c > 95 * 64) else "replicated factorisation"))),
+        "reduced_system": (f"nested dissection: {plan_info['nodes']} tree nodes, {plan_info['supertiles']} supertiles, "
+                           f"{sp_info['nonzero_supertiles']} of {sp_info['lower_supertiles']} lower supertiles factorised, "
+                           f"chain {plan_info['chain_blocks']} of {plan_info['rows'] // 64} blocks, "
+                           f"{sp_info['datum_images']} datum images" if sp_info["active"] else "dense (Buildxhat order)"),
+        "l2": "inputs larger than L2 (observations + records + reduced system > 126 MB); no flush needed"})
     line = {
         "metric": "observations/sec per Gauss-Newton iteration", "value": value, "unit": "obs/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": desc, "n_obs": prob.n_obs, "n_img": prob.numImg,
-                   "n_pts": prob.numPts, "u": prob.u, "u_c": prob.u_c, "inner_constraints": prob.settings.Inner_Constraints,
-                   "type": prob.settings.type, "parallelism": (f"point-sharded assembly x{world}, all-reduce of the reduced system, "
-                                   + ("replicated factorisation" if not (adj.shared_factorisation and prob.u_c > 95 * 64)
-                                      else "column-cyclic shared factorisation (panel broadcasts)")
-                                   + (", packed exchange" if os.environ.get("FEBA_PACKED_REDUCE", "0") == "1" else ""))
-                   if world > 1 else "single GPU",
-                   "reduced_system": (f"block-sparse: {sp_info['nonzero_supertiles']} of {sp_info['lower_supertiles']} lower "
-                                      f"supertiles factorised, {sp_info['datum_images']} datum images (FEBA_SPARSE=1)"
-                                      if sp_info["active"] else "dense"),
-                   "l2": "inputs larger than L2 (observations + reduced system > 126 MB); no flush needed"},
+        "config": cfg,
         "e2e": {"value": e2e_val, "unit": "obs/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(8 * u_loc),
                 "d2h_bytes_per_step": int(8 * u_loc + 16)},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels,
-        "fp64_dgemm_peak_tflops": dgemm_peak, "residual_stage_ms": rsd_ms,
-        "sigma02": sigma02,
+        "fp64_dgemm_peak_tflops": dgemm_peak,
+        "residual_stage_ms": rsd_ms, "residual_stage": {
+            "e2e_ms_pinned_outputs": rsd_ms, "e2e_ms_pageable_outputs": rsd_pageable_ms, "kernel_ms": float(rsd_kernel_ms),
+            "d2h_bytes": int(56 * n_rows)},
+        "adjustment": {"iterations": int(its), "deltasum": [float(x) for x in trace], "sigma02": sigma02,
+                       "xhat_l2": float(np.linalg.norm(xhat_end)), "xhat_sum": float(np.sum(xhat_end)),
+                       "xhat_cam_l2": float(np.linalg.norm(xhat_end[:prob.u_c]))},
+        "sigma02": sigma02, "create_s": t_create,
+        "parity": parity, "group_check": group_check,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
@@ -499,9 +644,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config4", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (tests only)")
-    ap.add_argument("--cpu-fraction", type=float, default=0.25,
-                    help="--impl reference: fraction of the points the linear stages are timed on per step")
+    ap.add_argument("--cpu-fraction", type=float, default=1.0,
+                    help="--impl reference: fraction of the points the linear stages are timed on per step (1 = the "
+                         "full workload, measured)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-iterations", type=int, default=12,
+                    help="cap on the iterations of the CPU port's whole adjustment (cpu_baseline + parity at N=1)")
+    ap.add_argument("--plan", type=int, default=0, help="feba_settings.plan: 0 automatic, -1 dense order, 1 nested dissection")
+    ap.add_argument("--replicated", action="store_true",
+                    help="N > 1: the replicated form (all-reduce of the whole reduced system) instead of the group form")
+    ap.add_argument("--no-group-check", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -14,11 +14,13 @@
 #include <new>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "../../include/feba.h"
 #include "feba_dev.h"
 #include "feba_kernels.h"
 #include "feba_model.cuh"
+#include "feba_order.h"
 #include "feba_sparse.h"
 
 using namespace feba;
@@ -32,31 +34,42 @@ struct feba_handle {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::vector<void*> allocs;
     // device state
     double *eop = nullptr, *iop = nullptr, *cam_box = nullptr, *img_tab = nullptr, *cam_tab = nullptr;
     double *xhat = nullptr, *sol = nullptr, *dcam = nullptr, *dcam_unscaled = nullptr, *work = nullptr;
-    double *ywork = nullptr, *Linv = nullptr, *dvec = nullptr;
+    double *ywork = nullptr, *Linv = nullptr, *dvec = nullptr, *dg = nullptr;
     double *covU = nullptr, *covQ = nullptr, *covY = nullptr, *covT = nullptr;   // covariance stage (lazy)
     bool cov_ready = false;
+    // plan of the reduced system (feba_order.h): row order, supertiles, pattern, owners
+    ReducedPlan plan;
+    std::vector<int> tile_chain, tile_owner, block_owner, row_first;
+    int2* blk_list = nullptr;     // non-zero 64x64 blocks of the lower triangle, then the augmented block row
+    int n_blk_list = 0;
     DagStreams dag;               // task-graph factorisation (large reduced systems)
     std::vector<cudaEvent_t> dag_events;
     bool use_dag = false;
-    DistCtx dist;                 // group of GPUs factorising together (feba_dist_init)
+    DistCtx dist;                 // group of GPUs (feba_create_shard, or the legacy feba_dist_init)
     GreenPair green;              // SM partitions of the task graph (chain | bulk), optional
-    bool dist_active = false;
-    // block-sparse form of the reduced system (FEBA_SPARSE=1, feba_sparse.h): supertile pattern incl. fill
-    // for chol_dag, datum-image flags on the device
-    bool sparse = false;
-    std::vector<unsigned char> nzmask;
-    std::vector<int> row_first;          // envelope of the pattern per 64-block row (backward substitution)
+    bool dist_active = false;     // legacy: column-cyclic shared factorisation of a dense system
+    // group run on a nested-dissection plan (feba_create_shard): this rank holds the points of its own subtrees
+    bool shard = false;
+    int rank = 0, world = 1;
+    int64_t n_obs_global = 0;
+    unsigned char* tie_mine = nullptr;    // device, n_tie: 1 = tie point owned by this rank
+    int top_row0 = 0;                     // first row of the shared top part (summed over the ranks)
+    double* xchg = nullptr;               // packed lower trapezoid of the shared top part
+    size_t xchg_count = 0;
     unsigned char* datum_dev = nullptr;
-    int sparse_nz = 0, sparse_all = 0;   // non-zero / all lower supertiles of the factorised part
     bool dag_cols = false;        // column form of the task graph (chol_cols), issued eagerly unless solve_graph
     bool solve_graph = true;      // capture the solve half into a CUDA graph
     double *scal = nullptr;       // [0] sumabs camera part, [1] sumabs points, [2] sum vx^2, [3] sum vy^2
     double *v_out = nullptr, *rsd_out = nullptr, *delta_out = nullptr;
+    double *v_pin = nullptr, *rsd_pin = nullptr;   // pinned staging of the residual stage (chunked D2H)
+    size_t pin_chunk = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_ev[2] = {nullptr, nullptr};
     int *opt = nullptr, *tie_pt = nullptr, *info = nullptr;
     double* scal_host = nullptr;  // pinned mirror of scal
     int* info_host = nullptr;
@@ -78,7 +91,7 @@ struct feba_handle {
     } g_assemble, g_solve;
     bool use_graph = true;
     bool capturing = false;
-    double timing[6] = {0, 0, 0, 0, 0, 0};
+    double timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool timing_valid = false;
     std::string err;
 };
@@ -102,6 +115,11 @@ int fail(feba_handle* h, int code, const char* fmt, ...) {
         if (e_ != cudaSuccess)                                                                       \
             return fail(h, FEBA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
                         __LINE__);                                                                   \
+    } while (0)
+
+#define NC(h, call)                                                                  \
+    do {                                                                             \
+        if ((call) != 0) return fail(h, FEBA_ERR_CUDA, "%s (%s:%d)", (h)->dist.err, __FILE__, __LINE__); \
     } while (0)
 
 // Event record that also works inside stream capture (external-record node keeps the timestamp).
@@ -147,22 +165,16 @@ cudaError_t pool_stream(feba_handle* h, int slot, int priority, cudaStream_t* ou
     return cudaStreamCreateWithPriority(out, cudaStreamNonBlocking, priority);
 }
 
-// Stream pool, events and SM partitions of the task-graph factorisation (large reduced systems,
-// >= 96 blocks, u_c >= 6,144).  Single GPU: about 13 supertiles per side, captured tile graph, whole GPU
-// shared (measured on u_c = 12,010: T = 6/8/12/14/16/20/24 blocks -> 48.7/32.6/26.3/25.3/25.6/27.7/
-// 28.1 ms, recursive form 30.2 ms; 4/8/12/16 streams -> 28.3/25.6/27.6/27.2 ms; a chain partition of
-// 8/16/24/32 SMs -> 30.1/28.0/27.9/28.4 ms: one GPU is bound by the bulk updates, not by the chain).
-// Group (feba_dist_init): about 19 supertiles, column form issued eagerly, 32 SMs for the panel chain
-// (2 GPUs, whole iteration: tile graph 32.2 ms; column form T=14 33.6, +32 SMs 31.2, T=10 30.6 ms).
-// FEBA_DAG_TILE=t (0 = recursive form), FEBA_DAG_STREAMS, FEBA_GREEN_SMS=r (multiple of 8, 0 = shared),
-// FEBA_DAG_FORM=cols|tiles, FEBA_SOLVE_GRAPH=0|1 override.
-int setup_pool(feba_handle* h, bool group) {
-    // tear down what an earlier call built
+void teardown_pool(feba_handle* h) {
     for (int s2 = 0; s2 < h->dag.n_streams; ++s2) {
         cudaStreamDestroy(h->dag.streams[s2]);
         if (h->dag.join[s2]) cudaEventDestroy(h->dag.join[s2]);
         h->dag.streams[s2] = nullptr;
         h->dag.join[s2] = nullptr;
+    }
+    if (h->dag.join[h->dag.n_streams]) {
+        cudaEventDestroy(h->dag.join[h->dag.n_streams]);
+        h->dag.join[h->dag.n_streams] = nullptr;
     }
     h->dag.n_streams = 0;
     if (h->dag.fork) cudaEventDestroy(h->dag.fork);
@@ -172,7 +184,64 @@ int setup_pool(feba_handle* h, bool group) {
     h->dag_events.clear();
     green_destroy(&h->green);
     h->use_dag = false;
+}
 
+// Stream pool and tile events of the task-graph factorisation.  n_hi streams get the high priority (slot 0
+// carries the critical path); n_events = (tiles + 1)^2.
+int make_pool(feba_handle* h, int NS, int n_hi, int n_events, int reserve_sms) {
+    teardown_pool(h);
+    if (NS < 2) NS = 2;
+    if (NS > 32) NS = 32;
+    int lo = 0, hi = 0;
+    CU(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    if (reserve_sms > 0) {
+        char why[128];
+        const int rc = green_create(h->device, reserve_sms, &h->green, why, sizeof(why));
+        if (std::getenv("FEBA_VERBOSE")) {
+            if (rc) fprintf(stderr, "[feba] %s; the task graph shares the whole GPU\n", why);
+            else fprintf(stderr, "[feba] SM partitions: chain %d, bulk %d\n", h->green.chain_sms, h->green.bulk_sms);
+        }
+    }
+    for (int s2 = 0; s2 < NS; ++s2) {
+        CU(h, pool_stream(h, s2, s2 < n_hi ? hi : lo, &h->dag.streams[s2]));
+        ++h->dag.n_streams;
+        CU(h, cudaEventCreateWithFlags(&h->dag.join[s2], cudaEventDisableTiming));
+    }
+    CU(h, cudaEventCreateWithFlags(&h->dag.fork, cudaEventDisableTiming));
+    h->dag_events.assign((size_t)n_events, nullptr);
+    for (auto& ev : h->dag_events) CU(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    h->dag.events = h->dag_events.data();
+    h->dag.n_events = (int)h->dag_events.size();
+    h->use_dag = true;
+    return FEBA_OK;
+}
+
+// Pool of the plan's task graph (chol_tiles).  Dense plan, one GPU, measured on u_c = 12,010: supertiles of
+// 6/8/12/14/16/20/24 blocks -> 48.7/32.6/26.3/25.3/25.6/27.7/28.1 ms, recursive form 30.2 ms; 4/8/12/16 streams ->
+// 28.3/25.6/27.6/27.2 ms.  Nested-dissection plans have many independent chains: 16 streams.
+// FEBA_DAG_STREAMS overrides.
+int setup_plan_pool(feba_handle* h) {
+    const ReducedPlan& pl = h->plan;
+    if (pl.NT < 2) {
+        teardown_pool(h);
+        return FEBA_OK;
+    }
+    const char* e_s = std::getenv("FEBA_DAG_STREAMS");
+    const int NS = e_s ? std::atoi(e_s) : (pl.masked ? 16 : 8);
+    // FEBA_DAG_FORM=cols: column form of the dense task graph (chol_cols, uniform supertiles), eager unless
+    // FEBA_SOLVE_GRAPH=1; the default is the tile form captured into the iteration's CUDA graph
+    const char* e_f = std::getenv("FEBA_DAG_FORM");
+    h->dag_cols = !pl.masked && e_f && std::strcmp(e_f, "cols") == 0 && NS >= 5;
+    h->solve_graph = !h->dag_cols;
+    if (const char* e_sg = std::getenv("FEBA_SOLVE_GRAPH")) h->solve_graph = std::atoi(e_sg) != 0;
+    return make_pool(h, NS, 1, (pl.NT + 1) * (pl.NT + 1), 0);
+}
+
+// Legacy group form of a DENSE system (feba_dist_init): about 19 uniform supertiles, column form issued eagerly,
+// 32 SMs for the panel chain (2 GPUs, whole iteration: tile graph 32.2 ms; column form T=14 33.6, +32 SMs 31.2,
+// T=10 30.6 ms).  FEBA_DAG_TILE=t, FEBA_DAG_STREAMS, FEBA_GREEN_SMS=r (multiple of 8, 0 = shared),
+// FEBA_DAG_FORM=cols|tiles, FEBA_SOLVE_GRAPH=0|1 override.
+int setup_legacy_group_pool(feba_handle* h) {
     const int nb = h->P.n_pad / kBlk;
     const char* e_t = std::getenv("FEBA_DAG_TILE");
     const char* e_s = std::getenv("FEBA_DAG_STREAMS");
@@ -181,96 +250,24 @@ int setup_pool(feba_handle* h, bool group) {
         T = std::atoi(e_t);
         if (T > 0 && nb < 2 * T) T = 0;
     } else if (nb >= 96) {
-        T = group ? (nb + 9) / 19 : (nb + 6) / 13;
+        T = (nb + 9) / 19;
         if (T < 8) T = 8;
         if (T > 24) T = 24;
     }
     const int NS = e_s ? std::atoi(e_s) : 8;
-    if (T <= 0 || NS < 2 || NS > 16) return FEBA_OK;
+    if (T <= 0 || NS < 2 || NS > 16) {
+        teardown_pool(h);
+        return FEBA_OK;
+    }
     h->dag.tile_blocks = T;
     const char* e_f = std::getenv("FEBA_DAG_FORM");
-    h->dag_cols = e_f ? std::strcmp(e_f, "cols") == 0 : group;
+    h->dag_cols = e_f ? std::strcmp(e_f, "cols") == 0 : true;
     const char* e_sg = std::getenv("FEBA_SOLVE_GRAPH");
     h->solve_graph = e_sg ? std::atoi(e_sg) != 0 : !h->dag_cols;
-    int lo = 0, hi = 0;
-    CU(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
     const char* e_g = std::getenv("FEBA_GREEN_SMS");
-    const int reserve = e_g ? std::atoi(e_g) : (group && h->dag_cols ? 32 : 0);
-    if (reserve > 0) {
-        char why[128];
-        const int rc = green_create(h->device, reserve, &h->green, why, sizeof(why));
-        if (std::getenv("FEBA_VERBOSE")) {
-            if (rc) fprintf(stderr, "[feba] %s; the task graph shares the whole GPU\n", why);
-            else fprintf(stderr, "[feba] SM partitions: chain %d, bulk %d\n", h->green.chain_sms, h->green.bulk_sms);
-        }
-    }
-    // priorities: stream 0 is the chain; in a group the panel streams (1..2 column form, 1..3 tile form) too
-    const int n_hi = group ? (h->dag_cols ? 3 : 4) : 1;
-    for (int s2 = 0; s2 < NS; ++s2) {
-        CU(h, pool_stream(h, s2, s2 < n_hi ? hi : lo, &h->dag.streams[s2]));
-        ++h->dag.n_streams;
-        CU(h, cudaEventCreateWithFlags(&h->dag.join[s2], cudaEventDisableTiming));
-    }
-    CU(h, cudaEventCreateWithFlags(&h->dag.fork, cudaEventDisableTiming));
+    const int reserve = e_g ? std::atoi(e_g) : (h->dag_cols ? 32 : 0);
     const int NT = (nb + T - 1) / T;
-    h->dag_events.assign((size_t)(NT + 1) * (NT + 1), nullptr);
-    for (auto& ev : h->dag_events) CU(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    h->dag.events = h->dag_events.data();
-    h->dag.n_events = (int)h->dag_events.size();
-    h->use_dag = true;
-    return FEBA_OK;
-}
-
-// FEBA_SPARSE=1: supertile pattern of the reduced system from the pair schedule (+ symbolic fill) and, for
-// free networks, the datum images of the sparse-datum form (feba_sparse.h).  Single GPU, tile task graph only;
-// anything else keeps the dense form.  Called once the pair schedule and the stream pool exist.
-int setup_sparse(feba_handle* h) {
-    h->sparse = false;
-    h->nzmask.clear();
-    DevProblem& P = h->P;
-    P.aug_rows = kAugRows;
-    P.datum = nullptr;
-    const char* e = std::getenv("FEBA_SPARSE");
-    if (!e || std::atoi(e) == 0 || !h->use_dag || h->dag_cols || h->dist_active) return FEBA_OK;
-    if (P.inner && P.ui != 6) return FEBA_OK;
-    const int nb = P.n_pad / kBlk, T = h->dag.tile_blocks;
-    std::vector<int> ab;
-    if (P.n_blocks > 0) {
-        std::vector<int4> blk((size_t)P.n_blocks);
-        CU(h, cudaMemcpyAsync(blk.data(), P.blocks, blk.size() * sizeof(int4), cudaMemcpyDeviceToHost, h->stream));
-        CU(h, cudaStreamSynchronize(h->stream));
-        ab.resize(2 * blk.size());
-        for (size_t i = 0; i < blk.size(); ++i) {
-            ab[2 * i] = blk[i].x;
-            ab[2 * i + 1] = blk[i].y;
-        }
-    }
-    std::vector<int> datum;
-    if (P.inner) datum = sparse_datum_images(P.n_img, P.ui, nb, T);
-    const SparsePattern pat = sparse_supertile_pattern(nb, T, P.ui, P.n_img, P.off_cam, P.n_red, P.n_blocks,
-                                                       ab.data(), datum);
-    h->nzmask = pat.nz;
-    h->row_first = pat.row_first_block(nb);
-    h->sparse_nz = h->sparse_all = 0;
-    for (int i = 0; i < pat.NT; ++i)
-        for (int j = 0; j <= i; ++j) {
-            ++h->sparse_all;
-            if (pat.at(i, j)) ++h->sparse_nz;
-        }
-    if (P.inner) {
-        std::vector<unsigned char> flags((size_t)P.n_img, 0);
-        for (int im : datum) flags[(size_t)im] = 1;
-        if (!h->datum_dev) CU(h, dev_alloc(h, &h->datum_dev, flags.size()));
-        CU(h, cudaMemcpyAsync(h->datum_dev, flags.data(), flags.size(), cudaMemcpyHostToDevice, h->stream));
-        CU(h, cudaStreamSynchronize(h->stream));
-        P.datum = h->datum_dev;
-        P.aug_rows = kSparseAugRows;
-    }
-    h->sparse = true;
-    if (std::getenv("FEBA_VERBOSE"))
-        fprintf(stderr, "[feba] sparse reduced system: %d of %d lower supertiles (T = %d blocks), %zu datum images\n",
-                h->sparse_nz, h->sparse_all, T, datum.size());
-    return FEBA_OK;
+    return make_pool(h, NS, h->dag_cols ? 3 : 4, (NT + 1) * (NT + 1), reserve);
 }
 
 int check_settings(const feba_problem* pr) {
@@ -293,6 +290,133 @@ int check_settings(const feba_problem* pr) {
     return FEBA_OK;
 }
 
+// Row order, supertiles and pattern of the reduced system.  world > 1 (feba_create_shard) needs a nested-
+// dissection plan with one subtree per rank; one GPU takes the masked plan when it shortens the chain of
+// diagonal factorisations AND the flop count to less than half of the dense form (BASELINE configs[3]: 42 of 188
+// blocks, 3.5e10 of 5.8e11 flop; configs[2], a much denser block: no), else the identity plan.
+int choose_plan(feba_handle* h, const feba_problem* pr, int n_seg, const std::vector<int>& seg_start,
+                const std::vector<int>& simg, const std::vector<int>& seg_pt, int world) {
+    const DevProblem& P = h->P;
+    const int cam_rows = P.uc * P.n_cam;
+    const int nb_id = (P.ui * P.n_img + cam_rows + kBlk - 1) / kBlk;
+    PlanOptions opt = plan_options_from_env();
+    if (pr->settings.plan < 0 && world == 1) opt.mode = -1;
+    if (pr->settings.plan > 0) opt.mode = 1;
+    auto identity = [&]() {
+        int T = 0;
+        if (const char* e_t = std::getenv("FEBA_DAG_TILE")) {
+            T = std::atoi(e_t);
+            if (T > 0 && nb_id < 2 * T) T = 0;
+        } else if (nb_id >= 96) {
+            T = (nb_id + 6) / 13;
+            if (T < 8) T = 8;
+            if (T > 24) T = 24;
+        }
+        h->plan = identity_plan(P.n_img, P.ui, cam_rows, T);
+        h->dag.tile_blocks = T > 0 ? T : 8;
+    };
+    const bool can_mask = P.ui > 0 && (!P.inner || P.ui == 6);
+    if (world == 1 && (opt.mode < 0 || !can_mask || (opt.mode == 0 && nb_id < opt.min_blocks))) {
+        identity();
+        return FEBA_OK;
+    }
+    if (world > 1 && !can_mask)
+        return fail(h, FEBA_ERR_INVALID, "feba_create_shard needs EOP unknowns (nothing to dissect)");
+    std::vector<unsigned char> seg_tie((size_t)n_seg);
+    for (int s2 = 0; s2 < n_seg; ++s2) seg_tie[(size_t)s2] = pr->pt_tie[seg_pt[(size_t)s2]] >= 0;
+    std::vector<int> ptr, idx;
+    image_adjacency(P.n_img, n_seg, seg_start.data(), simg.data(), seg_tie.data(), world > 1, ptr, idx);
+    std::vector<double> pos((size_t)P.n_img * 3);
+    for (int i = 0; i < P.n_img; ++i)
+        for (int k = 0; k < 3; ++k) pos[3 * (size_t)i + k] = pr->eop0[6 * (size_t)i + k];
+    ReducedPlan mp = masked_plan(P.n_img, P.ui, cam_rows, ptr.data(), idx.data(), pos.data(), P.inner != 0, world, opt);
+    if (world > 1) {
+        if (mp.world != world)
+            return fail(h, FEBA_ERR_INVALID, "the image block cannot be cut into %d subtrees: use the replicated form "
+                                             "(feba_create + feba_reduced_dev)", world);
+        h->plan = std::move(mp);
+        return FEBA_OK;
+    }
+    const double dense_flop = std::pow((double)kBlk * nb_id, 3) / 3;
+    const bool pays = mp.flop <= 0.5 * dense_flop && 2 * mp.chain_blocks <= nb_id;
+    if (opt.mode > 0 || pays) h->plan = std::move(mp);
+    else identity();
+    return FEBA_OK;
+}
+
+// Everything the solve half needs from the plan: tile arrays for chol_tiles, owners per 64-block, the envelope
+// for the backward substitution, the block list on the device, row maps on the device.
+int install_plan(feba_handle* h) {
+    DevProblem& P = h->P;
+    const ReducedPlan& pl = h->plan;
+    P.n_pad = pl.n_pad;
+    P.ld = P.n_pad + kBlk;
+    P.off_cam = pl.off_cam;
+    P.ext_off_cam = P.ui * P.n_img;
+    const int nb = P.n_pad / kBlk;
+    int* d_img_row = nullptr;
+    int* d_row_ext = nullptr;
+    CU(h, upload(h, &d_img_row, pl.img_row.data(), pl.img_row.size()));
+    CU(h, upload(h, &d_row_ext, pl.row_ext.data(), pl.row_ext.size()));
+    P.img_row = d_img_row;
+    P.row_ext = d_row_ext;
+    P.row_owner = nullptr;
+    P.rank = h->rank;
+    h->tile_chain.assign((size_t)pl.NT, 0);
+    h->tile_owner.assign((size_t)pl.NT, -1);
+    h->block_owner.assign((size_t)nb, -1);
+    if (pl.masked) {
+        for (int t = 0; t < pl.NT; ++t) {
+            const PlanNode& nd = pl.nodes[(size_t)pl.tile_node[(size_t)t]];
+            // slot 0 = critical path (root node); other nodes by depth level and position inside the level
+            h->tile_chain[(size_t)t] = pl.tile_node[(size_t)t] == 0 ? 0 : 1 + nd.lane + 5 * nd.depth;
+            h->tile_owner[(size_t)t] = h->shard ? nd.owner : -1;
+            for (int b = pl.tile_b0[(size_t)t]; b < pl.tile_b0[(size_t)t + 1]; ++b) h->block_owner[(size_t)b] = h->tile_owner[(size_t)t];
+        }
+        h->row_first = pl.row_first_block();
+    } else {
+        h->row_first.clear();
+    }
+    if (h->shard) {
+        std::vector<int> row_owner((size_t)P.n_pad);
+        for (int r = 0; r < P.n_pad; ++r) row_owner[(size_t)r] = h->block_owner[(size_t)(r / kBlk)];
+        int* d_ro = nullptr;
+        CU(h, upload(h, &d_ro, row_owner.data(), row_owner.size()));
+        P.row_owner = d_ro;
+        h->top_row0 = pl.top_tile0 < pl.NT ? pl.tile_b0[(size_t)pl.top_tile0] * kBlk : P.n_pad;
+    }
+    // block list: lower blocks of the non-zero tiles (every lower block for a dense plan), then the augmented row
+    std::vector<int2> list;
+    for (int ti = 0; ti < pl.NT; ++ti)
+        for (int tj = 0; tj <= ti; ++tj) {
+            if (!pl.at(ti, tj)) continue;
+            if (h->shard) {           // tiles of other ranks' subtrees are never touched here
+                const int oi = h->tile_owner[(size_t)ti], oj = h->tile_owner[(size_t)tj];
+                if ((oi >= 0 && oi != h->rank) || (oj >= 0 && oj != h->rank)) continue;
+            }
+            for (int bi = pl.tile_b0[(size_t)ti]; bi < pl.tile_b0[(size_t)ti + 1]; ++bi)
+                for (int bj = pl.tile_b0[(size_t)tj]; bj < pl.tile_b0[(size_t)tj + 1] && bj <= bi; ++bj)
+                    list.push_back(make_int2(bi, bj));
+        }
+    for (int bj = 0; bj < nb; ++bj) list.push_back(make_int2(nb, bj));
+    h->n_blk_list = (int)list.size();
+    CU(h, upload(h, &h->blk_list, list.data(), list.size()));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (std::getenv("FEBA_VERBOSE")) {
+        int nzt = 0, allt = 0;
+        for (int i = 0; i < pl.NT; ++i)
+            for (int j = 0; j <= i; ++j) {
+                ++allt;
+                nzt += pl.at(i, j) ? 1 : 0;
+            }
+        fprintf(stderr, "[feba] plan: %s, %d rows (u_c %d), %d supertiles, %d of %d lower supertiles non-zero, chain %d of %d "
+                        "blocks, %.2e flop (dense %.2e), %zu nodes, %zu datum images, world %d\n",
+                pl.masked ? "nested dissection" : "identity", pl.n_pad, P.n_red, pl.NT, nzt, allt, pl.chain_blocks, nb,
+                pl.flop, pl.flop_dense, pl.nodes.size(), pl.datum.size(), h->world);
+    }
+    return FEBA_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -306,25 +430,22 @@ void feba_destroy(feba_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     if (h->scal_host) cudaFreeHost(h->scal_host);
     if (h->info_host) cudaFreeHost(h->info_host);
+    if (h->v_pin) cudaFreeHost(h->v_pin);
+    if (h->rsd_pin) cudaFreeHost(h->rsd_pin);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (auto& e : h->copy_ev)
+        if (e) cudaEventDestroy(e);
     drop_graphs(h);
-    for (int s2 = 0; s2 < h->dag.n_streams; ++s2) {
-        cudaStreamDestroy(h->dag.streams[s2]);
-        if (h->dag.join[s2]) cudaEventDestroy(h->dag.join[s2]);
-    }
-    if (h->dag.join[h->dag.n_streams]) cudaEventDestroy(h->dag.join[h->dag.n_streams]);
-    if (h->dag.fork) cudaEventDestroy(h->dag.fork);
-    green_destroy(&h->green);
+    teardown_pool(h);
     if (h->dist.comm) dist_comm_destroy(&h->dist);
     if (h->dist.stream) cudaStreamDestroy(h->dist.stream);
-    for (auto& ev : h->dag_events)
-        if (ev) cudaEventDestroy(ev);
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
-int feba_create(const feba_problem* pr, feba_handle** out) {
+static int create_impl(const feba_problem* pr, int rank, int world, const void* id, feba_handle** out) {
     if (!pr || !out) return fail(nullptr, FEBA_ERR_INVALID, "null argument");
     *out = nullptr;
     int rc = check_settings(pr);
@@ -344,6 +465,9 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
             }
         }
     } guard{h};
+    h->rank = rank;
+    h->world = world;
+    h->shard = world > 1;
     CU(h, cudaGetDevice(&h->device));
     CU(h, cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device));
     CU(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -354,7 +478,6 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
     const feba_settings& s = pr->settings;
 
     DevProblem& P = h->P;
-    P.n_obs = pr->n_obs;
     P.n_img = pr->n_img;
     P.n_cam = pr->n_cam;
     P.n_pts = pr->n_pts;
@@ -379,12 +502,10 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
     for (int j = 0; j < P.NK; ++j) P.ccol[3 + j] = s.estimate_radial ? k++ : -1;
     for (int j = 0; j < 2; ++j) P.ccol[3 + P.NK + j] = s.estimate_decent ? k++ : -1;
     P.uc = k;
-    P.off_cam = P.ui * P.n_img;
-    P.n_red = P.off_cam + P.uc * P.n_cam;
+    P.n_red = P.ui * P.n_img + P.uc * P.n_cam;
     if (P.n_red < 1) return fail(h, FEBA_ERR_INVALID, "no EOP/IOP unknowns: nothing to adjust");
-    P.n_pad = (P.n_red + kBlk - 1) / kBlk * kBlk;
-    P.ld = P.n_pad + kBlk;
-    h->u = (int64_t)P.n_red + 3 * (int64_t)P.n_tie;
+    h->u = (int64_t)P.n_red + 3 * (int64_t)pr->n_tie;
+    h->n_obs_global = pr->n_obs;
 
     // ---- order the observations by object point (stable counting sort, PHO order inside a point)
     const int64_t n = pr->n_obs;
@@ -406,8 +527,8 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
         start[(size_t)p + 1] += start[p];
     }
     seg_start.push_back((int)n);
-    P.n_seg = (int)seg_pt.size();
-    std::vector<int> perm((size_t)n), simg((size_t)n), spt((size_t)n), oseg((size_t)n);
+    int n_seg = (int)seg_pt.size();
+    std::vector<int> perm((size_t)n), simg((size_t)n), spt((size_t)n);
     std::vector<double> sx((size_t)n), sy((size_t)n);
     {
         std::vector<int> cur(start.begin(), start.end() - 1);
@@ -420,38 +541,6 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
             sx[d] = pr->obs_x[i];
             sy[d] = pr->obs_y[i];
         }
-    }
-    for (int sg = 0; sg < P.n_seg; ++sg)
-        for (int o = seg_start[sg]; o < seg_start[sg + 1]; ++o) oseg[o] = sg;
-    // the multi-camera point pass keeps the per-camera blocks of a point in shared memory for at most
-    // kMaxCamPt (4) different cameras: refuse the problem HERE, before any state exists (the reference has no
-    // such limit, BuildAwG.m:110-155; documented in feba.h)
-    if (P.uc > 0 && pr->n_cam > 4) {
-        for (int j = 0; j < pr->n_img; ++j)
-            if (pr->img_cam[j] < 0 || pr->img_cam[j] >= pr->n_cam)
-                return fail(h, FEBA_ERR_INVALID, "img_cam[%d] out of range", j);
-        for (int sg = 0; sg < P.n_seg; ++sg) {
-            int cams[4], nc = 0;
-            for (int o = seg_start[sg]; o < seg_start[sg + 1]; ++o) {
-                const int c = pr->img_cam[simg[o]];
-                bool found = false;
-                for (int k = 0; k < nc; ++k) found = found || cams[k] == c;
-                if (found) continue;
-                if (nc == 4)
-                    return fail(h, FEBA_ERR_INVALID,
-                                "object point %d (CNT row, 0-based) is observed by images of more than 4 different "
-                                "cameras while camera parameters are estimated: unsupported (feba.h)", seg_pt[sg]);
-                cams[nc++] = c;
-            }
-        }
-    }
-    // image-major record positions (stable: point-major order is kept inside an image)
-    std::vector<int> img_start((size_t)pr->n_img + 1, 0), ipos((size_t)n);
-    for (int64_t o = 0; o < n; ++o) ++img_start[(size_t)simg[o] + 1];
-    for (int j = 0; j < pr->n_img; ++j) img_start[(size_t)j + 1] += img_start[j];
-    {
-        std::vector<int> cur(img_start.begin(), img_start.end() - 1);
-        for (int64_t o = 0; o < n; ++o) ipos[o] = cur[simg[o]]++;
     }
     // tie index <-> CNT row (main.m:362-375, Buildxhat.m:108-135)
     std::vector<int> tie_pt((size_t)pr->n_tie, -1);
@@ -469,15 +558,94 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
     for (int c = 0; c < pr->n_cam; ++c)
         if (std::fabs(pr->cam_box[5 * c]) != 1.0)
             return fail(h, FEBA_ERR_INVALID, "y_dir should be +-1 only (main.m:334-337)");
+    // the multi-camera point pass keeps the per-camera blocks of a point in shared memory for at most
+    // kMaxCamPt (4) different cameras: refuse the problem HERE, before any state exists (the reference has no
+    // such limit, BuildAwG.m:110-155; documented in feba.h)
+    if (P.uc > 0 && pr->n_cam > FEBA_MAX_CAMS_PER_POINT) {
+        for (int sg = 0; sg < n_seg; ++sg) {
+            int cams[FEBA_MAX_CAMS_PER_POINT], nc = 0;
+            for (int o = seg_start[sg]; o < seg_start[sg + 1]; ++o) {
+                const int c = pr->img_cam[simg[o]];
+                bool found = false;
+                for (int kk = 0; kk < nc; ++kk) found = found || cams[kk] == c;
+                if (found) continue;
+                if (nc == FEBA_MAX_CAMS_PER_POINT)
+                    return fail(h, FEBA_ERR_INVALID,
+                                "object point %d (CNT row, 0-based) is observed by images of more than %d different "
+                                "cameras while camera parameters are estimated: unsupported (feba.h)", seg_pt[sg],
+                                FEBA_MAX_CAMS_PER_POINT);
+                cams[nc++] = c;
+            }
+        }
+    }
+
+    // ---- plan of the reduced system; a group keeps only the points of this rank's subtrees
+    rc = choose_plan(h, pr, n_seg, seg_start, simg, seg_pt, world);
+    if (rc) return rc;
+    std::vector<unsigned char> tie_mine;
+    if (h->shard) {
+        std::vector<int> owner((size_t)n_seg);
+        if (!plan_point_owner(h->plan, n_seg, seg_start.data(), simg.data(), owner.data()))
+            return fail(h, FEBA_ERR_INVALID, "internal: a point's images do not lie on one path of the dissection tree");
+        std::vector<int> l_start, l_pt, l_perm, l_simg, l_spt;
+        std::vector<double> l_sx, l_sy;
+        tie_mine.assign((size_t)pr->n_tie, 0);
+        for (int sg = 0; sg < n_seg; ++sg) {
+            if (owner[(size_t)sg] != rank) continue;
+            l_start.push_back((int)l_perm.size());
+            l_pt.push_back(seg_pt[(size_t)sg]);
+            const int t = pr->pt_tie[seg_pt[(size_t)sg]];
+            if (t >= 0) tie_mine[(size_t)t] = 1;
+            for (int o = seg_start[(size_t)sg]; o < seg_start[(size_t)sg + 1]; ++o) {
+                l_perm.push_back(perm[(size_t)o]);
+                l_simg.push_back(simg[(size_t)o]);
+                l_spt.push_back(spt[(size_t)o]);
+                l_sx.push_back(sx[(size_t)o]);
+                l_sy.push_back(sy[(size_t)o]);
+            }
+        }
+        l_start.push_back((int)l_perm.size());
+        // tie points without any observation: rank 0 keeps them (their xhat entries only pass through)
+        for (int t = 0; t < pr->n_tie; ++t) {
+            const int p = tie_pt[(size_t)t];
+            if (rank == 0 && p >= 0 && start[(size_t)p + 1] == start[(size_t)p]) tie_mine[(size_t)t] = 1;
+        }
+        seg_start.swap(l_start);
+        seg_pt.swap(l_pt);
+        perm.swap(l_perm);
+        simg.swap(l_simg);
+        spt.swap(l_spt);
+        sx.swap(l_sx);
+        sy.swap(l_sy);
+        n_seg = (int)seg_pt.size();
+    }
+    const int64_t nl = (int64_t)perm.size();          // observations held by this handle
+    P.n_obs = nl;
+    P.n_seg = n_seg;
+    std::vector<int> oseg((size_t)nl);
+    for (int sg = 0; sg < n_seg; ++sg)
+        for (int o = seg_start[sg]; o < seg_start[sg + 1]; ++o) oseg[o] = sg;
+    // image-major record positions (stable: point-major order is kept inside an image)
+    std::vector<int> img_start((size_t)pr->n_img + 1, 0), ipos((size_t)nl);
+    for (int64_t o = 0; o < nl; ++o) ++img_start[(size_t)simg[o] + 1];
+    for (int j = 0; j < pr->n_img; ++j) img_start[(size_t)j + 1] += img_start[j];
+    {
+        std::vector<int> cur(img_start.begin(), img_start.end() - 1);
+        for (int64_t o = 0; o < nl; ++o) ipos[o] = cur[simg[o]]++;
+    }
 
     // ---- uploads
+    {
+        const int rc_plan = install_plan(h);
+        if (rc_plan) return rc_plan;
+    }
     double *ox, *oy, *xyz, *xyz_prev;
     int *oimg, *operm, *dseg_start, *dseg_pt, *dimg_cam, *dpt_tie, *dimg_start, *diobs, *doseg;
-    CU(h, upload(h, &ox, sx.data(), (size_t)n));
-    CU(h, upload(h, &oy, sy.data(), (size_t)n));
-    CU(h, upload(h, &oimg, simg.data(), (size_t)n));
-    CU(h, upload(h, &operm, perm.data(), (size_t)n));
-    CU(h, upload(h, &h->opt, spt.data(), (size_t)n));
+    CU(h, upload(h, &ox, sx.data(), (size_t)nl));
+    CU(h, upload(h, &oy, sy.data(), (size_t)nl));
+    CU(h, upload(h, &oimg, simg.data(), (size_t)nl));
+    CU(h, upload(h, &operm, perm.data(), (size_t)nl));
+    CU(h, upload(h, &h->opt, spt.data(), (size_t)nl));
     CU(h, upload(h, &dseg_start, seg_start.data(), seg_start.size()));
     CU(h, upload(h, &dseg_pt, seg_pt.data(), seg_pt.size()));
     CU(h, upload(h, &dimg_cam, pr->img_cam, (size_t)pr->n_img));
@@ -486,8 +654,9 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
     CU(h, upload(h, &dimg_start, img_start.data(), img_start.size()));
     CU(h, upload(h, &diobs, ipos.data(), ipos.size()));
     CU(h, upload(h, &doseg, oseg.data(), oseg.size()));
-    CU(h, dev_alloc(h, &P.rec1, (size_t)n * kRec1));
-    CU(h, dev_alloc(h, &P.rec2, (size_t)n * (2 + 2 * P.NC)));
+    if (h->shard) CU(h, upload(h, &h->tie_mine, tie_mine.data(), tie_mine.size()));
+    CU(h, dev_alloc(h, &P.rec1, (size_t)nl * kRec1));
+    CU(h, dev_alloc(h, &P.rec2, (size_t)nl * (2 + 2 * P.NC)));
     CU(h, upload(h, &h->eop, pr->eop0, (size_t)pr->n_img * 6));
     CU(h, upload(h, &h->iop, pr->iop0, (size_t)pr->n_cam * P.NC));
     CU(h, upload(h, &h->cam_box, pr->cam_box, (size_t)pr->n_cam * 5));
@@ -497,6 +666,7 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
     CU(h, dev_alloc(h, &h->cam_tab, (size_t)pr->n_cam * kCamStride));
     h->S_count = (size_t)P.ld * (size_t)P.ld;
     CU(h, dev_alloc(h, &P.S, h->S_count));
+    CU(h, cudaMemsetAsync(P.S, 0, h->S_count * sizeof(double), h->stream));
     CU(h, dev_alloc(h, &h->xhat, (size_t)h->u));
     CU(h, dev_alloc(h, &h->sol, (size_t)P.n_pad));
     CU(h, dev_alloc(h, &h->dcam, (size_t)P.n_pad));
@@ -505,8 +675,10 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
     CU(h, dev_alloc(h, &h->work, 64));
     CU(h, dev_alloc(h, &h->ywork, (size_t)P.n_pad));
     CU(h, dev_alloc(h, &h->dvec, (size_t)P.n_pad));
+    CU(h, dev_alloc(h, &h->dg, (size_t)P.n_pad));
     CU(h, dev_alloc(h, &h->Linv, (size_t)(P.n_pad / kBlk) * kBlk * kBlk));
-    CU(h, dev_alloc(h, &P.Gt, (size_t)(P.off_cam > 0 ? P.off_cam : 1) * 8));
+    CU(h, dev_alloc(h, &P.Gt, (size_t)P.n_pad * 8));
+    CU(h, cudaMemsetAsync(P.Gt, 0, (size_t)P.n_pad * 8 * sizeof(double), h->stream));
     CU(h, dev_alloc(h, &h->scal, 8));
     CU(h, dev_alloc(h, &h->info, 1));
     CU(h, cudaMallocHost((void**)&h->scal_host, 8 * sizeof(double)));
@@ -514,6 +686,7 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
     if (pr->n_tie > 0) CU(h, cudaMemsetAsync(P.dpts, 0, (size_t)pr->n_tie * 3 * sizeof(double), h->stream));
     CU(h, cudaMemsetAsync(h->dcam, 0, (size_t)P.n_pad * sizeof(double), h->stream));
     CU(h, cudaMemsetAsync(h->dcam_unscaled, 0, (size_t)P.n_pad * sizeof(double), h->stream));
+    CU(h, cudaMemsetAsync(h->Linv, 0, (size_t)(P.n_pad / kBlk) * kBlk * kBlk * sizeof(double), h->stream));
     P.ox = ox;
     P.oy = oy;
     P.oimg = oimg;
@@ -536,7 +709,7 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
     }
     CU(h, dev_alloc(h, &P.partial, (size_t)h->n_partial));
     {
-        const int rc_pool = setup_pool(h, false);
+        const int rc_pool = setup_plan_pool(h);
         if (rc_pool) return rc_pool;
     }
     CU(h, dev_alloc(h, &P.cam_part, (size_t)assemble_warps(P, h->sm_count) * kCamPart));
@@ -547,9 +720,24 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
         if (kp) h->allocs.push_back(kp);
         if (kb) h->allocs.push_back(kb);
     }
-    {
-        const int rc_sp = setup_sparse(h);
-        if (rc_sp) return rc_sp;
+    // sparse-datum form (feba_sparse.h) on a masked plan of a free network: flags of the datum images
+    if (h->plan.masked && P.inner) {
+        std::vector<unsigned char> flags((size_t)P.n_img, 0);
+        for (int im : h->plan.datum) flags[(size_t)im] = 1;
+        CU(h, upload(h, &h->datum_dev, flags.data(), flags.size()));
+        CU(h, cudaStreamSynchronize(h->stream));
+        P.datum = h->datum_dev;
+        P.aug_rows = kSparseAugRows;
+    }
+    if (h->shard) {
+        if (dist_comm_init(&h->dist, rank, world, id)) return fail(h, FEBA_ERR_CUDA, "%s", h->dist.err);
+        // packed lower trapezoid of the shared top part: per group of kPackCols block columns the rows from the
+        // group's first row down to the end of the augmented block row
+        const size_t ld = (size_t)P.ld, w = 8 * (size_t)kBlk;
+        size_t total = 0;
+        for (size_t c0 = (size_t)h->top_row0; c0 < ld; c0 += w) total += (ld - c0) * std::min(w, ld - c0);
+        h->xchg_count = total;
+        CU(h, dev_alloc(h, &h->xchg, total));
     }
     // xhat = Buildxhat of the uploaded tables (Buildxhat.m:22-135)
     CU(h, cudaMemsetAsync(h->xhat, 0, (size_t)h->u * sizeof(double), h->stream));
@@ -559,6 +747,18 @@ int feba_create(const feba_problem* pr, feba_handle** out) {
     guard.keep = true;
     *out = h;
     return FEBA_OK;
+}
+
+int feba_create(const feba_problem* pr, feba_handle** out) { return create_impl(pr, 0, 1, nullptr, out); }
+
+int feba_create_shard(const feba_problem* pr, int32_t rank, int32_t world, const void* id, size_t bytes,
+                      feba_handle** out) {
+    if (world < 1 || rank < 0 || rank >= world || (world & (world - 1)) != 0)
+        return fail(nullptr, FEBA_ERR_INVALID, "feba_create_shard: world must be a power of two and 0 <= rank < world");
+    if (world == 1) return create_impl(pr, 0, 1, nullptr, out);
+    if (!id || bytes != FEBA_DIST_ID_BYTES)
+        return fail(nullptr, FEBA_ERR_INVALID, "feba_create_shard: id must be %d bytes (feba_dist_unique_id)", FEBA_DIST_ID_BYTES);
+    return create_impl(pr, rank, world, id, out);
 }
 
 int feba_set_stream(feba_handle* h, void* stream) {
@@ -583,21 +783,18 @@ int feba_dist_unique_id(void* id, size_t bytes) {
 int feba_dist_init(feba_handle* h, int32_t rank, int32_t world, const void* id, size_t bytes) {
     if (!h || !id || bytes != FEBA_DIST_ID_BYTES || world < 1 || rank < 0 || rank >= world)
         return fail(h, FEBA_ERR_INVALID, "feba_dist_init: bad arguments");
-    if (h->dist.comm) return fail(h, FEBA_ERR_STATE, "feba_dist_init called twice");
+    if (h->dist.comm) return fail(h, FEBA_ERR_STATE, "feba_dist_init called twice (or on a feba_create_shard handle)");
+    if (h->plan.masked && world > 1)
+        return fail(h, FEBA_ERR_STATE, "feba_dist_init needs the identity row order on every rank: create the handle with "
+                                       "settings.plan = -1 (a nested-dissection plan of a group comes from feba_create_shard)");
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamSynchronize(h->stream));
     // the communicator is created by every rank even when this problem keeps the replicated solve
     if (dist_comm_init(&h->dist, rank, world, id)) return fail(h, FEBA_ERR_CUDA, "%s", h->dist.err);
     if (!h->use_dag || world == 1) return FEBA_OK;
     drop_graphs(h);
-    if (h->sparse) {                      // the block-sparse form is single-GPU: a group keeps the dense factorisation
-        h->sparse = false;
-        h->nzmask.clear();
-        h->P.aug_rows = kAugRows;
-        h->P.datum = nullptr;
-    }
     {
-        const int rc_pool = setup_pool(h, true);
+        const int rc_pool = setup_legacy_group_pool(h);
         if (rc_pool) return rc_pool;
     }
     if (!h->use_dag || h->dag.n_streams < 6) return FEBA_OK;
@@ -619,7 +816,7 @@ int feba_num_unknowns(const feba_handle* h, int64_t* u, int64_t* u_c) {
     return FEBA_OK;
 }
 
-int64_t feba_num_obs(const feba_handle* h) { return h ? h->P.n_obs : -1; }
+int64_t feba_num_obs(const feba_handle* h) { return h ? h->n_obs_global : -1; }
 
 int feba_set_xhat(feba_handle* h, const double* xhat, size_t u) {
     if (!h || !xhat) return FEBA_ERR_INVALID;
@@ -640,6 +837,12 @@ int feba_get_xhat(feba_handle* h, double* xhat, size_t u) {
     CU(h, cudaSetDevice(h->device));
     CU(h, launch_xhat_gather(h->P, h->sm_count, h->xhat, h->eop, h->iop, h->tie_pt, h->stream));
     ++h->launches;
+    if (h->shard && h->P.n_tie > 0) {
+        // every rank returns the whole vector: tie coordinates come from their owners (collective)
+        CU(h, launch_keep_own_ties(h->P.n_tie, h->tie_mine, h->xhat + h->P.n_red, h->stream));
+        NC(h, dist_allreduce_f64(&h->dist, h->xhat + h->P.n_red, 3 * (size_t)h->P.n_tie, h->stream));
+        ++h->launches;
+    }
     CU(h, cudaMemcpyAsync(xhat, h->xhat, u * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return FEBA_OK;
@@ -653,6 +856,8 @@ int feba_get_delta(feba_handle* h, double* delta, size_t u) {
     if (!h->delta_out) CU(h, dev_alloc(h, &h->delta_out, (size_t)h->u));
     CU(h, launch_delta_gather(h->P, h->sm_count, h->delta_out, h->stream));
     ++h->launches;
+    if (h->shard && h->P.n_tie > 0)       // increments of other ranks' tie points are zero here
+        NC(h, dist_allreduce_f64(&h->dist, h->delta_out + h->P.n_red, 3 * (size_t)h->P.n_tie, h->stream));
     CU(h, cudaMemcpyAsync(delta, h->delta_out, u * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return FEBA_OK;
@@ -663,7 +868,13 @@ static int enqueue_assemble(feba_handle* h) {
     DevProblem& P = h->P;
     CU(h, record(h, 0));
     CU(h, launch_tables(P, h->eop, h->iop, h->cam_box, h->img_tab, h->cam_tab, h->stream));
-    CU(h, cudaMemsetAsync(P.S, 0, h->S_count * sizeof(double), h->stream));
+    if (h->plan.masked) {
+        // only the structurally non-zero blocks are ever written (assembly, fill): the rest stays zero from create
+        CU(h, launch_clear_blocks(P, h->blk_list, h->n_blk_list, h->stream));
+        ++h->launches;
+    } else {
+        CU(h, cudaMemsetAsync(P.S, 0, h->S_count * sizeof(double), h->stream));
+    }
     CU(h, cudaMemsetAsync(h->info, 0, sizeof(int), h->stream));
     CU(h, record(h, 1));
     ++h->launches;
@@ -767,11 +978,48 @@ int feba_reduced_unpack(feba_handle* h) {
     return FEBA_OK;
 }
 
+// Copy the lower trapezoid of S from row/column `first` on (incl. the augmented block row) into one contiguous
+// buffer (pack) or back (unpack): per group of 8 block columns the rows from the group's first row down.
+static int trapezoid_copy(feba_handle* h, double* buf, size_t first, bool pack) {
+    const DevProblem& P = h->P;
+    const size_t ld = (size_t)P.ld, w = 8 * (size_t)kBlk;
+    size_t off = 0;
+    for (size_t c0 = first; c0 < ld; c0 += w) {
+        const size_t rows = ld - c0, cols = std::min(w, ld - c0);
+        double* sp = P.S + c0 + ld * c0;
+        if (pack)
+            CU(h, cudaMemcpy2DAsync(buf + off, rows * sizeof(double), sp, ld * sizeof(double), rows * sizeof(double), cols,
+                                    cudaMemcpyDeviceToDevice, h->stream));
+        else
+            CU(h, cudaMemcpy2DAsync(sp, ld * sizeof(double), buf + off, rows * sizeof(double), rows * sizeof(double), cols,
+                                    cudaMemcpyDeviceToDevice, h->stream));
+        off += rows * cols;
+    }
+    return FEBA_OK;
+}
+
+static TileView plan_view(const feba_handle* h) {
+    TileView V;
+    V.NT = h->plan.NT;
+    V.b0 = h->plan.tile_b0.data();
+    V.nz = h->plan.masked ? h->plan.nz.data() : nullptr;
+    V.chain = h->plan.masked ? h->tile_chain.data() : nullptr;
+    V.owner = h->shard ? h->tile_owner.data() : nullptr;
+    return V;
+}
+
 // ---- second half: inner-constraint border, factorisation, solve, update, back-substitution.
+// Group on a nested-dissection plan (feba_create_shard), exchanges on the handle's stream (NCCL):
+//   (1) diag(S), n_pad doubles: conditioning of G and Jacobi scaling must be identical on every rank;
+//   (2) after every rank has eliminated its own subtrees: the shared top part of S (lower trapezoid from
+//       top_row0 on, incl. the augmented block row) -- the only large message of an iteration;
+//   (3) the solution of the reduced system, n_pad doubles (own rows + rank 0's copy of the shared rows).
 static int enqueue_solve(feba_handle* h) {
     DevProblem& P = h->P;
-    CU(h, launch_border_scale(P, h->eop, h->dvec, h->info, h->stream, &h->launches));
     const int nb = P.n_pad / kBlk;
+    CU(h, launch_border_prepare(P, h->eop, h->dg, h->stream, &h->launches));
+    if (h->shard) NC(h, dist_allreduce_f64(&h->dist, h->dg, (size_t)P.n_pad, h->stream));
+    CU(h, launch_border_scale(P, h->dg, h->dvec, h->info, h->blk_list, h->n_blk_list, h->stream, &h->launches));
     if (h->use_dag && h->dag_cols) {
         const cudaError_t ed = chol_cols(P.S, P.ld, nb, h->Linv, h->info, h->dag, h->dist_active ? &h->dist : nullptr,
                                          h->stream, &h->launches);
@@ -781,14 +1029,31 @@ static int enqueue_solve(feba_handle* h) {
         const cudaError_t ed = chol_dag_dist(P.S, P.ld, nb, h->Linv, h->info, h->dag, h->dist, h->stream, &h->launches);
         if (ed == cudaErrorUnknown && h->dist.err[0]) return fail(h, FEBA_ERR_CUDA, "%s", h->dist.err);
         CU(h, ed);
-    } else if (h->use_dag)
-        CU(h, chol_dag(P.S, P.ld, nb, h->Linv, h->info, h->dag, h->stream, &h->launches,
-                       h->sparse ? h->nzmask.data() : nullptr));
-    else CU(h, chol_augmented(P.S, P.ld, nb, h->Linv, h->info, h->stream, &h->launches));
+    } else if (h->use_dag) {
+        const TileView V = plan_view(h);
+        const int top = h->shard ? h->plan.top_tile0 : V.NT;
+        CU(h, chol_tiles(P.S, P.ld, nb, h->Linv, h->info, h->dag, h->stream, &h->launches, V, 0, top, h->rank));
+        if (h->shard) {
+            CU(h, record(h, 6));
+            const int rc = trapezoid_copy(h, h->xchg, (size_t)h->top_row0, true);
+            if (rc) return rc;
+            NC(h, dist_allreduce_f64(&h->dist, h->xchg, h->xchg_count, h->stream));
+            const int rc2 = trapezoid_copy(h, h->xchg, (size_t)h->top_row0, false);
+            if (rc2) return rc2;
+            CU(h, record(h, 7));
+            CU(h, chol_tiles(P.S, P.ld, nb, h->Linv, h->info, h->dag, h->stream, &h->launches, V, top, V.NT, h->rank));
+        }
+    } else CU(h, chol_augmented(P.S, P.ld, nb, h->Linv, h->info, h->stream, &h->launches));
     CU(h, record(h, 3));
     CU(h, border_and_backsolve(P.S, P.ld, nb, h->Linv, P.inner, h->work, h->ywork, h->sol, h->info, h->sm_count,
                                h->stream, &h->launches, P.datum != nullptr,
-                               h->sparse ? h->row_first.data() : nullptr));
+                               h->plan.masked ? h->row_first.data() : nullptr,
+                               h->shard ? h->block_owner.data() : nullptr, h->rank));
+    if (h->shard) {
+        CU(h, launch_keep_own_rows(P, h->sol, h->stream));
+        ++h->launches;
+        NC(h, dist_allreduce_f64(&h->dist, h->sol, (size_t)P.n_pad, h->stream));
+    }
     CU(h, record(h, 4));
     CU(h, launch_update_cam(P, h->sol, h->dvec, h->dcam, h->dcam_unscaled, h->eop, h->iop, h->scal, h->stream));
     ++h->launches;
@@ -813,6 +1078,11 @@ static int solve_async(feba_handle* h) {
 }
 
 static int finish_iteration(feba_handle* h, double* dcam_sum, double* dpts_sum) {
+    if (h->shard) {
+        // sum|delta| over the tie points of all ranks (main.m:487) and the worst status: collective, on the stream
+        NC(h, dist_allreduce_f64(&h->dist, h->scal + 1, 1, h->stream));
+        NC(h, dist_allreduce_max_i32(&h->dist, h->info, 1, h->stream));
+    }
     CU(h, cudaMemcpyAsync(h->scal_host, h->scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaMemcpyAsync(h->info_host, h->info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
@@ -825,6 +1095,12 @@ static int finish_iteration(feba_handle* h, double* dcam_sum, double* dpts_sum) 
         tot += ms;
     }
     if (ok) h->timing[5] = tot;
+    h->timing[6] = 0.0;
+    if (ok && h->shard && h->use_dag) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]) == cudaSuccess) h->timing[6] = ms;
+        else cudaGetLastError();
+    }
     h->timing_valid = ok;
     if (h->dist_active && !h->dag_cols && h->g_solve.exec && h->g_solve.calls >= 5) dist_prof_report();
     if (dcam_sum) *dcam_sum = h->scal_host[0];
@@ -893,6 +1169,47 @@ int feba_solve(feba_handle* h, int32_t* iterations_out, double* trace_out, size_
     return FEBA_OK;
 }
 
+// Device -> host copy of a large result.  A destination in pinned (page-locked or registered) memory is written
+// by one DMA; pageable memory goes through two pinned staging buffers: chunk k+1 crosses PCIe on the copy stream
+// while the host moves chunk k into the caller's array (the driver's own pageable path serialises the two and
+// reached 2.2 GB/s on the 560 MB of BASELINE configs[3]: 249 of the 250 ms of the residual stage).
+static int copy_out(feba_handle* h, double* dst, const double* src_dev, size_t count) {
+    if (count == 0) return FEBA_OK;
+    cudaPointerAttributes at{};
+    const bool pinned = cudaPointerGetAttributes(&at, dst) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+        CU(h, cudaMemcpyAsync(dst, src_dev, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        return FEBA_OK;
+    }
+    constexpr size_t kChunk = (size_t)4 << 20;                 // doubles per staging buffer (32 MB)
+    if (!h->v_pin) {
+        CU(h, cudaMallocHost((void**)&h->v_pin, kChunk * sizeof(double)));
+        CU(h, cudaMallocHost((void**)&h->rsd_pin, kChunk * sizeof(double)));
+        CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (auto& e : h->copy_ev) CU(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->pin_chunk = kChunk;
+    }
+    CU(h, cudaStreamSynchronize(h->stream));                   // the result is complete
+    double* pin[2] = {h->v_pin, h->rsd_pin};
+    const size_t nchunk = (count + kChunk - 1) / kChunk;
+    auto issue = [&](size_t c) -> cudaError_t {
+        const size_t off = c * kChunk, len = std::min(kChunk, count - off);
+        cudaError_t e = cudaMemcpyAsync(pin[c & 1], src_dev + off, len * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(h->copy_ev[c & 1], h->copy_stream);
+        return e;
+    };
+    CU(h, issue(0));
+    for (size_t c = 0; c < nchunk; ++c) {
+        CU(h, cudaEventSynchronize(h->copy_ev[c & 1]));
+        if (c + 1 < nchunk) CU(h, issue(c + 1));               // the other buffer: its last reader finished an iteration ago
+        const size_t off = c * kChunk, len = std::min(kChunk, count - off);
+        std::memcpy(dst + off, pin[c & 1], len * sizeof(double));
+    }
+    return FEBA_OK;
+}
+
 int feba_residuals(feba_handle* h, double* v, double* rsd, double stats[6]) {
     if (!h) return FEBA_ERR_INVALID;
     if (h->iterations < 1) return fail(h, FEBA_ERR_STATE, "feba_residuals before any iteration (main.m:569 uses the last A, w, delta)");
@@ -901,22 +1218,47 @@ int feba_residuals(feba_handle* h, double* v, double* rsd, double stats[6]) {
                                        "already belong to the next linearisation point");
     CU(h, cudaSetDevice(h->device));
     DevProblem& P = h->P;
-    const size_t n = (size_t)P.n_obs;
-    if (v && !h->v_out) CU(h, dev_alloc(h, &h->v_out, 2 * n));
-    if (rsd && !h->rsd_out) CU(h, dev_alloc(h, &h->rsd_out, 5 * n));
-    CU(h, launch_residuals(P, h->sm_count, h->opt, P.xyz_prev, h->iop, v ? h->v_out : nullptr,
-                           rsd ? h->rsd_out : nullptr, h->stream));
+    const size_t n = (size_t)h->n_obs_global;               // rows of the PHO table (a shard fills its own rows)
+    // a group computes v / RSD on every rank when ANY output is wanted anywhere: callers pass the same arguments
+    if ((v || h->shard) && !h->v_out) CU(h, dev_alloc(h, &h->v_out, 2 * n));
+    if ((rsd || h->shard) && !h->rsd_out) CU(h, dev_alloc(h, &h->rsd_out, 5 * n));
+    double* vd = (v || h->shard) ? h->v_out : nullptr;
+    double* rd = (rsd || h->shard) ? h->rsd_out : nullptr;
+    if (h->shard) {
+        CU(h, cudaMemsetAsync(vd, 0, 2 * n * sizeof(double), h->stream));
+        CU(h, cudaMemsetAsync(rd, 0, 5 * n * sizeof(double), h->stream));
+    }
+    CU(h, record(h, 6));
+    CU(h, launch_residuals(P, h->sm_count, h->opt, P.xyz_prev, h->iop, vd, rd, h->stream));
     const int nblk = residual_blocks(P, h->sm_count);
     CU(h, launch_sum_partials(P.partial, nblk, 2, 0, h->scal + 2, h->stream));
     CU(h, launch_sum_partials(P.partial, nblk, 2, 1, h->scal + 3, h->stream));
     h->launches += 3;
-    if (v) CU(h, cudaMemcpyAsync(v, h->v_out, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (rsd) CU(h, cudaMemcpyAsync(rsd, h->rsd_out, 5 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, record(h, 7));
+    if (h->shard) {
+        // every rank returns the whole result: rows of other ranks' observations come from their owners
+        NC(h, dist_allreduce_f64(&h->dist, h->scal + 2, 2, h->stream));
+        NC(h, dist_allreduce_f64(&h->dist, vd, 2 * n, h->stream));
+        NC(h, dist_allreduce_f64(&h->dist, rd, 5 * n, h->stream));
+    }
     CU(h, cudaMemcpyAsync(h->scal_host + 2, h->scal + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (v) {
+        const int rc = copy_out(h, v, vd, 2 * n);
+        if (rc) return rc;
+    }
+    if (rsd) {
+        const int rc = copy_out(h, rsd, rd, 5 * n);
+        if (rc) return rc;
+    }
     CU(h, cudaStreamSynchronize(h->stream));
+    {
+        float ms = 0.f;
+        h->timing[7] = cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]) == cudaSuccess ? ms : 0.0;
+        cudaGetLastError();
+    }
     if (stats) {
         const double sxx = h->scal_host[2], syy = h->scal_host[3];
-        const double nn = (double)P.n_obs;
+        const double nn = (double)h->n_obs_global;
         const double rmsx = std::sqrt(sxx / nn), rmsy = std::sqrt(syy / nn);     // main.m:594-597, :998-1002
         stats[0] = rmsx;
         stats[1] = rmsy;
@@ -934,9 +1276,12 @@ int feba_cov_prepare(feba_handle* h) {
     if (h->iterations < 1 || h->phase != 0)
         return fail(h, FEBA_ERR_STATE, "feba_cov_prepare needs a completed iteration (Cx comes from the last N, main.m:432-444)");
     if (h->cov_ready) return FEBA_OK;
+    if (h->shard)
+        return fail(h, FEBA_ERR_STATE, "the covariance stage is not available on a feba_create_shard handle: run it on one "
+                                       "GPU (feba_create) from the converged xhat");
     if (h->P.datum)
-        return fail(h, FEBA_ERR_STATE, "the covariance stage needs the dense datum form: not available with FEBA_SPARSE=1 "
-                                       "on a free network");
+        return fail(h, FEBA_ERR_STATE, "the covariance stage needs the dense datum form: create the handle with "
+                                       "settings.plan = -1 (identity order) for a free network");
     CU(h, cudaSetDevice(h->device));
     DevProblem& P = h->P;
     const size_t nn = (size_t)P.n_pad * (size_t)P.n_pad;
@@ -1004,17 +1349,43 @@ int feba_last_timing(const feba_handle* h, double ms[6]) {
     return FEBA_OK;
 }
 
+int feba_last_timing_ex(const feba_handle* h, double ms[8]) {
+    if (!h || !ms) return FEBA_ERR_INVALID;
+    if (!h->timing_valid) return FEBA_ERR_STATE;
+    for (int i = 0; i < 8; ++i) ms[i] = h->timing[i];
+    return FEBA_OK;
+}
+
 int64_t feba_launch_count(const feba_handle* h) { return h ? h->launches : 0; }
 
 int feba_sparse_info(const feba_handle* h, int32_t info[4]) {
     if (!h || !info) return FEBA_ERR_INVALID;
-    info[0] = h->sparse ? 1 : 0;
-    info[1] = h->sparse ? h->sparse_nz : 0;
-    info[2] = h->sparse ? h->sparse_all : 0;
-    info[3] = 0;
-    if (h->sparse && h->P.datum) {
-        const std::vector<int> d = sparse_datum_images(h->P.n_img, h->P.ui, h->P.n_pad / kBlk, h->dag.tile_blocks);
-        info[3] = (int32_t)d.size();
+    const ReducedPlan& pl = h->plan;
+    info[0] = pl.masked ? 1 : 0;
+    info[1] = info[2] = 0;
+    for (int i = 0; i < pl.NT; ++i)
+        for (int j = 0; j <= i; ++j) {
+            ++info[2];
+            if (pl.at(i, j)) ++info[1];
+        }
+    info[3] = h->P.datum ? (int32_t)pl.datum.size() : 0;
+    return FEBA_OK;
+}
+
+int feba_plan_info(const feba_handle* h, int32_t info[8], double flop[2]) {
+    if (!h || !info) return FEBA_ERR_INVALID;
+    const ReducedPlan& pl = h->plan;
+    info[0] = pl.masked ? 1 : 0;
+    info[1] = pl.n_pad;
+    info[2] = pl.NT;
+    info[3] = (int32_t)pl.nodes.size();
+    info[4] = pl.chain_blocks;
+    info[5] = h->world;
+    info[6] = h->shard ? h->top_row0 : pl.n_pad;
+    info[7] = (int32_t)h->P.n_obs;
+    if (flop) {
+        flop[0] = pl.flop;
+        flop[1] = pl.flop_dense;
     }
     return FEBA_OK;
 }
@@ -1027,15 +1398,21 @@ int feba_debug_reduced(feba_handle* h, double* S_out, double* g_out) {
     CU(h, cudaSetDevice(h->device));
     const DevProblem& P = h->P;
     const size_t nr = (size_t)P.n_red;
+    // xhat order -> rows of the plan
+    std::vector<int> row(nr);
+    for (int r = 0; r < P.n_pad; ++r)
+        if (h->plan.row_ext[(size_t)r] >= 0) row[(size_t)h->plan.row_ext[(size_t)r]] = r;
     std::vector<double> col((size_t)P.ld);
     CU(h, cudaStreamSynchronize(h->stream));
     for (size_t c = 0; c < nr; ++c) {
-        CU(h, cudaMemcpy(col.data(), P.S + (size_t)P.ld * c, (size_t)P.ld * sizeof(double), cudaMemcpyDeviceToHost));
+        const size_t rc = (size_t)row[c];
+        CU(h, cudaMemcpy(col.data(), P.S + (size_t)P.ld * rc, (size_t)P.ld * sizeof(double), cudaMemcpyDeviceToHost));
         if (S_out)
-            for (size_t r = c; r < nr; ++r) {
-                S_out[r + nr * c] = col[r];
-                S_out[c + nr * r] = col[r];
-            }
+            for (size_t r = 0; r < nr; ++r)
+                if ((size_t)row[r] >= rc) {                  // stored lower triangle: rows at or below the diagonal
+                    S_out[r + nr * c] = col[(size_t)row[r]];
+                    S_out[c + nr * r] = col[(size_t)row[r]];
+                }
         if (g_out) g_out[c] = col[(size_t)P.n_pad];
     }
     return FEBA_OK;

@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(128) k_point_pass_mc(DevProblem P, int* __rest
                 }
                 // cross terms: rows of the OTHER cameras of this point x columns of this image
                 if (is_tie) {
-                    const size_t col0 = (size_t)P.ui * img;
+                    const size_t col0 = (size_t)P.img_row[img];
                     for (int k = 0; k < ncam; ++k) {
                         if (k == kown) continue;
                         const size_t rc = (size_t)P.off_cam + (size_t)P.uc * cams[k];
@@ -616,7 +616,7 @@ __global__ void __launch_bounds__(128) k_image_pass(DevProblem P) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int img = blockIdx.x; img < P.n_img; img += gridDim.x) {
         const int beg = P.img_start[img], end = P.img_start[img + 1];
-        const size_t col0 = (size_t)P.ui * img;
+        const size_t col0 = (size_t)P.img_row[img];
         // ---- sweep 1: Je' (P - Z Z') Je  (21 entries, lower) and Je' r (6)
         {
             double acc[27];
@@ -752,7 +752,7 @@ __global__ void __launch_bounds__(128) k_pair_pass(DevProblem P) {
             for (int s = 16; s > 0; s >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], s);
         }
         // lane k (and k + 32) writes entry k; every lane holds all sums after the butterfly
-        const size_t rowa = (size_t)P.ui * b.x, colb = (size_t)P.ui * b.y;
+        const size_t rowa = (size_t)P.img_row[b.x], colb = (size_t)P.img_row[b.y];   // row(a) >= row(b) by construction
         const bool diag = b.x == b.y;
 #pragma unroll
         for (int k = 0; k < 36; ++k) {
@@ -768,18 +768,22 @@ __global__ void __launch_bounds__(128) k_pair_pass(DevProblem P) {
 // ------------------------------------------------------------------------------------------
 // schedule construction (once per problem, on the device)
 
+// A pair (o, b) of observations of one tie point belongs to the block (image of o, image of b) when the image of b
+// comes EARLIER in the row order of the reduced system (img_row; the lower triangle is stored) -- or is the same
+// image (diagonal block, both orders).
 __global__ void k_pair_count(int64_t n_obs, const int* __restrict__ oseg, const int* __restrict__ seg_start,
                              const int* __restrict__ seg_pt, const int* __restrict__ pt_tie,
-                             const int* __restrict__ oimg, long long* __restrict__ cnt) {
+                             const int* __restrict__ oimg, const int* __restrict__ img_row,
+                             long long* __restrict__ cnt) {
     const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (o >= n_obs) return;
     const int seg = oseg[o];
     long long c = 0;
     if (pt_tie[seg_pt[seg]] >= 0) {
-        const int ia = oimg[o];
+        const int ia = oimg[o], ra = img_row[ia];
         for (int b = seg_start[seg]; b < seg_start[seg + 1]; ++b) {
             const int ib = oimg[b];
-            if (ib < ia || (ib == ia && b != o)) ++c;
+            if (img_row[ib] < ra || (ib == ia && b != o)) ++c;
         }
     }
     cnt[o] = c;
@@ -787,17 +791,18 @@ __global__ void k_pair_count(int64_t n_obs, const int* __restrict__ oseg, const 
 
 __global__ void k_pair_fill(int64_t n_obs, int n_img, const int* __restrict__ oseg, const int* __restrict__ seg_start,
                             const int* __restrict__ seg_pt, const int* __restrict__ pt_tie,
-                            const int* __restrict__ oimg, const long long* __restrict__ off,
+                            const int* __restrict__ oimg, const int* __restrict__ img_row,
+                            const long long* __restrict__ off,
                             unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals) {
     const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (o >= n_obs) return;
     const int seg = oseg[o];
     if (pt_tie[seg_pt[seg]] < 0) return;
-    const int ia = oimg[o];
+    const int ia = oimg[o], ra = img_row[ia];
     long long q = off[o];
     for (int b = seg_start[seg]; b < seg_start[seg + 1]; ++b) {
         const int ib = oimg[b];
-        if (ib < ia || (ib == ia && b != o)) {
+        if (img_row[ib] < ra || (ib == ia && b != o)) {
             keys[q] = (unsigned long long)ia * (unsigned long long)n_img + (unsigned long long)ib;
             vals[q] = ((unsigned long long)(unsigned)o << 32) | (unsigned)b;
             ++q;
@@ -852,7 +857,7 @@ cudaError_t build_pair_schedule(DevProblem& P, const int* d_oseg, long long* n_p
     SCHED_CU(talloc((void**)&off, (size_t)(n + 1) * sizeof(long long)));
     SCHED_CU(cudaMemsetAsync(cnt, 0, (size_t)(n + 1) * sizeof(long long), st));
     const int grid = (int)((n + 255) / 256);
-    k_pair_count<<<grid, 256, 0, st>>>(n, d_oseg, P.seg_start, P.seg_pt, P.pt_tie, P.oimg, cnt);
+    k_pair_count<<<grid, 256, 0, st>>>(n, d_oseg, P.seg_start, P.seg_pt, P.pt_tie, P.oimg, P.img_row, cnt);
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
     SCHED_CU(cub::DeviceScan::ExclusiveSum(nullptr, scratch_bytes, cnt, off, (int)(n + 1), st));
@@ -875,7 +880,8 @@ cudaError_t build_pair_schedule(DevProblem& P, const int* d_oseg, long long* n_p
     SCHED_CU(talloc((void**)&vals, (size_t)n_pairs * 8));
     SCHED_CU(talloc((void**)&keys2, (size_t)n_pairs * 8));
     SCHED_CU(talloc((void**)&vals2, (size_t)n_pairs * 8));
-    k_pair_fill<<<grid, 256, 0, st>>>(n, P.n_img, d_oseg, P.seg_start, P.seg_pt, P.pt_tie, P.oimg, off, keys, vals);
+    k_pair_fill<<<grid, 256, 0, st>>>(n, P.n_img, d_oseg, P.seg_start, P.seg_pt, P.pt_tie, P.oimg, P.img_row, off, keys,
+                                      vals);
     int bits = 1;
     while (bits < 64 && (1ull << bits) < (unsigned long long)P.n_img * (unsigned long long)P.n_img) ++bits;
     void* s2 = nullptr;

@@ -593,20 +593,30 @@ static bool upd1_bulk() {
     return v;
 }
 
-// nz (optional): (NT+1) x (NT+1) row-major pattern of the structurally non-zero supertiles INCLUDING fill
-// (feba_sparse.h::sparse_supertile_pattern); TRSM / UPDATE tasks on zero supertiles are not issued.
-cudaError_t chol_dag(double* A, int ld, int nb, double* Linv, int* info, const DagStreams& D, cudaStream_t main,
-                     int64_t* launches, const unsigned char* nz) {
-    const int T = D.tile_blocks;
-    const int NT = (nb + T - 1) / T;                  // supertiles of the factorised part
-    const int NR = NT + 1;                            // row supertiles: + the augmented block row
-    auto on = [&](int i, int j) { return nz == nullptr || nz[(size_t)i * NR + j] != 0; };
-    auto blk0 = [&](int t) { return t == NT ? nb : t * T; };                     // first 64-block of supertile t
-    auto nblk = [&](int t) { return t == NT ? 1 : (t == NT - 1 ? nb - T * (NT - 1) : T); };
-    if (NR * NR > D.n_events) return cudaErrorInvalidValue;
-    std::vector<int> last(NR * NR, -1);               // stream of the last writer of tile (i,j), -1: none yet
+// Task graph over the supertiles of a plan (feba_order.h): tile t covers the 64-blocks [b0[t], b0[t+1]); tile NT is
+// the augmented block row.  nz (optional): (NT+1) x (NT+1) row-major pattern of the structurally non-zero tiles
+// INCLUDING fill; TRSM / UPDATE tasks on zero tiles are not issued.  chain (optional): stream slot of every
+// tile's panel chain -- tiles of independent subtrees of a nested-dissection order get different slots so that
+// their DIAG / TRSM chains run side by side; slot 0 is the high-priority stream (root node).  Columns k in
+// [k_begin, k_end) whose owner is this rank (or shared, owner < 0) are eliminated: a group of GPUs calls it once
+// for its own subtrees, sums the shared trailing part over the ranks, and once more for the shared top.
+cudaError_t chol_tiles(double* A, int ld, int nb, double* Linv, int* info, const DagStreams& D, cudaStream_t main,
+                       int64_t* launches, const TileView& V, int k_begin, int k_end, int rank) {
+    const int NT = V.NT;
+    const int NR = NT + 1;
+    auto on = [&](int i, int j) { return V.nz == nullptr || V.nz[(size_t)i * NR + j] != 0; };
+    auto blk0 = [&](int t) { return t == NT ? nb : V.b0[t]; };
+    auto nblk = [&](int t) { return t == NT ? 1 : V.b0[t + 1] - V.b0[t]; };
+    auto mine = [&](int k) { return V.owner == nullptr || V.owner[k] < 0 || V.owner[k] == rank; };
+    if (NR * NR > D.n_events || D.n_streams < 2) return cudaErrorInvalidValue;
+    std::vector<int> last((size_t)NR * NR, -1);       // stream of the last writer of tile (i,j), -1: none yet
     auto tid = [&](int i, int j) { return i * NR + j; };
-    auto stream_of = [&](int i, int j) { return 1 + (i * 3 + j * 7) % (D.n_streams - 1); };
+    const int NB = D.n_streams - 1;                   // streams 1..NB: bulk and the chains of the subtrees
+    auto stream_of = [&](int i, int j) { return 1 + (i * 3 + j * 7) % NB; };
+    auto chain_of = [&](int k) {
+        if (V.chain == nullptr) return 0;
+        return V.chain[k] <= 0 ? 0 : 1 + (V.chain[k] - 1) % NB;
+    };
     cudaError_t e = cudaEventRecord(D.fork, main);
     if (e != cudaSuccess) return e;
     for (int s = 0; s < D.n_streams; ++s) {
@@ -614,12 +624,12 @@ cudaError_t chol_dag(double* A, int ld, int nb, double* Linv, int* info, const D
         if (e != cudaSuccess) return e;
     }
     auto acquire = [&](int sid, int i, int j) -> cudaError_t {
-        const int w = last[tid(i, j)];
+        const int w = last[(size_t)tid(i, j)];
         if (w >= 0 && w != sid) return cudaStreamWaitEvent(D.streams[sid], D.events[tid(i, j)], 0);
         return cudaSuccess;
     };
     auto release = [&](int sid, int i, int j) -> cudaError_t {
-        last[tid(i, j)] = sid;
+        last[(size_t)tid(i, j)] = sid;
         return cudaEventRecord(D.events[tid(i, j)], D.streams[sid]);
     };
 #define DAG_CU(x)                 \
@@ -627,15 +637,19 @@ cudaError_t chol_dag(double* A, int ld, int nb, double* Linv, int* info, const D
         e = (x);                  \
         if (e != cudaSuccess) return e; \
     } while (0)
-    for (int k = 0; k < NT; ++k) {
-        {   // DIAG(k), critical path
-            DAG_CU(acquire(0, k, k));
-            DAG_CU(rchol(A, ld, Linv, blk0(k), nblk(k), -1, info, D.streams[0], launches));
-            DAG_CU(release(0, k, k));
+    for (int k = k_begin; k < k_end && k < NT; ++k) {
+        if (!mine(k) || nblk(k) == 0) continue;
+        const int ck = chain_of(k);
+        {   // DIAG(k)
+            DAG_CU(acquire(ck, k, k));
+            DAG_CU(rchol(A, ld, Linv, blk0(k), nblk(k), -1, info, D.streams[ck], launches));
+            DAG_CU(release(ck, k, k));
         }
+        int first_row = -1;                           // first coupled tile below k: the next link of the chain
         for (int i = k + 1; i < NR; ++i) {
-            if (!on(i, k)) continue;
-            const int sid = (i == k + 1) ? 0 : stream_of(i, k);
+            if (!on(i, k) || nblk(i) == 0) continue;
+            if (first_row < 0) first_row = i;
+            const int sid = (i == first_row) ? ck : stream_of(i, k);
             DAG_CU(acquire(sid, k, k));
             DAG_CU(acquire(sid, i, k));
             DAG_CU(rtrsm(A, ld, A, ld, Linv, blk0(i), nblk(i), blk0(k), nblk(k), D.streams[sid], launches));
@@ -643,13 +657,13 @@ cudaError_t chol_dag(double* A, int ld, int nb, double* Linv, int* info, const D
         }
         for (int i = k + 1; i < NR; ++i)
             for (int j = k + 1; j <= i; ++j) {
-                if (!on(i, k) || !on(j, k)) continue;
+                if (!on(i, k) || !on(j, k) || nblk(i) == 0 || nblk(j) == 0) continue;
                 if (j == NT && i == NT) {
                     // augmented diagonal block T (never factorised): plain lower update
                 } else if (j >= NT) {
                     continue;
                 }
-                const int sid = (i == k + 1 && j == k + 1 && !upd1_bulk()) ? 0 : stream_of(i, j);
+                const int sid = (i == first_row && j == first_row && !upd1_bulk()) ? ck : stream_of(i, j);
                 DAG_CU(acquire(sid, i, k));
                 DAG_CU(acquire(sid, j, k));
                 DAG_CU(acquire(sid, i, j));
@@ -1146,10 +1160,17 @@ __global__ void __launch_bounds__(256) k_backstep(const double* __restrict__ A, 
     if (blockIdx.x == 0 && tid < kBlk) x_out[(size_t)k * kBlk + tid] = sx[tid];
 }
 
+// block_owner (host, nb entries, optional; group runs): blocks of subtrees owned by other ranks are skipped --
+// their rows of `sol` stay zero and come from the owners through the sum over the ranks that follows.
 cudaError_t border_and_backsolve(double* A, int ld, int nb, const double* Linv, int inner, double* work,
                                  double* ywork, double* sol, int* info, int sm_count, cudaStream_t st,
-                                 int64_t* launches, int sparse_datum, const int* row_first_block) {
+                                 int64_t* launches, int sparse_datum, const int* row_first_block,
+                                 const int* block_owner, int rank) {
     const int n_pad = nb * kBlk;
+    if (block_owner) {
+        cudaError_t e0 = cudaMemsetAsync(sol, 0, (size_t)n_pad * sizeof(double), st);
+        if (e0 != cudaSuccess) return e0;
+    }
     if (inner) {
         if (sparse_datum) k_border_solve_sparse<<<1, 32, 0, st>>>(A, ld, n_pad, work, info);
         else k_border_solve<<<1, 32, 0, st>>>(A, ld, n_pad, work, info);
@@ -1159,6 +1180,7 @@ cudaError_t border_and_backsolve(double* A, int ld, int nb, const double* Linv, 
     k_combine<<<(n_pad + 255) / 256, 256, 0, st>>>(A, ld, n_pad, ncoef, work, ywork);
     ++*launches;
     for (int k = nb - 1; k >= 0; --k) {
+        if (block_owner && block_owner[k] >= 0 && block_owner[k] != rank) continue;
         int c_begin = row_first_block ? row_first_block[k] * kBlk : 0;
         if (c_begin > k * kBlk) c_begin = k * kBlk;
         int grid = (k * kBlk - c_begin + 7) / 8;

@@ -16,10 +16,19 @@ struct DevProblem {
     int n_img, n_cam, n_pts, n_tie, n_seg;
     int type, NK, NC;             // NC = NK + 5 camera columns (xp yp c k1..kNK p1 p2)
     int ui, uc;                   // estimated unknowns per image / per camera (BuildAwG.m:24-25)
-    int n_red;                    // u_c = ui*n_img + uc*n_cam  (size of the reduced system)
-    int n_pad;                    // n_red rounded up to kBlk
+    int n_red;                    // u_c = ui*n_img + uc*n_cam  (unknowns of the reduced system, Buildxhat.m:5-15)
+    int n_pad;                    // rows of the factorised matrix: u_c + padding, a multiple of kBlk
     int ld;                       // leading dimension of S  (= n_pad + kBlk: augmented rows)
-    int off_cam;                  // ui*n_img
+    int off_cam;                  // ROW of the first camera unknown
+    int ext_off_cam;              // ui*n_img: index of the first camera unknown in xhat (Buildxhat.m:52-106)
+    // row order of the reduced system (feba_order.h): identity = Buildxhat order, or nested dissection
+    const int* img_row;           // n_img: row of the first unknown of every image
+    const int* row_ext;           // n_pad: index in the EOP/IOP part of xhat of every row, -1 = padding row
+    // group of GPUs sharing one adjustment (feba_create_shard): owner rank of every row (-1: shared top row) or
+    // null (single GPU); shared rows are initialised (padding diagonal, datum term, G rows) by rank 0 only, so
+    // that the sum over the ranks counts them once
+    const int* row_owner;
+    int rank;
     int inner;                    // Inner_Constraints
     int ecol[6];                  // slot of EOP q inside the image block or -1
     int ccol[16];                 // slot of camera parameter q inside the camera block or -1
@@ -63,6 +72,28 @@ struct DevProblem {
 
 // Opt-in dynamic shared memory above 48 KB is a per-device function attribute: remember per device
 // (bit i = device i configured) so that handles on several GPUs of one process all work.
+// row of the reduced system of entry e (< n_red) of the EOP/IOP part of xhat
+#ifdef __CUDACC__
+__device__ __forceinline__ int row_of_ext(const DevProblem& P, int e) {
+    if (e < P.ext_off_cam) {
+        const int im = e / P.ui;
+        return P.img_row[im] + (e - im * P.ui);
+    }
+    return P.off_cam + (e - P.ext_off_cam);
+}
+// this rank initialises row r (see row_owner)
+__device__ __forceinline__ bool row_init_here(const DevProblem& P, int r) {
+    if (P.row_owner == nullptr) return true;
+    const int o = P.row_owner[r];
+    return o == P.rank || (o < 0 && P.rank == 0);
+}
+// row r holds an EOP unknown of an image (not a camera unknown, not padding)
+__device__ __forceinline__ bool is_image_row(const DevProblem& P, int r) {
+    const int e = P.row_ext[r];
+    return e >= 0 && e < P.ext_off_cam;
+}
+#endif
+
 struct SmemOptIn {
     unsigned long long done = 0;
     template <typename F>

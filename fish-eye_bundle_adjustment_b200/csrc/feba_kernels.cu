@@ -30,12 +30,13 @@ __global__ void k_G_rows(DevProblem P, const double* __restrict__ eop) {
     if (i >= P.n_img) return;
     double G[6][7];
     inner_constraint_rows(eop + 6 * i, G);
+    const size_t row0 = (size_t)P.img_row[i];              // inner constraints: all six EOPs are unknowns
     for (int q = 0; q < 6; ++q) {
         for (int c = 0; c < 7; ++c) {
-            P.S[(size_t)(P.n_pad + 1 + c) + (size_t)P.ld * (6 * i + q)] = G[q][c];
-            P.Gt[8 * (size_t)(6 * i + q) + c] = G[q][c];
+            P.S[(size_t)(P.n_pad + 1 + c) + (size_t)P.ld * (row0 + q)] = G[q][c];
+            P.Gt[8 * (row0 + q) + c] = G[q][c];
         }
-        P.Gt[8 * (size_t)(6 * i + q) + 7] = 0.0;
+        P.Gt[8 * (row0 + q) + 7] = 0.0;
     }
 }
 
@@ -49,10 +50,10 @@ __global__ void k_G_rows(DevProblem P, const double* __restrict__ eop) {
 // with c the column norms of G, A1 = Gn'Gn, A2 = Gn' diag(S) Gn, Gn = G diag(1/c).
 // One CTA: Gram reductions over the 6 n_img rows, 7x7 algebra on thread 0, rows rewritten in place
 // (compact copy Gt and the augmented rows 1..7 of S).
-__global__ void __launch_bounds__(256) k_G_condition(DevProblem P, int* __restrict__ info) {
+__global__ void __launch_bounds__(256) k_G_condition(DevProblem P, const double* __restrict__ dg, int* __restrict__ info) {
     __shared__ double red[256];
     __shared__ double A1[7][7], A2[7][7], Cm[7][7], cn[7];
-    const int tid = threadIdx.x, ne = P.off_cam;
+    const int tid = threadIdx.x, ne = P.n_pad;             // image rows only (Gt is zero on all other rows)
     // one sweep over the rows: column norms, then both Gram matrices from the raw sums
     // (A1 = Gn'Gn and A2 = Gn' diag(S) Gn with Gn = G diag(cn): scale the raw sums by cn_i cn_j)
     {
@@ -60,10 +61,11 @@ __global__ void __launch_bounds__(256) k_G_condition(DevProblem P, int* __restri
 #pragma unroll
         for (int e = 0; e < 28; ++e) a1[e] = a2[e] = 0.0;
         for (int r = tid; r < ne; r += 256) {
+            if (!is_image_row(P, r)) continue;
             double g[7];
 #pragma unroll
             for (int k = 0; k < 7; ++k) g[k] = P.Gt[8 * (size_t)r + k];
-            const double sd = P.S[(size_t)r + (size_t)P.ld * r];
+            const double sd = dg[r];                            // diag(S), summed over the ranks of a group
             int e = 0;
 #pragma unroll
             for (int i = 0; i < 7; ++i)
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(256) k_G_condition(DevProblem P, int* __restri
     }
     __syncthreads();
     for (int r = tid; r < ne; r += 256) {
+        if (!is_image_row(P, r)) continue;
         double g[7], o[7];
 #pragma unroll
         for (int k = 0; k < 7; ++k) g[k] = P.Gt[8 * (size_t)r + k];
@@ -163,8 +166,8 @@ __global__ void __launch_bounds__(256) k_G_condition(DevProblem P, int* __restri
 // k_border_scale form M_s = S + E E' instead of the dense S + G~ G~'.  Augmented rows 1..7 keep all of G~.
 __global__ void k_datum_split(DevProblem P) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= P.off_cam) return;
-    const bool is_datum = P.datum[r / 6] != 0;
+    if (r >= P.n_pad || !is_image_row(P, r)) return;
+    const bool is_datum = P.datum[P.row_ext[r] / 6] != 0;
     double* g = P.Gt + 8 * (size_t)r;
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
@@ -176,8 +179,8 @@ __global__ void k_datum_split(DevProblem P) {
 
 // Unit diagonal on the padding rows so the padded matrix stays positive definite.
 __global__ void k_pad_diag(DevProblem P) {
-    const int i = P.n_red + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < P.n_pad) P.S[(size_t)i + (size_t)P.ld * i] = 1.0;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.n_pad && P.row_ext[i] < 0 && row_init_here(P, i)) P.S[(size_t)i + (size_t)P.ld * i] = 1.0;
 }
 
 // Jacobi scaling of the system that is factorised:  M = S + Gc Gc' (Gc is non-zero
@@ -185,11 +188,17 @@ __global__ void k_pad_diag(DevProblem P) {
 // millimetres, radians, pixels and scaled distortion terms (diag(M) spans 1e0..1e9 on the bundled
 // data, cond(M) ~ 1e11): Cholesky itself is insensitive to this scaling, the inverted 64x64
 // diagonal factors used by the DMMA triangular solves are not, so M is equilibrated first.
-__global__ void k_diag_scale(DevProblem P, double* __restrict__ dvec, int* __restrict__ info) {
+__global__ void k_diag_extract(DevProblem P, double* __restrict__ dg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.n_pad) dg[i] = P.S[(size_t)i + (size_t)P.ld * i];
+}
+
+__global__ void k_diag_scale(DevProblem P, const double* __restrict__ dg, double* __restrict__ dvec,
+                             int* __restrict__ info) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_pad) return;
-    double d = P.S[(size_t)i + (size_t)P.ld * i];
-    if (P.inner && i < P.off_cam) {
+    double d = P.row_ext[i] < 0 ? 1.0 : dg[i];                  // padding rows: unit diagonal
+    if (P.inner && is_image_row(P, i)) {
         const double* g = P.Gt + 8 * (size_t)i;
 #pragma unroll
         for (int k = 0; k < 7; ++k) d += g[k] * g[k];
@@ -201,28 +210,46 @@ __global__ void k_diag_scale(DevProblem P, double* __restrict__ dvec, int* __res
     dvec[i] = rsqrt(d);
 }
 
-// One pass over the lower triangle: M~_rc = (S_rc + G_r . G_c) d_r d_c, and the augmented rows
-// (right-hand side g, columns of G) scaled by d_c.  x: rows (coalesced), y: columns.
-__global__ void __launch_bounds__(256) k_border_scale(DevProblem P, const double* __restrict__ dvec) {
-    const int r = blockIdx.x * 32 + threadIdx.x;
-    const int c = blockIdx.y * 8 + threadIdx.y;
-    if (blockIdx.x * 32 + 31 < blockIdx.y * 8) return;            // tile entirely above the diagonal
-    if (c >= P.n_pad) return;
-    const double dc = dvec[c];
-    if (r < P.n_pad) {
-        if (r >= c) {
-            double v = P.S[(size_t)r + (size_t)P.ld * c];
-            if (P.inner && r < P.off_cam) {                       // then c <= r < off_cam as well
-                const double4* gr = reinterpret_cast<const double4*>(P.Gt + 8 * (size_t)r);
-                const double4* gc = reinterpret_cast<const double4*>(P.Gt + 8 * (size_t)c);
-                const double4 r0 = gr[0], r1 = gr[1], c0 = gc[0], c1 = gc[1];
-                v += r0.x * c0.x + r0.y * c0.y + r0.z * c0.z + r0.w * c0.w + r1.x * c1.x + r1.y * c1.y + r1.z * c1.z;
+// One pass over the structurally non-zero 64x64 blocks of the lower triangle (block list of the plan; every
+// lower block for a dense plan): M~_rc = (S_rc + G_r . G_c) d_r d_c, and the augmented rows (right-hand side
+// g, columns of G / E) scaled by d_c.  One CTA of 32 x 8 threads per block, x over rows (coalesced).
+__global__ void __launch_bounds__(256) k_border_scale(DevProblem P, const double* __restrict__ dvec,
+                                                      const int2* __restrict__ blocks) {
+    const int2 b = blocks[blockIdx.x];                    // x: block row, y: block column (x >= y)
+    const bool aug = b.x * kBlk >= P.n_pad;
+    for (int cc = threadIdx.y; cc < kBlk; cc += 8) {
+        const int c = b.y * kBlk + cc;
+        const double dc = dvec[c];
+        const bool c_img = P.inner && !aug && is_image_row(P, c);
+        for (int rr = threadIdx.x; rr < kBlk; rr += 32) {
+            const int r = b.x * kBlk + rr;
+            if (aug) {
+                // row 0 (right-hand side) is a partial sum of this rank; rows 1.. (G~, E) are the same on every
+                // rank of a group: kept by the rank that initialises column c, zero elsewhere
+                if (rr < P.aug_rows)
+                    P.S[(size_t)r + (size_t)P.ld * c] =
+                        (rr == 0 || row_init_here(P, c)) ? P.S[(size_t)r + (size_t)P.ld * c] * dc : 0.0;
+            } else if (r >= c) {
+                double v = P.S[(size_t)r + (size_t)P.ld * c];
+                if (c_img && is_image_row(P, r) && row_init_here(P, r)) {
+                    const double4* gr = reinterpret_cast<const double4*>(P.Gt + 8 * (size_t)r);
+                    const double4* gc = reinterpret_cast<const double4*>(P.Gt + 8 * (size_t)c);
+                    const double4 r0 = gr[0], r1 = gr[1], c0 = gc[0], c1 = gc[1];
+                    v += r0.x * c0.x + r0.y * c0.y + r0.z * c0.z + r0.w * c0.w + r1.x * c1.x + r1.y * c1.y + r1.z * c1.z;
+                }
+                P.S[(size_t)r + (size_t)P.ld * c] = v * dvec[r] * dc;
             }
-            P.S[(size_t)r + (size_t)P.ld * c] = v * dvec[r] * dc;
         }
-    } else if (r < P.n_pad + P.aug_rows) {
-        P.S[(size_t)r + (size_t)P.ld * c] *= dc;
     }
+}
+
+// Clear the structurally non-zero blocks of S (the assembly adds into them, the factorisation fills them)
+// and the augmented block row; everything else is never written and stays zero from the handle's creation.
+__global__ void __launch_bounds__(256) k_clear_blocks(DevProblem P, const int2* __restrict__ blocks) {
+    const int2 b = blocks[blockIdx.x];
+    double* base = P.S + (size_t)b.x * kBlk + (size_t)P.ld * b.y * kBlk;
+    for (int cc = threadIdx.y; cc < kBlk; cc += 8)
+        for (int rr = threadIdx.x; rr < kBlk; rr += 32) base[rr + (size_t)P.ld * cc] = 0.0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -241,7 +268,7 @@ __global__ void k_xhat_scatter(DevProblem P, const double* __restrict__ xhat, do
         } else if (i < n_e + n_c) {
             const int64_t r = i - n_e;
             const int cam = (int)(r / P.NC), q = (int)(r - (int64_t)cam * P.NC);
-            if (P.ccol[q] >= 0) iop[r] = xhat[(int64_t)P.off_cam + (int64_t)P.uc * cam + P.ccol[q]];
+            if (P.ccol[q] >= 0) iop[r] = xhat[(int64_t)P.ext_off_cam + (int64_t)P.uc * cam + P.ccol[q]];
         } else {
             const int64_t r = i - n_e - n_c;
             const int t = (int)(r / 3), k = (int)(r - 3 * (int64_t)t);
@@ -266,7 +293,7 @@ __global__ void k_xhat_gather(DevProblem P, double* __restrict__ xhat, const dou
         } else if (i < n_e + n_c) {
             const int64_t r = i - n_e;
             const int cam = (int)(r / P.NC), q = (int)(r - (int64_t)cam * P.NC);
-            if (P.ccol[q] >= 0) xhat[(int64_t)P.off_cam + (int64_t)P.uc * cam + P.ccol[q]] = iop[r];
+            if (P.ccol[q] >= 0) xhat[(int64_t)P.ext_off_cam + (int64_t)P.uc * cam + P.ccol[q]] = iop[r];
         } else {
             const int64_t r = i - n_e - n_c;
             const int t = (int)(r / 3), k = (int)(r - 3 * (int64_t)t);
@@ -281,7 +308,7 @@ __global__ void k_delta_gather(DevProblem P, double* __restrict__ delta) {
     const int64_t n = (int64_t)P.n_red + 3 * (int64_t)P.n_tie;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x)
-        delta[i] = i < P.n_red ? P.dcam_unscaled[i] : P.dpts[i - P.n_red];
+        delta[i] = i < P.n_red ? P.dcam_unscaled[row_of_ext(P, (int)i)] : P.dpts[i - P.n_red];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -324,16 +351,17 @@ __global__ void k_update_cam(DevProblem P, const double* __restrict__ sol, const
     double acc = 0.0;
     for (int i = threadIdx.x; i < P.n_pad; i += blockDim.x) {
         double d = 0.0, du = 0.0;
-        if (i < P.n_red) {
+        const int e = P.row_ext[i];                // entry of xhat this row belongs to, -1: padding
+        if (e >= 0) {
             d = -sol[i] * dvec[i];                 // undo the Jacobi scaling of the reduced system
             du = d;
-            if (i < P.off_cam) {
-                const int im = i / P.ui, slot = i - im * P.ui;
+            if (e < P.ext_off_cam) {
+                const int im = e / P.ui, slot = e - im * P.ui;
                 int q = 0;
                 for (int k = 0; k < 6; ++k) if (P.ecol[k] == slot) q = k;
                 eop[6 * im + q] += du;
             } else {
-                const int r = i - P.off_cam;
+                const int r = e - P.ext_off_cam;
                 const int cam = r / P.uc, slot = r - cam * P.uc;
                 int q = 0;
                 for (int k = 0; k < P.NC; ++k) if (P.ccol[k] == slot) q = k;
@@ -389,7 +417,7 @@ __global__ void __launch_bounds__(128) k_backsub(DevProblem P) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
                 if (P.ecol[i] >= 0) {
-                    const double d = P.dcam[P.ui * img + P.ecol[i]];
+                    const double d = P.dcam[P.img_row[img] + P.ecol[i]];
                     q[0] += J.Je[0][i] * d;
                     q[1] += J.Je[1][i] * d;
                 }
@@ -477,7 +505,7 @@ __global__ void __launch_bounds__(256) k_residuals(DevProblem P, const int* __re
         observation<NK, HAS_CAM>(P.type, x, y, P.img_tab + kImgStride * img, P.cam_tab + kCamStride * cam,
                                  xyz_prev[3 * pt], xyz_prev[3 * pt + 1], xyz_prev[3 * pt + 2], J);
         double v[2];
-        residual_of<NK, HAS_CAM>(J, P.ecol, P.ccol, P.dcam_unscaled + P.ui * img,
+        residual_of<NK, HAS_CAM>(J, P.ecol, P.ccol, P.dcam_unscaled + P.img_row[img],
                                  P.dcam_unscaled + P.off_cam + P.uc * cam, tie >= 0 ? P.dpts + 3 * tie : nullptr, v);
         sx += v[0] * v[0];
         sy += v[1] * v[1];
@@ -534,11 +562,12 @@ __device__ __forceinline__ double cov_entry(const DevProblem& P, const double* _
 __global__ void k_cov_diag_cam(DevProblem P, const double* __restrict__ Q, const double* __restrict__ Y,
                                const double* __restrict__ T7inv, const double* __restrict__ dvec,
                                double* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;          // entry of the EOP/IOP part of xhat
     if (i >= P.n_red) return;
-    double q = cov_entry(P, Q, Y, T7inv, dvec, i, i);
-    if (i >= P.off_cam) {
-        const int r = i - P.off_cam;
+    const int row = row_of_ext(P, i);
+    double q = cov_entry(P, Q, Y, T7inv, dvec, row, row);
+    if (i >= P.ext_off_cam) {
+        const int r = i - P.ext_off_cam;
         const int cam = r / P.uc, slot = r - cam * P.uc;
         int p = 0;
         for (int k = 0; k < P.NC; ++k) if (P.ccol[k] == slot) p = k;
@@ -557,7 +586,7 @@ __global__ void k_cov_block(DevProblem P, const double* __restrict__ Q, const do
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= k * k) return;
     const int a = e / k, b = e - a * k;
-    out[e] = cov_entry(P, Q, Y, T7inv, dvec, (int)idx[a], (int)idx[b]);
+    out[e] = cov_entry(P, Q, Y, T7inv, dvec, row_of_ext(P, (int)idx[a]), row_of_ext(P, (int)idx[b]));
 }
 
 // Tie-point variances: Q_pp = V^-1 + V^-1 (W_p' Qxx_cc W_p) V^-1 per tie point, from the
@@ -660,7 +689,7 @@ __global__ void __launch_bounds__(128) k_cov_points(DevProblem P, const double* 
             int rowa = 0;
             if (acta) {
                 const int img = P.oimg[oa];
-                rowa = P.ui * img;
+                rowa = P.img_row[img];
                 ObsJac<NK> J;
                 observation<NK, false>(P.type, P.ox[oa], P.oy[oa], P.img_tab + kImgStride * img,
                                        P.cam_tab + kCamStride * P.img_cam[img], X, Yc_, Z, J);
@@ -721,7 +750,7 @@ __global__ void __launch_bounds__(128) k_cov_points(DevProblem P, const double* 
                     }
                 } else if (ob < end) {
                     const int img = P.oimg[ob];
-                    const int rowb = P.ui * img;
+                    const int rowb = P.img_row[img];
                     ObsJac<NK> Jb;
                     observation<NK, false>(P.type, P.ox[ob], P.oy[ob], P.img_tab + kImgStride * img,
                                            P.cam_tab + kCamStride * P.img_cam[img], X, Yc_, Z, Jb);
@@ -846,24 +875,40 @@ cudaError_t launch_tables(const DevProblem& P, const double* eop, const double* 
     return cudaGetLastError();
 }
 
-cudaError_t launch_border_scale(const DevProblem& P, const double* eop, double* dvec, int* info, cudaStream_t st,
-                                int64_t* launches) {
+cudaError_t launch_clear_blocks(const DevProblem& P, const int2* blocks, int n_blocks, cudaStream_t st) {
+    if (n_blocks > 0) k_clear_blocks<<<n_blocks, dim3(32, 8), 0, st>>>(P, blocks);
+    return cudaGetLastError();
+}
+
+// first half of the border stage: G rows of the current EOPs and dg = diag(S) of this rank's partial system
+// (a group sums dg over its ranks before launch_border_scale: conditioning of G and Jacobi scaling must be
+// the same everywhere)
+cudaError_t launch_border_prepare(const DevProblem& P, const double* eop, double* dg, cudaStream_t st, int64_t* launches) {
     if (P.inner) {
         k_G_rows<<<(P.n_img + 127) / 128, 128, 0, st>>>(P, eop);
-        k_G_condition<<<1, 256, 0, st>>>(P, info);
-        *launches += 2;
+        ++*launches;
+    }
+    k_diag_extract<<<(P.n_pad + 255) / 256, 256, 0, st>>>(P, dg);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_border_scale(const DevProblem& P, const double* dg, double* dvec, int* info, const int2* blocks,
+                                int n_blocks, cudaStream_t st, int64_t* launches) {
+    if (P.inner) {
+        k_G_condition<<<1, 256, 0, st>>>(P, dg, info);
+        ++*launches;
         if (P.datum) {
-            k_datum_split<<<(P.off_cam + 255) / 256, 256, 0, st>>>(P);
+            k_datum_split<<<(P.n_pad + 255) / 256, 256, 0, st>>>(P);
             ++*launches;
         }
     }
     if (P.n_pad > P.n_red) {
-        k_pad_diag<<<1, 64, 0, st>>>(P);
+        k_pad_diag<<<(P.n_pad + 255) / 256, 256, 0, st>>>(P);
         ++*launches;
     }
-    k_diag_scale<<<(P.n_pad + 255) / 256, 256, 0, st>>>(P, dvec, info);
-    dim3 blk(32, 8), grd((P.n_pad + P.aug_rows + 31) / 32, (P.n_pad + 7) / 8);
-    k_border_scale<<<grd, blk, 0, st>>>(P, dvec);
+    k_diag_scale<<<(P.n_pad + 255) / 256, 256, 0, st>>>(P, dg, dvec, info);
+    k_border_scale<<<n_blocks, dim3(32, 8), 0, st>>>(P, dvec, blocks);
     *launches += 2;
     return cudaGetLastError();
 }
@@ -889,6 +934,29 @@ cudaError_t launch_backsub(const DevProblem& P, int sm_count, cudaStream_t st) {
     } else {
         FEBA_NK_DISPATCH(P.NK, hc, (k_backsub<NK_, HC_, 32><<<grid, 128, 0, st>>>(P)));
     }
+    return cudaGetLastError();
+}
+
+// group runs: keep the rows this rank contributes (its own subtrees; shared rows on rank 0), zero the rest, so
+// that the sum over the ranks gives every row exactly once
+__global__ void k_keep_own_rows(DevProblem P, double* __restrict__ vec) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.n_pad && !row_init_here(P, i)) vec[i] = 0.0;
+}
+
+cudaError_t launch_keep_own_rows(const DevProblem& P, double* vec, cudaStream_t st) {
+    k_keep_own_rows<<<(P.n_pad + 255) / 256, 256, 0, st>>>(P, vec);
+    return cudaGetLastError();
+}
+
+// group runs: zero the entries of tie points owned by other ranks (tie_mine[t] = 1: owned here)
+__global__ void k_keep_own_ties(int64_t n_tie, const unsigned char* __restrict__ tie_mine, double* __restrict__ xyz3) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < 3 * n_tie && !tie_mine[i / 3]) xyz3[i] = 0.0;
+}
+
+cudaError_t launch_keep_own_ties(int64_t n_tie, const unsigned char* tie_mine, double* xyz3, cudaStream_t st) {
+    if (n_tie > 0) k_keep_own_ties<<<(unsigned)((3 * n_tie + 255) / 256), 256, 0, st>>>(n_tie, tie_mine, xyz3);
     return cudaGetLastError();
 }
 

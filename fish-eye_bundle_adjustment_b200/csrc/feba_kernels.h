@@ -15,8 +15,14 @@ cudaError_t launch_xhat_gather(const DevProblem& P, int sm_count, double* xhat, 
                                const double* iop, const int* tie_pt, cudaStream_t st);
 cudaError_t launch_delta_gather(const DevProblem& P, int sm_count, double* delta, cudaStream_t st);
 // G rows (inner constraints), padding diagonal, M = S + Gc Gc' and its Jacobi scaling d = diag(M)^-1/2
-cudaError_t launch_border_scale(const DevProblem& P, const double* eop, double* dvec, int* info, cudaStream_t st,
-                                int64_t* launches);
+// blocks: (block row, block column) of the structurally non-zero 64x64 blocks of the lower triangle followed by the
+// blocks of the augmented block row (row index = n_pad / 64), as listed by the handle from its plan
+cudaError_t launch_border_prepare(const DevProblem& P, const double* eop, double* dg, cudaStream_t st, int64_t* launches);
+cudaError_t launch_border_scale(const DevProblem& P, const double* dg, double* dvec, int* info, const int2* blocks,
+                                int n_blocks, cudaStream_t st, int64_t* launches);
+cudaError_t launch_keep_own_rows(const DevProblem& P, double* vec, cudaStream_t st);
+cudaError_t launch_keep_own_ties(int64_t n_tie, const unsigned char* tie_mine, double* xyz3, cudaStream_t st);
+cudaError_t launch_clear_blocks(const DevProblem& P, const int2* blocks, int n_blocks, cudaStream_t st);
 // feba_assemble.cu: schedule (once) and the three assembly passes (per iteration)
 cudaError_t build_pair_schedule(DevProblem& P, const int* d_oseg, long long* n_pairs_out, void** keep_pairs,
                                 void** keep_blocks, cudaStream_t st);
@@ -43,15 +49,22 @@ cudaError_t chol_augmented(double* A, int ld, int nb, double* Linv, int* info, c
 struct DagStreams {
     int tile_blocks = 8;            // supertile size in 64-blocks
     int n_streams = 0;              // streams[0] has high priority (critical path)
-    cudaStream_t streams[16] = {};
+    cudaStream_t streams[32] = {};
     cudaEvent_t fork = nullptr;
-    cudaEvent_t join[17] = {};         // [n_streams] belongs to the collective stream of a group run
+    cudaEvent_t join[33] = {};         // [n_streams] belongs to the collective stream of a group run
     cudaEvent_t* events = nullptr;  // one per tile (row supertile, column supertile)
     int n_events = 0;
 };
-// nz: optional supertile pattern incl. fill (feba_sparse.h), (NT+1) x (NT+1) row-major; null = dense
-cudaError_t chol_dag(double* A, int ld, int nb, double* Linv, int* info, const DagStreams& D, cudaStream_t main,
-                     int64_t* launches, const unsigned char* nz = nullptr);
+// Supertiles of a plan of the reduced system (feba_order.h) as the task graph needs them (host arrays).
+struct TileView {
+    int NT = 0;                           // tiles of the factorised part; tile NT is the augmented block row
+    const int* b0 = nullptr;              // NT + 1 entries: first 64-block of tile t, b0[NT] = nb
+    const unsigned char* nz = nullptr;    // (NT+1) x (NT+1) row-major pattern incl. fill; null = dense
+    const int* chain = nullptr;           // per tile: stream slot of its panel chain (0 = critical path); null = 0
+    const int* owner = nullptr;           // per tile: owning rank, -1 = every rank; null = everything local
+};
+cudaError_t chol_tiles(double* A, int ld, int nb, double* Linv, int* info, const DagStreams& D, cudaStream_t main,
+                       int64_t* launches, const TileView& V, int k_begin, int k_end, int rank);
 
 // feba_green.cu -- two disjoint SM partitions of one device (green contexts): `chain` for the panel
 // chain of the factorisation, `bulk` for its trailing updates.  -1 when the driver cannot provide them.
@@ -99,7 +112,8 @@ void dist_prof_report();   // FEBA_DIST_PROF=1: prints the time stamps of the la
 // row_first_block (host, nb entries, optional): first 64-block column that can be non-zero in each block row.
 cudaError_t border_and_backsolve(double* A, int ld, int nb, const double* Linv, int inner, double* work,
                                  double* ywork, double* sol, int* info, int sm_count, cudaStream_t st,
-                                 int64_t* launches, int sparse_datum = 0, const int* row_first_block = nullptr);
+                                 int64_t* launches, int sparse_datum = 0, const int* row_first_block = nullptr,
+                                 const int* block_owner = nullptr, int rank = 0);
 
 // Covariance stage: U = L^-T, Q = M~^-1 (n_pad x n_pad, lower valid), Y = M~^-1 G~ (n_pad x 8), T7inv 7x7.
 cudaError_t chol_inverse(double* A, int ld, int nb, const double* Linv, int inner, double* U, double* Q, double* Y,

@@ -26,6 +26,7 @@ EXPORTS = (
     "feba_iterate_solve", "feba_get_delta", "feba_residuals", "feba_solve", "feba_last_timing",
     "feba_launch_count", "feba_sparse_info", "feba_debug_reduced", "feba_cov_prepare", "feba_cov_diag", "feba_cov_block", "feba_iterate_async", "feba_iterate_solve_async", "feba_sync",
     "feba_dist_unique_id", "feba_dist_init", "feba_reduced_pack", "feba_reduced_unpack",
+    "feba_create_shard", "feba_last_timing_ex", "feba_plan_info",
 )
 
 
@@ -45,7 +46,7 @@ class FebaSettings(C.Structure):
     _fields_ = [("estimate_eop", C.c_int32 * 6), ("estimate_xp", C.c_int32), ("estimate_yp", C.c_int32),
                 ("estimate_c", C.c_int32), ("estimate_radial", C.c_int32), ("num_radial", C.c_int32),
                 ("estimate_decent", C.c_int32), ("inner_constraints", C.c_int32), ("type", C.c_int32),
-                ("iteration_cap", C.c_int32), ("reserved", C.c_int32), ("sigma_x", C.c_double),
+                ("iteration_cap", C.c_int32), ("plan", C.c_int32), ("sigma_x", C.c_double),
                 ("sigma_y", C.c_double), ("threshold", C.c_double)]
 
 
@@ -81,6 +82,9 @@ def load() -> C.CDLL:
     lib = C.CDLL(LIB_PATH)
     H = C.c_void_p
     lib.feba_create.argtypes = [C.POINTER(FebaProblem), C.POINTER(H)]
+    lib.feba_create_shard.argtypes = [C.POINTER(FebaProblem), C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(H)]
+    lib.feba_last_timing_ex.argtypes = [H, _pd]
+    lib.feba_plan_info.argtypes = [H, C.POINTER(C.c_int32), _pd]
     lib.feba_destroy.argtypes = [H]
     lib.feba_destroy.restype = None
     lib.feba_last_error.argtypes = [H]
@@ -125,9 +129,11 @@ def _ip(a: np.ndarray):
     return a.ctypes.data_as(_pi)
 
 
-def settings_struct(s) -> FebaSettings:
-    """``data.settings`` -> ``feba_settings`` (include/feba.h)."""
+def settings_struct(s, plan: int = 0) -> FebaSettings:
+    """``data.settings`` -> ``feba_settings`` (include/feba.h).  ``plan``: row order of the reduced system
+    (0 automatic, -1 Buildxhat order / dense, 1 force nested dissection)."""
     fs = FebaSettings()
+    fs.plan = int(plan)
     for q, f in enumerate(s.eop_flags):
         fs.estimate_eop[q] = int(f)
     fs.estimate_xp, fs.estimate_yp, fs.estimate_c = int(s.Estimate_xp), int(s.Estimate_yp), int(s.Estimate_c)
@@ -142,7 +148,9 @@ def settings_struct(s) -> FebaSettings:
 class Handle:
     """One adjustment on one GPU (the current CUDA device at construction)."""
 
-    def __init__(self, prob: Problem):
+    def __init__(self, prob: Problem, plan: int = 0, group=None):
+        """``plan``: feba_settings.plan.  ``group`` = (rank, world, unique_id): one rank of a group of GPUs working
+        on ONE adjustment (feba_create_shard; every rank passes the complete problem)."""
         self._lib = load()
         self._h = C.c_void_p()
         f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
@@ -157,10 +165,15 @@ class Handle:
         fp.obs_x, fp.obs_y, fp.obs_img, fp.obs_pt = _dp(keep["x"]), _dp(keep["y"]), _ip(keep["im"]), _ip(keep["pt"])
         fp.img_cam, fp.eop0, fp.iop0, fp.cam_box = _ip(keep["ic"]), _dp(keep["eop"]), _dp(keep["iop"]), _dp(keep["box"])
         fp.xyz0, fp.pt_tie = _dp(keep["xyz"]), _ip(keep["tie"])
-        fp.settings = settings_struct(prob.settings)
+        fp.settings = settings_struct(prob.settings, plan)
         if keep["iop"].shape != (prob.numCam, 3 + prob.settings.NK + 2):
             raise FebaError(FEBA_ERR_INVALID, "iop0 must be numCam x (3+NK+2)")
-        rc = self._lib.feba_create(C.byref(fp), C.byref(self._h))
+        if group is not None and group[1] > 1:
+            rank, world, uid = group
+            buf = C.create_string_buffer(bytes(uid), DIST_ID_BYTES)
+            rc = self._lib.feba_create_shard(C.byref(fp), rank, world, buf, DIST_ID_BYTES, C.byref(self._h))
+        else:
+            rc = self._lib.feba_create(C.byref(fp), C.byref(self._h))
         if rc != 0:
             text = self._lib.feba_last_error(None).decode()
             self._h = C.c_void_p()
@@ -168,7 +181,7 @@ class Handle:
         u, uc = C.c_int64(), C.c_int64()
         self._lib.feba_num_unknowns(self._h, C.byref(u), C.byref(uc))
         self.u, self.u_c = int(u.value), int(uc.value)
-        self.n_obs = int(self._lib.feba_num_obs(self._h))
+        self.n_obs = int(self._lib.feba_num_obs(self._h))      # rows of the PHO table (global for a group)
         assert self.n_obs == prob.n_obs
 
     # -- lifetime
@@ -271,10 +284,13 @@ class Handle:
         self._check(self._lib.feba_solve(self._h, C.byref(it), _dp(trace), cap))
         return int(it.value), trace[:min(int(it.value), cap)].copy()
 
-    def residuals(self, want_v: bool = True, want_rsd: bool = True):
-        """main.m:569-601 + BuildRSD.  Returns dict(v, RSD, RMSx, RMSy, RMS, sigma02, sxx, syy)."""
-        v = np.empty(2 * self.n_obs, dtype=np.float64) if want_v else None
-        rsd = np.empty((self.n_obs, 5), dtype=np.float64) if want_rsd else None
+    def residuals(self, want_v: bool = True, want_rsd: bool = True, v_out: Optional[np.ndarray] = None,
+                  rsd_out: Optional[np.ndarray] = None):
+        """main.m:569-601 + BuildRSD.  Returns dict(v, RSD, RMSx, RMSy, RMS, sigma02, sxx, syy).
+        ``v_out`` (2 n_obs) / ``rsd_out`` (n_obs x 5): caller-owned output arrays; page-locked ones (e.g. views of a
+        pinned torch tensor) are written by one DMA instead of through the library's staging buffers."""
+        v = (np.empty(2 * self.n_obs, dtype=np.float64) if v_out is None else v_out) if want_v else None
+        rsd = (np.empty((self.n_obs, 5), dtype=np.float64) if rsd_out is None else rsd_out) if want_rsd else None
         st = np.zeros(6, dtype=np.float64)
         self._check(self._lib.feba_residuals(self._h, _dp(v) if want_v else None,
                                              _dp(rsd) if want_rsd else None, _dp(st)))
@@ -298,6 +314,21 @@ class Handle:
         self._check(self._lib.feba_last_timing(self._h, _dp(ms)))
         return dict(prep_ms=ms[0], assemble_ms=ms[1], factor_ms=ms[2], solve_ms=ms[3], update_ms=ms[4],
                     total_ms=ms[5])
+
+    def last_timing_ex(self):
+        ms = np.zeros(8, dtype=np.float64)
+        self._check(self._lib.feba_last_timing_ex(self._h, _dp(ms)))
+        return dict(prep_ms=ms[0], assemble_ms=ms[1], factor_ms=ms[2], solve_ms=ms[3], update_ms=ms[4],
+                    total_ms=ms[5], exchange_ms=ms[6], residual_kernel_ms=ms[7])
+
+    def plan_info(self) -> dict:
+        """Row order / supertiles of the reduced system in use (feba_plan_info)."""
+        v = (C.c_int32 * 8)()
+        fl = np.zeros(2, dtype=np.float64)
+        self._check(self._lib.feba_plan_info(self._h, v, _dp(fl)))
+        return dict(nested_dissection=bool(v[0]), rows=int(v[1]), supertiles=int(v[2]), nodes=int(v[3]),
+                    chain_blocks=int(v[4]), world=int(v[5]), top_row0=int(v[6]), local_obs=int(v[7]),
+                    flop=float(fl[0]), flop_dense=float(fl[1]))
 
     def launch_count(self) -> int:
         return int(self._lib.feba_launch_count(self._h))

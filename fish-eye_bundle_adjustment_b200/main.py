@@ -54,10 +54,11 @@ def covariance_outputs(h: Handle, prob: Problem, sigma02: float, images: Optiona
 
 
 def adjust(prob: Problem, xhat0: Optional[np.ndarray] = None, verbose: bool = True,
-           handle: Optional[Handle] = None, cov: bool = False) -> dict:
+           handle: Optional[Handle] = None, cov: bool = False, plan: int = 0) -> dict:
     """main.m:386-602 for an already built ``data``.  Returns xhat, iterations, deltasum trace,
     v, RSD (n_obs x 5: r vx vy vr vt), RMSx, RMSy, RMS, sigma02, elapsed seconds; with ``cov`` also
-    the covariance outputs of the EOP/IOP unknowns (``covariance_outputs``)."""
+    the covariance outputs of the EOP/IOP unknowns (``covariance_outputs``).  ``plan``: row order of the
+    reduced system (feba_settings.plan: 0 automatic, -1 Buildxhat order / dense, 1 nested dissection)."""
     prob.validate()
     t0 = time.perf_counter()                                              # main.m:386 tic
     if xhat0 is None:
@@ -65,7 +66,7 @@ def adjust(prob: Problem, xhat0: Optional[np.ndarray] = None, verbose: bool = Tr
         if err:
             raise FebaError(1, "Error building xhat")                     # main.m:389-393
     own = handle is None
-    h = Handle(prob) if own else handle
+    h = Handle(prob, plan=plan) if own else handle
     try:
         h.set_xhat(xhat0)
         s = prob.settings
@@ -92,7 +93,16 @@ def adjust(prob: Problem, xhat0: Optional[np.ndarray] = None, verbose: bool = Tr
         res.update(xhat=xhat, iterations=count, deltasum=trace, elapsed=elapsed,
                    delta=h.get_delta(), timing=h.last_timing(), launches=h.launch_count())
         if cov:
-            res.update(covariance_outputs(h, prob, res["sigma02"], images=range(prob.numImg)))
+            if h.sparse_info()["datum_images"] > 0:
+                # Cx is the top-left block of the inverse of the bordered DENSE normal matrix (main.m:432): the
+                # nested-dissection plan of a free network factorises S + E E' instead.  Repeat the LAST iteration
+                # (same linearisation point: xhat - delta) in the dense order and take the covariances there.
+                with Handle(prob, plan=-1) as hd:
+                    hd.set_xhat(xhat - res["delta"])
+                    hd.iterate()
+                    res.update(covariance_outputs(hd, prob, res["sigma02"], images=range(prob.numImg)))
+            else:
+                res.update(covariance_outputs(h, prob, res["sigma02"], images=range(prob.numImg)))
         return res
     finally:
         if own:

@@ -2,7 +2,16 @@
 
 Every observation adds to the normal equations (main.m:424-425), so object points are the shard
 unit: all observations of a point live on one rank, which makes V_p, W_p and the point's whole
-Schur contribution local; the camera-block sums are additive.  Per iteration:
+Schur contribution local; the camera-block sums are additive.  Two forms:
+
+``GroupAdjustment`` (default of bench.py): ``feba_create_shard``.  The library cuts the image block by nested
+dissection into one subtree per rank plus shared separators, every rank keeps the points of its subtree,
+eliminates its subtree locally and only the shared top part of the reduced system is summed over NVLink; all
+collectives (NCCL) are issued inside ``feba_iterate`` on the handle's stream.  Every rank passes the complete
+problem and works with the global xhat.
+
+``ShardedAdjustment`` (replicated form, also what the gloo CPU tests exercise): contiguous point ranges, the WHOLE
+reduced system is summed by the caller.  Per iteration:
 
     rank r:  feba_iterate_assemble()            partial S_r, g_r of its points
     all   :  all_reduce(sum) of the reduced-system buffer (NCCL over NVLink; gloo in CPU tests)
@@ -93,8 +102,37 @@ class DeviceBuffer:
                                              strides=None)
 
 
+class GroupAdjustment:
+    """One rank of a group of GPUs on a nested-dissection plan (feba_create_shard).  ``prob`` is the COMPLETE
+    problem on every rank; ``xhat`` vectors are global.  Needs an initialised NCCL process group (the library
+    creates its own communicator from an id broadcast through it)."""
+
+    def __init__(self, prob: Problem, group=None, plan: int = 0):
+        import torch
+        import torch.distributed as dist
+        from .lib import Handle, dist_unique_id
+        self.dist, self.torch, self.group = dist, torch, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        ids = [dist_unique_id() if self.rank == 0 else None]
+        dist.broadcast_object_list(ids, src=src, group=group)
+        self.h = Handle(prob, plan=plan, group=(self.rank, self.world, ids[0]))
+        # kernels, copies and the library's collectives are ordered on torch's current stream (callers make a
+        # non-default stream current: the library captures CUDA graphs on it)
+        self.h.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.shared_factorisation = True
+
+    def iterate(self) -> float:
+        return self.h.iterate()
+
+    def iterate_async(self):
+        self.h.iterate_async()
+
+
 class ShardedAdjustment:
-    """One rank of a sharded run.  ``handle`` is a ``lib.Handle`` of ``shard.prob``."""
+    """One rank of a sharded run in the replicated form.  ``handle`` is a ``lib.Handle`` of ``shard.prob`` created
+    with ``plan=-1`` (every rank must use the same row order of the reduced system: the identity order)."""
 
     def __init__(self, handle, shard: Shard, group=None):
         import torch
@@ -107,9 +145,9 @@ class ShardedAdjustment:
         # opt-in until it has been timed on the 8-GPU box: exchange the packed lower trapezoids only
         self._packed = os.environ.get("FEBA_PACKED_REDUCE", "0") == "1"
         if self.world > 1 and handle.sparse_info()["active"]:
-            # the supertile pattern of FEBA_SPARSE=1 comes from THIS shard's pair schedule; the summed system
-            # has the union of all shards' patterns
-            raise RuntimeError("FEBA_SPARSE=1 (block-sparse reduced system) is single-GPU: unset it for sharded runs")
+            # a nested-dissection plan computed from THIS shard's images differs from rank to rank: the summed
+            # buffers would not line up
+            raise RuntimeError("the replicated form needs the identity row order: create the handle with plan=-1")
         if self.world > 1:
             # kernels, copies and the collective are all ordered on torch's current stream (callers
             # should make a non-default stream current: the library captures CUDA graphs on it)

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define FEBA_VERSION 100
+#define FEBA_VERSION 200
 #define FEBA_MAX_NK 8 /* largest Num_Radial_Distortions supported by the kernels */
 /* Limits the reference does not have (BuildAwG.m:110-155): Num_Radial_Distortions <= FEBA_MAX_NK, and, when
  * camera parameters are estimated for more than one camera, an object point may be seen by images of at most
@@ -62,7 +62,10 @@ typedef struct feba_settings {
     int32_t type;               /* typeint 0..4: fisheye pinhole equisolid orthographic
                                    stereographic                        (BuildAwG.m:184-208) */
     int32_t iteration_cap;      /* Iteration_Cap   (main.m:153, used by feba_solve only) */
-    int32_t reserved;
+    int32_t plan;               /* row order of the reduced camera system: 0 = automatic (nested dissection when it
+                                   pays, csrc/feba_order.h), -1 = the order of Buildxhat.m (dense factorisation;
+                                   needed by the covariance stage of a free network and by feba_dist_init),
+                                   1 = force nested dissection.  No counterpart in the reference (dense inverse). */
     double sigma_x;             /* Meas_std                             (main.m:123)     */
     double sigma_y;             /* Meas_std_y, = sigma_x when absent    (main.m:397-402) */
     double threshold;           /* Threshold_Value (main.m:154, used by feba_solve only) */
@@ -98,6 +101,20 @@ typedef struct feba_handle feba_handle;
 /* Upload the problem to the current CUDA device, sort/segment observations by point, allocate
  * block storage.  Replaces the per-iteration allocations of BuildAwG.m:29-42. */
 int feba_create(const feba_problem *problem, feba_handle **out);
+/* One rank of a GROUP of GPUs working on ONE adjustment (one process per GPU, each on its own
+ * device).  Every rank passes the SAME, COMPLETE problem and the id of feba_dist_unique_id() (created by one rank
+ * and shipped to the others); world must be a power of two.  Collective: wraps ncclCommInitRank.  The image block
+ * is cut by nested dissection into `world` subtrees plus shared separators (csrc/feba_order.h); a rank keeps the
+ * object points whose images lie in its subtree (all observations of a point stay together, so V_p, W_p and the
+ * point's Schur contribution are local, main.m:424-425 being a sum over observations), eliminates its subtree
+ * locally, and only the shared top part of the reduced system is summed over NVLink (ncclAllReduce) before the
+ * replicated top factorisation.  On such a handle feba_iterate / feba_sync / feba_get_xhat / feba_get_delta /
+ * feba_residuals are collective calls (every rank makes them in the same order) and work on the GLOBAL xhat and
+ * PHO-row layouts: each rank receives the complete result.  Fails with FEBA_ERR_INVALID when the block cannot be
+ * cut into `world` parts; callers then use the replicated form below (feba_create per rank on a point shard +
+ * feba_iterate_assemble / feba_reduced_dev / feba_iterate_solve). */
+int feba_create_shard(const feba_problem *problem, int32_t rank, int32_t world, const void *id, size_t id_bytes,
+                      feba_handle **out);
 /* Run this handle's kernels and copies on a caller-owned CUDA stream (a cudaStream_t passed as
  * void*; e.g. the stream the caller's NCCL all-reduce is enqueued on).  Default: a private
  * non-blocking stream. */
@@ -182,16 +199,24 @@ int feba_cov_block(feba_handle *h, const int64_t *idx, int32_t k, double *out);
  * ms[2] border + Cholesky (includes the caller's all-reduce in a multi-GPU run), ms[3] border
  * solve + backward substitution, ms[4] update + point back-substitution, ms[5] total. */
 int feba_last_timing(const feba_handle *h, double ms[6]);
+/* The same six entries, then ms[6] = exchange of the shared top part inside ms[2] on a feba_create_shard handle
+ * (pack + ncclAllReduce + unpack; 0 otherwise), ms[7] = device time of the last feba_residuals kernel stage. */
+int feba_last_timing_ex(const feba_handle *h, double ms[8]);
 
 /* Kernel launches issued by this handle since creation (for bench.py's gpu_launches). */
 int64_t feba_launch_count(const feba_handle *h);
 
-/* Block-sparse form of the reduced system (opt-in: environment FEBA_SPARSE=1 when the handle is created;
- * one GPU, reduced systems of 96 blocks or more; csrc/feba_sparse.h).  info[0] = 1 when active, info[1] /
+/* Block-sparse form of the reduced system (automatic, see feba_settings.plan; csrc/feba_order.h, feba_sparse.h;
+ * environment FEBA_SPARSE=0 or FEBA_PLAN=-1 keep the dense form).  info[0] = 1 when active, info[1] /
  * info[2] = structurally non-zero / all lower supertiles of the factorised part (symbolic fill included),
  * info[3] = number of datum images of the sparse-datum form (0: no inner constraints).  The reference has no
  * counterpart: main.m:432,442 invert the dense bordered matrix. */
 int feba_sparse_info(const feba_handle *h, int32_t info[4]);
+/* Plan of the reduced system in use: info = {nested dissection (1) or identity order (0), rows incl. padding,
+ * supertiles, tree nodes, 64-blocks on the longest chain of dependent diagonal factorisations, world, first row
+ * of the shared top part (= rows when single GPU), observations held by this handle}; flop = {factorisation flop
+ * of the plan's task graph, dense (64 blocks)^3 / 3}.  flop may be NULL. */
+int feba_plan_info(const feba_handle *h, int32_t info[8], double flop[2]);
 
 /* Diagnostic for parity tests: the point-eliminated camera system left by a pending
  * feba_iterate_assemble() (S = N_cc - W V^-1 W', g = u_c - W V^-1 u_p; main.m:424-425 reduced),

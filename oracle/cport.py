@@ -29,11 +29,47 @@ class OracleProblem(C.Structure):
                 ("py", C.c_double), ("pt_start", _pi), ("pt_obs", _pi)]
 
 
+def _host_signature() -> str:
+    """CPU model + ISA flags of this machine: the library is compiled with -march=native, so a copy built on
+    another machine (the repository snapshot travels between boxes) must be rebuilt."""
+    try:
+        with open("/proc/cpuinfo") as fh:
+            txt = fh.read()
+        model = next((ln for ln in txt.splitlines() if ln.startswith("model name")), "")
+        flags = next((ln for ln in txt.splitlines() if ln.startswith("flags")), "")
+        import hashlib
+        return hashlib.sha1((model + flags).encode()).hexdigest()
+    except OSError:
+        return "unknown"
+
+
 def build(force: bool = False) -> str:
     src = os.path.join(HERE, "feba_oracle.c")
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
-        subprocess.run(["make", "-C", HERE], check=True, stdout=subprocess.DEVNULL)
+    mk = os.path.join(HERE, "Makefile")
+    sig_file = os.path.join(HERE, "_build", "host.sig")
+    sig = _host_signature()
+    try:
+        same_host = open(sig_file).read().strip() == sig
+    except OSError:
+        same_host = False
+    stale = (not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(src), os.path.getmtime(mk)))
+    if force or stale or not same_host:
+        subprocess.run(["make", "-B", "-C", HERE], check=True, stdout=subprocess.DEVNULL)
+        with open(sig_file, "w") as fh:
+            fh.write(sig)
     return LIB
+
+
+def set_threads(n: int) -> int:
+    """OpenMP threads of the C restatement AND the BLAS/LAPACK threads of the dense solve; returns the OpenMP count
+    in effect (bench.py: all host cores, also under a launcher that exported OMP_NUM_THREADS=1)."""
+    lib().feba_oracle_set_threads(int(n))
+    try:
+        from threadpoolctl import threadpool_limits
+        set_threads._blas = threadpool_limits(limits=int(n), user_api="blas")
+    except Exception:        # threadpoolctl missing: BLAS keeps its own default
+        pass
+    return int(lib().feba_oracle_threads())
 
 
 _lib = None
@@ -48,6 +84,7 @@ def lib():
         _lib.feba_oracle_backsub.argtypes = [C.POINTER(OracleProblem), _pd, _pd, _pd, _pd]
         _lib.feba_oracle_residuals.argtypes = [C.POINTER(OracleProblem), _pd, _pd, _pd]
         _lib.feba_oracle_obs.argtypes = [C.c_int, C.c_int, C.c_long] + [_pd] * 10
+        _lib.feba_oracle_set_threads.argtypes = [C.c_int]
     return _lib
 
 

@@ -388,6 +388,15 @@ int feba_oracle_obs(int type, int NK, long n, const double* x, const double* y, 
     return 0;
 }
 
+/* OpenMP threads of the next calls (bench.py: all host cores, also when a launcher exported OMP_NUM_THREADS=1) */
+void feba_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int feba_oracle_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -46,7 +46,7 @@ def main():
     for mode in ("0", "1") + (("1p",) if args.packed else ()):
         os.environ["FEBA_DIST_CHOL"] = mode[0]
         os.environ["FEBA_PACKED_REDUCE"] = "1" if mode.endswith("p") else "0"
-        h = fb.Handle(shard.prob)
+        h = fb.Handle(shard.prob, plan=-1)       # replicated form: identity row order on every rank
         h.set_stream(stream.cuda_stream)
         adj = sh.ShardedAdjustment(h, shard)
         h.set_xhat(x0)

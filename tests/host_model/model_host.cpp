@@ -127,3 +127,62 @@ extern "C" void feba_host_sparse_row_first(int nb, int T, const unsigned char* n
     const std::vector<int> v = P.row_first_block(nb);
     for (int k = 0; k < nb; ++k) out_nb[k] = v[(size_t)k];
 }
+
+// ---- plan of the reduced system (csrc/feba_order.h): nested-dissection row order, supertiles, pattern, owners
+#include "../../fish-eye_bundle_adjustment_b200/csrc/feba_order.h"
+
+// adjacency from observations sorted by point (what feba_create does): returns nnz, fills ptr (n_img+1); idx via
+// a second call with idx_out != null (capacity cap)
+extern "C" int feba_host_adjacency(int n_img, int n_seg, const int* seg_start, const int* simg, const unsigned char* seg_tie,
+                                   int couple_control, int* ptr_out, int* idx_out, int cap) {
+    std::vector<int> ptr, idx;
+    feba::image_adjacency(n_img, n_seg, seg_start, simg, seg_tie, couple_control != 0, ptr, idx);
+    for (size_t i = 0; i < ptr.size(); ++i) ptr_out[i] = ptr[i];
+    if (idx_out)
+        for (size_t i = 0; i < idx.size() && (int)i < cap; ++i) idx_out[i] = idx[i];
+    return (int)idx.size();
+}
+
+extern "C" void* feba_host_plan_masked(int n_img, int ui, int cam_rows, const int* adj_ptr, const int* adj_idx,
+                                       const double* pos, int inner, int world, int max_depth, int leaf_images,
+                                       int tile_max) {
+    feba::PlanOptions o;
+    if (max_depth >= 0) o.max_depth = max_depth;
+    if (leaf_images > 0) o.leaf_images = leaf_images;
+    if (tile_max > 0) o.tile_max = tile_max;
+    return new feba::ReducedPlan(feba::masked_plan(n_img, ui, cam_rows, adj_ptr, adj_idx, pos, inner != 0, world, o));
+}
+extern "C" void* feba_host_plan_identity(int n_img, int ui, int cam_rows, int tile_blocks) {
+    return new feba::ReducedPlan(feba::identity_plan(n_img, ui, cam_rows, tile_blocks));
+}
+extern "C" void feba_host_plan_free(void* p) { delete static_cast<feba::ReducedPlan*>(p); }
+// info: n_pad, NT, off_cam, n_nodes, n_datum, world (-1: group not possible), top_tile0, chain_blocks
+extern "C" void feba_host_plan_info(const void* p, int* info8, double* flop2) {
+    const feba::ReducedPlan& P = *static_cast<const feba::ReducedPlan*>(p);
+    info8[0] = P.n_pad; info8[1] = P.NT; info8[2] = P.off_cam; info8[3] = (int)P.nodes.size();
+    info8[4] = (int)P.datum.size(); info8[5] = P.world; info8[6] = P.top_tile0; info8[7] = P.chain_blocks;
+    flop2[0] = P.flop; flop2[1] = P.flop_dense;
+}
+// img_row[n_img], row_ext[n_pad], tile_b0[NT+1], nz[(NT+1)^2], tile_node[NT], datum[n_datum], img_node[n_img],
+// node_info[n_nodes*6] = parent depth owner tile0 n_tiles lane, first_block[nb]
+extern "C" void feba_host_plan_arrays(const void* p, int* img_row, int* row_ext, int* tile_b0, unsigned char* nz,
+                                      int* tile_node, int* datum, int* img_node, int* node_info, int* first_block) {
+    const feba::ReducedPlan& P = *static_cast<const feba::ReducedPlan*>(p);
+    std::copy(P.img_row.begin(), P.img_row.end(), img_row);
+    std::copy(P.row_ext.begin(), P.row_ext.end(), row_ext);
+    std::copy(P.tile_b0.begin(), P.tile_b0.end(), tile_b0);
+    std::copy(P.nz.begin(), P.nz.end(), nz);
+    std::copy(P.tile_node.begin(), P.tile_node.end(), tile_node);
+    std::copy(P.datum.begin(), P.datum.end(), datum);
+    std::copy(P.img_node.begin(), P.img_node.end(), img_node);
+    for (size_t i = 0; i < P.nodes.size(); ++i) {
+        const feba::PlanNode& n = P.nodes[i];
+        const int v[6] = {n.parent, n.depth, n.owner, n.tile0, n.n_tiles, n.lane};
+        std::copy(v, v + 6, node_info + 6 * i);
+    }
+    const std::vector<int> fb = P.row_first_block();
+    std::copy(fb.begin(), fb.end(), first_block);
+}
+extern "C" int feba_host_plan_point_owner(const void* p, int n_seg, const int* seg_start, const int* simg, int* owner) {
+    return feba::plan_point_owner(*static_cast<const feba::ReducedPlan*>(p), n_seg, seg_start, simg, owner) ? 0 : 1;
+}

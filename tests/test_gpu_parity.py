@@ -15,50 +15,7 @@ from tests import golden
 pytestmark = pytest.mark.gpu
 
 
-def group_rel(prob, a, b):
-    """max over parameter groups of ||a_g - b_g|| / ||b_g|| -- the scaled, group-normalised error of
-    SURVEY.md 7.2-1.  Groups: EOP positions, EOP angles, (xp, yp, c), radial terms in their scaled
-    units K_j r_max^(2j), decentering terms scaled by r_max^2, tie-point coordinates."""
-    L = model.layout(prob)
-    ui, uc, NK = L["u_img"], L["u_cam"], L["NK"]
-    box = prob.cam_box
-    rmax2 = ((box[:, 3] - box[:, 1]) * 0.5) ** 2 + ((box[:, 4] - box[:, 2]) * 0.5) ** 2
-    a, b = a.copy(), b.copy()
-    groups = []
-    if ui:
-        e = np.arange(L["off_cam"]).reshape(prob.numImg, ui)
-        pos = [L["ecols"][q] for q in range(3) if L["ecols"][q] >= 0]
-        ang = [L["ecols"][q] for q in range(3, 6) if L["ecols"][q] >= 0]
-        if pos:
-            groups.append(e[:, pos].ravel())
-        if ang:
-            groups.append(e[:, ang].ravel())
-    cam0 = L["off_cam"] + uc * np.arange(prob.numCam)
-    lin = [cam0 + L["ccols"][q] for q in range(3) if L["ccols"][q] >= 0]
-    if lin:
-        groups.append(np.concatenate(lin))
-    if L["ccols"][3] >= 0:
-        rad = []
-        for j in range(NK):
-            idx = cam0 + L["ccols"][3 + j]
-            a[idx] *= rmax2 ** (j + 1); b[idx] *= rmax2 ** (j + 1)
-            rad.append(idx)
-        groups.append(np.concatenate(rad))
-    if L["ccols"][3 + NK] >= 0:
-        dec = []
-        for j in range(2):
-            idx = cam0 + L["ccols"][3 + NK + j]
-            a[idx] *= rmax2; b[idx] *= rmax2
-            dec.append(idx)
-        groups.append(np.concatenate(dec))
-    if prob.numtie:
-        groups.append(np.arange(L["off_tie"], L["u"]))
-    worst = 0.0
-    for g in groups:
-        den = np.linalg.norm(b[g])
-        if den > 0:
-            worst = max(worst, np.linalg.norm(a[g] - b[g]) / den)
-    return worst
+from oracle.compare import group_rel  # noqa: E402  (scaled, group-normalised error of SURVEY.md 7.2-1)
 
 
 def reduced_oracle(prob, xhat):
@@ -238,6 +195,32 @@ def test_baseline_configs_against_c_oracle(idx, scale):
     assert abs(out["sigma02"] - ref["sigma02"]) < 1e-8 * ref["sigma02"]
     assert group_rel(prob, out["xhat"], ref["xhat"]) < 1e-9
     assert 0.9 < out["sigma02"] < 1.1                      # the noise model of the generator (sigma = 0.3 px)
+
+
+def test_headline_configuration_full_size_against_c_oracle():
+    """BASELINE.json configs[3] at its FULL size (2,000 images / 1M points / ~10M observations, u_c = 12,010): the
+    configuration bench.py times, with the library's default choices (nested-dissection plan, sparse datum, task
+    graph), whole loop + residual stage against the C restatement of the reference algorithm.  Tolerances of the
+    north star: xhat 1e-9 (group-normalised), v 1e-8 max|v|, sigma02 1e-8, identical iteration count."""
+    from oracle import cport
+    prob = synth.baseline_config(3, scale=1.0)
+    err, xhat0, _ = fb.Buildxhat(prob)
+    with fb.Handle(prob) as h:
+        info = h.plan_info()
+        assert info["nested_dissection"] and 2 * info["chain_blocks"] <= info["rows"] // 64
+        out = fb.adjust(prob, xhat0, verbose=False, handle=h)
+    ref = cport.CPort(prob).gauss_newton(xhat0)
+    assert out["iterations"] == ref["iterations"]
+    assert abs(out["deltasum"][0] - ref["deltasum"][0]) < 1e-7 * ref["deltasum"][0]
+    vmax = np.max(np.abs(ref["v"]))
+    assert np.max(np.abs(out["v"] - ref["v"])) < 1e-8 * vmax
+    assert abs(out["sigma02"] - ref["sigma02"]) < 1e-8 * ref["sigma02"]
+    assert group_rel(prob, out["xhat"], ref["xhat"]) < 1e-9
+    # the dense form of the library (Buildxhat order, dense datum, dense task graph) on the same problem
+    dense = fb.adjust(prob, xhat0, verbose=False, plan=-1)
+    assert dense["iterations"] == ref["iterations"]
+    assert group_rel(prob, dense["xhat"], ref["xhat"]) < 1e-9
+    assert np.max(np.abs(dense["v"] - ref["v"])) < 1e-8 * vmax
 
 
 def test_full_size_properties_config4_shape():
