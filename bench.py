@@ -124,7 +124,21 @@ def make_workload(name: str, scale: float):
     idx, desc = WORKLOADS[name]
     if name == "config5":
         name = "config5block"            # the reference arm times one block of the sweep
+    # FEBA_BENCH_CACHE=<dir>: keep the generated network between runs on one box (sweeps; generation of
+    # configs[3] takes ~45 s of host time and is not part of any timed region)
+    cache = os.environ.get("FEBA_BENCH_CACHE")
+    path = os.path.join(cache, f"workload_{name}_{scale}.pkl") if cache else None
+    if path and os.path.exists(path):
+        import pickle
+        with open(path, "rb") as fh:
+            return pickle.load(fh), desc
     prob = fb.synth.baseline_config(idx, scale=scale)
+    if path:
+        import pickle
+        os.makedirs(cache, exist_ok=True)
+        with open(path + f".{os.getpid()}", "wb") as fh:
+            pickle.dump(prob, fh, protocol=4)
+        os.replace(path + f".{os.getpid()}", path)
     return prob, desc
 
 

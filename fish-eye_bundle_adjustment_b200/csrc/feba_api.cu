@@ -46,7 +46,8 @@ struct feba_handle {
     ReducedPlan plan;
     std::vector<int> tile_chain, tile_owner, block_owner, row_first;
     int2* blk_list = nullptr;     // non-zero 64x64 blocks of the lower triangle, then the augmented block row
-    int n_blk_list = 0;
+    int n_blk_list = 0;           // all of them (cleared per iteration)
+    int n_blk_scale = 0;          // without the last entry, the augmented diagonal block (border / scaling pass)
     DagStreams dag;               // task-graph factorisation (large reduced systems)
     std::vector<cudaEvent_t> dag_events;
     bool use_dag = false;
@@ -399,6 +400,8 @@ int install_plan(feba_handle* h) {
                     list.push_back(make_int2(bi, bj));
         }
     for (int bj = 0; bj < nb; ++bj) list.push_back(make_int2(nb, bj));
+    h->n_blk_scale = (int)list.size();
+    list.push_back(make_int2(nb, nb));      // augmented diagonal block T = -B' M^-1 B: cleared, never scaled
     h->n_blk_list = (int)list.size();
     CU(h, upload(h, &h->blk_list, list.data(), list.size()));
     CU(h, cudaStreamSynchronize(h->stream));
@@ -618,6 +621,64 @@ static int create_impl(const feba_problem* pr, int rank, int world, const void* 
         sx.swap(l_sx);
         sy.swap(l_sy);
         n_seg = (int)seg_pt.size();
+    }
+    // ---- processing order of the object points: along a space-filling (Morton) curve through the initial
+    // coordinates, so that consecutive points are seen by the same images (the per-image tables, the records of an
+    // image and the increments of its unknowns are touched together).  Outputs keep the PHO / TIE order.
+    if (n_seg > 1 && !(std::getenv("FEBA_POINT_ORDER") && std::atoi(std::getenv("FEBA_POINT_ORDER")) == 0)) {
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int sg = 0; sg < n_seg; ++sg)
+            for (int k2 = 0; k2 < 3; ++k2) {
+                const double v = pr->xyz0[3 * (size_t)seg_pt[(size_t)sg] + k2];
+                if (v < lo[k2]) lo[k2] = v;
+                if (v > hi[k2]) hi[k2] = v;
+            }
+        auto spread = [](unsigned long long v) {          // 21 bits -> every third bit
+            v &= 0x1fffffULL;
+            v = (v | v << 32) & 0x1f00000000ffffULL;
+            v = (v | v << 16) & 0x1f0000ff0000ffULL;
+            v = (v | v << 8) & 0x100f00f00f00f00fULL;
+            v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
+            v = (v | v << 2) & 0x1249249249249249ULL;
+            return v;
+        };
+        std::vector<std::pair<unsigned long long, int>> key((size_t)n_seg);
+        for (int sg = 0; sg < n_seg; ++sg) {
+            unsigned long long code = 0;
+            for (int k2 = 0; k2 < 3; ++k2) {
+                const double ext = hi[k2] - lo[k2];
+                const double t = ext > 0 ? (pr->xyz0[3 * (size_t)seg_pt[(size_t)sg] + k2] - lo[k2]) / ext : 0.0;
+                unsigned long long q = std::isfinite(t) ? (unsigned long long)(t * 2097151.0) : 0ULL;
+                code |= spread(q) << k2;
+            }
+            key[(size_t)sg] = {code, sg};
+        }
+        std::sort(key.begin(), key.end());
+        std::vector<int> n_start, n_pt, n_perm((size_t)perm.size()), n_simg((size_t)perm.size()), n_spt((size_t)perm.size());
+        std::vector<double> n_sx((size_t)perm.size()), n_sy((size_t)perm.size());
+        n_start.reserve((size_t)n_seg + 1);
+        n_pt.reserve((size_t)n_seg);
+        size_t w = 0;
+        for (int q = 0; q < n_seg; ++q) {
+            const int sg = key[(size_t)q].second;
+            n_start.push_back((int)w);
+            n_pt.push_back(seg_pt[(size_t)sg]);
+            for (int o = seg_start[(size_t)sg]; o < seg_start[(size_t)sg + 1]; ++o, ++w) {
+                n_perm[w] = perm[(size_t)o];
+                n_simg[w] = simg[(size_t)o];
+                n_spt[w] = spt[(size_t)o];
+                n_sx[w] = sx[(size_t)o];
+                n_sy[w] = sy[(size_t)o];
+            }
+        }
+        n_start.push_back((int)w);
+        seg_start.swap(n_start);
+        seg_pt.swap(n_pt);
+        perm.swap(n_perm);
+        simg.swap(n_simg);
+        spt.swap(n_spt);
+        sx.swap(n_sx);
+        sy.swap(n_sy);
     }
     const int64_t nl = (int64_t)perm.size();          // observations held by this handle
     P.n_obs = nl;
@@ -1019,7 +1080,7 @@ static int enqueue_solve(feba_handle* h) {
     const int nb = P.n_pad / kBlk;
     CU(h, launch_border_prepare(P, h->eop, h->dg, h->stream, &h->launches));
     if (h->shard) NC(h, dist_allreduce_f64(&h->dist, h->dg, (size_t)P.n_pad, h->stream));
-    CU(h, launch_border_scale(P, h->dg, h->dvec, h->info, h->blk_list, h->n_blk_list, h->stream, &h->launches));
+    CU(h, launch_border_scale(P, h->dg, h->dvec, h->info, h->blk_list, h->n_blk_scale, h->stream, &h->launches));
     if (h->use_dag && h->dag_cols) {
         const cudaError_t ed = chol_cols(P.S, P.ld, nb, h->Linv, h->info, h->dag, h->dist_active ? &h->dist : nullptr,
                                          h->stream, &h->launches);
@@ -1045,10 +1106,12 @@ static int enqueue_solve(feba_handle* h) {
         }
     } else CU(h, chol_augmented(P.S, P.ld, nb, h->Linv, h->info, h->stream, &h->launches));
     CU(h, record(h, 3));
-    CU(h, border_and_backsolve(P.S, P.ld, nb, h->Linv, P.inner, h->work, h->ywork, h->sol, h->info, h->sm_count,
-                               h->stream, &h->launches, P.datum != nullptr,
-                               h->plan.masked ? h->row_first.data() : nullptr,
-                               h->shard ? h->block_owner.data() : nullptr, h->rank));
+    {
+        const TileView Vb = plan_view(h);
+        CU(h, border_and_backsolve(P.S, P.ld, nb, h->Linv, P.inner, h->work, h->ywork, h->sol, h->info, h->sm_count,
+                                   h->stream, &h->launches, P.datum != nullptr, h->plan.masked ? &Vb : nullptr,
+                                   h->shard ? h->block_owner.data() : nullptr, h->rank));
+    }
     if (h->shard) {
         CU(h, launch_keep_own_rows(P, h->sol, h->stream));
         ++h->launches;

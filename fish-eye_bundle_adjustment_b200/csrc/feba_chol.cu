@@ -10,8 +10,10 @@
 // The one real dense contraction of the path (trailing SYRK/GEMM updates) runs on the FP64
 // tensor pipe: mma.sync.m8n8k4.f64 (DMMA).  tcgen05 has no FP64 kind, so the warp-level DMMA is
 // the tensor path for doubles on sm_100a as well.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <initializer_list>
 #include <vector>
 
 #include "feba_dev.h"
@@ -600,8 +602,96 @@ static bool upd1_bulk() {
 // their DIAG / TRSM chains run side by side; slot 0 is the high-priority stream (root node).  Columns k in
 // [k_begin, k_end) whose owner is this rank (or shared, owner < 0) are eliminated: a group of GPUs calls it once
 // for its own subtrees, sums the shared trailing part over the ranks, and once more for the shared top.
+// The same tasks while `main` is being CAPTURED into a CUDA graph: every task is issued on `main` itself after
+// the stream's capture dependencies have been set to exactly the graph nodes that last wrote the tiles the task
+// reads or writes (cudaStreamUpdateCaptureDependencies), and the nodes the task leaves behind become the new
+// last writers of its output tile.  The captured graph then carries the TRUE dependencies of the factorisation
+// and nothing else: with a pool of streams, two unrelated tasks that share a stream are ordered by it (measured on
+// BASELINE configs[3], nested-dissection plan, 1,689 kernel nodes: 8 / 16 / 32 streams -> 9.9 / 9.1 / 7.0 ms).
+static cudaError_t chol_tiles_captured(double* A, int ld, int nb, double* Linv, int* info, cudaStream_t main,
+                                       int64_t* launches, const TileView& V, int k_begin, int k_end, int rank) {
+    const int NT = V.NT;
+    const int NR = NT + 1;
+    auto on = [&](int i, int j) { return V.nz == nullptr || V.nz[(size_t)i * NR + j] != 0; };
+    auto blk0 = [&](int t) { return t == NT ? nb : V.b0[t]; };
+    auto nblk = [&](int t) { return t == NT ? 1 : V.b0[t + 1] - V.b0[t]; };
+    auto mine = [&](int k) { return V.owner == nullptr || V.owner[k] < 0 || V.owner[k] == rank; };
+    auto tid = [&](int i, int j) { return (size_t)i * NR + j; };
+    typedef std::vector<cudaGraphNode_t> NodeSet;
+    auto current = [&](NodeSet& out) -> cudaError_t {
+        cudaStreamCaptureStatus st;
+        const cudaGraphNode_t* deps = nullptr;
+        size_t nd = 0;
+        cudaError_t e = cudaStreamGetCaptureInfo(main, &st, nullptr, nullptr, &deps, &nd);
+        if (e != cudaSuccess) return e;
+        if (st != cudaStreamCaptureStatusActive) return cudaErrorInvalidValue;
+        out.assign(deps, deps + nd);
+        return cudaSuccess;
+    };
+    NodeSet base;
+    cudaError_t e = current(base);
+    if (e != cudaSuccess) return e;
+    std::vector<NodeSet> last((size_t)NR * NR);       // empty: not written in this call -> whatever preceded it
+    std::vector<char> written((size_t)NR * NR, 0);
+    NodeSet scratch;
+    auto begin_task = [&](std::initializer_list<size_t> tiles) -> cudaError_t {
+        scratch.clear();
+        for (size_t t : tiles) {
+            const NodeSet& d = written[t] ? last[t] : base;
+            scratch.insert(scratch.end(), d.begin(), d.end());
+        }
+        std::sort(scratch.begin(), scratch.end());
+        scratch.erase(std::unique(scratch.begin(), scratch.end()), scratch.end());
+        return cudaStreamUpdateCaptureDependencies(main, scratch.data(), scratch.size(), cudaStreamSetCaptureDependencies);
+    };
+    auto end_task = [&](size_t t) -> cudaError_t {
+        written[t] = 1;
+        return current(last[t]);
+    };
+#define DAG_CU(x)                 \
+    do {                          \
+        e = (x);                  \
+        if (e != cudaSuccess) return e; \
+    } while (0)
+    for (int k = k_begin; k < k_end && k < NT; ++k) {
+        if (!mine(k) || nblk(k) == 0) continue;
+        DAG_CU(begin_task({tid(k, k)}));
+        DAG_CU(rchol(A, ld, Linv, blk0(k), nblk(k), -1, info, main, launches));
+        DAG_CU(end_task(tid(k, k)));
+        for (int i = k + 1; i < NR; ++i) {
+            if (!on(i, k) || nblk(i) == 0) continue;
+            DAG_CU(begin_task({tid(k, k), tid(i, k)}));
+            DAG_CU(rtrsm(A, ld, A, ld, Linv, blk0(i), nblk(i), blk0(k), nblk(k), main, launches));
+            DAG_CU(end_task(tid(i, k)));
+        }
+        for (int i = k + 1; i < NR; ++i)
+            for (int j = k + 1; j <= i; ++j) {
+                if (!on(i, k) || !on(j, k) || nblk(i) == 0 || nblk(j) == 0) continue;
+                if (j >= NT && !(j == NT && i == NT)) continue;     // augmented diagonal block: plain lower update
+                DAG_CU(begin_task({tid(i, k), tid(j, k), tid(i, j)}));
+                DAG_CU(gemm_nt(AT(A, ld, blk0(i), blk0(j)), ld, AT(A, ld, blk0(i), blk0(k)), ld,
+                               AT(A, ld, blk0(j), blk0(k)), ld, nblk(i), nblk(j), nblk(k), i == j ? 1 : 0, main, launches));
+                DAG_CU(end_task(tid(i, j)));
+            }
+    }
+#undef DAG_CU
+    // join: everything that follows depends on every task (and on what preceded the call)
+    scratch = base;
+    for (size_t t = 0; t < last.size(); ++t)
+        if (written[t]) scratch.insert(scratch.end(), last[t].begin(), last[t].end());
+    std::sort(scratch.begin(), scratch.end());
+    scratch.erase(std::unique(scratch.begin(), scratch.end()), scratch.end());
+    return cudaStreamUpdateCaptureDependencies(main, scratch.data(), scratch.size(), cudaStreamSetCaptureDependencies);
+}
+
 cudaError_t chol_tiles(double* A, int ld, int nb, double* Linv, int* info, const DagStreams& D, cudaStream_t main,
                        int64_t* launches, const TileView& V, int k_begin, int k_end, int rank) {
+    {
+        static const bool exact = !(std::getenv("FEBA_EXACT_DEPS") && std::atoi(std::getenv("FEBA_EXACT_DEPS")) == 0);
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (exact && cudaStreamIsCapturing(main, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusActive)
+            return chol_tiles_captured(A, ld, nb, Linv, info, main, launches, V, k_begin, k_end, rank);
+    }
     const int NT = V.NT;
     const int NR = NT + 1;
     auto on = [&](int i, int j) { return V.nz == nullptr || V.nz[(size_t)i * NR + j] != 0; };
@@ -1124,12 +1214,20 @@ __global__ void k_combine(const double* __restrict__ A, int ld, int n_pad, int n
 // Backward substitution L' x = y, one launch per 64-block step k = nb-1 .. 0:
 //   x_k = L_kk^-T y_k (every CTA recomputes it from the inverted diagonal factor -- 4096 FMAs -- so
 //   no second launch is needed), CTA 0 stores it, then y_c -= sum_r L[k*64+r][c] x_k[r] for the
-//   columns c < k*64, one warp per column.
-// c_begin: first column that can be non-zero in block row k (0 = dense; sparse form: the envelope of the
-// supertile pattern -- supertiles left of it were never written and are exactly zero).
+//   columns c < k*64 that can be non-zero in block row k, one warp per column.
+// The columns come as up to kMaxSeg ranges [c0, c1): a dense system has one range [0, k*64); with a plan
+// (feba_order.h) only the column tiles coupled with the row's tile are visited -- supertiles outside the pattern
+// were never written and are exactly zero -- which also keeps the steps of independent subtrees of a
+// nested-dissection order apart, so that they may run side by side.
+constexpr int kMaxSeg = 24;
+struct ColSegs {
+    int n;
+    int c0[kMaxSeg], c1[kMaxSeg];
+};
+
 __global__ void __launch_bounds__(256) k_backstep(const double* __restrict__ A, int ld, int k,
                                                   const double* __restrict__ Linv_k, double* __restrict__ y,
-                                                  double* __restrict__ x_out, int c_begin) {
+                                                  double* __restrict__ x_out, ColSegs segs) {
     __shared__ double sx[kBlk];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double* yk = y + (size_t)k * kBlk;
@@ -1147,14 +1245,22 @@ __global__ void __launch_bounds__(256) k_backstep(const double* __restrict__ A, 
         if (qq == 0) sx[j] = acc;
     }
     __syncthreads();
-    const int ncols = k * kBlk;
     const double x0 = sx[lane], x1 = sx[lane + 32];
-    for (int c = c_begin + blockIdx.x * 8 + warp; c < ncols; c += gridDim.x * 8) {
-        const double* colp = A + (size_t)k * kBlk + (size_t)ld * c;
-        double acc = colp[lane] * x0 + colp[lane + 32] * x1;
+    int done = 0;                                   // columns of the earlier ranges
+    for (int sgi = 0; sgi < segs.n; ++sgi) {
+        const int c0 = segs.c0[sgi], len = segs.c1[sgi] - c0;
+        // global column index over all ranges -> CTAs and warps as if the ranges were one
+        int first = (blockIdx.x * 8 + warp) - done % (gridDim.x * 8);
+        if (first < 0) first += gridDim.x * 8;
+        for (int q = first; q < len; q += gridDim.x * 8) {
+            const int c = c0 + q;
+            const double* colp = A + (size_t)k * kBlk + (size_t)ld * c;
+            double acc = colp[lane] * x0 + colp[lane + 32] * x1;
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-        if (lane == 0) y[c] -= acc;
+            for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+            if (lane == 0) y[c] -= acc;
+        }
+        done += len;
     }
     // other CTAs may still be reading y_k, so the solution goes to a separate vector
     if (blockIdx.x == 0 && tid < kBlk) x_out[(size_t)k * kBlk + tid] = sx[tid];
@@ -1162,9 +1268,12 @@ __global__ void __launch_bounds__(256) k_backstep(const double* __restrict__ A, 
 
 // block_owner (host, nb entries, optional; group runs): blocks of subtrees owned by other ranks are skipped --
 // their rows of `sol` stay zero and come from the owners through the sum over the ranks that follows.
+// V (optional): the plan's tiles and pattern.  While `st` is being captured into a CUDA graph the steps get their
+// true dependencies (as chol_tiles_captured): a step waits for the last writers of y in its own tile and in the
+// column tiles it updates.
 cudaError_t border_and_backsolve(double* A, int ld, int nb, const double* Linv, int inner, double* work,
                                  double* ywork, double* sol, int* info, int sm_count, cudaStream_t st,
-                                 int64_t* launches, int sparse_datum, const int* row_first_block,
+                                 int64_t* launches, int sparse_datum, const TileView* V,
                                  const int* block_owner, int rank) {
     const int n_pad = nb * kBlk;
     if (block_owner) {
@@ -1179,15 +1288,104 @@ cudaError_t border_and_backsolve(double* A, int ld, int nb, const double* Linv, 
     const int ncoef = inner ? (sparse_datum ? 2 * kDatumCols : kDatumCols) : 0;
     k_combine<<<(n_pad + 255) / 256, 256, 0, st>>>(A, ld, n_pad, ncoef, work, ywork);
     ++*launches;
+    const bool masked = V && V->nz;
+    const int NT = V ? V->NT : 1, NR = NT + 1;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    static const bool exact_env = !(std::getenv("FEBA_EXACT_DEPS") && std::atoi(std::getenv("FEBA_EXACT_DEPS")) == 0);
+    const bool exact = masked && exact_env && cudaStreamIsCapturing(st, &cap) == cudaSuccess &&
+                       cap == cudaStreamCaptureStatusActive;
+    typedef std::vector<cudaGraphNode_t> NodeSet;
+    NodeSet base, scratch;
+    std::vector<NodeSet> last;
+    std::vector<char> written;
+    auto current = [&](NodeSet& out) -> cudaError_t {
+        cudaStreamCaptureStatus s2;
+        const cudaGraphNode_t* deps = nullptr;
+        size_t nd = 0;
+        cudaError_t e = cudaStreamGetCaptureInfo(st, &s2, nullptr, nullptr, &deps, &nd);
+        if (e != cudaSuccess) return e;
+        out.assign(deps, deps + nd);
+        return cudaSuccess;
+    };
+    if (exact) {
+        cudaError_t e = current(base);
+        if (e != cudaSuccess) return e;
+        last.resize((size_t)NT);
+        written.assign((size_t)NT, 0);
+    }
+    std::vector<int> tiles;                               // column tiles a step updates (plus its own)
+    int t_of_k = NT - 1;
     for (int k = nb - 1; k >= 0; --k) {
         if (block_owner && block_owner[k] >= 0 && block_owner[k] != rank) continue;
-        int c_begin = row_first_block ? row_first_block[k] * kBlk : 0;
-        if (c_begin > k * kBlk) c_begin = k * kBlk;
-        int grid = (k * kBlk - c_begin + 7) / 8;
+        ColSegs segs;
+        segs.n = 0;
+        tiles.clear();
+        if (!masked) {
+            segs.n = 1;
+            segs.c0[0] = 0;
+            segs.c1[0] = k * kBlk;
+        } else {
+            while (t_of_k > 0 && V->b0[t_of_k] > k) --t_of_k;
+            const int t = t_of_k;
+            auto add = [&](int c0, int c1) {
+                if (c1 <= c0) return;
+                if (segs.n > 0 && segs.c1[segs.n - 1] == c0) segs.c1[segs.n - 1] = c1;
+                else if (segs.n < kMaxSeg) { segs.c0[segs.n] = c0; segs.c1[segs.n] = c1; ++segs.n; }
+                else segs.n = kMaxSeg + 1;                  // too many ranges: one range over everything below
+            };
+            for (int j = 0; j < t && segs.n <= kMaxSeg; ++j)
+                if (V->nz[(size_t)t * NR + j] && V->b0[j + 1] > V->b0[j]) {
+                    add(V->b0[j] * kBlk, V->b0[j + 1] * kBlk);
+                    tiles.push_back(j);
+                }
+            if (segs.n <= kMaxSeg) add(V->b0[t] * kBlk, k * kBlk);
+            if (segs.n > kMaxSeg) {
+                int first = 0;
+                while (first < t && !V->nz[(size_t)t * NR + first]) ++first;
+                segs.n = 1;
+                segs.c0[0] = V->b0[first] * kBlk;
+                segs.c1[0] = k * kBlk;
+                tiles.clear();
+                for (int j = first; j < t; ++j) tiles.push_back(j);
+            }
+            tiles.push_back(t);
+        }
+        int cols = 0;
+        for (int q = 0; q < segs.n; ++q) cols += segs.c1[q] - segs.c0[q];
+        int grid = (cols + 7) / 8;
         if (grid > 2 * sm_count) grid = 2 * sm_count;
         if (grid < 1) grid = 1;
-        k_backstep<<<grid, 256, 0, st>>>(A, ld, k, LINV(Linv, k), ywork, sol, c_begin);
+        if (exact) {
+            scratch.clear();
+            for (int j : tiles) {
+                const NodeSet& d = written[(size_t)j] ? last[(size_t)j] : base;
+                scratch.insert(scratch.end(), d.begin(), d.end());
+            }
+            std::sort(scratch.begin(), scratch.end());
+            scratch.erase(std::unique(scratch.begin(), scratch.end()), scratch.end());
+            cudaError_t e = cudaStreamUpdateCaptureDependencies(st, scratch.data(), scratch.size(), cudaStreamSetCaptureDependencies);
+            if (e != cudaSuccess) return e;
+        }
+        k_backstep<<<grid, 256, 0, st>>>(A, ld, k, LINV(Linv, k), ywork, sol, segs);
         ++*launches;
+        if (exact) {
+            NodeSet now;
+            cudaError_t e = current(now);
+            if (e != cudaSuccess) return e;
+            for (int j : tiles) {
+                last[(size_t)j] = now;
+                written[(size_t)j] = 1;
+            }
+        }
+    }
+    if (exact) {
+        scratch = base;
+        for (size_t t = 0; t < last.size(); ++t)
+            if (written[t]) scratch.insert(scratch.end(), last[t].begin(), last[t].end());
+        std::sort(scratch.begin(), scratch.end());
+        scratch.erase(std::unique(scratch.begin(), scratch.end()), scratch.end());
+        cudaError_t e = cudaStreamUpdateCaptureDependencies(st, scratch.data(), scratch.size(), cudaStreamSetCaptureDependencies);
+        if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();
 }

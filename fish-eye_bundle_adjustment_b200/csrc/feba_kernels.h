@@ -109,10 +109,11 @@ void dist_prof_report();   // FEBA_DIST_PROF=1: prints the time stamps of the la
 // ywork (n_pad) := combination of the augmented rows: y = Y'(0,:) + sum_k kvec[k] Y'(1+k,:) where kvec
 // solves the 7x7 border system (inner != 0), else y = Y'(0,:).  Then sol := L^-T y.
 // sparse_datum != 0: 14 coefficients from the border of the sparse-datum form (feba_sparse.h).
-// row_first_block (host, nb entries, optional): first 64-block column that can be non-zero in each block row.
+// V (optional): tiles / pattern of the plan -- block rows visit the coupled column tiles only.
+// block_owner / rank (optional, group runs): blocks owned by other ranks are skipped, their rows of sol stay 0.
 cudaError_t border_and_backsolve(double* A, int ld, int nb, const double* Linv, int inner, double* work,
                                  double* ywork, double* sol, int* info, int sm_count, cudaStream_t st,
-                                 int64_t* launches, int sparse_datum = 0, const int* row_first_block = nullptr,
+                                 int64_t* launches, int sparse_datum = 0, const TileView* V = nullptr,
                                  const int* block_owner = nullptr, int rank = 0);
 
 // Covariance stage: U = L^-T, Q = M~^-1 (n_pad x n_pad, lower valid), Y = M~^-1 G~ (n_pad x 8), T7inv 7x7.
