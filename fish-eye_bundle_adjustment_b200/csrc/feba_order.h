@@ -35,7 +35,7 @@ struct PlanOptions {
     int mode = 0;            // 0 automatic, 1 force a masked plan, -1 force the identity plan
     int max_depth = 12;      // deepest level of the dissection
     int leaf_images = 96;    // parts of at most this many images are not cut further
-    int tile_max = 8;        // supertile cap in 64-row blocks
+    int tile_max = 6;        // supertile cap in 64-row blocks (config 4, factorisation: 6 / 8 / 12 / 16 -> 2.8 / 3.1 / 3.1 / 3.7 ms)
     double sep_frac = 0.30;  // a cut whose separator exceeds this fraction of the part is rejected
     int identity_tile = 0;   // identity plan: uniform supertiles of this many blocks (0: one tile)
     int min_blocks = 48;     // automatic mode: smaller reduced systems keep the identity plan
