@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfeba.so")
 SOURCES = ("feba_api.cu", "feba_kernels.cu", "feba_assemble.cu", "feba_chol.cu", "feba_dist.cu", "feba_green.cu",
            "feba_pack.cpp")            # the last one is host-only C++ (problem build, include/feba_pack.h)
-HEADERS = ("feba_dev.h", "feba_kernels.h", "feba_model.cuh", "feba_sparse.h", "feba_order.h", os.path.join("..", "..", "include", "feba.h"),
+HEADERS = ("feba_dev.h", "feba_kernels.h", "feba_model.cuh", "feba_sparse.h", "feba_order.h", "feba_chunks.h", os.path.join("..", "..", "include", "feba.h"),
            os.path.join("..", "..", "include", "feba_pack.h"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall,-pthread,-Wno-unknown-pragmas", "--use_fast_math=false"]

@@ -20,6 +20,7 @@
 #include "feba_dev.h"
 #include "feba_kernels.h"
 #include "feba_model.cuh"
+#include "feba_chunks.h"
 #include "feba_order.h"
 #include "feba_sparse.h"
 
@@ -78,6 +79,8 @@ struct feba_handle {
     double* packed = nullptr;     // lower trapezoids of S, contiguous (feba_reduced_pack)
     size_t packed_count = 0;
     long long n_pairs = 0;
+    ChunkDev chunks{};            // chunk form of the assembly (feba_chunks.h); n_chunks == 0: image-major form
+    bool use_chunks = false;
     int64_t u = 0;
     int n_partial = 0;
     int64_t launches = 0;
@@ -643,10 +646,14 @@ static int create_impl(const feba_problem* pr, int rank, int world, const void* 
             return v;
         };
         std::vector<std::pair<unsigned long long, int>> key((size_t)n_seg);
+        // one scale for the three axes (the largest extent): a flat block (aerial: little relief) is ordered by its
+        // two long axes -- scaling every axis to its own extent would make the curve 3-D there and a run of 64 points
+        // five times wider (measured on BASELINE configs[3]: 31 instead of ~13 images per chunk of the assembly)
+        double ext = 0.0;
+        for (int k2 = 0; k2 < 3; ++k2) ext = std::max(ext, hi[k2] - lo[k2]);
         for (int sg = 0; sg < n_seg; ++sg) {
             unsigned long long code = 0;
             for (int k2 = 0; k2 < 3; ++k2) {
-                const double ext = hi[k2] - lo[k2];
                 const double t = ext > 0 ? (pr->xyz0[3 * (size_t)seg_pt[(size_t)sg] + k2] - lo[k2]) / ext : 0.0;
                 unsigned long long q = std::isfinite(t) ? (unsigned long long)(t * 2097151.0) : 0ULL;
                 code |= spread(q) << k2;
@@ -774,12 +781,60 @@ static int create_impl(const feba_problem* pr, int rank, int world, const void* 
         if (rc_pool) return rc_pool;
     }
     CU(h, dev_alloc(h, &P.cam_part, (size_t)assemble_warps(P, h->sm_count) * kCamPart));
+    // ---- assembly schedule, static for the life of the handle: chunk form (feba_chunks.h) unless several cameras
+    // have unknowns (that point pass adds cross-camera terms itself) or FEBA_CHUNKS=0
     {
-        // image-pair schedule of the Schur blocks: static for the life of the handle
-        void *kp = nullptr, *kb = nullptr;
-        CU(h, build_pair_schedule(P, doseg, &h->n_pairs, &kp, &kb, h->stream));
-        if (kp) h->allocs.push_back(kp);
-        if (kb) h->allocs.push_back(kb);
+        const bool mc = P.uc > 0 && P.n_cam > 1;
+        const char* e_c = std::getenv("FEBA_CHUNKS");
+        if (!mc && n_seg > 0 && !(e_c && std::atoi(e_c) == 0)) {
+            std::vector<unsigned char> seg_tie((size_t)n_seg);
+            for (int sg = 0; sg < n_seg; ++sg) seg_tie[(size_t)sg] = pr->pt_tie[seg_pt[(size_t)sg]] >= 0;
+            ChunkSchedule cs = build_chunks(P.n_img, n_seg, seg_start.data(), simg.data(), seg_tie.data(),
+                                            h->plan.img_row.data());
+            if (cs.ok && cs.n_chunks > 0) {
+                ChunkDev& D = h->chunks;
+                int *d_obs0, *d_img0, *d_slot_obs0, *d_blk0, *d_pair0, *d_slot_img, *d_tptr, *d_tslots, *d_ba, *d_bb, *d_bptr, *d_bslots;
+                unsigned short* d_slot_obs;
+                unsigned int* d_pairs;
+                CU(h, upload(h, &d_obs0, cs.obs0.data(), cs.obs0.size()));
+                CU(h, upload(h, &d_img0, cs.img0.data(), cs.img0.size()));
+                CU(h, upload(h, &d_slot_obs0, cs.slot_obs0.data(), cs.slot_obs0.size()));
+                CU(h, upload(h, &d_slot_obs, reinterpret_cast<const unsigned short*>(cs.slot_obs.data()), cs.slot_obs.size()));
+                CU(h, upload(h, &d_blk0, cs.blk0.data(), cs.blk0.size()));
+                CU(h, upload(h, &d_pair0, cs.bslot_pair0.data(), cs.bslot_pair0.size()));
+                CU(h, upload(h, &d_pairs, reinterpret_cast<const unsigned int*>(cs.pairs.data()), cs.pairs.size()));
+                CU(h, upload(h, &d_slot_img, cs.slot_img.data(), cs.slot_img.size()));
+                CU(h, upload(h, &d_tptr, cs.timg_ptr.data(), cs.timg_ptr.size()));
+                CU(h, upload(h, &d_tslots, cs.timg_slots.data(), cs.timg_slots.size()));
+                CU(h, upload(h, &d_ba, cs.tblk_a.data(), cs.tblk_a.size()));
+                CU(h, upload(h, &d_bb, cs.tblk_b.data(), cs.tblk_b.size()));
+                CU(h, upload(h, &d_bptr, cs.tblk_ptr.data(), cs.tblk_ptr.size()));
+                CU(h, upload(h, &d_bslots, cs.tblk_slots.data(), cs.tblk_slots.size()));
+                CU(h, dev_alloc(h, &D.img_part, cs.slot_img.size() * (size_t)kImgPart));
+                CU(h, dev_alloc(h, &D.blk_part, cs.bslot_a.size() * (size_t)kBlkPart));
+                CU(h, cudaStreamSynchronize(h->stream));        // the schedule's host vectors go out of scope
+                D.n_chunks = cs.n_chunks;
+                D.obs0 = d_obs0; D.img0 = d_img0; D.slot_obs0 = d_slot_obs0; D.slot_obs = d_slot_obs;
+                D.blk0 = d_blk0; D.bslot_pair0 = d_pair0; D.pairs = d_pairs;
+                D.slot_img = d_slot_img; D.timg_ptr = d_tptr; D.timg_slots = d_tslots;
+                D.n_tblk = (int)cs.tblk_a.size();
+                D.tblk_a = d_ba; D.tblk_b = d_bb; D.tblk_ptr = d_bptr; D.tblk_slots = d_bslots;
+                h->n_pairs = cs.n_pairs;
+                h->use_chunks = true;
+                P.ipos = nullptr;                                // records at the observations' own positions
+                if (std::getenv("FEBA_VERBOSE"))
+                    fprintf(stderr, "[feba] assembly: %d chunks, %zu image slots, %zu block slots (%d distinct image pairs), "
+                                    "%lld observation pairs\n", cs.n_chunks, cs.slot_img.size(), cs.bslot_a.size(),
+                            D.n_tblk, cs.n_pairs);
+            }
+        }
+        if (!h->use_chunks) {
+            // image-major form: image-pair schedule of the Schur blocks on the device
+            void *kp = nullptr, *kb = nullptr;
+            CU(h, build_pair_schedule(P, doseg, &h->n_pairs, &kp, &kb, h->stream));
+            if (kp) h->allocs.push_back(kp);
+            if (kb) h->allocs.push_back(kb);
+        }
     }
     // sparse-datum form (feba_sparse.h) on a masked plan of a free network: flags of the datum images
     if (h->plan.masked && P.inner) {
@@ -939,7 +994,7 @@ static int enqueue_assemble(feba_handle* h) {
     CU(h, cudaMemsetAsync(h->info, 0, sizeof(int), h->stream));
     CU(h, record(h, 1));
     ++h->launches;
-    CU(h, launch_assemble(P, h->sm_count, h->info, h->stream, &h->launches));
+    CU(h, launch_assemble(P, h->sm_count, h->info, h->stream, &h->launches, h->use_chunks ? &h->chunks : nullptr));
     CU(h, record(h, 2));
     return FEBA_OK;
 }

@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
                     Zm[r][2] = t0 * i20 + t1 * i21 + t2 * i22;
                     ra[r] = pw[r] * J.w[r] - (Zm[r][0] * ut[0] + Zm[r][1] * ut[1] + Zm[r][2] * ut[2]);
                 }
-                sm.pos[lane] = P.ipos[o];
+                sm.pos[lane] = P.ipos ? P.ipos[o] : o;      // image-major (round-1 form) or the observation's own position
                 double* r1 = buf + kRec1 * lane;
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(128) k_point_pass_mc(DevProblem P, int* __rest
                     Zm[r][2] = t0 * i20 + t1 * i21 + t2 * i22;
                     ra[r] = pw[r] * J.w[r] - (Zm[r][0] * ut[0] + Zm[r][1] * ut[1] + Zm[r][2] * ut[2]);
                 }
-                sm.pos[lane] = P.ipos[o];
+                sm.pos[lane] = P.ipos ? P.ipos[o] : o;      // image-major (round-1 form) or the observation's own position
                 double* r1 = buf + kRec1 * lane;
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
@@ -766,6 +766,185 @@ __global__ void __launch_bounds__(128) k_pair_pass(DevProblem P) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Chunk form of the image / image-pair passes (feba_chunks.h): records are chunk-major (the point pass wrote them
+// at the observations' own positions), one CTA per chunk of consecutive points, one LANE per item:
+//   image slot  : the chunk's observations of one image -> diagonal block (21), right-hand side (6),
+//                 camera x image block (NC x 6), the sums of k_image_pass;
+//   block slot  : the chunk's observation pairs of one image pair -> 6 x 6 block, the sums of k_pair_pass;
+// results go to PARTIAL blocks (one writer each).  The ~200 KB of records of a chunk are read from HBM once and
+// re-read from L1/L2 (each record enters ~9 pairs).
+constexpr int kImgPartDev = 108;      // = feba_chunks.h::kImgPart: 27 + 6 * 13, padded to a multiple of 4
+
+template <int NK, bool HAS_CAM>
+__global__ void __launch_bounds__(256, 2) k_chunk_reduce(DevProblem P, ChunkDev C) {
+    constexpr int NC = NK + 5;
+    constexpr int R2 = 2 + 2 * NC;
+    constexpr int CG = 5;                                        // camera rows per image sub-item
+    constexpr int NSUB = HAS_CAM ? 1 + (NC + CG - 1) / CG : 1;   // diagonal block + rhs, then groups of camera rows
+    for (int c = blockIdx.x; c < C.n_chunks; c += gridDim.x) {
+        const size_t o0 = (size_t)C.obs0[c];
+        const int s_lo = C.img0[c], n_is = C.img0[c + 1] - s_lo;
+        const int b_lo = C.blk0[c], n_bs = C.blk0[c + 1] - b_lo;
+        const int n_items = n_bs + NSUB * n_is;
+        // one LANE per item, working through the item's pairs / observations with its sums in registers: no
+        // cross-lane reduction, and 32 independent gather streams per warp.  Image pairs come longest first
+        // (feba_chunks.h), so the lanes of a warp finish together.
+        for (int item = threadIdx.x; item < n_items; item += blockDim.x) {
+            if (item < n_bs) {
+                const int bs = b_lo + item;
+                const int q0 = C.bslot_pair0[bs], q1 = C.bslot_pair0[bs + 1];
+                double acc[36];
+#pragma unroll
+                for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+                for (int q = q0; q < q1; ++q) {
+                    const unsigned int pr = C.pairs[q];
+                    const double2* ra2 = reinterpret_cast<const double2*>(P.rec1 + (size_t)kRec1 * (o0 + (pr & 0xffffu)));
+                    const double2* rb2 = reinterpret_cast<const double2*>(P.rec1 + (size_t)kRec1 * (o0 + (pr >> 16)));
+                    double ra[kRec1], rb[kRec1];
+#pragma unroll
+                    for (int k = 0; k < kRec1 / 2; ++k) {
+                        const double2 va = ra2[k], vb = rb2[k];
+                        ra[2 * k] = va.x; ra[2 * k + 1] = va.y;
+                        rb[2 * k] = vb.x; rb[2 * k + 1] = vb.y;
+                    }
+                    const double c00 = ra[12] * rb[12] + ra[13] * rb[13] + ra[14] * rb[14];
+                    const double c01 = ra[12] * rb[15] + ra[13] * rb[16] + ra[14] * rb[17];
+                    const double c10 = ra[15] * rb[12] + ra[16] * rb[13] + ra[17] * rb[14];
+                    const double c11 = ra[15] * rb[15] + ra[16] * rb[16] + ra[17] * rb[17];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        const double e0 = ra[i] * c00 + ra[6 + i] * c10, e1 = ra[i] * c01 + ra[6 + i] * c11;
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) acc[6 * i + j] += e0 * rb[j] + e1 * rb[6 + j];
+                    }
+                }
+                double2* out = reinterpret_cast<double2*>(C.blk_part + (size_t)36 * bs);
+#pragma unroll
+                for (int k = 0; k < 18; ++k) out[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
+            } else {
+                const int r = item - n_bs;
+                const int sub = r / n_is, slot = s_lo + (r - sub * n_is);
+                const int q0 = C.slot_obs0[slot], q1 = C.slot_obs0[slot + 1];
+                double* out = C.img_part + (size_t)kImgPartDev * slot;
+                if (sub == 0) {   // diagonal block Je'(P - Z Z')Je and right-hand side Je' r
+                    double acc[27];
+#pragma unroll
+                    for (int k = 0; k < 27; ++k) acc[k] = 0.0;
+                    for (int q = q0; q < q1; ++q) {
+                        const size_t t = o0 + C.slot_obs[q];
+                        const double2* r1v = reinterpret_cast<const double2*>(P.rec1 + (size_t)kRec1 * t);
+                        double r1[kRec1];
+#pragma unroll
+                        for (int k = 0; k < kRec1 / 2; ++k) { const double2 v = r1v[k]; r1[2 * k] = v.x; r1[2 * k + 1] = v.y; }
+                        const double2 rav = *reinterpret_cast<const double2*>(P.rec2 + (size_t)R2 * t);
+                        const double p00 = P.px - (r1[12] * r1[12] + r1[13] * r1[13] + r1[14] * r1[14]);
+                        const double p01 = -(r1[12] * r1[15] + r1[13] * r1[16] + r1[14] * r1[17]);
+                        const double p11 = P.py - (r1[15] * r1[15] + r1[16] * r1[16] + r1[17] * r1[17]);
+                        int e = 0;
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) {
+                            const double t0 = p00 * r1[i] + p01 * r1[6 + i], t1 = p01 * r1[i] + p11 * r1[6 + i];
+#pragma unroll
+                            for (int j = 0; j <= i; ++j) acc[e++] += t0 * r1[j] + t1 * r1[6 + j];
+                        }
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) acc[21 + i] += r1[i] * rav.x + r1[6 + i] * rav.y;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 27; ++k) out[k] = acc[k];
+                } else if (HAS_CAM) {   // camera rows j0 .. j0 + CG - 1 of the camera x image block  sum_a H_a Je_a
+                    const int j0 = CG * (sub - 1);
+                    double acc[CG * 6];
+#pragma unroll
+                    for (int k = 0; k < CG * 6; ++k) acc[k] = 0.0;
+                    for (int q = q0; q < q1; ++q) {
+                        const size_t t = o0 + C.slot_obs[q];
+                        const double2* r1v = reinterpret_cast<const double2*>(P.rec1 + (size_t)kRec1 * t);
+                        const double2* r2v = reinterpret_cast<const double2*>(P.rec2 + (size_t)R2 * t + 2);
+                        double Je[2][6];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const double2 v0 = r1v[k], v1 = r1v[3 + k];
+                            Je[0][2 * k] = v0.x; Je[0][2 * k + 1] = v0.y;
+                            Je[1][2 * k] = v1.x; Je[1][2 * k + 1] = v1.y;
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < CG; ++jj) {
+                            if (j0 + jj < NC) {
+                                const double2 hv = r2v[j0 + jj];
+#pragma unroll
+                                for (int i = 0; i < 6; ++i) acc[6 * jj + i] += hv.x * Je[0][i] + hv.y * Je[1][i];
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < CG; ++jj)
+                        if (j0 + jj < NC) {
+#pragma unroll
+                            for (int i = 0; i < 6; ++i) out[27 + 6 * (j0 + jj) + i] = acc[6 * jj + i];
+                        }
+                }
+            }
+        }
+    }
+}
+
+// Final sums of the image partials: one CTA of 128 threads per image, thread e owns entry e of the partial
+// (diagonal block, right-hand side, camera x image block); slots are added in chunk order.
+__global__ void __launch_bounds__(128) k_sum_img_parts(DevProblem P, ChunkDev C) {
+    const int NE = 27 + (P.uc > 0 ? 6 * P.NC : 0);
+    const int e = threadIdx.x;
+    for (int img = blockIdx.x; img < P.n_img; img += gridDim.x) {
+        if (e >= NE) continue;
+        double tot = 0.0;
+        for (int q = C.timg_ptr[img]; q < C.timg_ptr[img + 1]; ++q)
+            tot += C.img_part[(size_t)kImgPartDev * C.timg_slots[q] + e];
+        const size_t col0 = (size_t)P.img_row[img];
+        if (e < 21) {
+            int i = 0;
+            while ((i + 1) * (i + 2) / 2 <= e) ++i;
+            const int j = e - i * (i + 1) / 2;
+            if (P.ecol[i] >= 0 && P.ecol[j] >= 0) P.S[(col0 + P.ecol[i]) + (size_t)P.ld * (col0 + P.ecol[j])] += tot;
+        } else if (e < 27) {
+            if (P.ecol[e - 21] >= 0) P.S[(size_t)P.n_pad + (size_t)P.ld * (col0 + P.ecol[e - 21])] += tot;
+        } else {
+            const int j = (e - 27) / 6, i = (e - 27) - 6 * j;
+            if (P.ccol[j] >= 0 && P.ecol[i] >= 0) {
+                const int cam = P.img_cam[img];
+                P.S[(size_t)(P.off_cam + P.uc * cam + P.ccol[j]) + (size_t)P.ld * (col0 + P.ecol[i])] += tot;
+            }
+        }
+    }
+}
+
+// Final sums of the image-pair partials: one warp per distinct image pair (row(a) >= row(b)), lanes over the 36
+// entries, slots in chunk order:  S[i_a, i_b] -= sum.
+__global__ void __launch_bounds__(128) k_sum_blk_parts(DevProblem P, ChunkDev C) {
+    const int lane = threadIdx.x & 31;
+    const int nwarp = gridDim.x * (blockDim.x >> 5);
+    for (int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < C.n_tblk; t += nwarp) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int q = C.tblk_ptr[t]; q < C.tblk_ptr[t + 1]; ++q) {
+            const double* p = C.blk_part + (size_t)36 * C.tblk_slots[q];
+            a0 += p[lane];
+            if (lane < 4) a1 += p[32 + lane];
+        }
+        const int ia = C.tblk_a[t], ib = C.tblk_b[t];
+        const size_t rowa = (size_t)P.img_row[ia], colb = (size_t)P.img_row[ib];
+        const bool diag = ia == ib;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = lane + 32 * h;
+            if (k < 36) {
+                const int i = k / 6, j = k - 6 * i;
+                if (P.ecol[i] >= 0 && P.ecol[j] >= 0 && (!diag || j <= i))
+                    P.S[(rowa + P.ecol[i]) + (size_t)P.ld * (colb + P.ecol[j])] -= (h ? a1 : a0);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // schedule construction (once per problem, on the device)
 
 // A pair (o, b) of observations of one tie point belongs to the block (image of o, image of b) when the image of b
@@ -988,9 +1167,37 @@ static cudaError_t launch_point_pass_mc_t(const DevProblem& P, int sm_count, int
     return cudaGetLastError();
 }
 
-cudaError_t launch_assemble(const DevProblem& P, int sm_count, int* info, cudaStream_t st, int64_t* launches) {
+cudaError_t launch_assemble(const DevProblem& P, int sm_count, int* info, cudaStream_t st, int64_t* launches,
+                            const ChunkDev* chunks) {
     const bool hc = P.uc > 0;
     const bool mc = hc && P.n_cam > 1;
+    if (chunks && !mc && P.n_seg > 0) {
+        // chunk form: point pass (records at the observations' own positions), one CTA per chunk for the image
+        // and image-pair partials, fixed-order final sums
+        cudaError_t e = cudaSuccess;
+        if (group_lanes(P) == 16) {
+            FEBA_NK_DISPATCH2(P.NK, hc, (e = launch_point_pass_t<NK_, HC_, 16>(P, sm_count, st)));
+        } else {
+            FEBA_NK_DISPATCH2(P.NK, hc, (e = launch_point_pass_t<NK_, HC_, 32>(P, sm_count, st)));
+        }
+        if (e != cudaSuccess) return e;
+        int grid = chunks->n_chunks < sm_count * 4 ? chunks->n_chunks : sm_count * 4;
+        FEBA_NK_DISPATCH2(P.NK, hc, (k_chunk_reduce<NK_, HC_><<<grid, 256, 0, st>>>(P, *chunks)));
+        *launches += 2;
+        if (hc) {
+            k_cam_reduce<<<1, 1024, 0, st>>>(P, assemble_warps(P, sm_count));
+            ++*launches;
+        }
+        k_sum_img_parts<<<P.n_img < sm_count * 8 ? P.n_img : sm_count * 8, 128, 0, st>>>(P, *chunks);
+        ++*launches;
+        if (chunks->n_tblk > 0) {
+            int g2 = (chunks->n_tblk + 3) / 4;
+            if (g2 > sm_count * 16) g2 = sm_count * 16;
+            k_sum_blk_parts<<<g2, 128, 0, st>>>(P, *chunks);
+            ++*launches;
+        }
+        return cudaGetLastError();
+    }
     if (P.n_seg > 0) {
         cudaError_t e = cudaSuccess;
         if (mc) {

@@ -27,7 +27,32 @@ cudaError_t launch_clear_blocks(const DevProblem& P, const int2* blocks, int n_b
 cudaError_t build_pair_schedule(DevProblem& P, const int* d_oseg, long long* n_pairs_out, void** keep_pairs,
                                 void** keep_blocks, cudaStream_t st);
 int assemble_warps(const DevProblem& P, int sm_count);
-cudaError_t launch_assemble(const DevProblem& P, int sm_count, int* info, cudaStream_t st, int64_t* launches);
+// chunk schedule on the device (feba_chunks.h; arrays owned by the handle)
+struct ChunkDev {
+    int n_chunks;
+    const int* obs0;
+    const int* img0;
+    const int* slot_obs0;
+    const unsigned short* slot_obs;
+    const int* blk0;
+    const int* bslot_pair0;
+    const unsigned int* pairs;
+    double* img_part;       // image slots x kImgPart: [0,21) diagonal block (packed lower), [21,27) rhs, [27, 27+6NC) H Je
+    double* blk_part;       // block slots x 36
+    // final sums
+    const int* slot_img;
+    const int* timg_ptr;
+    const int* timg_slots;
+    int n_tblk;
+    const int* tblk_a;
+    const int* tblk_b;
+    const int* tblk_ptr;
+    const int* tblk_slots;
+};
+// chunks == nullptr: the image-major form of round 1 (image pass + image-pair pass over the pair schedule; always
+// used with several cameras AND camera unknowns)
+cudaError_t launch_assemble(const DevProblem& P, int sm_count, int* info, cudaStream_t st, int64_t* launches,
+                            const ChunkDev* chunks = nullptr);
 int backsub_warps(const DevProblem& P, int sm_count);
 cudaError_t launch_backsub(const DevProblem& P, int sm_count, cudaStream_t st);
 cudaError_t launch_update_cam(const DevProblem& P, const double* sol, const double* dvec, double* dcam,

@@ -198,7 +198,8 @@ struct Cut {
 
 // Cut `part` across axis `ax` after its first `na` images (sorted along ax): side[] = 1 for the first group, 2 for
 // the second; the separator is the smaller of the two boundaries.  `side` is a scratch array of n zeros.
-inline Cut cut_at(const Graph& g, const std::vector<int>& sorted, int na, std::vector<unsigned char>& side) {
+// force: -1 = the smaller boundary, 1 / 0 = the boundary of the first / second group.
+inline Cut cut_at(const Graph& g, const std::vector<int>& sorted, int na, std::vector<unsigned char>& side, int force = -1) {
     Cut c;
     const int n = (int)sorted.size();
     for (int k = 0; k < n; ++k) side[(size_t)sorted[(size_t)k]] = k < na ? 1 : 2;
@@ -210,7 +211,7 @@ inline Cut cut_at(const Graph& g, const std::vector<int>& sorted, int na, std::v
         for (int q = g.ptr[v]; q < g.ptr[v + 1] && !touch; ++q) touch = side[(size_t)g.idx[q]] == other;
         if (touch) (side[(size_t)v] == 1 ? bA : bB).push_back(v);
     }
-    const bool fromA = bA.size() <= bB.size();
+    const bool fromA = force < 0 ? bA.size() <= bB.size() : force == 1;
     c.from_first = fromA;
     c.sep = fromA ? bA : bB;
     for (int v : c.sep) side[(size_t)v] = 3;
@@ -244,19 +245,31 @@ inline Cut best_cut(const Graph& g, const std::vector<int>& part, std::vector<un
         axes[0] = o[0];
         axes[1] = ext[o[1]] > 0.0 ? o[1] : -1;
     }
+    // candidates: both axes x both sides of the cut; the cut position is moved so that the halves WITHOUT the
+    // separator balance.  Score: separator size, penalised by the imbalance of the halves (a group of GPUs waits
+    // for its largest subtree; on one GPU the longest chain does).
+    double best_score = 1e300;
     for (int c = 0; c < 2; ++c) {
         if (c == 1 && axes[1] < 0) break;
         std::vector<int> sorted = part;
         sort_along(g, sorted, axes[c]);
-        Cut first = cut_at(g, sorted, n / 2, side);
-        if (!first.ok) continue;
-        // second pass: move the cut so that the halves WITHOUT the separator balance
-        int na = n / 2 + (first.from_first ? (int)first.sep.size() / 2 : -(int)first.sep.size() / 2);
-        if (na < 1) na = 1;
-        if (na > n - 1) na = n - 1;
-        Cut second = cut_at(g, sorted, na, side);
-        Cut& pick = (second.ok && second.sep.size() <= first.sep.size() + first.sep.size() / 8) ? second : first;
-        if (!best.ok || pick.sep.size() < best.sep.size()) best = pick;
+        for (int from_first = 1; from_first >= 0; --from_first) {
+            Cut first = cut_at(g, sorted, n / 2, side, from_first);
+            if (!first.ok) continue;
+            int na = n / 2 + (from_first ? (int)first.sep.size() / 2 : -(int)first.sep.size() / 2);
+            if (na < 1) na = 1;
+            if (na > n - 1) na = n - 1;
+            Cut second = cut_at(g, sorted, na, side, from_first);
+            for (Cut* cand : {&first, &second}) {
+                if (!cand->ok) continue;
+                const double imb = std::fabs((double)cand->A.size() - (double)cand->B.size()) / n;
+                const double score = (double)cand->sep.size() * (1.0 + 3.0 * imb);
+                if (score < best_score) {
+                    best_score = score;
+                    best = *cand;
+                }
+            }
+        }
     }
     return best;
 }
@@ -571,17 +584,18 @@ inline ReducedPlan masked_plan(int n_img, int ui, int cam_rows, const int* adj_p
 // Returns false when a point's images do not lie on one root-to-leaf path (adjacency built without it).
 inline bool plan_point_owner(const ReducedPlan& P, int n_seg, const int* seg_start, const int* simg, int* owner_out) {
     bool ok = true;
+    const int world = P.world > 0 ? P.world : 1;
+    std::vector<long long> load((size_t)world, 0);
+    std::vector<int> deepest_of((size_t)n_seg, -1);
+    // pass 1: points of owned subtrees
     for (int s = 0; s < n_seg; ++s) {
         int deepest = -1;
         for (int o = seg_start[s]; o < seg_start[s + 1]; ++o) {
             const int nd = P.img_node[(size_t)simg[o]];
             if (deepest < 0 || P.nodes[(size_t)nd].depth > P.nodes[(size_t)deepest].depth) deepest = nd;
         }
-        if (deepest < 0) {
-            owner_out[s] = s % (P.world > 0 ? P.world : 1);
-            continue;
-        }
-        const PlanNode& d = P.nodes[(size_t)deepest];
+        deepest_of[(size_t)s] = deepest;
+        if (deepest < 0) continue;
         // every image of the point must sit in an ancestor-or-self of the deepest node
         for (int o = seg_start[s]; o < seg_start[s + 1] && ok; ++o) {
             int a = deepest;
@@ -589,7 +603,28 @@ inline bool plan_point_owner(const ReducedPlan& P, int n_seg, const int* seg_sta
             while (a >= 0 && a != nd) a = P.nodes[(size_t)a].parent;
             if (a < 0) ok = false;
         }
-        owner_out[s] = d.owner >= 0 ? d.owner : d.rank_lo + s % (d.rank_hi - d.rank_lo);
+        const PlanNode& d = P.nodes[(size_t)deepest];
+        if (d.owner >= 0) {
+            owner_out[s] = d.owner;
+            load[(size_t)d.owner] += seg_start[s + 1] - seg_start[s];
+        }
+    }
+    // pass 2: points that touch shared top nodes only go to the least loaded rank below their deepest node
+    // (in point order: deterministic), which also evens out subtrees of different size
+    for (int s = 0; s < n_seg; ++s) {
+        const int deepest = deepest_of[(size_t)s];
+        int lo = 0, hi = world;
+        if (deepest >= 0) {
+            const PlanNode& d = P.nodes[(size_t)deepest];
+            if (d.owner >= 0) continue;
+            lo = d.rank_lo;
+            hi = d.rank_hi;
+        }
+        int pick = lo;
+        for (int r = lo + 1; r < hi; ++r)
+            if (load[(size_t)r] < load[(size_t)pick]) pick = r;
+        owner_out[s] = pick;
+        load[(size_t)pick] += seg_start[s + 1] - seg_start[s];
     }
     return ok;
 }

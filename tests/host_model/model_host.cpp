@@ -186,3 +186,40 @@ extern "C" void feba_host_plan_arrays(const void* p, int* img_row, int* row_ext,
 extern "C" int feba_host_plan_point_owner(const void* p, int n_seg, const int* seg_start, const int* simg, int* owner) {
     return feba::plan_point_owner(*static_cast<const feba::ReducedPlan*>(p), n_seg, seg_start, simg, owner) ? 0 : 1;
 }
+
+// ---- chunk schedule of the assembly (csrc/feba_chunks.h)
+#include "../../fish-eye_bundle_adjustment_b200/csrc/feba_chunks.h"
+
+extern "C" void* feba_host_chunks(int n_img, int n_seg, const int* seg_start, const int* simg, const unsigned char* seg_tie,
+                                  const int* img_row) {
+    return new feba::ChunkSchedule(feba::build_chunks(n_img, n_seg, seg_start, simg, seg_tie, img_row));
+}
+extern "C" void feba_host_chunks_free(void* p) { delete static_cast<feba::ChunkSchedule*>(p); }
+// sizes: n_chunks, image slots, block slots, pairs, distinct image pairs, ok
+extern "C" void feba_host_chunks_sizes(const void* p, long long* out6) {
+    const feba::ChunkSchedule& C = *static_cast<const feba::ChunkSchedule*>(p);
+    out6[0] = C.n_chunks; out6[1] = (long long)C.slot_img.size(); out6[2] = (long long)C.bslot_a.size();
+    out6[3] = C.n_pairs; out6[4] = (long long)C.tblk_a.size(); out6[5] = C.ok ? 1 : 0;
+}
+extern "C" void feba_host_chunks_arrays(const void* p, int* obs0, int* img0, int* slot_img, int* slot_obs0, int* slot_obs,
+                                        int* blk0, int* bslot_a, int* bslot_b, int* bslot_pair0, unsigned int* pairs,
+                                        int* timg_ptr, int* timg_slots, int* tblk_a, int* tblk_b, int* tblk_ptr,
+                                        int* tblk_slots) {
+    const feba::ChunkSchedule& C = *static_cast<const feba::ChunkSchedule*>(p);
+    std::copy(C.obs0.begin(), C.obs0.end(), obs0);
+    std::copy(C.img0.begin(), C.img0.end(), img0);
+    std::copy(C.slot_img.begin(), C.slot_img.end(), slot_img);
+    std::copy(C.slot_obs0.begin(), C.slot_obs0.end(), slot_obs0);
+    for (size_t i = 0; i < C.slot_obs.size(); ++i) slot_obs[i] = C.slot_obs[i];
+    std::copy(C.blk0.begin(), C.blk0.end(), blk0);
+    std::copy(C.bslot_a.begin(), C.bslot_a.end(), bslot_a);
+    std::copy(C.bslot_b.begin(), C.bslot_b.end(), bslot_b);
+    std::copy(C.bslot_pair0.begin(), C.bslot_pair0.end(), bslot_pair0);
+    std::copy(C.pairs.begin(), C.pairs.end(), pairs);
+    std::copy(C.timg_ptr.begin(), C.timg_ptr.end(), timg_ptr);
+    std::copy(C.timg_slots.begin(), C.timg_slots.end(), timg_slots);
+    std::copy(C.tblk_a.begin(), C.tblk_a.end(), tblk_a);
+    std::copy(C.tblk_b.begin(), C.tblk_b.end(), tblk_b);
+    std::copy(C.tblk_ptr.begin(), C.tblk_ptr.end(), tblk_ptr);
+    std::copy(C.tblk_slots.begin(), C.tblk_slots.end(), tblk_slots);
+}
