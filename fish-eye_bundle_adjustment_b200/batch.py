@@ -3,9 +3,10 @@ BatchRun.m sweep).
 
 The reference's ``BatchRun.m:57-65`` calls ``main`` on one data folder after the other.  Small
 blocks (u_c ~ 1,200) are launch- and latency-bound on a B200, so here every block gets its own
-handle -- and with it its own CUDA stream and CUDA graphs -- and the Gauss-Newton loops advance in
-lock step: one ``feba_iterate_async`` per still-active block, then one ``feba_sync`` each.  Kernels of
-different blocks overlap on the device; there is no exchange between blocks (replicas only).
+handle -- and with it its own CUDA stream -- and the Gauss-Newton loops advance in lock step: ONE CUDA graph
+holds a step of every still-active block (``feba_batch``: the handles' streams fork from the first one inside the
+capture and join it again), then one ``feba_sync`` each.  Kernels of different blocks overlap on the device; there
+is no exchange between blocks (replicas only).
 Results are bit-identical to running the blocks one at a time (each block's arithmetic is untouched).
 """
 from __future__ import annotations
@@ -14,7 +15,7 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-from .lib import Handle
+from .lib import Batch, Handle
 from .problem import Buildxhat, Problem
 
 
@@ -39,9 +40,15 @@ def adjust_batch(problems: Sequence[Problem], xhat0s: Optional[Sequence[np.ndarr
         count = [0] * n
         trace: List[List[float]] = [[] for _ in range(n)]
         active = [i for i in range(n) if deltasum[i] > problems[i].settings.threshold]
+        batch, batch_of = None, None
         while active:
-            for i in active:                                     # enqueue one iteration of every active block
-                handles[i].iterate_async()
+            # one step of every active block: a single captured CUDA graph from the second step on (feba_batch);
+            # the batch is rebuilt when blocks drop out (they converge after different numbers of iterations)
+            if batch_of != active:
+                if batch is not None:
+                    batch.close()
+                batch, batch_of = Batch([handles[i] for i in active]), list(active)
+            batch.iterate_async()
             nxt = []
             for i in active:                                     # main.m:484-493 per block
                 deltasum[i] = handles[i].sync()
@@ -51,6 +58,8 @@ def adjust_batch(problems: Sequence[Problem], xhat0s: Optional[Sequence[np.ndarr
                 if deltasum[i] > s.threshold and count[i] < s.Iteration_Cap:
                     nxt.append(i)
             active = nxt
+        if batch is not None:
+            batch.close()
         out = []
         for i, h in enumerate(handles):
             res = h.residuals() if want_residuals else {}

@@ -1268,6 +1268,124 @@ int feba_iterate(feba_handle* h, double* deltasum_out) {
     return feba_sync(h, deltasum_out);
 }
 
+// ---- BatchRun sweep (BatchRun.m:57-65): many small independent adjustments on one GPU.
+// One Gauss-Newton step of EVERY handle of the batch is captured into ONE CUDA graph (the handles' streams fork
+// from the first handle's stream and join it again), so a step of the whole sweep costs one graph launch on the
+// host instead of two per block; on the device the blocks run side by side.  Each block's arithmetic is untouched:
+// results are bit-identical to feba_iterate per handle.
+struct feba_batch {
+    std::vector<feba_handle*> hs;
+    cudaGraphExec_t exec = nullptr;
+    cudaEvent_t fork = nullptr, done = nullptr;
+    std::vector<cudaEvent_t> join;
+    std::vector<int64_t> launches;        // kernel launches of one step, per handle
+};
+
+void feba_batch_destroy(feba_batch* b) {
+    if (!b) return;
+    if (b->exec) cudaGraphExecDestroy(b->exec);
+    if (b->fork) cudaEventDestroy(b->fork);
+    if (b->done) cudaEventDestroy(b->done);
+    for (auto& e : b->join)
+        if (e) cudaEventDestroy(e);
+    delete b;
+}
+
+int feba_batch_create(feba_handle* const* handles, int32_t n, feba_batch** out) {
+    if (!handles || !out || n < 1) return fail(nullptr, FEBA_ERR_INVALID, "feba_batch_create: bad arguments");
+    *out = nullptr;
+    for (int i = 0; i < n; ++i) {
+        feba_handle* h = handles[i];
+        if (!h || h->shard || h->dist_active || h->device != handles[0]->device)
+            return fail(nullptr, FEBA_ERR_INVALID, "feba_batch_create: handle %d is null, on another device or part of a group", i);
+        if (h->stream == nullptr || h->stream == cudaStreamLegacy || !h->use_graph)
+            return fail(nullptr, FEBA_ERR_INVALID, "feba_batch_create: handle %d cannot be captured (legacy default stream or FEBA_NO_GRAPH)", i);
+        for (int j = 0; j < i; ++j)
+            if (handles[j] == h || handles[j]->stream == h->stream)
+                return fail(nullptr, FEBA_ERR_INVALID, "feba_batch_create: handles %d and %d are the same or share a stream", j, i);
+    }
+    feba_batch* b = new (std::nothrow) feba_batch();
+    if (!b) return fail(nullptr, FEBA_ERR_INVALID, "out of host memory");
+    b->hs.assign(handles, handles + n);
+    b->join.assign((size_t)n, nullptr);
+    b->launches.assign((size_t)n, 0);
+    bool ok = cudaSetDevice(handles[0]->device) == cudaSuccess &&
+              cudaEventCreateWithFlags(&b->fork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming) == cudaSuccess;
+    for (auto& e : b->join) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        feba_batch_destroy(b);
+        return fail(nullptr, FEBA_ERR_CUDA, "feba_batch_create: event creation failed");
+    }
+    *out = b;
+    return FEBA_OK;
+}
+
+int feba_batch_iterate_async(feba_batch* b) {
+    if (!b) return FEBA_ERR_INVALID;
+    feba_handle* h0 = b->hs[0];
+    CU(h0, cudaSetDevice(h0->device));
+    const size_t n = b->hs.size();
+    bool warm = true;
+    for (feba_handle* h : b->hs) {
+        if (h->phase != 0) return fail(h0, FEBA_ERR_STATE, "feba_batch_iterate_async: a handle has a pending feba_iterate_assemble");
+        warm = warm && h->g_assemble.calls > 0 && h->g_solve.calls > 0;
+    }
+    if (!warm) {      // first step of a handle runs eagerly (kernel attributes are set on first use): no capture yet
+        for (feba_handle* h : b->hs) {
+            const int rc = feba_iterate_async(h);
+            if (rc) return fail(h0, rc, "%s", h->err.c_str());
+        }
+        return FEBA_OK;
+    }
+    // the step starts after whatever the handles have pending on their own streams
+    for (size_t i = 1; i < n; ++i) {
+        CU(h0, cudaEventRecord(b->join[i], b->hs[i]->stream));
+        CU(h0, cudaStreamWaitEvent(h0->stream, b->join[i], 0));
+    }
+    if (!b->exec) {
+        CU(h0, cudaStreamBeginCapture(h0->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = FEBA_OK;
+        cudaError_t e = cudaEventRecord(b->fork, h0->stream);
+        for (size_t i = 1; i < n && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(b->hs[i]->stream, b->fork, 0);
+        for (size_t i = 0; i < n && e == cudaSuccess && rc == FEBA_OK; ++i) {
+            feba_handle* h = b->hs[i];
+            const int64_t before = h->launches;
+            h->capturing = true;
+            rc = enqueue_assemble(h);
+            if (rc == FEBA_OK) rc = enqueue_solve(h);
+            h->capturing = false;
+            b->launches[i] = h->launches - before;
+        }
+        for (size_t i = 1; i < n && e == cudaSuccess && rc == FEBA_OK; ++i) {
+            e = cudaEventRecord(b->join[i], b->hs[i]->stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(h0->stream, b->join[i], 0);
+        }
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ee = cudaStreamEndCapture(h0->stream, &graph);
+        if (rc || e != cudaSuccess || ee != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            if (rc) return rc;
+            return fail(h0, FEBA_ERR_CUDA, "feba_batch_iterate_async: capture failed: %s",
+                        cudaGetErrorString(e != cudaSuccess ? e : ee));
+        }
+        const cudaError_t ei = cudaGraphInstantiate(&b->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        CU(h0, ei);
+    } else {
+        for (size_t i = 0; i < n; ++i) b->hs[i]->launches += b->launches[i];
+    }
+    CU(h0, cudaGraphLaunch(b->exec, h0->stream));
+    // feba_sync(h) waits on h's own stream: order it after the step
+    CU(h0, cudaEventRecord(b->done, h0->stream));
+    for (size_t i = 1; i < n; ++i) CU(h0, cudaStreamWaitEvent(b->hs[i]->stream, b->done, 0));
+    for (feba_handle* h : b->hs) {
+        ++h->iterations;
+        h->cov_ready = false;
+    }
+    return FEBA_OK;
+}
+
 int feba_solve(feba_handle* h, int32_t* iterations_out, double* trace_out, size_t trace_cap) {
     if (!h) return FEBA_ERR_INVALID;
     // main.m:407-494: deltasum = 100; while deltasum > threshold; ...; if count >= cap, break

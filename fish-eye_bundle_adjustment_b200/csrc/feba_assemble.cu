@@ -775,80 +775,140 @@ __global__ void __launch_bounds__(128) k_pair_pass(DevProblem P) {
 // re-read from L1/L2 (each record enters ~9 pairs).
 constexpr int kImgPartDev = 108;      // = feba_chunks.h::kImgPart: 27 + 6 * 13, padded to a multiple of 4
 
+// Shared-memory copy of a chunk's records: per observation Je (2x6), Y = Je' Z (6x3, formed once here instead of
+// once per pair) and r (2), row stride 33 doubles (odd: the 32 lanes of a warp, each reading ITS OWN record with
+// 8-byte loads, hit different banks).  Gathering whole 144-byte records per lane from global memory costs one L1
+// wavefront per 16-byte load per lane -- the bound the image-pair pass of round 1 ran into (810 M wavefronts =
+// 2.9 ms on BASELINE configs[3]); from shared memory the same gather is several times cheaper, and every record
+// comes in from HBM once.
+constexpr int kRecS = 33;
+constexpr int kChunkObsDev = 416;      // = feba_chunks.h::kChunkObs; larger chunks (one huge point) gather from global
+constexpr size_t kChunkSmem = (size_t)kChunkObsDev * kRecS * sizeof(double);    // 109,824 B: two CTAs per SM
+
 template <int NK, bool HAS_CAM>
 __global__ void __launch_bounds__(256, 2) k_chunk_reduce(DevProblem P, ChunkDev C) {
     constexpr int NC = NK + 5;
     constexpr int R2 = 2 + 2 * NC;
     constexpr int CG = 5;                                        // camera rows per image sub-item
     constexpr int NSUB = HAS_CAM ? 1 + (NC + CG - 1) / CG : 1;   // diagonal block + rhs, then groups of camera rows
+    extern __shared__ __align__(16) double srec[];
     for (int c = blockIdx.x; c < C.n_chunks; c += gridDim.x) {
         const size_t o0 = (size_t)C.obs0[c];
+        const int n_ob = C.obs0[c + 1] - C.obs0[c];
         const int s_lo = C.img0[c], n_is = C.img0[c + 1] - s_lo;
         const int b_lo = C.blk0[c], n_bs = C.blk0[c + 1] - b_lo;
-        const int n_items = n_bs + NSUB * n_is;
+        const int n_items = 2 * n_bs + NSUB * n_is;
+        const bool staged = n_ob <= kChunkObsDev;
+        __syncthreads();                                         // the previous chunk's readers are done
+        if (staged) {
+            for (int ob = threadIdx.x; ob < n_ob; ob += blockDim.x) {
+                const double2* q = reinterpret_cast<const double2*>(P.rec1 + (size_t)kRec1 * (o0 + ob));
+                double r[kRec1];
+#pragma unroll
+                for (int k = 0; k < kRec1 / 2; ++k) { const double2 v = q[k]; r[2 * k] = v.x; r[2 * k + 1] = v.y; }
+                const double2 rav = *reinterpret_cast<const double2*>(P.rec2 + (size_t)R2 * (o0 + ob));
+                double* d = srec + ob * kRecS;
+#pragma unroll
+                for (int k = 0; k < 12; ++k) d[k] = r[k];
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) d[12 + 3 * i + k] = r[i] * r[12 + k] + r[6 + i] * r[15 + k];
+                d[30] = rav.x;
+                d[31] = rav.y;
+            }
+        }
+        __syncthreads();
+        // Je (12) and Y (18) of chunk-local observation t
+        auto rec_of = [&](int t, double* je, double* y) {
+            if (staged) {
+                const double* q = srec + t * kRecS;
+                if (je) {
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) je[k] = q[k];
+                }
+                if (y) {
+#pragma unroll
+                    for (int k = 0; k < 18; ++k) y[k] = q[12 + k];
+                }
+            } else {
+                const double2* q = reinterpret_cast<const double2*>(P.rec1 + (size_t)kRec1 * (o0 + t));
+                double r[kRec1];
+#pragma unroll
+                for (int k = 0; k < kRec1 / 2; ++k) { const double2 v = q[k]; r[2 * k] = v.x; r[2 * k + 1] = v.y; }
+                if (je) {
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) je[k] = r[k];
+                }
+                if (y) {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i)
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) y[3 * i + k] = r[i] * r[12 + k] + r[6 + i] * r[15 + k];
+                }
+            }
+        };
         // one LANE per item, working through the item's pairs / observations with its sums in registers: no
-        // cross-lane reduction, and 32 independent gather streams per warp.  Image pairs come longest first
-        // (feba_chunks.h), so the lanes of a warp finish together.
+        // cross-lane reduction, 32 independent record streams per warp.  Items: the two 3 x 6 halves of every image
+        // pair (longest pairs first, feba_chunks.h: the lanes of a warp finish together), then per image its
+        // diagonal block + right-hand side and its camera rows in groups of five.
         for (int item = threadIdx.x; item < n_items; item += blockDim.x) {
-            if (item < n_bs) {
-                const int bs = b_lo + item;
+            if (item < 2 * n_bs) {
+                const int bs = b_lo + (item >> 1), half = item & 1;
                 const int q0 = C.bslot_pair0[bs], q1 = C.bslot_pair0[bs + 1];
-                double acc[36];
+                double acc[18];
 #pragma unroll
-                for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+                for (int k = 0; k < 18; ++k) acc[k] = 0.0;
+                unsigned int pr = q0 < q1 ? C.pairs[q0] : 0u;
                 for (int q = q0; q < q1; ++q) {
-                    const unsigned int pr = C.pairs[q];
-                    const double2* ra2 = reinterpret_cast<const double2*>(P.rec1 + (size_t)kRec1 * (o0 + (pr & 0xffffu)));
-                    const double2* rb2 = reinterpret_cast<const double2*>(P.rec1 + (size_t)kRec1 * (o0 + (pr >> 16)));
-                    double ra[kRec1], rb[kRec1];
+                    const unsigned int cur = pr;
+                    if (q + 1 < q1) pr = C.pairs[q + 1];         // next index pair while this one is worked on
+                    double ya[18], yb[18];
+                    rec_of((int)(cur & 0xffffu), nullptr, ya);
+                    rec_of((int)(cur >> 16), nullptr, yb);
 #pragma unroll
-                    for (int k = 0; k < kRec1 / 2; ++k) {
-                        const double2 va = ra2[k], vb = rb2[k];
-                        ra[2 * k] = va.x; ra[2 * k + 1] = va.y;
-                        rb[2 * k] = vb.x; rb[2 * k + 1] = vb.y;
-                    }
-                    const double c00 = ra[12] * rb[12] + ra[13] * rb[13] + ra[14] * rb[14];
-                    const double c01 = ra[12] * rb[15] + ra[13] * rb[16] + ra[14] * rb[17];
-                    const double c10 = ra[15] * rb[12] + ra[16] * rb[13] + ra[17] * rb[14];
-                    const double c11 = ra[15] * rb[15] + ra[16] * rb[16] + ra[17] * rb[17];
+                    for (int i = 0; i < 3; ++i) {
+                        const double a0 = ya[9 * half + 3 * i], a1 = ya[9 * half + 3 * i + 1], a2 = ya[9 * half + 3 * i + 2];
 #pragma unroll
-                    for (int i = 0; i < 6; ++i) {
-                        const double e0 = ra[i] * c00 + ra[6 + i] * c10, e1 = ra[i] * c01 + ra[6 + i] * c11;
-#pragma unroll
-                        for (int j = 0; j < 6; ++j) acc[6 * i + j] += e0 * rb[j] + e1 * rb[6 + j];
+                        for (int j = 0; j < 6; ++j) acc[6 * i + j] += a0 * yb[3 * j] + a1 * yb[3 * j + 1] + a2 * yb[3 * j + 2];
                     }
                 }
-                double2* out = reinterpret_cast<double2*>(C.blk_part + (size_t)36 * bs);
+                double2* out = reinterpret_cast<double2*>(C.blk_part + (size_t)36 * bs + 18 * half);
 #pragma unroll
-                for (int k = 0; k < 18; ++k) out[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
+                for (int k = 0; k < 9; ++k) out[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
             } else {
-                const int r = item - n_bs;
+                const int r = item - 2 * n_bs;
                 const int sub = r / n_is, slot = s_lo + (r - sub * n_is);
                 const int q0 = C.slot_obs0[slot], q1 = C.slot_obs0[slot + 1];
                 double* out = C.img_part + (size_t)kImgPartDev * slot;
-                if (sub == 0) {   // diagonal block Je'(P - Z Z')Je and right-hand side Je' r
+                if (sub == 0) {   // diagonal block Je'P Je - Y Y' (= Je'(P - Z Z')Je) and right-hand side Je' r
                     double acc[27];
 #pragma unroll
                     for (int k = 0; k < 27; ++k) acc[k] = 0.0;
                     for (int q = q0; q < q1; ++q) {
-                        const size_t t = o0 + C.slot_obs[q];
-                        const double2* r1v = reinterpret_cast<const double2*>(P.rec1 + (size_t)kRec1 * t);
-                        double r1[kRec1];
-#pragma unroll
-                        for (int k = 0; k < kRec1 / 2; ++k) { const double2 v = r1v[k]; r1[2 * k] = v.x; r1[2 * k + 1] = v.y; }
-                        const double2 rav = *reinterpret_cast<const double2*>(P.rec2 + (size_t)R2 * t);
-                        const double p00 = P.px - (r1[12] * r1[12] + r1[13] * r1[13] + r1[14] * r1[14]);
-                        const double p01 = -(r1[12] * r1[15] + r1[13] * r1[16] + r1[14] * r1[17]);
-                        const double p11 = P.py - (r1[15] * r1[15] + r1[16] * r1[16] + r1[17] * r1[17]);
+                        const int t = C.slot_obs[q];
+                        double je[12], y[18];
+                        rec_of(t, je, y);
+                        double ra0, ra1;
+                        if (staged) {
+                            ra0 = srec[t * kRecS + 30];
+                            ra1 = srec[t * kRecS + 31];
+                        } else {
+                            const double2 rav = *reinterpret_cast<const double2*>(P.rec2 + (size_t)R2 * (o0 + t));
+                            ra0 = rav.x;
+                            ra1 = rav.y;
+                        }
                         int e = 0;
 #pragma unroll
                         for (int i = 0; i < 6; ++i) {
-                            const double t0 = p00 * r1[i] + p01 * r1[6 + i], t1 = p01 * r1[i] + p11 * r1[6 + i];
+                            const double t0 = P.px * je[i], t1 = P.py * je[6 + i];
 #pragma unroll
-                            for (int j = 0; j <= i; ++j) acc[e++] += t0 * r1[j] + t1 * r1[6 + j];
+                            for (int j = 0; j <= i; ++j)
+                                acc[e++] += t0 * je[j] + t1 * je[6 + j] -
+                                            (y[3 * i] * y[3 * j] + y[3 * i + 1] * y[3 * j + 1] + y[3 * i + 2] * y[3 * j + 2]);
                         }
 #pragma unroll
-                        for (int i = 0; i < 6; ++i) acc[21 + i] += r1[i] * rav.x + r1[6 + i] * rav.y;
+                        for (int i = 0; i < 6; ++i) acc[21 + i] += je[i] * ra0 + je[6 + i] * ra1;
                     }
 #pragma unroll
                     for (int k = 0; k < 27; ++k) out[k] = acc[k];
@@ -858,23 +918,17 @@ __global__ void __launch_bounds__(256, 2) k_chunk_reduce(DevProblem P, ChunkDev 
 #pragma unroll
                     for (int k = 0; k < CG * 6; ++k) acc[k] = 0.0;
                     for (int q = q0; q < q1; ++q) {
-                        const size_t t = o0 + C.slot_obs[q];
-                        const double2* r1v = reinterpret_cast<const double2*>(P.rec1 + (size_t)kRec1 * t);
-                        const double2* r2v = reinterpret_cast<const double2*>(P.rec2 + (size_t)R2 * t + 2);
-                        double Je[2][6];
+                        const int t = C.slot_obs[q];
+                        const double2* r2v = reinterpret_cast<const double2*>(P.rec2 + (size_t)R2 * (o0 + t) + 2);
+                        double2 hv[CG];
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-                            const double2 v0 = r1v[k], v1 = r1v[3 + k];
-                            Je[0][2 * k] = v0.x; Je[0][2 * k + 1] = v0.y;
-                            Je[1][2 * k] = v1.x; Je[1][2 * k + 1] = v1.y;
-                        }
+                        for (int jj = 0; jj < CG; ++jj) hv[jj] = j0 + jj < NC ? r2v[j0 + jj] : make_double2(0.0, 0.0);
+                        double je[12];
+                        rec_of(t, je, nullptr);
 #pragma unroll
                         for (int jj = 0; jj < CG; ++jj) {
-                            if (j0 + jj < NC) {
-                                const double2 hv = r2v[j0 + jj];
 #pragma unroll
-                                for (int i = 0; i < 6; ++i) acc[6 * jj + i] += hv.x * Je[0][i] + hv.y * Je[1][i];
-                            }
+                            for (int i = 0; i < 6; ++i) acc[6 * jj + i] += hv[jj].x * je[i] + hv[jj].y * je[6 + i];
                         }
                     }
 #pragma unroll
@@ -1181,8 +1235,13 @@ cudaError_t launch_assemble(const DevProblem& P, int sm_count, int* info, cudaSt
             FEBA_NK_DISPATCH2(P.NK, hc, (e = launch_point_pass_t<NK_, HC_, 32>(P, sm_count, st)));
         }
         if (e != cudaSuccess) return e;
-        int grid = chunks->n_chunks < sm_count * 4 ? chunks->n_chunks : sm_count * 4;
-        FEBA_NK_DISPATCH2(P.NK, hc, (k_chunk_reduce<NK_, HC_><<<grid, 256, 0, st>>>(P, *chunks)));
+        int grid = chunks->n_chunks < sm_count * 2 ? chunks->n_chunks : sm_count * 2;
+        {
+            static SmemOptIn opt[2 * 9];
+            FEBA_NK_DISPATCH2(P.NK, hc, (e = opt[2 * NK_ + (HC_ ? 1 : 0)].ensure(k_chunk_reduce<NK_, HC_>, kChunkSmem)));
+            if (e != cudaSuccess) return e;
+        }
+        FEBA_NK_DISPATCH2(P.NK, hc, (k_chunk_reduce<NK_, HC_><<<grid, 256, kChunkSmem, st>>>(P, *chunks)));
         *launches += 2;
         if (hc) {
             k_cam_reduce<<<1, 1024, 0, st>>>(P, assemble_warps(P, sm_count));

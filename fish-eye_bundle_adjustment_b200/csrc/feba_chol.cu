@@ -163,34 +163,29 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
     return y;
 }
 
-__global__ void __launch_bounds__(256) k_potrf64_inv(double* __restrict__ A, int ld, double* __restrict__ Linv,
-                                                    int* __restrict__ info) {
-    extern __shared__ __align__(16) double psm[];
-    double(*sA)[kBlk + 1] = reinterpret_cast<double(*)[kBlk + 1]>(psm);                          // matrix -> L
-    double(*sI)[kBlk + 1] = reinterpret_cast<double(*)[kBlk + 1]>(psm + kBlk * (kBlk + 1));      // Linv
-    double(*sT)[16][17] = reinterpret_cast<double(*)[16][17]>(psm + 2 * kBlk * (kBlk + 1));      // block products
-    double* rdiag = psm + 2 * kBlk * (kBlk + 1) + 3 * 16 * 17;                                   // 1 / L_jj
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    POTRF_T(0);
-    {
-        // all 16 loads of a thread in flight together (a rolled load->store loop costs one L2 round
-        // trip per iteration: 4.2k of the kernel's 44k cycles)
-        double v[16];
-        const int r = tid & 63, c0 = tid >> 6;
-#pragma unroll
-        for (int t = 0; t < 16; ++t) {
-            const int c = c0 + 4 * t;
-            v[t] = (r >= c) ? A[r + (size_t)ld * c] : 0.0;
-        }
-#pragma unroll
-        for (int t = 0; t < 16; ++t) {
-            const int c = c0 + 4 * t;
-            sA[r][c] = v[t];
-            sI[r][c] = 0.0;
-        }
-    }
-    __syncthreads();
-    POTRF_T(1);
+// shared-memory views of one 64x64 factorisation (2 * 64 * 65 + 3 * 16 * 17 + 64 doubles)
+struct PotrfSmem {
+    double (*sA)[kBlk + 1];      // matrix (lower triangle, upper zero) -> L
+    double (*sI)[kBlk + 1];      // zero -> L^-1
+    double (*sT)[16][17];        // block products of the inverse
+    double* rdiag;               // 1 / L_jj
+};
+constexpr size_t kPotrfSmemDoubles = 2 * kBlk * (kBlk + 1) + 3 * 16 * 17 + kBlk;
+
+__device__ __forceinline__ PotrfSmem potrf_views(double* psm) {
+    PotrfSmem S;
+    S.sA = reinterpret_cast<double(*)[kBlk + 1]>(psm);
+    S.sI = reinterpret_cast<double(*)[kBlk + 1]>(psm + kBlk * (kBlk + 1));
+    S.sT = reinterpret_cast<double(*)[16][17]>(psm + 2 * kBlk * (kBlk + 1));
+    S.rdiag = psm + 2 * kBlk * (kBlk + 1) + 3 * 16 * 17;
+    return S;
+}
+
+// sA := chol(sA) (lower), 256 threads, all of them call; returns true when a pivot was not positive
+__device__ __forceinline__ bool potrf64_factor(const PotrfSmem& S, int tid) {
+    double(*sA)[kBlk + 1] = S.sA;
+    double* rdiag = S.rdiag;
+    const int lane = tid & 31, warp = tid >> 5;
     bool bad = false;
 #pragma unroll 1
     for (int kb = 0; kb < 4; ++kb) {
@@ -224,7 +219,7 @@ __global__ void __launch_bounds__(256) k_potrf64_inv(double* __restrict__ A, int
             }
         }
         __syncthreads();
-        POTRF_T(10 + 3 * kb);
+        
         // (2) panel below the diagonal block: one thread per row, column-oriented substitution (after
         // x_j is final the remaining right-hand sides are updated independently: short dependency chain)
         const int nrow = 48 - o;
@@ -243,7 +238,7 @@ __global__ void __launch_bounds__(256) k_potrf64_inv(double* __restrict__ A, int
             for (int c = 0; c < 16; ++c) sA[r][o + c] = x[c];
         }
         __syncthreads();
-        POTRF_T(11 + 3 * kb);
+        
         // (3) trailing update, lower triangle of the remaining nrow x nrow block: thread (row i, group g of
         // 5) keeps its row of the panel in registers and walks the columns jj = g, g+5, ... <= i, two
         // independent accumulation chains at a time.  (A DMMA version of this update and of the inverse
@@ -275,19 +270,17 @@ __global__ void __launch_bounds__(256) k_potrf64_inv(double* __restrict__ A, int
             }
         }
         __syncthreads();
-        POTRF_T(12 + 3 * kb);
+        
     }
-    POTRF_T(5);
-    if (bad && lane == 0) atomicExch(info, 1);
-    {
-        const int r = tid & 63, c0 = tid >> 6;
-#pragma unroll
-        for (int t = 0; t < 16; ++t) {
-            const int c = c0 + 4 * t;
-            if (r >= c) A[r + (size_t)ld * c] = sA[r][c];
-        }
-    }
-    POTRF_T(6);
+    return bad;
+}
+
+// sI := sA^-1 (lower), 256 threads; sI must be zero above and at entry
+__device__ __forceinline__ void potrf64_inverse(const PotrfSmem& S, int tid) {
+    double(*sA)[kBlk + 1] = S.sA;
+    double(*sI)[kBlk + 1] = S.sI;
+    double(*sT)[16][17] = S.sT;
+    double* rdiag = S.rdiag;
     // ---- inverse, diagonal blocks: thread (b, c) solves L_bb x = e_c, column-oriented
     if (tid < 64) {
         const int o = tid & ~15, c = tid & 15;
@@ -304,7 +297,6 @@ __global__ void __launch_bounds__(256) k_potrf64_inv(double* __restrict__ A, int
         for (int i = 0; i < 16; ++i) sI[o + i][o + c] = x[i];
     }
     __syncthreads();
-    POTRF_T(7);
     // ---- off-diagonal blocks by block distance dist = i - j (fully unrolled: every bound is static, so
     // the shared-memory loads of a dot product are issued together instead of one round trip per term)
     const int er = tid >> 4, ec = tid & 15;            // one entry of a 16x16 block per thread
@@ -331,6 +323,48 @@ __global__ void __launch_bounds__(256) k_potrf64_inv(double* __restrict__ A, int
         }
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(256) k_potrf64_inv(double* __restrict__ A, int ld, double* __restrict__ Linv,
+                                                    int* __restrict__ info) {
+    extern __shared__ __align__(16) double psm[];
+    const PotrfSmem S = potrf_views(psm);
+    double(*sA)[kBlk + 1] = S.sA;
+    double(*sI)[kBlk + 1] = S.sI;
+    const int tid = threadIdx.x, lane = tid & 31;
+    POTRF_T(0);
+    {
+        // all 16 loads of a thread in flight together (a rolled load->store loop costs one L2 round
+        // trip per iteration: 4.2k of the kernel's 44k cycles)
+        double v[16];
+        const int r = tid & 63, c0 = tid >> 6;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int c = c0 + 4 * t;
+            v[t] = (r >= c) ? A[r + (size_t)ld * c] : 0.0;
+        }
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int c = c0 + 4 * t;
+            sA[r][c] = v[t];
+            sI[r][c] = 0.0;
+        }
+    }
+    __syncthreads();
+    POTRF_T(1);
+    const bool bad = potrf64_factor(S, tid);
+    POTRF_T(5);
+    if (bad && lane == 0) atomicExch(info, 1);
+    {
+        const int r = tid & 63, c0 = tid >> 6;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int c = c0 + 4 * t;
+            if (r >= c) A[r + (size_t)ld * c] = sA[r][c];
+        }
+    }
+    POTRF_T(6);
+    potrf64_inverse(S, tid);
     POTRF_T(8);
     {
         const int r = tid & 63, c0 = tid >> 6;
@@ -353,9 +387,10 @@ __global__ void __launch_bounds__(256) k_potrf64_inv(double* __restrict__ A, int
 // blocks: those small launches were latency-bound (profiles/: 685 leaf + ~370 small GEMM launches,
 // ~13 ms of a 42 ms factorisation under ncu).
 constexpr int TS = 68;                      // smem stride (doubles) of a 64-wide tile row: == 4 mod 16
-constexpr int TF_MAX = 4;
+constexpr int TF_MAX = 4;                  // 64-row strips (139 KB of shared memory)
+constexpr int TF_MAX16 = 6;                // 16-row strips: a whole supertile column of the plan (tile_max = 6) per launch
 constexpr size_t kTrsmFusedSmem = (size_t)(TF_MAX + 2) * 64 * TS * sizeof(double);
-constexpr size_t kTrsmFusedSmem16 = (size_t)(TF_MAX * 64 * 20 + 2 * 64 * TS) * sizeof(double);
+constexpr size_t kTrsmFusedSmem16 = (size_t)(TF_MAX16 * 64 * 20 + 2 * 64 * TS) * sizeof(double);
 
 // dst[k][i] = src[i + ld * k] for ROWS rows x 64 columns, 16-byte chunks, 256 threads
 template <int ROWS, int STRIDE>
@@ -379,7 +414,7 @@ __global__ void __launch_bounds__(256) k_trsm_fused(double* X, int ldx, const do
     extern __shared__ __align__(16) double fsm[];
     constexpr int XS = RM == 64 ? TS : 20;        // row stride of the X tiles (== 4 mod 16 either way)
     double(*Xs)[64][XS] = reinterpret_cast<double(*)[64][XS]>(fsm);                          // [tile][k][row]
-    double(*Ls)[64][TS] = reinterpret_cast<double(*)[64][TS]>(fsm + (size_t)TF_MAX * 64 * XS); // [buf][k][n]
+    double(*Ls)[64][TS] = reinterpret_cast<double(*)[64][TS]>(fsm + (size_t)(RM == 64 ? TF_MAX : TF_MAX16) * 64 * XS); // [buf][k][n]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // RM = 64: 2 x 4 warps of 32 rows x 16 columns; RM = 16: 1 x 8 warps of 16 rows x 8 columns
     constexpr int MF = RM == 64 ? 4 : 2, NF = RM == 64 ? 2 : 1;
@@ -525,7 +560,7 @@ static cudaError_t gemm_nt(double* C, int ldc, const double* A, int lda, const d
 // Below five blocks the whole solve is one fused launch (k_trsm_fused).
 static cudaError_t rtrsm(double* X, int ldx, double* A, int ld, const double* Linv, int r0, int mr, int c0, int n,
                          cudaStream_t st, int64_t* launches) {
-    if (n <= TF_MAX) {
+    if (n <= TF_MAX || (n <= TF_MAX16 && mr <= 74)) {
         static SmemOptIn o64, o16;
         cudaError_t e0 = o64.ensure(k_trsm_fused<64>, kTrsmFusedSmem);
         if (e0 == cudaSuccess) e0 = o16.ensure(k_trsm_fused<16>, kTrsmFusedSmem16);

@@ -21,7 +21,8 @@
 
 namespace feba {
 
-constexpr int kChunkObs = 640;    // observations per chunk (soft cap: a single point may exceed it)
+constexpr int kChunkObs = 416;    // observations per chunk (soft cap: a single point may exceed it); 416 records of
+                                  // 33 doubles = 107 KB of shared memory: two chunks in flight per SM
 constexpr int kChunkPts = 64;     // points per chunk
 constexpr int kImgPart = 108;     // doubles per (chunk, image) partial: 21 + 6 + 6 (NK + 5) <= 105, padded
 constexpr int kBlkPart = 36;      // doubles per (chunk, image pair) partial

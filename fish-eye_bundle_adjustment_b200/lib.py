@@ -27,6 +27,7 @@ EXPORTS = (
     "feba_launch_count", "feba_sparse_info", "feba_debug_reduced", "feba_cov_prepare", "feba_cov_diag", "feba_cov_block", "feba_iterate_async", "feba_iterate_solve_async", "feba_sync",
     "feba_dist_unique_id", "feba_dist_init", "feba_reduced_pack", "feba_reduced_unpack",
     "feba_create_shard", "feba_last_timing_ex", "feba_plan_info",
+    "feba_batch_create", "feba_batch_iterate_async", "feba_batch_destroy",
 )
 
 
@@ -85,6 +86,10 @@ def load() -> C.CDLL:
     lib.feba_create_shard.argtypes = [C.POINTER(FebaProblem), C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(H)]
     lib.feba_last_timing_ex.argtypes = [H, _pd]
     lib.feba_plan_info.argtypes = [H, C.POINTER(C.c_int32), _pd]
+    lib.feba_batch_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(C.c_void_p)]
+    lib.feba_batch_iterate_async.argtypes = [C.c_void_p]
+    lib.feba_batch_destroy.argtypes = [C.c_void_p]
+    lib.feba_batch_destroy.restype = None
     lib.feba_destroy.argtypes = [H]
     lib.feba_destroy.restype = None
     lib.feba_last_error.argtypes = [H]
@@ -339,3 +344,32 @@ class Handle:
         v = (C.c_int32 * 4)()
         self._check(self._lib.feba_sparse_info(self._h, v))
         return dict(active=bool(v[0]), nonzero_supertiles=int(v[1]), lower_supertiles=int(v[2]), datum_images=int(v[3]))
+
+
+class Batch:
+    """feba_batch: independent handles on one device advancing together, one CUDA graph launch per step."""
+
+    def __init__(self, handles):
+        self._lib = load()
+        self.handles = list(handles)
+        arr = (C.c_void_p * len(self.handles))(*[h._h for h in self.handles])
+        self._b = C.c_void_p()
+        rc = self._lib.feba_batch_create(arr, len(self.handles), C.byref(self._b))
+        if rc != 0:
+            raise FebaError(rc, self._lib.feba_last_error(None).decode())
+
+    def iterate_async(self):
+        rc = self._lib.feba_batch_iterate_async(self._b)
+        if rc != 0:
+            raise FebaError(rc, self._lib.feba_last_error(self.handles[0]._h).decode())
+
+    def close(self):
+        if getattr(self, "_b", None) is not None and self._b.value:
+            self._lib.feba_batch_destroy(self._b)
+            self._b = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

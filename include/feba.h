@@ -182,6 +182,16 @@ int feba_residuals(feba_handle *h, double *v, double *rsd, double stats[6]);
  * iterations_out, trace_out[<=cap] (deltasum per iteration, may be NULL). */
 int feba_solve(feba_handle *h, int32_t *iterations_out, double *trace_out, size_t trace_cap);
 
+/* BatchRun sweep (BatchRun.m:57-65: main() over many data folders): a batch of independent handles on ONE device
+ * advances by one Gauss-Newton step per call.  From the second step on the step of ALL handles is ONE captured CUDA
+ * graph (one launch on the host; the blocks run side by side on the device).  Follow with feba_sync() per handle
+ * for its deltasum.  Handles that have converged are dropped by creating a new batch of the remaining ones.
+ * Results are bit-identical to feba_iterate() per handle. */
+typedef struct feba_batch feba_batch;
+int feba_batch_create(feba_handle *const *handles, int32_t n, feba_batch **out);
+int feba_batch_iterate_async(feba_batch *b);
+void feba_batch_destroy(feba_batch *b);
+
 /* Covariance outputs from the normal matrix of the LAST iteration, as the reference
  * keeps Cx = NG^-1(1:u,1:u) of its last loop pass (main.m:432-444).  Values are COFACTORS: multiply
  * by sigma02 for Cx (main.m:602).

@@ -129,7 +129,7 @@ def test_chunk_partials_sum_to_the_reduced_system(host, permute_rows):
 
 def test_a_point_with_more_observations_than_the_cap_gets_its_own_chunk(host):
     prob = fb.synth.make_network(720, 900, 8, 5, mode="mixed", n_control=20)
-    # one control point observed by every image: 720 observations > kChunkObs = 640
+    # one control point observed by every image: 720 observations > kChunkObs = 416
     p = int(np.nonzero(prob.pt_tie < 0)[0][0])
     extra = np.arange(prob.numImg, dtype=np.int32)
     prob.obs_img = np.concatenate([prob.obs_img, extra])
@@ -142,6 +142,6 @@ def test_a_point_with_more_observations_than_the_cap_gets_its_own_chunk(host):
         assert sizes.max() >= 720 and sizes.sum() == prob.n_obs
         big = int(np.argmax(sizes))
         assert ch.img0[big + 1] - ch.img0[big] == prob.numImg           # every image has a slot in that chunk
-        assert np.all(sizes[np.arange(ch.n_chunks) != big] <= 640)
+        assert np.all(sizes[np.arange(ch.n_chunks) != big] <= 416)
     finally:
         ch.close()

@@ -29,7 +29,7 @@ from oracle import exact, sparse
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "host_model", "model_host.cpp")
 HDRS = [os.path.join(ROOT, "fish-eye_bundle_adjustment_b200", "csrc", f)
-        for f in ("feba_model.cuh", "feba_sparse.h", "feba_order.h")]
+        for f in ("feba_model.cuh", "feba_sparse.h", "feba_order.h", "feba_chunks.h")]
 LIB = os.path.join(ROOT, "tests", "_build", "libfeba_model_host.so")
 _pd, _pi, _pb = C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_ubyte)
 
