@@ -781,12 +781,15 @@ static int create_impl(const feba_problem* pr, int rank, int world, const void* 
         if (rc_pool) return rc_pool;
     }
     CU(h, dev_alloc(h, &P.cam_part, (size_t)assemble_warps(P, h->sm_count) * kCamPart));
-    // ---- assembly schedule, static for the life of the handle: chunk form (feba_chunks.h) unless several cameras
-    // have unknowns (that point pass adds cross-camera terms itself) or FEBA_CHUNKS=0
+    // ---- assembly schedule, static for the life of the handle: image-major form (pair schedule built on the device),
+    // or the chunk form (feba_chunks.h) on request
     {
         const bool mc = P.uc > 0 && P.n_cam > 1;
         const char* e_c = std::getenv("FEBA_CHUNKS");
-        if (!mc && n_seg > 0 && !(e_c && std::atoi(e_c) == 0)) {
+        // opt-in (FEBA_CHUNKS=1): measured on BASELINE configs[3] the chunk form cuts the DRAM traffic of the image /
+        // image-pair stage from 20 GB to 4.3 GB but is instruction-bound (2.9e9 warp instructions: index handling and
+        // cross-lane sums per 21-pair block) -- 5.8 ms against 4.5 ms for the image-major passes (profiles/r2d_*)
+        if (!mc && n_seg > 0 && e_c && std::atoi(e_c) != 0) {
             std::vector<unsigned char> seg_tie((size_t)n_seg);
             for (int sg = 0; sg < n_seg; ++sg) seg_tie[(size_t)sg] = pr->pt_tie[seg_pt[(size_t)sg]] >= 0;
             ChunkSchedule cs = build_chunks(P.n_img, n_seg, seg_start.data(), simg.data(), seg_tie.data(),

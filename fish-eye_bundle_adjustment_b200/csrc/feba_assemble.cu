@@ -785,22 +785,37 @@ constexpr int kRecS = 33;
 constexpr int kChunkObsDev = 416;      // = feba_chunks.h::kChunkObs; larger chunks (one huge point) gather from global
 constexpr size_t kChunkSmem = (size_t)kChunkObsDev * kRecS * sizeof(double);    // 109,824 B: two CTAs per SM
 
+// Sum v[0..31] over the lanes of a warp so that lane l ends with entry l (in v[0]): 31 shuffles instead of the
+// 160 of a full butterfly per entry.
+__device__ __forceinline__ double warp_reduce_scatter32(double (&v)[32], int lane) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const double send = upper ? v[i] : v[i + s];
+            const double keep = upper ? v[i + s] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    return v[0];
+}
+
 template <int NK, bool HAS_CAM>
 __global__ void __launch_bounds__(256, 2) k_chunk_reduce(DevProblem P, ChunkDev C) {
     constexpr int NC = NK + 5;
     constexpr int R2 = 2 + 2 * NC;
-    constexpr int CG = 5;                                        // camera rows per image sub-item
-    constexpr int NSUB = HAS_CAM ? 1 + (NC + CG - 1) / CG : 1;   // diagonal block + rhs, then groups of camera rows
     extern __shared__ __align__(16) double srec[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int c = blockIdx.x; c < C.n_chunks; c += gridDim.x) {
         const size_t o0 = (size_t)C.obs0[c];
         const int n_ob = C.obs0[c + 1] - C.obs0[c];
         const int s_lo = C.img0[c], n_is = C.img0[c + 1] - s_lo;
         const int b_lo = C.blk0[c], n_bs = C.blk0[c + 1] - b_lo;
-        const int n_items = 2 * n_bs + NSUB * n_is;
         const bool staged = n_ob <= kChunkObsDev;
         __syncthreads();                                         // the previous chunk's readers are done
         if (staged) {
+            // one thread per observation: its ten 16-byte loads are in flight together
             for (int ob = threadIdx.x; ob < n_ob; ob += blockDim.x) {
                 const double2* q = reinterpret_cast<const double2*>(P.rec1 + (size_t)kRec1 * (o0 + ob));
                 double r[kRec1];
@@ -848,44 +863,56 @@ __global__ void __launch_bounds__(256, 2) k_chunk_reduce(DevProblem P, ChunkDev 
                 }
             }
         };
-        // one LANE per item, working through the item's pairs / observations with its sums in registers: no
-        // cross-lane reduction, 32 independent record streams per warp.  Items: the two 3 x 6 halves of every image
-        // pair (longest pairs first, feba_chunks.h: the lanes of a warp finish together), then per image its
-        // diagonal block + right-hand side and its camera rows in groups of five.
-        for (int item = threadIdx.x; item < n_items; item += blockDim.x) {
-            if (item < 2 * n_bs) {
-                const int bs = b_lo + (item >> 1), half = item & 1;
+        // one WARP per item, lanes over the item's observation pairs / observations (every lane reads ITS OWN
+        // records from shared memory), sums combined by a reduce-scatter; items of a chunk are dealt out over the
+        // eight warps.  The index of a warp's NEXT item is loaded while the current one is worked on.
+        const int n_items = n_bs + n_is;
+        for (int item = warp; item < n_items; item += (int)(blockDim.x >> 5)) {
+            if (item < n_bs) {
+                const int bs = b_lo + item;
                 const int q0 = C.bslot_pair0[bs], q1 = C.bslot_pair0[bs + 1];
-                double acc[18];
+                double* out = C.blk_part + (size_t)36 * bs;
+                // rows 0..2 and rows 3..5 of the 6 x 6 block in two sweeps over the pairs (18 sums live at a time:
+                // the whole block plus two records would not fit 128 registers)
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    double acc[32];
 #pragma unroll
-                for (int k = 0; k < 18; ++k) acc[k] = 0.0;
-                unsigned int pr = q0 < q1 ? C.pairs[q0] : 0u;
-                for (int q = q0; q < q1; ++q) {
-                    const unsigned int cur = pr;
-                    if (q + 1 < q1) pr = C.pairs[q + 1];         // next index pair while this one is worked on
-                    double ya[18], yb[18];
-                    rec_of((int)(cur & 0xffffu), nullptr, ya);
-                    rec_of((int)(cur >> 16), nullptr, yb);
+                    for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+                    for (int q = q0 + lane; q < q1; q += 32) {
+                        const unsigned int pr = C.pairs[q];
+                        double yb[18];
+                        rec_of((int)(pr >> 16), nullptr, yb);
+                        const int ta = (int)(pr & 0xffffu);
+                        double ya[9];
+                        if (staged) {
+                            const double* qa = srec + ta * kRecS + 12 + 9 * half;
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        const double a0 = ya[9 * half + 3 * i], a1 = ya[9 * half + 3 * i + 1], a2 = ya[9 * half + 3 * i + 2];
+                            for (int k = 0; k < 9; ++k) ya[k] = qa[k];
+                        } else {
+                            double yfull[18];
+                            rec_of(ta, nullptr, yfull);
 #pragma unroll
-                        for (int j = 0; j < 6; ++j) acc[6 * i + j] += a0 * yb[3 * j] + a1 * yb[3 * j + 1] + a2 * yb[3 * j + 2];
+                            for (int k = 0; k < 9; ++k) ya[k] = half ? yfull[9 + k] : yfull[k];
+                        }
+#pragma unroll
+                        for (int i = 0; i < 3; ++i)
+#pragma unroll
+                            for (int j = 0; j < 6; ++j)
+                                acc[6 * i + j] += ya[3 * i] * yb[3 * j] + ya[3 * i + 1] * yb[3 * j + 1] + ya[3 * i + 2] * yb[3 * j + 2];
                     }
+                    const double v0 = warp_reduce_scatter32(acc, lane);
+                    if (lane < 18) out[18 * half + lane] = v0;
                 }
-                double2* out = reinterpret_cast<double2*>(C.blk_part + (size_t)36 * bs + 18 * half);
-#pragma unroll
-                for (int k = 0; k < 9; ++k) out[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
             } else {
-                const int r = item - 2 * n_bs;
-                const int sub = r / n_is, slot = s_lo + (r - sub * n_is);
+                const int slot = s_lo + (item - n_bs);
                 const int q0 = C.slot_obs0[slot], q1 = C.slot_obs0[slot + 1];
                 double* out = C.img_part + (size_t)kImgPartDev * slot;
-                if (sub == 0) {   // diagonal block Je'P Je - Y Y' (= Je'(P - Z Z')Je) and right-hand side Je' r
-                    double acc[27];
+                {   // diagonal block Je'P Je - Y Y' (= Je'(P - Z Z')Je) and right-hand side Je' r
+                    double acc[32];
 #pragma unroll
-                    for (int k = 0; k < 27; ++k) acc[k] = 0.0;
-                    for (int q = q0; q < q1; ++q) {
+                    for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+                    for (int q = q0 + lane; q < q1; q += 32) {
                         const int t = C.slot_obs[q];
                         double je[12], y[18];
                         rec_of(t, je, y);
@@ -910,33 +937,32 @@ __global__ void __launch_bounds__(256, 2) k_chunk_reduce(DevProblem P, ChunkDev 
 #pragma unroll
                         for (int i = 0; i < 6; ++i) acc[21 + i] += je[i] * ra0 + je[6 + i] * ra1;
                     }
+                    const double v0 = warp_reduce_scatter32(acc, lane);
+                    if (lane < 27) out[lane] = v0;
+                }
+                if (HAS_CAM) {   // camera x image block  sum_a H_a Je_a  (NC x 6), 32 entries at a time
 #pragma unroll
-                    for (int k = 0; k < 27; ++k) out[k] = acc[k];
-                } else if (HAS_CAM) {   // camera rows j0 .. j0 + CG - 1 of the camera x image block  sum_a H_a Je_a
-                    const int j0 = CG * (sub - 1);
-                    double acc[CG * 6];
+                    for (int g0 = 0; g0 < NC * 6; g0 += 30) {          // five camera rows = 30 entries per pass
+                        double acc[32];
 #pragma unroll
-                    for (int k = 0; k < CG * 6; ++k) acc[k] = 0.0;
-                    for (int q = q0; q < q1; ++q) {
-                        const int t = C.slot_obs[q];
-                        const double2* r2v = reinterpret_cast<const double2*>(P.rec2 + (size_t)R2 * (o0 + t) + 2);
-                        double2 hv[CG];
+                        for (int k = 0; k < 32; ++k) acc[k] = 0.0;
+                        for (int q = q0 + lane; q < q1; q += 32) {
+                            const int t = C.slot_obs[q];
+                            const double2* r2v = reinterpret_cast<const double2*>(P.rec2 + (size_t)R2 * (o0 + t) + 2);
+                            double je[12];
+                            rec_of(t, je, nullptr);
 #pragma unroll
-                        for (int jj = 0; jj < CG; ++jj) hv[jj] = j0 + jj < NC ? r2v[j0 + jj] : make_double2(0.0, 0.0);
-                        double je[12];
-                        rec_of(t, je, nullptr);
+                            for (int jj = 0; jj < 5; ++jj) {
+                                if (g0 / 6 + jj < NC) {
+                                    const double2 hv = r2v[g0 / 6 + jj];
 #pragma unroll
-                        for (int jj = 0; jj < CG; ++jj) {
-#pragma unroll
-                            for (int i = 0; i < 6; ++i) acc[6 * jj + i] += hv[jj].x * je[i] + hv[jj].y * je[6 + i];
+                                    for (int i = 0; i < 6; ++i) acc[6 * jj + i] += hv.x * je[i] + hv.y * je[6 + i];
+                                }
+                            }
                         }
+                        const double v0 = warp_reduce_scatter32(acc, lane);
+                        if (lane < 30 && g0 + lane < NC * 6) out[27 + g0 + lane] = v0;
                     }
-#pragma unroll
-                    for (int jj = 0; jj < CG; ++jj)
-                        if (j0 + jj < NC) {
-#pragma unroll
-                            for (int i = 0; i < 6; ++i) out[27 + 6 * (j0 + jj) + i] = acc[6 * jj + i];
-                        }
                 }
             }
         }

@@ -519,6 +519,134 @@ __global__ void __launch_bounds__(256) k_trsm_fused(double* X, int ldx, const do
         }
 }
 
+#define AT(A, ld, br, bc) ((A) + (size_t)(br) * kBlk + (size_t)(ld) * (bc) * kBlk)
+#define LINV(W, b) ((W) + (size_t)(b) * kBlk * kBlk)
+
+// ------------------------------------------------------------------------------------------
+// Left-looking factorisation of ONE 64-block column j of a supertile (blocks [b0, b0 + n) on the diagonal) in ONE
+// launch: CTA r handles block row i = j + r of the tile,
+//     D = A[j,j] - sum_{k<j} A[j,k] A[j,k]'   and   L = chol(D), Linv = L^-1     -- by EVERY CTA, redundantly
+//     r == 0 stores L and Linv;   r > 0:  A[i,j] = (A[i,j] - sum_{k<j} A[i,k] A[j,k]') Linv'.
+// The recursive form issues potrf -> triangular solve -> symmetric update per block, three dependent launches on
+// the critical path of the factorisation (~67 us per block on BASELINE configs[3]); here the 20 us diagonal
+// factorisation is repeated by the few CTAs of the column instead of being waited for, and a block of the chain
+// costs one launch.  Products on DMMA (m8n8k4), tiles through shared memory.
+constexpr size_t kColumnSmem = (kPotrfSmemDoubles + 2 * 64 * TS) * sizeof(double);
+
+__global__ void __launch_bounds__(256) k_chol_column(double* __restrict__ A, int ld, double* __restrict__ Linv,
+                                                     int b0, int j, int* __restrict__ info) {
+    extern __shared__ __align__(16) double csm[];
+    const PotrfSmem S = potrf_views(csm);
+    double(*Tj)[TS] = reinterpret_cast<double(*)[TS]>(csm + kPotrfSmemDoubles);            // A[j,k] as [k][row]
+    double(*Ti)[TS] = reinterpret_cast<double(*)[TS]>(csm + kPotrfSmemDoubles + 64 * TS);  // A[i,k] as [k][row]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp & 1, wn = warp >> 1;
+    const int row0 = wm * 32, col0 = wn * 16;
+    const int lr = lane >> 2, lk = lane & 3;
+    const int bj = b0 + j, bi = bj + (int)blockIdx.x;
+    const bool diag = blockIdx.x == 0;
+    double accD[4][2][2], accR[4][2][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) accD[i][jj][0] = accD[i][jj][1] = accR[i][jj][0] = accR[i][jj][1] = 0.0;
+    for (int k = 0; k < j; ++k) {
+        __syncthreads();                                     // the tiles of the previous step have been read
+        load_tile<64, TS>(Tj, AT(A, ld, bj, b0 + k), ld, tid);
+        if (!diag) load_tile<64, TS>(Ti, AT(A, ld, bi, b0 + k), ld, tid);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < 16; ++kk) {
+            double aj[4], ai[4], b[2];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) aj[t] = Tj[kk * 4 + lk][row0 + t * 8 + lr];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) b[t] = Tj[kk * 4 + lk][col0 + t * 8 + lr];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) dmma884(accD[i][jj][0], accD[i][jj][1], aj[i], b[jj]);
+            if (!diag) {
+#pragma unroll
+                for (int t = 0; t < 4; ++t) ai[t] = Ti[kk * 4 + lk][row0 + t * 8 + lr];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) dmma884(accR[i][jj][0], accR[i][jj][1], ai[i], b[jj]);
+            }
+        }
+    }
+    __syncthreads();
+    // D -> sA (lower triangle, zero above), sI := 0; the row block's right-hand side R -> Ti as [column][row]
+    {
+        const double* Djj = AT(A, ld, bj, bj);
+        const double* Cij = AT(A, ld, bi, bj);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = row0 + i * 8 + lr, c = col0 + jj * 8 + 2 * lk + h;
+                    S.sA[r][c] = r >= c ? Djj[r + (size_t)ld * c] - accD[i][jj][h] : 0.0;
+                    S.sI[r][c] = 0.0;
+                    if (!diag) Ti[c][r] = Cij[r + (size_t)ld * c] - accR[i][jj][h];
+                }
+    }
+    __syncthreads();
+    const bool bad = potrf64_factor(S, tid);
+    if (diag) {
+        if (bad && lane == 0) atomicExch(info, 1);
+        const int r = tid & 63, c0 = tid >> 6;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int c = c0 + 4 * t;
+            if (r >= c) A[(size_t)bj * kBlk + r + (size_t)ld * ((size_t)bj * kBlk + c)] = S.sA[r][c];
+        }
+    }
+    potrf64_inverse(S, tid);
+    __syncthreads();
+    if (diag) {
+        double* Lout = LINV(Linv, bj);
+        const int r = tid & 63, c0 = tid >> 6;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int c = c0 + 4 * t;
+            Lout[r + (size_t)kBlk * c] = S.sI[r][c];
+        }
+        return;
+    }
+    // X = R Linv':  X(r, n) = sum_c R(r, c) Linv(n, c)
+    double acc[4][2][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) acc[i][jj][0] = acc[i][jj][1] = 0.0;
+#pragma unroll 4
+    for (int kk = 0; kk < 16; ++kk) {
+        double a[4], b[2];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) a[t] = Ti[kk * 4 + lk][row0 + t * 8 + lr];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) b[t] = S.sI[col0 + t * 8 + lr][kk * 4 + lk];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) dmma884(acc[i][jj][0], acc[i][jj][1], a[i], b[jj]);
+    }
+    double* Xg = AT(A, ld, bi, bj);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            const int r = row0 + i * 8 + lr, c = col0 + jj * 8 + 2 * lk;
+            Xg[r + (size_t)ld * c] = acc[i][jj][0];
+            Xg[r + (size_t)ld * (c + 1)] = acc[i][jj][1];
+        }
+}
+
 // Timing experiments only (results are garbage): FEBA_CHOL_SKIP bitmask drops kernel classes from the
 // factorisation -- 1: potrf64, 2: fused triangular leaves, 4: products with < 256 tiles, 8: the rest.
 static int chol_skip() {
@@ -552,9 +680,6 @@ static cudaError_t gemm_nt(double* C, int ldc, const double* A, int lda, const d
     return cudaGetLastError();
 }
 
-#define AT(A, ld, br, bc) ((A) + (size_t)(br) * kBlk + (size_t)(ld) * (bc) * kBlk)
-
-#define LINV(W, b) ((W) + (size_t)(b) * kBlk * kBlk)
 
 // X (mr x n blocks at block (r0, c0)) := X * L^-T with L the n x n block triangle at (c0, c0).
 // Below five blocks the whole solve is one fused launch (k_trsm_fused).
@@ -605,6 +730,24 @@ static cudaError_t rchol(double* A, int ld, double* Linv, int b0, int n, int aug
                 1, st, launches);
     if (e != cudaSuccess) return e;
     return rchol(A, ld, Linv, b0 + n1, n2, aug_blk, info, st, launches);
+}
+
+// DIAG task of the task graph: blocks [b0, b0 + n) on the diagonal.  Supertiles of a plan (<= kColumnMax blocks) go
+// column by column through k_chol_column, one launch per block; larger ones keep the recursive form, whose big
+// products use many CTAs.  FEBA_CHOL_COLUMNS=0: always recursive.
+constexpr int kColumnMax = 8;
+static cudaError_t chol_diag_tile(double* A, int ld, double* Linv, int b0, int n, int* info, cudaStream_t st,
+                                  int64_t* launches) {
+    static const bool use_columns = !(std::getenv("FEBA_CHOL_COLUMNS") && std::atoi(std::getenv("FEBA_CHOL_COLUMNS")) == 0);
+    if (!use_columns || n > kColumnMax || (chol_skip() & 1)) return rchol(A, ld, Linv, b0, n, -1, info, st, launches);
+    static SmemOptIn opt;
+    cudaError_t e0 = opt.ensure(k_chol_column, kColumnSmem);
+    if (e0 != cudaSuccess) return e0;
+    for (int j = 0; j < n; ++j) {
+        k_chol_column<<<n - j, 256, kColumnSmem, st>>>(A, ld, Linv, b0, j, info);
+        ++*launches;
+    }
+    return cudaGetLastError();
 }
 
 cudaError_t chol_augmented(double* A, int ld, int nb, double* Linv, int* info, cudaStream_t st, int64_t* launches) {
@@ -691,7 +834,7 @@ static cudaError_t chol_tiles_captured(double* A, int ld, int nb, double* Linv, 
     for (int k = k_begin; k < k_end && k < NT; ++k) {
         if (!mine(k) || nblk(k) == 0) continue;
         DAG_CU(begin_task({tid(k, k)}));
-        DAG_CU(rchol(A, ld, Linv, blk0(k), nblk(k), -1, info, main, launches));
+        DAG_CU(chol_diag_tile(A, ld, Linv, blk0(k), nblk(k), info, main, launches));
         DAG_CU(end_task(tid(k, k)));
         for (int i = k + 1; i < NR; ++i) {
             if (!on(i, k) || nblk(i) == 0) continue;
@@ -767,7 +910,7 @@ cudaError_t chol_tiles(double* A, int ld, int nb, double* Linv, int* info, const
         const int ck = chain_of(k);
         {   // DIAG(k)
             DAG_CU(acquire(ck, k, k));
-            DAG_CU(rchol(A, ld, Linv, blk0(k), nblk(k), -1, info, D.streams[ck], launches));
+            DAG_CU(chol_diag_tile(A, ld, Linv, blk0(k), nblk(k), info, D.streams[ck], launches));
             DAG_CU(release(ck, k, k));
         }
         int first_row = -1;                           // first coupled tile below k: the next link of the chain
