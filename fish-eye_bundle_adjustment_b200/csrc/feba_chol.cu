@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(256) k_trsm_fused(double* X, int ldx, const do
 // Left-looking factorisation of ONE 64-block column j of a supertile (blocks [b0, b0 + n) on the diagonal) in ONE
 // launch: CTA r handles block row i = j + r of the tile,
 //     D = A[j,j] - sum_{k<j} A[j,k] A[j,k]'   and   L = chol(D), Linv = L^-1     -- by EVERY CTA, redundantly
-//     r == 0 stores L and Linv;   r > 0:  A[i,j] = (A[i,j] - sum_{k<j} A[i,k] A[j,k]') Linv'.
+//     r == 0 stores Linv (A[j,j] keeps D, see below);   r > 0:  A[i,j] = (A[i,j] - sum_{k<j} A[i,k] A[j,k]') Linv'.
 // The recursive form issues potrf -> triangular solve -> symmetric update per block, three dependent launches on
 // the critical path of the factorisation (~67 us per block on BASELINE configs[3]); here the 20 us diagonal
 // factorisation is repeated by the few CTAs of the column instead of being waited for, and a block of the chain
@@ -597,15 +597,10 @@ __global__ void __launch_bounds__(256) k_chol_column(double* __restrict__ A, int
     }
     __syncthreads();
     const bool bad = potrf64_factor(S, tid);
-    if (diag) {
-        if (bad && lane == 0) atomicExch(info, 1);
-        const int r = tid & 63, c0 = tid >> 6;
-#pragma unroll
-        for (int t = 0; t < 16; ++t) {
-            const int c = c0 + 4 * t;
-            if (r >= c) A[(size_t)bj * kBlk + r + (size_t)ld * ((size_t)bj * kBlk + c)] = S.sA[r][c];
-        }
-    }
+    // A[j,j] is NOT overwritten with L: the other CTAs of this launch read it (D) at their own pace, and no later
+    // kernel reads the diagonal block of a factor -- triangular solves use Linv (forward: k_trsm_fused, backward:
+    // k_backstep, inverse: rtrsm_identity) and the off-diagonal blocks only
+    if (diag && bad && lane == 0) atomicExch(info, 1);
     potrf64_inverse(S, tid);
     __syncthreads();
     if (diag) {
