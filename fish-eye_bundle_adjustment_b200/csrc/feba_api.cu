@@ -1133,12 +1133,36 @@ static TileView plan_view(const feba_handle* h) {
 //   (2) after every rank has eliminated its own subtrees: the shared top part of S (lower trapezoid from
 //       top_row0 on, incl. the augmented block row) -- the only large message of an iteration;
 //   (3) the solution of the reduced system, n_pad doubles (own rows + rank 0's copy of the shared rows).
-static int enqueue_solve(feba_handle* h) {
+static int enqueue_solve_pre(feba_handle* h) {
     DevProblem& P = h->P;
-    const int nb = P.n_pad / kBlk;
     CU(h, launch_border_prepare(P, h->eop, h->dg, h->stream, &h->launches));
     if (h->shard) NC(h, dist_allreduce_f64(&h->dist, h->dg, (size_t)P.n_pad, h->stream));
     CU(h, launch_border_scale(P, h->dg, h->dvec, h->info, h->blk_list, h->n_blk_scale, h->stream, &h->launches));
+    return FEBA_OK;
+}
+
+static int enqueue_solve_post(feba_handle* h) {
+    DevProblem& P = h->P;
+    CU(h, launch_update_cam(P, h->sol, h->dvec, h->dcam, h->dcam_unscaled, h->eop, h->iop, h->scal, h->stream));
+    ++h->launches;
+    if (P.n_tie > 0 && P.n_seg > 0) {
+        CU(h, launch_backsub(P, h->sm_count, h->stream));
+        CU(h, launch_sum_partials(P.partial, backsub_warps(P, h->sm_count), 1, 0, h->scal + 1, h->stream));
+        h->launches += 2;
+    } else {
+        CU(h, cudaMemsetAsync(h->scal + 1, 0, sizeof(double), h->stream));
+    }
+    CU(h, record(h, 5));
+    return FEBA_OK;
+}
+
+static int enqueue_solve(feba_handle* h) {
+    DevProblem& P = h->P;
+    const int nb = P.n_pad / kBlk;
+    {
+        const int rc_pre = enqueue_solve_pre(h);
+        if (rc_pre) return rc_pre;
+    }
     if (h->use_dag && h->dag_cols) {
         const cudaError_t ed = chol_cols(P.S, P.ld, nb, h->Linv, h->info, h->dag, h->dist_active ? &h->dist : nullptr,
                                          h->stream, &h->launches);
@@ -1176,17 +1200,7 @@ static int enqueue_solve(feba_handle* h) {
         NC(h, dist_allreduce_f64(&h->dist, h->sol, (size_t)P.n_pad, h->stream));
     }
     CU(h, record(h, 4));
-    CU(h, launch_update_cam(P, h->sol, h->dvec, h->dcam, h->dcam_unscaled, h->eop, h->iop, h->scal, h->stream));
-    ++h->launches;
-    if (P.n_tie > 0 && P.n_seg > 0) {
-        CU(h, launch_backsub(P, h->sm_count, h->stream));
-        CU(h, launch_sum_partials(P.partial, backsub_warps(P, h->sm_count), 1, 0, h->scal + 1, h->stream));
-        h->launches += 2;
-    } else {
-        CU(h, cudaMemsetAsync(h->scal + 1, 0, sizeof(double), h->stream));
-    }
-    CU(h, record(h, 5));
-    return FEBA_OK;
+    return enqueue_solve_post(h);
 }
 
 static int solve_async(feba_handle* h) {
@@ -1278,6 +1292,11 @@ int feba_iterate(feba_handle* h, double* deltasum_out) {
 // results are bit-identical to feba_iterate per handle.
 struct feba_batch {
     std::vector<feba_handle*> hs;
+    // systems of one shape and small enough for the single-chain form: factorisation and backward substitution
+    // of ALL of them run as batched launches (blockIdx.y = system), nb + 1 and nb launches per step in total
+    bool fused = false;
+    double **dA = nullptr, **dLinv = nullptr, **dy = nullptr, **dsol = nullptr;
+    int** dinfo = nullptr;
     cudaGraphExec_t exec = nullptr;
     cudaEvent_t fork = nullptr, done = nullptr;
     std::vector<cudaEvent_t> join;
@@ -1289,6 +1308,8 @@ void feba_batch_destroy(feba_batch* b) {
     if (b->exec) cudaGraphExecDestroy(b->exec);
     if (b->fork) cudaEventDestroy(b->fork);
     if (b->done) cudaEventDestroy(b->done);
+    for (void* p : {(void*)b->dA, (void*)b->dLinv, (void*)b->dy, (void*)b->dsol, (void*)b->dinfo})
+        if (p) cudaFree(p);
     for (auto& e : b->join)
         if (e) cudaEventDestroy(e);
     delete b;
@@ -1319,6 +1340,33 @@ int feba_batch_create(feba_handle* const* handles, int32_t n, feba_batch** out) 
     if (!ok) {
         feba_batch_destroy(b);
         return fail(nullptr, FEBA_ERR_CUDA, "feba_batch_create: event creation failed");
+    }
+    // one shape, single-chain form, dense datum: the factorisation can be batched
+    b->fused = n > 1 && !(std::getenv("FEBA_BATCH_FUSED") && std::atoi(std::getenv("FEBA_BATCH_FUSED")) == 0);
+    for (int i = 0; i < n && b->fused; ++i) {
+        const feba_handle* h = handles[i];
+        b->fused = !h->use_dag && !h->plan.masked && h->P.n_pad == handles[0]->P.n_pad && h->P.inner == handles[0]->P.inner &&
+                   h->P.datum == nullptr && h->P.n_pad / kBlk <= 32;
+    }
+    if (b->fused) {
+        std::vector<double*> vA, vL, vy, vs;
+        std::vector<int*> vi;
+        for (int i = 0; i < n; ++i) {
+            vA.push_back(handles[i]->P.S);
+            vL.push_back(handles[i]->Linv);
+            vy.push_back(handles[i]->ywork);
+            vs.push_back(handles[i]->sol);
+            vi.push_back(handles[i]->info);
+        }
+        auto up = [&](void** dst, const void* src, size_t bytes) {
+            return cudaMalloc(dst, bytes) == cudaSuccess && cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+        };
+        const size_t pb = (size_t)n * sizeof(void*);
+        if (!(up((void**)&b->dA, vA.data(), pb) && up((void**)&b->dLinv, vL.data(), pb) && up((void**)&b->dy, vy.data(), pb) &&
+              up((void**)&b->dsol, vs.data(), pb) && up((void**)&b->dinfo, vi.data(), pb))) {
+            feba_batch_destroy(b);
+            return fail(nullptr, FEBA_ERR_CUDA, "feba_batch_create: device allocation failed");
+        }
     }
     *out = b;
     return FEBA_OK;
@@ -1351,18 +1399,57 @@ int feba_batch_iterate_async(feba_batch* b) {
         int rc = FEBA_OK;
         cudaError_t e = cudaEventRecord(b->fork, h0->stream);
         for (size_t i = 1; i < n && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(b->hs[i]->stream, b->fork, 0);
-        for (size_t i = 0; i < n && e == cudaSuccess && rc == FEBA_OK; ++i) {
-            feba_handle* h = b->hs[i];
-            const int64_t before = h->launches;
-            h->capturing = true;
-            rc = enqueue_assemble(h);
-            if (rc == FEBA_OK) rc = enqueue_solve(h);
-            h->capturing = false;
-            b->launches[i] = h->launches - before;
+        std::vector<int64_t> before(n);
+        for (size_t i = 0; i < n; ++i) {
+            before[i] = b->hs[i]->launches;
+            b->hs[i]->capturing = true;
         }
-        for (size_t i = 1; i < n && e == cudaSuccess && rc == FEBA_OK; ++i) {
-            e = cudaEventRecord(b->join[i], b->hs[i]->stream);
-            if (e == cudaSuccess) e = cudaStreamWaitEvent(h0->stream, b->join[i], 0);
+        // every handle's stream runs `stage`, then the first handle's stream waits for all of them
+        auto all_handles = [&](int (*stage)(feba_handle*)) {
+            for (size_t i = 0; i < n && e == cudaSuccess && rc == FEBA_OK; ++i) rc = stage(b->hs[i]);
+            for (size_t i = 1; i < n && e == cudaSuccess && rc == FEBA_OK; ++i) {
+                e = cudaEventRecord(b->join[i], b->hs[i]->stream);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(h0->stream, b->join[i], 0);
+            }
+        };
+        // the other streams continue after what the first one has done so far
+        auto release = [&]() {
+            if (e == cudaSuccess && rc == FEBA_OK) e = cudaEventRecord(b->fork, h0->stream);
+            for (size_t i = 1; i < n && e == cudaSuccess && rc == FEBA_OK; ++i) e = cudaStreamWaitEvent(b->hs[i]->stream, b->fork, 0);
+        };
+        if (!b->fused) {
+            all_handles([](feba_handle* h) {
+                const int r1 = enqueue_assemble(h);
+                return r1 ? r1 : enqueue_solve(h);
+            });
+        } else {
+            const int nb = h0->P.n_pad / kBlk;
+            all_handles([](feba_handle* h) {
+                const int r1 = enqueue_assemble(h);
+                return r1 ? r1 : enqueue_solve_pre(h);
+            });
+            if (e == cudaSuccess && rc == FEBA_OK)
+                e = chol_augmented_batched(b->dA, h0->P.ld, nb, b->dLinv, b->dinfo, (int)n, h0->stream, &h0->launches);
+            release();
+            all_handles([](feba_handle* h) {
+                cudaError_t e3 = record(h, 3);
+                if (e3 == cudaSuccess)
+                    e3 = border_and_combine(h->P.S, h->P.ld, h->P.n_pad / kBlk, h->P.inner, h->work, h->ywork, h->info, h->stream,
+                                            &h->launches, 0);
+                return e3 == cudaSuccess ? (int)FEBA_OK : fail(h, FEBA_ERR_CUDA, "border stage: %s", cudaGetErrorString(e3));
+            });
+            if (e == cudaSuccess && rc == FEBA_OK)
+                e = backsolve_batched(b->dA, h0->P.ld, nb, b->dLinv, b->dy, b->dsol, (int)n, h0->sm_count, h0->stream, &h0->launches);
+            release();
+            all_handles([](feba_handle* h) {
+                const cudaError_t e4 = record(h, 4);
+                if (e4 != cudaSuccess) return fail(h, FEBA_ERR_CUDA, "event: %s", cudaGetErrorString(e4));
+                return enqueue_solve_post(h);
+            });
+        }
+        for (size_t i = 0; i < n; ++i) {
+            b->hs[i]->capturing = false;
+            b->launches[i] = b->hs[i]->launches - before[i];
         }
         cudaGraph_t graph = nullptr;
         const cudaError_t ee = cudaStreamEndCapture(h0->stream, &graph);

@@ -533,8 +533,10 @@ __global__ void __launch_bounds__(256) k_trsm_fused(double* X, int ldx, const do
 // costs one launch.  Products on DMMA (m8n8k4), tiles through shared memory.
 constexpr size_t kColumnSmem = (kPotrfSmemDoubles + 2 * 64 * TS) * sizeof(double);
 
-__global__ void __launch_bounds__(256) k_chol_column(double* __restrict__ A, int ld, double* __restrict__ Linv,
-                                                     int b0, int j, int* __restrict__ info) {
+// finish != 0 (one CTA): only D = A[j,j] - sum_{k<j} A[j,k] A[j,k]' is formed and stored (lower triangle) -- the
+// Schur complement T of the augmented block row, which is never factorised.
+__device__ __forceinline__ void chol_column_body(double* __restrict__ A, int ld, double* __restrict__ Linv, int b0, int j,
+                                                 int* __restrict__ info, int finish) {
     extern __shared__ __align__(16) double csm[];
     const PotrfSmem S = potrf_views(csm);
     double(*Tj)[TS] = reinterpret_cast<double(*)[TS]>(csm + kPotrfSmemDoubles);            // A[j,k] as [k][row]
@@ -596,6 +598,15 @@ __global__ void __launch_bounds__(256) k_chol_column(double* __restrict__ A, int
                 }
     }
     __syncthreads();
+    if (finish) {
+        const int r = tid & 63, c0 = tid >> 6;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int c = c0 + 4 * t;
+            if (r >= c) A[(size_t)bj * kBlk + r + (size_t)ld * ((size_t)bj * kBlk + c)] = S.sA[r][c];
+        }
+        return;
+    }
     const bool bad = potrf64_factor(S, tid);
     // A[j,j] is NOT overwritten with L: the other CTAs of this launch read it (D) at their own pace, and no later
     // kernel reads the diagonal block of a factor -- triangular solves use Linv (forward: k_trsm_fused, backward:
@@ -640,6 +651,18 @@ __global__ void __launch_bounds__(256) k_chol_column(double* __restrict__ A, int
             Xg[r + (size_t)ld * c] = acc[i][jj][0];
             Xg[r + (size_t)ld * (c + 1)] = acc[i][jj][1];
         }
+}
+
+__global__ void __launch_bounds__(256) k_chol_column(double* __restrict__ A, int ld, double* __restrict__ Linv,
+                                                     int b0, int j, int* __restrict__ info, int finish) {
+    chol_column_body(A, ld, Linv, b0, j, info, finish);
+}
+
+// The same column of MANY independent systems of one shape (BatchRun sweep, feba_batch): blockIdx.y = system.
+__global__ void __launch_bounds__(256) k_chol_column_batched(double* const* __restrict__ As, int ld,
+                                                             double* const* __restrict__ Linvs, int b0, int j,
+                                                             int* const* __restrict__ infos, int finish) {
+    chol_column_body(As[blockIdx.y], ld, Linvs[blockIdx.y], b0, j, infos[blockIdx.y], finish);
 }
 
 // Timing experiments only (results are garbage): FEBA_CHOL_SKIP bitmask drops kernel classes from the
@@ -739,14 +762,43 @@ static cudaError_t chol_diag_tile(double* A, int ld, double* Linv, int b0, int n
     cudaError_t e0 = opt.ensure(k_chol_column, kColumnSmem);
     if (e0 != cudaSuccess) return e0;
     for (int j = 0; j < n; ++j) {
-        k_chol_column<<<n - j, 256, kColumnSmem, st>>>(A, ld, Linv, b0, j, info);
+        k_chol_column<<<n - j, 256, kColumnSmem, st>>>(A, ld, Linv, b0, j, info, 0);
         ++*launches;
     }
     return cudaGetLastError();
 }
 
+// Small systems (<= kAugColumnsMax blocks): nb + 1 launches instead of ~3 nb -- column j of the factor with the
+// augmented block row as its last row block, then the Schur complement T of the augmented block.
+constexpr int kAugColumnsMax = 32;
 cudaError_t chol_augmented(double* A, int ld, int nb, double* Linv, int* info, cudaStream_t st, int64_t* launches) {
-    return rchol(A, ld, Linv, 0, nb + 1, nb, info, st, launches);
+    static const bool use_columns = !(std::getenv("FEBA_CHOL_COLUMNS") && std::atoi(std::getenv("FEBA_CHOL_COLUMNS")) == 0);
+    if (!use_columns || nb > kAugColumnsMax || (chol_skip() & 1)) return rchol(A, ld, Linv, 0, nb + 1, nb, info, st, launches);
+    static SmemOptIn opt;
+    cudaError_t e0 = opt.ensure(k_chol_column, kColumnSmem);
+    if (e0 != cudaSuccess) return e0;
+    for (int j = 0; j < nb; ++j) {
+        k_chol_column<<<nb + 1 - j, 256, kColumnSmem, st>>>(A, ld, Linv, 0, j, info, 0);
+        ++*launches;
+    }
+    k_chol_column<<<1, 256, kColumnSmem, st>>>(A, ld, Linv, 0, nb, info, 1);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+// The same for a batch of systems of one shape: pointer arrays on the device, one launch per column for all.
+cudaError_t chol_augmented_batched(double* const* As, int ld, int nb, double* const* Linvs, int* const* infos, int n_sys,
+                                   cudaStream_t st, int64_t* launches) {
+    static SmemOptIn opt;
+    cudaError_t e0 = opt.ensure(k_chol_column_batched, kColumnSmem);
+    if (e0 != cudaSuccess) return e0;
+    for (int j = 0; j < nb; ++j) {
+        k_chol_column_batched<<<dim3(nb + 1 - j, n_sys), 256, kColumnSmem, st>>>(As, ld, Linvs, 0, j, infos, 0);
+        ++*launches;
+    }
+    k_chol_column_batched<<<dim3(1, n_sys), 256, kColumnSmem, st>>>(As, ld, Linvs, 0, nb, infos, 1);
+    ++*launches;
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1398,9 +1450,9 @@ struct ColSegs {
     int c0[kMaxSeg], c1[kMaxSeg];
 };
 
-__global__ void __launch_bounds__(256) k_backstep(const double* __restrict__ A, int ld, int k,
-                                                  const double* __restrict__ Linv_k, double* __restrict__ y,
-                                                  double* __restrict__ x_out, ColSegs segs) {
+__device__ __forceinline__ void backstep_body(const double* __restrict__ A, int ld, int k,
+                                              const double* __restrict__ Linv_k, double* __restrict__ y,
+                                              double* __restrict__ x_out, const ColSegs& segs) {
     __shared__ double sx[kBlk];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double* yk = y + (size_t)k * kBlk;
@@ -1437,6 +1489,52 @@ __global__ void __launch_bounds__(256) k_backstep(const double* __restrict__ A, 
     }
     // other CTAs may still be reading y_k, so the solution goes to a separate vector
     if (blockIdx.x == 0 && tid < kBlk) x_out[(size_t)k * kBlk + tid] = sx[tid];
+}
+
+__global__ void __launch_bounds__(256) k_backstep(const double* __restrict__ A, int ld, int k,
+                                                  const double* __restrict__ Linv_k, double* __restrict__ y,
+                                                  double* __restrict__ x_out, ColSegs segs) {
+    backstep_body(A, ld, k, Linv_k, y, x_out, segs);
+}
+
+// blockIdx.y = system of a batch of equal shape (feba_batch)
+__global__ void __launch_bounds__(256) k_backstep_batched(double* const* __restrict__ As, int ld, int k,
+                                                          double* const* __restrict__ Linvs, double* const* __restrict__ ys,
+                                                          double* const* __restrict__ xs, ColSegs segs) {
+    backstep_body(As[blockIdx.y], ld, k, Linvs[blockIdx.y] + (size_t)k * kBlk * kBlk, ys[blockIdx.y], xs[blockIdx.y], segs);
+}
+
+// backward substitution of a batch of dense systems of one shape: nb launches for all of them
+cudaError_t backsolve_batched(double* const* As, int ld, int nb, double* const* Linvs, double* const* ys, double* const* xs,
+                              int n_sys, int sm_count, cudaStream_t st, int64_t* launches) {
+    for (int k = nb - 1; k >= 0; --k) {
+        ColSegs segs;
+        segs.n = 1;
+        segs.c0[0] = 0;
+        segs.c1[0] = k * kBlk;
+        int grid = (k * kBlk + 7) / 8;
+        const int cap = (2 * sm_count + n_sys - 1) / n_sys > 1 ? (2 * sm_count + n_sys - 1) / n_sys : 1;
+        if (grid > cap) grid = cap;
+        if (grid < 1) grid = 1;
+        k_backstep_batched<<<dim3(grid, n_sys), 256, 0, st>>>(As, ld, k, Linvs, ys, xs, segs);
+        ++*launches;
+    }
+    return cudaGetLastError();
+}
+
+// border solve + combination only (the first part of border_and_backsolve), for callers that batch the rest
+cudaError_t border_and_combine(double* A, int ld, int nb, int inner, double* work, double* ywork, int* info,
+                               cudaStream_t st, int64_t* launches, int sparse_datum) {
+    const int n_pad = nb * kBlk;
+    if (inner) {
+        if (sparse_datum) k_border_solve_sparse<<<1, 32, 0, st>>>(A, ld, n_pad, work, info);
+        else k_border_solve<<<1, 32, 0, st>>>(A, ld, n_pad, work, info);
+        ++*launches;
+    }
+    const int ncoef = inner ? (sparse_datum ? 2 * kDatumCols : kDatumCols) : 0;
+    k_combine<<<(n_pad + 255) / 256, 256, 0, st>>>(A, ld, n_pad, ncoef, work, ywork);
+    ++*launches;
+    return cudaGetLastError();
 }
 
 // block_owner (host, nb entries, optional; group runs): blocks of subtrees owned by other ranks are skipped --

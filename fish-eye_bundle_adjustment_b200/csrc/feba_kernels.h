@@ -70,6 +70,13 @@ cudaError_t launch_residuals(const DevProblem& P, int sm_count, const int* opt, 
 // Linv: nb blocks of kBlk x kBlk (column-major): inverses of the diagonal factors.
 // info (device int) is set non-zero when a pivot is not positive.
 cudaError_t chol_augmented(double* A, int ld, int nb, double* Linv, int* info, cudaStream_t st, int64_t* launches);
+// Batches of systems of one shape (feba_batch): device arrays of pointers, one launch per column / step for all.
+cudaError_t chol_augmented_batched(double* const* As, int ld, int nb, double* const* Linvs, int* const* infos, int n_sys,
+                                   cudaStream_t st, int64_t* launches);
+cudaError_t backsolve_batched(double* const* As, int ld, int nb, double* const* Linvs, double* const* ys, double* const* xs,
+                              int n_sys, int sm_count, cudaStream_t st, int64_t* launches);
+cudaError_t border_and_combine(double* A, int ld, int nb, int inner, double* work, double* ywork, int* info,
+                               cudaStream_t st, int64_t* launches, int sparse_datum);
 // Stream pool + events of the task-graph form (owned by the handle).
 struct DagStreams {
     int tile_blocks = 8;            // supertile size in 64-blocks

@@ -48,6 +48,12 @@ def main():
         err, x0, _ = fb.Buildxhat(prob)
         dense = run(prob, x0, -1)
         sp = run(prob, x0, plan)
+        sp2 = run(prob, x0, plan)
+        # the task graph only reorders INDEPENDENT tiles: reruns are bit-identical (a missing dependency -- a race --
+        # shows up here; compute-sanitizer is not available on this pool)
+        if not (np.array_equal(sp["xhat"], sp2["xhat"]) and np.array_equal(sp["v"], sp2["v"]) and np.array_equal(sp["d1"], sp2["d1"])):
+            print(f"[{mode}] FAIL: two runs of the plan form differ")
+            ok = False
         ref = sparse.gauss_newton(prob, x0) if n_img < 400 else cport.CPort(prob).gauss_newton(x0)
         assert not dense["info"]["active"]
         print(f"[{mode}] u_c {prob.u_c}  plan {sp['plan']}  {sp['info']}")
