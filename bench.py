@@ -468,7 +468,7 @@ def run_ours(args, rank, world, local_rank):
                 "peak_source": "cuBLAS DGEMM 8192^3 measured live in this run (FP64 is not in MEASURED_PEAKS.json); "
                                "DMMA issue peak by microbenchmark 37.1 TFLOP/s (profiles/r1_dmma_rate_microbench.txt)"}
     else:
-        tr, tr_src = ncu_traffic("assembly")
+        tr, tr_src = ncu_traffic("assembly (")
         roof = {"kernel": "k_point_pass + k_image_pass + k_pair_pass (fused BuildAwG + normal blocks + Schur); achieved = "
                           "algorithmic bytes of SURVEY 8(d) over the assembly phase",
                 "bound": "hbm", "achieved": kernels["assemble_schur"]["GBps"], "peak": hbm_peak, "unit": "GB/s",
