@@ -1238,6 +1238,7 @@ static int finish_iteration(feba_handle* h, double* dcam_sum, double* dpts_sum) 
     }
     h->timing_valid = ok;
     if (h->dist_active && !h->dag_cols && h->g_solve.exec && h->g_solve.calls >= 5) dist_prof_report();
+    if (h->g_solve.exec && h->g_solve.calls >= 5) chain_prof_report();
     if (dcam_sum) *dcam_sum = h->scal_host[0];
     if (dpts_sum) *dpts_sum = h->scal_host[1];
     if (*h->info_host == 1)

@@ -41,7 +41,9 @@ template <int NK, int G>
 struct alignas(16) PtSmem {
     static constexpr int NC = NK + 5;
     double rowJc[G][2][NC];
+    double rowPJc[G][2][NC];      // P Jc: the weighted rows, so that the sums below are one product per term
     double rowJt[G][2][3];
+    double rowPJt[G][2][3];
     double roww[G][2];
     double Wc[NC][3];
     double Fc[NC][3];
@@ -108,30 +110,36 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
                 for (int r = 0; r < 2; ++r) {
                     if (HAS_CAM) {
 #pragma unroll
-                        for (int j = 0; j < NC; ++j) sm.rowJc[lane][r][j] = act ? J.Jc[r][j] : 0.0;
+                        for (int j = 0; j < NC; ++j) {
+                            sm.rowJc[lane][r][j] = act ? J.Jc[r][j] : 0.0;
+                            sm.rowPJc[lane][r][j] = act ? J.Jc[r][j] * pw[r] : 0.0;
+                        }
                     }
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) sm.rowJt[lane][r][k] = act ? J.Jt[r][k] : 0.0;
+                    for (int k = 0; k < 3; ++k) {
+                        sm.rowJt[lane][r][k] = act ? J.Jt[r][k] : 0.0;
+                        sm.rowPJt[lane][r][k] = act ? J.Jt[r][k] * pw[r] : 0.0;
+                    }
                     sm.roww[lane][r] = act ? J.w[r] : 0.0;
                 }
                 __syncwarp(gmask);
                 const int nrow = min(G, end - c0);
+                // (x * p) * y with the product x * p taken once per row: the same roundings as x * p * y per term
                 if (HAS_CAM) {
 #pragma unroll
                     for (int t = 0; t < DPL; ++t) {
                         if (lane + G * t < ND) {
                             double a = 0.0;
                             for (int l = 0; l < nrow; ++l)
-                                a += sm.rowJc[l][0][dI[t]] * pw[0] * sm.rowJc[l][0][dJ[t]] +
-                                     sm.rowJc[l][1][dI[t]] * pw[1] * sm.rowJc[l][1][dJ[t]];
+                                a += sm.rowPJc[l][0][dI[t]] * sm.rowJc[l][0][dJ[t]] +
+                                     sm.rowPJc[l][1][dI[t]] * sm.rowJc[l][1][dJ[t]];
                             dacc[t] += a;
                         }
                     }
                     if (lane < NC) {
                         double a = 0.0;
                         for (int l = 0; l < nrow; ++l)
-                            a += sm.rowJc[l][0][lane] * pw[0] * sm.roww[l][0] +
-                                 sm.rowJc[l][1][lane] * pw[1] * sm.roww[l][1];
+                            a += sm.rowPJc[l][0][lane] * sm.roww[l][0] + sm.rowPJc[l][1][lane] * sm.roww[l][1];
                         gcacc += a;
                     }
                     if (is_tie) {
@@ -142,8 +150,7 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
                                 const int i = e / 3, k = e - 3 * i;
                                 double a = 0.0;
                                 for (int l = 0; l < nrow; ++l)
-                                    a += sm.rowJc[l][0][i] * pw[0] * sm.rowJt[l][0][k] +
-                                         sm.rowJc[l][1][i] * pw[1] * sm.rowJt[l][1][k];
+                                    a += sm.rowPJc[l][0][i] * sm.rowJt[l][0][k] + sm.rowPJc[l][1][i] * sm.rowJt[l][1][k];
                                 wcacc[t] += a;
                             }
                         }
@@ -155,13 +162,11 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
                         const int i = lane < 1 ? 0 : (lane < 3 ? 1 : 2);
                         const int k = lane - i * (i + 1) / 2;
                         for (int l = 0; l < nrow; ++l)
-                            a += sm.rowJt[l][0][i] * pw[0] * sm.rowJt[l][0][k] +
-                                 sm.rowJt[l][1][i] * pw[1] * sm.rowJt[l][1][k];
+                            a += sm.rowPJt[l][0][i] * sm.rowJt[l][0][k] + sm.rowPJt[l][1][i] * sm.rowJt[l][1][k];
                     } else {
                         const int k = lane - 6;
                         for (int l = 0; l < nrow; ++l)
-                            a += sm.rowJt[l][0][k] * pw[0] * sm.roww[l][0] +
-                                 sm.rowJt[l][1][k] * pw[1] * sm.roww[l][1];
+                            a += sm.rowPJt[l][0][k] * sm.roww[l][0] + sm.rowPJt[l][1][k] * sm.roww[l][1];
                     }
                     vacc += a;
                 }
@@ -217,7 +222,7 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
         // ---------------- pass 2: per-observation records, staged through shared memory (the
         // pass-1 row buffers are dead by now) and written as 16-byte units, contiguous per record,
         // at the observation's position in the image-major record arrays
-        double* buf = &sm.rowJc[0][0][0];              // (2 NC + 8) * G doubles, >= G * max(18, R2)
+        double* buf = &sm.rowJc[0][0][0];              // rowJc .. roww: (4 NC + 14) * G doubles, >= G * max(18, R2)
         for (int a0 = beg; a0 < end; a0 += G) {
             const int o = a0 + lane;
             const bool act = o < end;

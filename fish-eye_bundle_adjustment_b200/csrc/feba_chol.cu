@@ -833,6 +833,28 @@ static bool upd1_bulk() {
 // last writers of its output tile.  The captured graph then carries the TRUE dependencies of the factorisation
 // and nothing else: with a pool of streams, two unrelated tasks that share a stream are ordered by it (measured on
 // BASELINE configs[3], nested-dissection plan, 1,689 kernel nodes: 8 / 16 / 32 streams -> 9.9 / 9.1 / 7.0 ms).
+// FEBA_CHAIN_PROF=1: time stamps (external event nodes of the captured graph) when the DIAG task of every supertile
+// may start and when it ends; chain_prof_report() prints them after a replay.  Diagnostic only.
+struct ChainProf {
+    std::vector<cudaEvent_t> ev;       // 2 per recorded tile: start, end
+    std::vector<int> tile, blocks, chain;
+    cudaEvent_t origin = nullptr;
+    bool printed = false;
+};
+static ChainProf g_chain;
+
+void chain_prof_report() {
+    if (g_chain.ev.empty() || g_chain.printed || !g_chain.origin) return;
+    g_chain.printed = true;
+    fprintf(stderr, "[feba chain prof] tile blocks slot | DIAG may start, DIAG ends (ms after the factorisation began)\n");
+    for (size_t i = 0; i < g_chain.tile.size(); ++i) {
+        float a = -1.f, b = -1.f;
+        if (cudaEventElapsedTime(&a, g_chain.origin, g_chain.ev[2 * i]) != cudaSuccess) cudaGetLastError();
+        if (cudaEventElapsedTime(&b, g_chain.origin, g_chain.ev[2 * i + 1]) != cudaSuccess) cudaGetLastError();
+        fprintf(stderr, "[feba chain prof] %3d %2d %3d | %7.3f %7.3f\n", g_chain.tile[i], g_chain.blocks[i], g_chain.chain[i], a, b);
+    }
+}
+
 static cudaError_t chol_tiles_captured(double* A, int ld, int nb, double* Linv, int* info, cudaStream_t main,
                                        int64_t* launches, const TileView& V, int k_begin, int k_end, int rank) {
     const int NT = V.NT;
@@ -878,10 +900,31 @@ static cudaError_t chol_tiles_captured(double* A, int ld, int nb, double* Linv, 
         e = (x);                  \
         if (e != cudaSuccess) return e; \
     } while (0)
+    static const bool prof_env = std::getenv("FEBA_CHAIN_PROF") != nullptr;
+    const bool prof = prof_env && g_chain.ev.empty() == (k_begin == 0) && !g_chain.printed;
+    auto stamp = [&](cudaEvent_t* out) -> cudaError_t {
+        cudaError_t e2 = cudaEventCreate(out);
+        if (e2 != cudaSuccess) return e2;
+        return cudaEventRecordWithFlags(*out, main, cudaEventRecordExternal);
+    };
+    if (prof && k_begin == 0) DAG_CU(stamp(&g_chain.origin));
     for (int k = k_begin; k < k_end && k < NT; ++k) {
         if (!mine(k) || nblk(k) == 0) continue;
         DAG_CU(begin_task({tid(k, k)}));
+        if (prof) {
+            cudaEvent_t ev;
+            DAG_CU(stamp(&ev));
+            g_chain.ev.push_back(ev);
+        }
         DAG_CU(chol_diag_tile(A, ld, Linv, blk0(k), nblk(k), info, main, launches));
+        if (prof) {
+            cudaEvent_t ev;
+            DAG_CU(stamp(&ev));
+            g_chain.ev.push_back(ev);
+            g_chain.tile.push_back(k);
+            g_chain.blocks.push_back(nblk(k));
+            g_chain.chain.push_back(V.chain ? V.chain[k] : 0);
+        }
         DAG_CU(end_task(tid(k, k)));
         for (int i = k + 1; i < NR; ++i) {
             if (!on(i, k) || nblk(i) == 0) continue;

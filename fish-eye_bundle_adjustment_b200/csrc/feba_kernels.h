@@ -138,6 +138,7 @@ cudaError_t chol_dag_dist(double* A, int ld, int nb, double* Linv, int* info, co
 cudaError_t chol_cols(double* A, int ld, int nb, double* Linv, int* info, const DagStreams& D, DistCtx* dist,
                       cudaStream_t main, int64_t* launches);
 void dist_prof_report();   // FEBA_DIST_PROF=1: prints the time stamps of the last replay once
+void chain_prof_report();  // FEBA_CHAIN_PROF=1: when the DIAG task of every supertile could start / ended (last replay), once
 // ywork (n_pad) := combination of the augmented rows: y = Y'(0,:) + sum_k kvec[k] Y'(1+k,:) where kvec
 // solves the 7x7 border system (inner != 0), else y = Y'(0,:).  Then sol := L^-T y.
 // sparse_datum != 0: 14 coefficients from the border of the sparse-datum form (feba_sparse.h).
