@@ -40,7 +40,7 @@ struct feba_handle {
     // device state
     double *eop = nullptr, *iop = nullptr, *cam_box = nullptr, *img_tab = nullptr, *cam_tab = nullptr;
     double *xhat = nullptr, *sol = nullptr, *dcam = nullptr, *dcam_unscaled = nullptr, *work = nullptr;
-    double *ywork = nullptr, *Linv = nullptr, *dvec = nullptr, *dg = nullptr;
+    double *ywork = nullptr, *Linv = nullptr, *dvec = nullptr, *dg = nullptr, *gwork = nullptr;
     double *covU = nullptr, *covQ = nullptr, *covY = nullptr, *covT = nullptr;   // covariance stage (lazy)
     bool cov_ready = false;
     // plan of the reduced system (feba_order.h): row order, supertiles, pattern, owners
@@ -744,6 +744,7 @@ static int create_impl(const feba_problem* pr, int rank, int world, const void* 
     CU(h, dev_alloc(h, &h->ywork, (size_t)P.n_pad));
     CU(h, dev_alloc(h, &h->dvec, (size_t)P.n_pad));
     CU(h, dev_alloc(h, &h->dg, (size_t)P.n_pad));
+    CU(h, dev_alloc(h, &h->gwork, (size_t)kGworkDoubles));
     CU(h, dev_alloc(h, &h->Linv, (size_t)(P.n_pad / kBlk) * kBlk * kBlk));
     CU(h, dev_alloc(h, &P.Gt, (size_t)P.n_pad * 8));
     CU(h, cudaMemsetAsync(P.Gt, 0, (size_t)P.n_pad * 8 * sizeof(double), h->stream));
@@ -780,7 +781,7 @@ static int create_impl(const feba_problem* pr, int rank, int world, const void* 
         const int rc_pool = setup_plan_pool(h);
         if (rc_pool) return rc_pool;
     }
-    CU(h, dev_alloc(h, &P.cam_part, (size_t)assemble_warps(P, h->sm_count) * kCamPart));
+    CU(h, dev_alloc(h, &P.cam_part, (size_t)cam_part_rows(P, h->sm_count) * kCamPart));
     // ---- assembly schedule, static for the life of the handle: image-major form (pair schedule built on the device),
     // or the chunk form (feba_chunks.h) on request
     {
@@ -997,7 +998,7 @@ static int enqueue_assemble(feba_handle* h) {
     CU(h, cudaMemsetAsync(h->info, 0, sizeof(int), h->stream));
     CU(h, record(h, 1));
     ++h->launches;
-    CU(h, launch_assemble(P, h->sm_count, h->info, h->stream, &h->launches, h->use_chunks ? &h->chunks : nullptr));
+    CU(h, launch_assemble(P, h->sm_count, h->info, h->stream, &h->launches, h->opt, h->use_chunks ? &h->chunks : nullptr));
     CU(h, record(h, 2));
     return FEBA_OK;
 }
@@ -1137,7 +1138,7 @@ static int enqueue_solve_pre(feba_handle* h) {
     DevProblem& P = h->P;
     CU(h, launch_border_prepare(P, h->eop, h->dg, h->stream, &h->launches));
     if (h->shard) NC(h, dist_allreduce_f64(&h->dist, h->dg, (size_t)P.n_pad, h->stream));
-    CU(h, launch_border_scale(P, h->dg, h->dvec, h->info, h->blk_list, h->n_blk_scale, h->stream, &h->launches));
+    CU(h, launch_border_scale(P, h->dg, h->dvec, h->info, h->blk_list, h->n_blk_scale, h->gwork, h->stream, &h->launches));
     return FEBA_OK;
 }
 

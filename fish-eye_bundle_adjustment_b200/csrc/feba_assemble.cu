@@ -125,23 +125,9 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
                 __syncwarp(gmask);
                 const int nrow = min(G, end - c0);
                 // (x * p) * y with the product x * p taken once per row: the same roundings as x * p * y per term
+                // (the direct camera sums  sum Jc'P Jc  and  sum Jc'P w  over ALL observations need no per-point
+                    // structure: k_cam_direct forms them, one thread per observation)
                 if (HAS_CAM) {
-#pragma unroll
-                    for (int t = 0; t < DPL; ++t) {
-                        if (lane + G * t < ND) {
-                            double a = 0.0;
-                            for (int l = 0; l < nrow; ++l)
-                                a += sm.rowPJc[l][0][dI[t]] * sm.rowJc[l][0][dJ[t]] +
-                                     sm.rowPJc[l][1][dI[t]] * sm.rowJc[l][1][dJ[t]];
-                            dacc[t] += a;
-                        }
-                    }
-                    if (lane < NC) {
-                        double a = 0.0;
-                        for (int l = 0; l < nrow; ++l)
-                            a += sm.rowPJc[l][0][lane] * sm.roww[l][0] + sm.rowPJc[l][1][lane] * sm.roww[l][1];
-                        gcacc += a;
-                    }
                     if (is_tie) {
 #pragma unroll
                         for (int t = 0; t < WPL; ++t) {
@@ -578,6 +564,50 @@ __global__ void __launch_bounds__(128) k_point_pass_mc(DevProblem P, int* __rest
             }
             __syncwarp(gmask);
         }
+    }
+}
+
+// Direct camera terms of a single-camera problem:  sum_a Jc_a' P Jc_a  (packed lower, ND entries) and
+// sum_a Jc_a' P w_a  (NC) over ALL observations -- one thread per observation, its ND + NC sums in registers, a
+// fixed-order reduction per CTA, one row of the camera partial buffer per CTA (k_cam_reduce adds the rows of
+// the point pass, which hold the Schur parts -Fc Fc', -Fc ut, and these).  In the point pass the same sums cost
+// ND + NC shared-memory row loops per point on lanes that are mostly idle there.
+template <int NK>
+__global__ void __launch_bounds__(256) k_cam_direct(DevProblem P, const int* __restrict__ opt, int row0) {
+    constexpr int NC = NK + 5;
+    constexpr int ND = NC * (NC + 1) / 2;
+    constexpr int NE = ND + NC;
+    __shared__ double red[8][NE];
+    double acc[NE];
+#pragma unroll
+    for (int k = 0; k < NE; ++k) acc[k] = 0.0;
+    for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < P.n_obs; o += (int64_t)gridDim.x * blockDim.x) {
+        const int img = P.oimg[o], pt = opt[o];
+        ObsJac<NK> J;
+        observation<NK, true>(P.type, P.ox[o], P.oy[o], P.img_tab + kImgStride * img, P.cam_tab + kCamStride * P.img_cam[img],
+                              P.xyz[3 * pt], P.xyz[3 * pt + 1], P.xyz[3 * pt + 2], J);
+        int e = 0;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const double t0 = J.Jc[0][i] * P.px, t1 = J.Jc[1][i] * P.py;
+#pragma unroll
+            for (int j = 0; j <= i; ++j) acc[e++] += t0 * J.Jc[0][j] + t1 * J.Jc[1][j];
+            acc[ND + i] += t0 * J.w[0] + t1 * J.w[1];
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], s);
+        if (lane == 0) red[warp][k] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < NE) {
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += red[w][threadIdx.x];
+        P.cam_part[(size_t)kCamPart * (row0 + blockIdx.x) + threadIdx.x] = tot;
     }
 }
 
@@ -1231,6 +1261,27 @@ static int point_pass_grid(const DevProblem& P, int sm_count) {
 
 // number of point groups in the grid = rows of the camera partial buffer
 int assemble_warps(const DevProblem& P, int sm_count) { return point_pass_grid(P, sm_count) * (128 / group_lanes(P)); }
+// rows of the camera partial buffer: one per point group of the point pass + one per CTA of k_cam_direct
+int cam_part_rows(const DevProblem& P, int sm_count) { return assemble_warps(P, sm_count) + sm_count; }
+
+template <int NK>
+static cudaError_t launch_cam_direct_t(const DevProblem& P, const int* opt, int sm_count, cudaStream_t st) {
+    k_cam_direct<NK><<<sm_count, 256, 0, st>>>(P, opt, assemble_warps(P, sm_count));
+    return cudaGetLastError();
+}
+static cudaError_t launch_cam_direct(const DevProblem& P, const int* opt, int sm_count, cudaStream_t st) {
+    switch (P.NK) {
+        case 1: return launch_cam_direct_t<1>(P, opt, sm_count, st);
+        case 2: return launch_cam_direct_t<2>(P, opt, sm_count, st);
+        case 3: return launch_cam_direct_t<3>(P, opt, sm_count, st);
+        case 4: return launch_cam_direct_t<4>(P, opt, sm_count, st);
+        case 5: return launch_cam_direct_t<5>(P, opt, sm_count, st);
+        case 6: return launch_cam_direct_t<6>(P, opt, sm_count, st);
+        case 7: return launch_cam_direct_t<7>(P, opt, sm_count, st);
+        case 8: return launch_cam_direct_t<8>(P, opt, sm_count, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
 
 template <int NK, bool HC, int G>
 static cudaError_t launch_point_pass_t(const DevProblem& P, int sm_count, cudaStream_t st) {
@@ -1253,7 +1304,7 @@ static cudaError_t launch_point_pass_mc_t(const DevProblem& P, int sm_count, int
 }
 
 cudaError_t launch_assemble(const DevProblem& P, int sm_count, int* info, cudaStream_t st, int64_t* launches,
-                            const ChunkDev* chunks) {
+                            const int* opt, const ChunkDev* chunks) {
     const bool hc = P.uc > 0;
     const bool mc = hc && P.n_cam > 1;
     if (chunks && !mc && P.n_seg > 0) {
@@ -1275,8 +1326,10 @@ cudaError_t launch_assemble(const DevProblem& P, int sm_count, int* info, cudaSt
         FEBA_NK_DISPATCH2(P.NK, hc, (k_chunk_reduce<NK_, HC_><<<grid, 256, kChunkSmem, st>>>(P, *chunks)));
         *launches += 2;
         if (hc) {
-            k_cam_reduce<<<1, 1024, 0, st>>>(P, assemble_warps(P, sm_count));
-            ++*launches;
+            e = launch_cam_direct(P, opt, sm_count, st);
+            if (e != cudaSuccess) return e;
+            k_cam_reduce<<<1, 1024, 0, st>>>(P, cam_part_rows(P, sm_count));
+            *launches += 2;
         }
         k_sum_img_parts<<<P.n_img < sm_count * 8 ? P.n_img : sm_count * 8, 128, 0, st>>>(P, *chunks);
         ++*launches;
@@ -1311,8 +1364,10 @@ cudaError_t launch_assemble(const DevProblem& P, int sm_count, int* info, cudaSt
         FEBA_NK_DISPATCH2(P.NK, hc, (k_image_pass<NK_, HC_><<<grid, 128, 0, st>>>(P)));
         ++*launches;
         if (hc && !mc) {
-            k_cam_reduce<<<1, 1024, 0, st>>>(P, assemble_warps(P, sm_count));
-            ++*launches;
+            e = launch_cam_direct(P, opt, sm_count, st);
+            if (e != cudaSuccess) return e;
+            k_cam_reduce<<<1, 1024, 0, st>>>(P, cam_part_rows(P, sm_count));
+            *launches += 2;
         }
         if (P.n_blocks > 0) {
             // resident CTAs per SM (measured 1, 2, 4, 8 on config 4: 13.4, 11.3, 12.0, 11.1 ms assembly).

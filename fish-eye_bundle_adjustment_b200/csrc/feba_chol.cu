@@ -1456,10 +1456,17 @@ __global__ void k_border_solve(const double* __restrict__ A, int ld, int n_pad, 
 // work[0..13] = coefficients of the augmented rows 1..14 (k, -t).
 __global__ void k_border_solve_sparse(const double* __restrict__ A, int ld, int n_pad, double* __restrict__ work,
                                       int* __restrict__ info) {
+    __shared__ double Ts[kSparseAugRows][kSparseAugRows];
+    for (int e = threadIdx.x; e < kSparseAugRows * kSparseAugRows; e += blockDim.x) {     // all loads in flight together
+        const int i = e / kSparseAugRows, j = e - i * kSparseAugRows;
+        const int r = i > j ? i : j, c = i > j ? j : i;                                    // lower triangle holds T
+        Ts[i][j] = A[(size_t)(n_pad + r) + (size_t)ld * (n_pad + c)];
+    }
+    __syncthreads();
     if (threadIdx.x != 0) return;
     double T[kSparseAugRows][kSparseAugRows];
     for (int i = 0; i < kSparseAugRows; ++i)
-        for (int j = 0; j <= i; ++j) T[i][j] = T[j][i] = A[(size_t)(n_pad + i) + (size_t)ld * (n_pad + j)];
+        for (int j = 0; j < kSparseAugRows; ++j) T[i][j] = Ts[i][j];
     double coef[2 * kDatumCols];
     if (!sparse_border_solve(T, coef)) {
         atomicExch(info, 2);

@@ -48,115 +48,137 @@ __global__ void k_G_rows(DevProblem P, const double* __restrict__ eop) {
 // C is chosen so that, in the Jacobi-scaled system, the datum directions get eigenvalue ~1:
 //   C C' = (G'G)^-1 (G' diag(S) G) (G'G)^-1,   C = diag(1/c) A1^-1 chol(A2)
 // with c the column norms of G, A1 = Gn'Gn, A2 = Gn' diag(S) Gn, Gn = G diag(1/c).
-// One CTA: Gram reductions over the 6 n_img rows, 7x7 algebra on thread 0, rows rewritten in place
-// (compact copy Gt and the augmented rows 1..7 of S).
-__global__ void __launch_bounds__(256) k_G_condition(DevProblem P, const double* __restrict__ dg, int* __restrict__ info) {
-    __shared__ double red[256];
-    __shared__ double A1[7][7], A2[7][7], Cm[7][7], cn[7];
-    const int tid = threadIdx.x, ne = P.n_pad;             // image rows only (Gt is zero on all other rows)
-    // one sweep over the rows: column norms, then both Gram matrices from the raw sums
-    // (A1 = Gn'Gn and A2 = Gn' diag(S) Gn with Gn = G diag(cn): scale the raw sums by cn_i cn_j)
+// Three small launches (the single-CTA version took 0.26 ms on BASELINE configs[3] -- on the critical path of
+// every iteration at every number of GPUs): (1) Gram sums of the image rows, one partial per CTA, (2) fixed-order
+// sum of the partials + the 7x7 algebra on one thread -> C, (3) rows rewritten in place (compact copy Gt and the
+// augmented rows 1..7 of S).
+constexpr int kGramCtas = 64;
+
+__global__ void __launch_bounds__(256) k_G_gram(DevProblem P, const double* __restrict__ dg, double* __restrict__ part) {
+    __shared__ double red[8][56];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double a[56];                                       // a1 (28, lower of G'G) then a2 (28, lower of G' diag(S) G)
+#pragma unroll
+    for (int e = 0; e < 56; ++e) a[e] = 0.0;
+    for (int r = blockIdx.x * 256 + tid; r < P.n_pad; r += gridDim.x * 256) {
+        if (!is_image_row(P, r)) continue;
+        double g[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) g[k] = P.Gt[8 * (size_t)r + k];
+        const double sd = dg[r];                        // diag(S), summed over the ranks of a group
+        int e = 0;
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                const double p = g[i] * g[j];
+                a[e] += p;
+                a[28 + e] += p * sd;
+                ++e;
+            }
+    }
+#pragma unroll
+    for (int e = 0; e < 56; ++e) {
+#pragma unroll
+        for (int s2 = 16; s2 > 0; s2 >>= 1) a[e] += __shfl_xor_sync(0xffffffffu, a[e], s2);
+        if (lane == 0) red[warp][e] = a[e];
+    }
+    __syncthreads();
+    if (tid < 56) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][tid];
+        part[56 * blockIdx.x + tid] = t;
+    }
+}
+
+// Cm (7x7, row-major, 49 doubles) from the Gram partials
+__global__ void k_G_matrix(const double* __restrict__ part, int n_part, double* __restrict__ Cout) {
+    __shared__ double tot[56];
+    if (threadIdx.x < 56) {
+        double t = 0.0;
+        for (int c = 0; c < n_part; ++c) t += part[56 * c + threadIdx.x];
+        tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    double A1[7][7], A2[7][7], Cm[7][7], cn[7];
     {
-        double a1[28], a2[28];
-#pragma unroll
-        for (int e = 0; e < 28; ++e) a1[e] = a2[e] = 0.0;
-        for (int r = tid; r < ne; r += 256) {
-            if (!is_image_row(P, r)) continue;
-            double g[7];
-#pragma unroll
-            for (int k = 0; k < 7; ++k) g[k] = P.Gt[8 * (size_t)r + k];
-            const double sd = dg[r];                            // diag(S), summed over the ranks of a group
-            int e = 0;
-#pragma unroll
-            for (int i = 0; i < 7; ++i)
-#pragma unroll
-                for (int j = 0; j <= i; ++j) {
-                    const double p = g[i] * g[j];
-                    a1[e] += p;
-                    a2[e] += p * sd;
-                    ++e;
-                }
-        }
         int e = 0;
         for (int i = 0; i < 7; ++i)
             for (int j = 0; j <= i; ++j, ++e) {
-                for (int pass = 0; pass < 2; ++pass) {
-                    red[tid] = pass ? a2[e] : a1[e];
-                    __syncthreads();
-                    for (int st = 128; st > 0; st >>= 1) { if (tid < st) red[tid] += red[tid + st]; __syncthreads(); }
-                    if (tid == 0) { if (pass) A2[i][j] = A2[j][i] = red[0]; else A1[i][j] = A1[j][i] = red[0]; }
-                    __syncthreads();
-                }
+                A1[i][j] = A1[j][i] = tot[e];
+                A2[i][j] = A2[j][i] = tot[28 + e];
             }
-        if (tid == 0) {
-            for (int k = 0; k < 7; ++k) cn[k] = A1[k][k] > 0.0 ? 1.0 / sqrt(A1[k][k]) : 1.0;
-            for (int i = 0; i < 7; ++i)
-                for (int j = 0; j < 7; ++j) { A1[i][j] *= cn[i] * cn[j]; A2[i][j] *= cn[i] * cn[j]; }
-        }
-        __syncthreads();
     }
-    if (tid == 0) {
-        // Lw = chol(A2) (lower); on failure fall back to sqrt(mean diagonal) * I
-        double Lw[7][7];
-        bool ok = true;
-        for (int i = 0; i < 7; ++i)
-            for (int j = 0; j < 7; ++j) Lw[i][j] = 0.0;
-        for (int j = 0; j < 7 && ok; ++j) {
-            double d = A2[j][j];
-            for (int k = 0; k < j; ++k) d -= Lw[j][k] * Lw[j][k];
-            if (!(d > 1e-14 * A2[j][j])) { ok = false; break; }
-            Lw[j][j] = sqrt(d);
-            for (int i = j + 1; i < 7; ++i) {
-                double v = A2[i][j];
-                for (int k = 0; k < j; ++k) v -= Lw[i][k] * Lw[j][k];
-                Lw[i][j] = v / Lw[j][j];
-            }
+    for (int k = 0; k < 7; ++k) cn[k] = A1[k][k] > 0.0 ? 1.0 / sqrt(A1[k][k]) : 1.0;
+    for (int i = 0; i < 7; ++i)
+        for (int j = 0; j < 7; ++j) { A1[i][j] *= cn[i] * cn[j]; A2[i][j] *= cn[i] * cn[j]; }
+    // Lw = chol(A2) (lower); on failure fall back to sqrt(mean diagonal) * I
+    double Lw[7][7];
+    bool ok = true;
+    for (int i = 0; i < 7; ++i)
+        for (int j = 0; j < 7; ++j) Lw[i][j] = 0.0;
+    for (int j = 0; j < 7 && ok; ++j) {
+        double d = A2[j][j];
+        for (int k = 0; k < j; ++k) d -= Lw[j][k] * Lw[j][k];
+        if (!(d > 1e-14 * A2[j][j])) { ok = false; break; }
+        Lw[j][j] = sqrt(d);
+        for (int i = j + 1; i < 7; ++i) {
+            double v = A2[i][j];
+            for (int k = 0; k < j; ++k) v -= Lw[i][k] * Lw[j][k];
+            Lw[i][j] = v / Lw[j][j];
         }
-        // X = A1^-1 Lw by Gaussian elimination with partial pivoting
-        double Q[7][14];
-        for (int i = 0; i < 7; ++i)
-            for (int j = 0; j < 7; ++j) { Q[i][j] = A1[i][j]; Q[i][7 + j] = Lw[i][j]; }
-        for (int c = 0; c < 7 && ok; ++c) {
-            int p = c;
-            for (int r = c + 1; r < 7; ++r) if (fabs(Q[r][c]) > fabs(Q[p][c])) p = r;
-            if (!(fabs(Q[p][c]) > 1e-13)) { ok = false; break; }
-            if (p != c) for (int j = 0; j < 14; ++j) { const double t = Q[c][j]; Q[c][j] = Q[p][j]; Q[p][j] = t; }
-            for (int r = 0; r < 7; ++r) {
-                if (r == c) continue;
-                const double f = Q[r][c] / Q[c][c];
-                for (int j = c; j < 14; ++j) Q[r][j] -= f * Q[c][j];
-            }
-        }
-        if (ok) {
-            for (int i = 0; i < 7; ++i)
-                for (int j = 0; j < 7; ++j) Cm[i][j] = cn[i] * Q[i][7 + j] / Q[i][i];
-        } else {
-            double tr = 0.0;
-            for (int i = 0; i < 7; ++i) tr += A2[i][i];
-            const double sc = tr > 0.0 ? sqrt(tr / 7.0) : 1.0;
-            for (int i = 0; i < 7; ++i)
-                for (int j = 0; j < 7; ++j) Cm[i][j] = (i == j) ? cn[i] * sc : 0.0;
-        }
-        (void)info;
     }
+    // X = A1^-1 Lw by Gaussian elimination with partial pivoting
+    double Q[7][14];
+    for (int i = 0; i < 7; ++i)
+        for (int j = 0; j < 7; ++j) { Q[i][j] = A1[i][j]; Q[i][7 + j] = Lw[i][j]; }
+    for (int c = 0; c < 7 && ok; ++c) {
+        int p = c;
+        for (int r = c + 1; r < 7; ++r) if (fabs(Q[r][c]) > fabs(Q[p][c])) p = r;
+        if (!(fabs(Q[p][c]) > 1e-13)) { ok = false; break; }
+        if (p != c) for (int j = 0; j < 14; ++j) { const double t = Q[c][j]; Q[c][j] = Q[p][j]; Q[p][j] = t; }
+        for (int r = 0; r < 7; ++r) {
+            if (r == c) continue;
+            const double f = Q[r][c] / Q[c][c];
+            for (int j = c; j < 14; ++j) Q[r][j] -= f * Q[c][j];
+        }
+    }
+    if (ok) {
+        for (int i = 0; i < 7; ++i)
+            for (int j = 0; j < 7; ++j) Cm[i][j] = cn[i] * Q[i][7 + j] / Q[i][i];
+    } else {
+        double tr = 0.0;
+        for (int i = 0; i < 7; ++i) tr += A2[i][i];
+        const double sc = tr > 0.0 ? sqrt(tr / 7.0) : 1.0;
+        for (int i = 0; i < 7; ++i)
+            for (int j = 0; j < 7; ++j) Cm[i][j] = (i == j) ? cn[i] * sc : 0.0;
+    }
+    for (int i = 0; i < 7; ++i)
+        for (int j = 0; j < 7; ++j) Cout[7 * i + j] = Cm[i][j];
+}
+
+__global__ void __launch_bounds__(256) k_G_apply(DevProblem P, const double* __restrict__ Cin) {
+    __shared__ double Cm[49];
+    if (threadIdx.x < 49) Cm[threadIdx.x] = Cin[threadIdx.x];
     __syncthreads();
-    for (int r = tid; r < ne; r += 256) {
-        if (!is_image_row(P, r)) continue;
-        double g[7], o[7];
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= P.n_pad || !is_image_row(P, r)) return;
+    double g[7], o[7];
 #pragma unroll
-        for (int k = 0; k < 7; ++k) g[k] = P.Gt[8 * (size_t)r + k];
+    for (int k = 0; k < 7; ++k) g[k] = P.Gt[8 * (size_t)r + k];
 #pragma unroll
-        for (int j = 0; j < 7; ++j) {
-            double acc = 0.0;
+    for (int j = 0; j < 7; ++j) {
+        double acc = 0.0;
 #pragma unroll
-            for (int k = 0; k < 7; ++k) acc += g[k] * Cm[k][j];
-            o[j] = acc;
-        }
+        for (int k = 0; k < 7; ++k) acc += g[k] * Cm[7 * k + j];
+        o[j] = acc;
+    }
 #pragma unroll
-        for (int j = 0; j < 7; ++j) {
-            P.Gt[8 * (size_t)r + j] = o[j];
-            P.S[(size_t)(P.n_pad + 1 + j) + (size_t)P.ld * r] = o[j];
-        }
+    for (int j = 0; j < 7; ++j) {
+        P.Gt[8 * (size_t)r + j] = o[j];
+        P.S[(size_t)(P.n_pad + 1 + j) + (size_t)P.ld * r] = o[j];
     }
 }
 
@@ -894,10 +916,13 @@ cudaError_t launch_border_prepare(const DevProblem& P, const double* eop, double
 }
 
 cudaError_t launch_border_scale(const DevProblem& P, const double* dg, double* dvec, int* info, const int2* blocks,
-                                int n_blocks, cudaStream_t st, int64_t* launches) {
+                                int n_blocks, double* gwork, cudaStream_t st, int64_t* launches) {
     if (P.inner) {
-        k_G_condition<<<1, 256, 0, st>>>(P, dg, info);
-        ++*launches;
+        // gwork: kGramCtas x 56 Gram partials, then the 7 x 7 matrix C
+        k_G_gram<<<kGramCtas, 256, 0, st>>>(P, dg, gwork);
+        k_G_matrix<<<1, 64, 0, st>>>(gwork, kGramCtas, gwork + 56 * kGramCtas);
+        k_G_apply<<<(P.n_pad + 255) / 256, 256, 0, st>>>(P, gwork + 56 * kGramCtas);
+        *launches += 3;
         if (P.datum) {
             k_datum_split<<<(P.n_pad + 255) / 256, 256, 0, st>>>(P);
             ++*launches;

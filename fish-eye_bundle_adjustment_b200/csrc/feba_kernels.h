@@ -18,8 +18,10 @@ cudaError_t launch_delta_gather(const DevProblem& P, int sm_count, double* delta
 // blocks: (block row, block column) of the structurally non-zero 64x64 blocks of the lower triangle followed by the
 // blocks of the augmented block row (row index = n_pad / 64), as listed by the handle from its plan
 cudaError_t launch_border_prepare(const DevProblem& P, const double* eop, double* dg, cudaStream_t st, int64_t* launches);
+// gwork: 64 * 56 + 64 doubles of scratch (Gram partials and the conditioning matrix of the inner-constraint rows)
+constexpr int kGworkDoubles = 64 * 56 + 64;
 cudaError_t launch_border_scale(const DevProblem& P, const double* dg, double* dvec, int* info, const int2* blocks,
-                                int n_blocks, cudaStream_t st, int64_t* launches);
+                                int n_blocks, double* gwork, cudaStream_t st, int64_t* launches);
 cudaError_t launch_keep_own_rows(const DevProblem& P, double* vec, cudaStream_t st);
 cudaError_t launch_keep_own_ties(int64_t n_tie, const unsigned char* tie_mine, double* xyz3, cudaStream_t st);
 cudaError_t launch_clear_blocks(const DevProblem& P, const int2* blocks, int n_blocks, cudaStream_t st);
@@ -51,8 +53,10 @@ struct ChunkDev {
 };
 // chunks == nullptr: the image-major form of round 1 (image pass + image-pair pass over the pair schedule; always
 // used with several cameras AND camera unknowns)
+// opt: object point (CNT row) of every observation (the direct camera sums run one thread per observation)
 cudaError_t launch_assemble(const DevProblem& P, int sm_count, int* info, cudaStream_t st, int64_t* launches,
-                            const ChunkDev* chunks = nullptr);
+                            const int* opt, const ChunkDev* chunks = nullptr);
+int cam_part_rows(const DevProblem& P, int sm_count);
 int backsub_warps(const DevProblem& P, int sm_count);
 cudaError_t launch_backsub(const DevProblem& P, int sm_count, cudaStream_t st);
 cudaError_t launch_update_cam(const DevProblem& P, const double* sol, const double* dvec, double* dcam,
