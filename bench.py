@@ -363,12 +363,21 @@ def run_ours(args, rank, world, local_rank):
     bufs[0][:] = h.get_xhat()
     cur = [0]
 
+    owned = mode == "group"            # a group keeps xhat split over the ranks: each rank moves its own part
+    bufs[1][:] = bufs[0]
+    n_moved = prob.u_c + 3 * h.num_owned_ties() if owned else u_loc
+
     def e2e_step():
         # the caller's xhat goes in from pinned host memory, the updated xhat comes back into the
         # other pinned buffer (main.m:484 keeps xhat on the host between iterations)
-        h.set_xhat(bufs[cur[0]])
-        ds = step_sync()
-        h.get_xhat(bufs[1 - cur[0]])
+        if owned:
+            h.set_xhat_owned(bufs[cur[0]])
+            ds = step_sync()
+            h.get_xhat_owned(bufs[1 - cur[0]])
+        else:
+            h.set_xhat(bufs[cur[0]])
+            ds = step_sync()
+            h.get_xhat(bufs[1 - cur[0]])
         cur[0] = 1 - cur[0]
         return ds
 
@@ -528,8 +537,11 @@ def run_ours(args, rank, world, local_rank):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": cfg,
-        "e2e": {"value": e2e_val, "unit": "obs/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(8 * u_loc),
-                "d2h_bytes_per_step": int(8 * u_loc + 16)},
+        "e2e": {"value": e2e_val, "unit": "obs/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(8 * n_moved),
+                "d2h_bytes_per_step": int(8 * n_moved + 16),
+                "note": ("per rank: the EOP/IOP part + the tie points the rank owns (feba_set_xhat_owned / "
+                         "feba_get_xhat_owned); the complete vector is gathered once after the loop") if owned else
+                        "the complete xhat each way (feba_set_xhat / feba_get_xhat)"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels,
         "fp64_dgemm_peak_tflops": dgemm_peak,
         "residual_stage_ms": rsd_ms, "residual_stage": {

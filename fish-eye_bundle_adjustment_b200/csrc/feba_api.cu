@@ -60,6 +60,10 @@ struct feba_handle {
     int rank = 0, world = 1;
     int64_t n_obs_global = 0;
     unsigned char* tie_mine = nullptr;    // device, n_tie: 1 = tie point owned by this rank
+    std::vector<int> own_ties;            // tie indices owned by this rank (ascending); device copy + packed staging
+    int* own_ties_dev = nullptr;
+    double* own_packed = nullptr;         // device, 3 per owned tie
+    double* own_pin = nullptr;            // pinned host staging: u_c + 3 per owned tie
     int top_row0 = 0;                     // first row of the shared top part (summed over the ranks)
     double* xchg = nullptr;               // packed lower trapezoid of the shared top part
     size_t xchg_count = 0;
@@ -436,6 +440,7 @@ void feba_destroy(feba_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     if (h->scal_host) cudaFreeHost(h->scal_host);
     if (h->info_host) cudaFreeHost(h->info_host);
+    if (h->own_pin) cudaFreeHost(h->own_pin);
     if (h->v_pin) cudaFreeHost(h->v_pin);
     if (h->rsd_pin) cudaFreeHost(h->rsd_pin);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -722,7 +727,14 @@ static int create_impl(const feba_problem* pr, int rank, int world, const void* 
     CU(h, upload(h, &dimg_start, img_start.data(), img_start.size()));
     CU(h, upload(h, &diobs, ipos.data(), ipos.size()));
     CU(h, upload(h, &doseg, oseg.data(), oseg.size()));
-    if (h->shard) CU(h, upload(h, &h->tie_mine, tie_mine.data(), tie_mine.size()));
+    if (h->shard) {
+        CU(h, upload(h, &h->tie_mine, tie_mine.data(), tie_mine.size()));
+        for (int t = 0; t < pr->n_tie; ++t)
+            if (tie_mine[(size_t)t]) h->own_ties.push_back(t);
+        CU(h, upload(h, &h->own_ties_dev, h->own_ties.data(), h->own_ties.size()));
+        CU(h, dev_alloc(h, &h->own_packed, 3 * h->own_ties.size()));
+        CU(h, cudaMallocHost((void**)&h->own_pin, ((size_t)P.n_red + 3 * h->own_ties.size() + 1) * sizeof(double)));
+    }
     CU(h, dev_alloc(h, &P.rec1, (size_t)nl * kRec1));
     CU(h, dev_alloc(h, &P.rec2, (size_t)nl * (2 + 2 * P.NC)));
     CU(h, upload(h, &h->eop, pr->eop0, (size_t)pr->n_img * 6));
@@ -966,6 +978,66 @@ int feba_get_xhat(feba_handle* h, double* xhat, size_t u) {
     CU(h, cudaMemcpyAsync(xhat, h->xhat, u * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return FEBA_OK;
+}
+
+// Owned-only transfers of a group handle (feba_create_shard): the EOP/IOP part and the tie points THIS rank owns.
+// A distributed caller keeps xhat split over the ranks between iterations; the full-vector calls above move and
+// all-reduce 8 u bytes on every rank.  On a single-GPU handle they are feba_set_xhat / feba_get_xhat.
+int feba_set_xhat_owned(feba_handle* h, const double* xhat, size_t u) {
+    if (!h || !xhat) return FEBA_ERR_INVALID;
+    if (!h->shard) return feba_set_xhat(h, xhat, u);
+    if ((int64_t)u != h->u) return fail(h, FEBA_ERR_INVALID, "xhat has %zu entries, expected %lld", u, (long long)h->u);
+    CU(h, cudaSetDevice(h->device));
+    const size_t nr = (size_t)h->P.n_red, no = h->own_ties.size();
+    std::memcpy(h->own_pin, xhat, nr * sizeof(double));
+    for (size_t i = 0; i < no; ++i) {
+        const double* src = xhat + nr + 3 * (size_t)h->own_ties[i];
+        double* dst = h->own_pin + nr + 3 * i;
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    }
+    CU(h, cudaMemcpyAsync(h->xhat, h->own_pin, nr * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (no) {
+        CU(h, cudaMemcpyAsync(h->own_packed, h->own_pin + nr, 3 * no * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CU(h, launch_ties_pack((int)no, h->own_ties_dev, (int64_t)nr, h->xhat, h->own_packed, true, h->stream));
+    }
+    // coordinates of other ranks' tie points in the device copy of xhat are whatever they were: no observation of
+    // this rank uses them, and the collective feba_get_xhat takes every tie from its owner
+    CU(h, launch_xhat_scatter(h->P, h->sm_count, h->xhat, h->eop, h->iop, h->tie_pt, h->stream));
+    h->launches += 2;
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->iterations = 0;
+    h->phase = 0;
+    return FEBA_OK;
+}
+
+int feba_get_xhat_owned(feba_handle* h, double* xhat, size_t u) {
+    if (!h || !xhat) return FEBA_ERR_INVALID;
+    if (!h->shard) return feba_get_xhat(h, xhat, u);
+    if ((int64_t)u != h->u) return fail(h, FEBA_ERR_INVALID, "xhat has %zu entries, expected %lld", u, (long long)h->u);
+    CU(h, cudaSetDevice(h->device));
+    const size_t nr = (size_t)h->P.n_red, no = h->own_ties.size();
+    CU(h, launch_xhat_gather(h->P, h->sm_count, h->xhat, h->eop, h->iop, h->tie_pt, h->stream));
+    ++h->launches;
+    CU(h, cudaMemcpyAsync(h->own_pin, h->xhat, nr * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (no) {
+        CU(h, launch_ties_pack((int)no, h->own_ties_dev, (int64_t)nr, h->xhat, h->own_packed, false, h->stream));
+        ++h->launches;
+        CU(h, cudaMemcpyAsync(h->own_pin + nr, h->own_packed, 3 * no * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(h, cudaStreamSynchronize(h->stream));
+    std::memcpy(xhat, h->own_pin, nr * sizeof(double));
+    for (size_t i = 0; i < no; ++i) {
+        double* dst = xhat + nr + 3 * (size_t)h->own_ties[i];
+        const double* src = h->own_pin + nr + 3 * i;
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    }
+    return FEBA_OK;
+}
+
+// number of tie points this handle owns (all of them on a single-GPU handle)
+int64_t feba_num_owned_ties(const feba_handle* h) {
+    if (!h) return -1;
+    return h->shard ? (int64_t)h->own_ties.size() : (int64_t)h->P.n_tie;
 }
 
 int feba_get_delta(feba_handle* h, double* delta, size_t u) {

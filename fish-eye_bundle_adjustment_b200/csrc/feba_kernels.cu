@@ -985,6 +985,26 @@ cudaError_t launch_keep_own_ties(int64_t n_tie, const unsigned char* tie_mine, d
     return cudaGetLastError();
 }
 
+// group runs, owned-only transfers: packed coordinates of the tie points this rank owns <-> xhat on the device
+__global__ void k_ties_pack(int n_own, const int* __restrict__ own_ties, int64_t n_red, const double* __restrict__ xhat,
+                            double* __restrict__ packed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 3 * n_own) packed[i] = xhat[n_red + 3 * (int64_t)own_ties[i / 3] + i % 3];
+}
+__global__ void k_ties_unpack(int n_own, const int* __restrict__ own_ties, int64_t n_red, double* __restrict__ xhat,
+                              const double* __restrict__ packed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 3 * n_own) xhat[n_red + 3 * (int64_t)own_ties[i / 3] + i % 3] = packed[i];
+}
+cudaError_t launch_ties_pack(int n_own, const int* own_ties, int64_t n_red, double* xhat, double* packed, bool unpack,
+                             cudaStream_t st) {
+    if (n_own <= 0) return cudaSuccess;
+    const int grid = (3 * n_own + 255) / 256;
+    if (unpack) k_ties_unpack<<<grid, 256, 0, st>>>(n_own, own_ties, n_red, xhat, packed);
+    else k_ties_pack<<<grid, 256, 0, st>>>(n_own, own_ties, n_red, xhat, packed);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_update_cam(const DevProblem& P, const double* sol, const double* dvec, double* dcam,
                               double* dcam_unscaled, double* eop, double* iop, double* out_sumabs, cudaStream_t st) {
     k_update_cam<<<1, 1024, 0, st>>>(P, sol, dvec, dcam, dcam_unscaled, eop, iop, out_sumabs);

@@ -28,6 +28,7 @@ EXPORTS = (
     "feba_dist_unique_id", "feba_dist_init", "feba_reduced_pack", "feba_reduced_unpack",
     "feba_create_shard", "feba_last_timing_ex", "feba_plan_info",
     "feba_batch_create", "feba_batch_iterate_async", "feba_batch_destroy",
+    "feba_set_xhat_owned", "feba_get_xhat_owned", "feba_num_owned_ties",
 )
 
 
@@ -101,6 +102,10 @@ def load() -> C.CDLL:
     lib.feba_set_xhat.argtypes = [H, _pd, C.c_size_t]
     lib.feba_get_xhat.argtypes = [H, _pd, C.c_size_t]
     lib.feba_get_delta.argtypes = [H, _pd, C.c_size_t]
+    lib.feba_set_xhat_owned.argtypes = [H, _pd, C.c_size_t]
+    lib.feba_get_xhat_owned.argtypes = [H, _pd, C.c_size_t]
+    lib.feba_num_owned_ties.argtypes = [H]
+    lib.feba_num_owned_ties.restype = C.c_int64
     lib.feba_iterate.argtypes = [H, _pd]
     lib.feba_iterate_assemble.argtypes = [H]
     lib.feba_reduced_dev.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
@@ -223,6 +228,19 @@ class Handle:
         x = np.empty(self.u, dtype=np.float64) if out is None else out
         self._check(self._lib.feba_get_xhat(self._h, _dp(x), x.size))
         return x
+
+    def set_xhat_owned(self, xhat: np.ndarray):
+        """Group handle: upload the EOP/IOP part and the tie points this rank owns only (feba_set_xhat_owned)."""
+        x = np.ascontiguousarray(xhat, dtype=np.float64)
+        self._check(self._lib.feba_set_xhat_owned(self._h, _dp(x), x.size))
+
+    def get_xhat_owned(self, out: np.ndarray) -> np.ndarray:
+        """Group handle: write the EOP/IOP part and the tie points this rank owns into ``out`` (not collective)."""
+        self._check(self._lib.feba_get_xhat_owned(self._h, _dp(out), out.size))
+        return out
+
+    def num_owned_ties(self) -> int:
+        return int(self._lib.feba_num_owned_ties(self._h))
 
     def get_delta(self) -> np.ndarray:
         d = np.empty(self.u, dtype=np.float64)

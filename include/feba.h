@@ -132,6 +132,15 @@ int64_t feba_num_obs(const feba_handle *h);
 int feba_set_xhat(feba_handle *h, const double *xhat, size_t u);
 int feba_get_xhat(feba_handle *h, double *xhat, size_t u);
 
+/* Owned-only transfers for a feba_create_shard handle: the EOP/IOP part (replicated) and the coordinates of the tie
+ * points THIS rank owns; the other entries of the caller's vector are neither read nor written.  A distributed
+ * caller that keeps xhat split over the ranks between iterations uses these per step and the collective
+ * feba_get_xhat once at the end.  Not collective.  On a single-GPU handle they equal feba_set_xhat / feba_get_xhat.
+ * feba_num_owned_ties: how many tie points that is. */
+int feba_set_xhat_owned(feba_handle *h, const double *xhat, size_t u);
+int feba_get_xhat_owned(feba_handle *h, double *xhat, size_t u);
+int64_t feba_num_owned_ties(const feba_handle *h);
+
 /* One Gauss-Newton step = body of the while loop main.m:412-494:
  * BuildAwG + normal equations + (bordered) solve + un-scaling + xhat += delta.
  * deltasum_out = sumabs(delta) (main.m:487).  */

@@ -46,6 +46,20 @@ def main():
         res = h.residuals()
         xh = h.get_xhat()
         info = h.plan_info()
+        # owned-only transfers: the EOP/IOP part + this rank's tie points, bit-identical to the collective result;
+        # every tie point is owned by exactly one rank; upload of the owned parts + collective download = identity
+        xo = np.full(h.u, np.nan)
+        h.get_xhat_owned(xo)
+        got = ~np.isnan(xo)
+        owned_ok = bool(np.array_equal(xo[got], xh[got])) and int(got.sum()) == prob.u_c + 3 * h.num_owned_ties()
+        n_own = torch.tensor([float(h.num_owned_ties())], dtype=torch.float64, device="cuda")
+        dist.all_reduce(n_own)
+        owned_ok = owned_ok and int(n_own.item()) == prob.numtie
+        h.set_xhat_owned(xh)
+        owned_ok = owned_ok and bool(np.array_equal(h.get_xhat(), xh))
+        flag_own = torch.tensor([1.0 if owned_ok else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(flag_own, op=dist.ReduceOp.MIN)
+        owned_ok = flag_own.item() > 0
         # every rank holds the same complete result
         chk = torch.tensor([float(np.sum(xh)), float(np.sum(res["v"])), float(res["sigma02"]), float(it)],
                            dtype=torch.float64, device="cuda")
@@ -72,9 +86,9 @@ def main():
             e_s = abs(res["sigma02"] - ref["sigma02"]) / ref["sigma02"]
             print(f"[{mode}] world {world} plan {info}\n[{mode}] iterations {it} (one GPU {it1}, oracle {ref['iterations']})  "
                   f"first step vs one GPU {e_step:.2e}  xhat vs one GPU {e_x1:.2e}  vs oracle {e_xo:.2e}  v {e_v:.2e}  "
-                  f"sigma02 {e_s:.2e}  identical on all ranks {same}")
+                  f"sigma02 {e_s:.2e}  identical on all ranks {same}  owned-only transfers {owned_ok}")
             good = (it == it1 == ref["iterations"] and e_step < 1e-9 and e_x1 < 1e-9 and e_xo < 1e-9 and e_v < 1e-8
-                    and e_s < 1e-8 and same and info["world"] == world)
+                    and e_s < 1e-8 and same and owned_ok and info["world"] == world)
             ok = ok and good
         dist.barrier()
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
