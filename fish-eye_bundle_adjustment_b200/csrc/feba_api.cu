@@ -13,6 +13,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 #include <algorithm>
 
@@ -980,6 +981,41 @@ int feba_get_xhat(feba_handle* h, double* xhat, size_t u) {
     return FEBA_OK;
 }
 
+// host copy between the caller's xhat (tie part, scattered) and the packed staging buffer, a few threads
+static void owned_host_copy(const std::vector<int>& own, double* packed, double* xhat_ties, bool to_packed) {
+    const size_t no = own.size();
+    const int nth = no > 20000 ? 4 : 1;
+    auto work = [&](int t) {
+        const size_t lo = no * (size_t)t / nth, hi = no * (size_t)(t + 1) / nth;
+        for (size_t i = lo; i < hi; ++i) {
+            double* a = packed + 3 * i;
+            double* b = xhat_ties + 3 * (size_t)own[i];
+            if (to_packed) { a[0] = b[0]; a[1] = b[1]; a[2] = b[2]; }
+            else { b[0] = a[0]; b[1] = a[1]; b[2] = a[2]; }
+        }
+    };
+    if (nth == 1) {
+        work(0);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 1; t < nth; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+}
+
+// device address of a caller's buffer when it is page-locked host memory the device can address, else null
+static double* mapped_host(const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    static const bool off = [] { const char* e = std::getenv("FEBA_ZERO_COPY"); return e && e[0] == '0'; }();
+    return off ? nullptr : static_cast<double*>(at.devicePointer);
+}
+
 // Owned-only transfers of a group handle (feba_create_shard): the EOP/IOP part and the tie points THIS rank owns.
 // A distributed caller keeps xhat split over the ranks between iterations; the full-vector calls above move and
 // all-reduce 8 u bytes on every rank.  On a single-GPU handle they are feba_set_xhat / feba_get_xhat.
@@ -989,12 +1025,19 @@ int feba_set_xhat_owned(feba_handle* h, const double* xhat, size_t u) {
     if ((int64_t)u != h->u) return fail(h, FEBA_ERR_INVALID, "xhat has %zu entries, expected %lld", u, (long long)h->u);
     CU(h, cudaSetDevice(h->device));
     const size_t nr = (size_t)h->P.n_red, no = h->own_ties.size();
-    std::memcpy(h->own_pin, xhat, nr * sizeof(double));
-    for (size_t i = 0; i < no; ++i) {
-        const double* src = xhat + nr + 3 * (size_t)h->own_ties[i];
-        double* dst = h->own_pin + nr + 3 * i;
-        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    if (double* dx = mapped_host(xhat)) {
+        // page-locked caller buffer: the device reads the owned entries where they lie
+        CU(h, cudaMemcpyAsync(h->xhat, xhat, nr * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CU(h, launch_ties_copy_owned((int)no, h->own_ties_dev, dx + nr, h->xhat + nr, h->stream));
+        CU(h, launch_xhat_scatter(h->P, h->sm_count, h->xhat, h->eop, h->iop, h->tie_pt, h->stream));
+        h->launches += 2;
+        CU(h, cudaStreamSynchronize(h->stream));
+        h->iterations = 0;
+        h->phase = 0;
+        return FEBA_OK;
     }
+    std::memcpy(h->own_pin, xhat, nr * sizeof(double));
+    owned_host_copy(h->own_ties, h->own_pin + nr, const_cast<double*>(xhat) + nr, true);
     CU(h, cudaMemcpyAsync(h->xhat, h->own_pin, nr * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     if (no) {
         CU(h, cudaMemcpyAsync(h->own_packed, h->own_pin + nr, 3 * no * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -1018,6 +1061,13 @@ int feba_get_xhat_owned(feba_handle* h, double* xhat, size_t u) {
     const size_t nr = (size_t)h->P.n_red, no = h->own_ties.size();
     CU(h, launch_xhat_gather(h->P, h->sm_count, h->xhat, h->eop, h->iop, h->tie_pt, h->stream));
     ++h->launches;
+    if (double* dx = mapped_host(xhat)) {
+        CU(h, cudaMemcpyAsync(xhat, h->xhat, nr * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(h, launch_ties_copy_owned((int)no, h->own_ties_dev, h->xhat + nr, dx + nr, h->stream));
+        ++h->launches;
+        CU(h, cudaStreamSynchronize(h->stream));
+        return FEBA_OK;
+    }
     CU(h, cudaMemcpyAsync(h->own_pin, h->xhat, nr * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (no) {
         CU(h, launch_ties_pack((int)no, h->own_ties_dev, (int64_t)nr, h->xhat, h->own_packed, false, h->stream));
@@ -1026,11 +1076,7 @@ int feba_get_xhat_owned(feba_handle* h, double* xhat, size_t u) {
     }
     CU(h, cudaStreamSynchronize(h->stream));
     std::memcpy(xhat, h->own_pin, nr * sizeof(double));
-    for (size_t i = 0; i < no; ++i) {
-        double* dst = xhat + nr + 3 * (size_t)h->own_ties[i];
-        const double* src = h->own_pin + nr + 3 * i;
-        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
-    }
+    owned_host_copy(h->own_ties, h->own_pin + nr, xhat + nr, false);
     return FEBA_OK;
 }
 

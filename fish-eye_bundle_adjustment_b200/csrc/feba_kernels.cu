@@ -996,6 +996,21 @@ __global__ void k_ties_unpack(int n_own, const int* __restrict__ own_ties, int64
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 3 * n_own) xhat[n_red + 3 * (int64_t)own_ties[i / 3] + i % 3] = packed[i];
 }
+// same layout on both sides (the tie part of xhat): only the owned entries move.  One side may be page-locked HOST
+// memory addressed by the device (zero copy over PCIe): no staging buffer, no host-side gather
+__global__ void k_ties_copy_owned(int n_own, const int* __restrict__ own_ties, const double* __restrict__ src,
+                                  double* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 3 * n_own) {
+        const int64_t at = 3 * (int64_t)own_ties[i / 3] + i % 3;
+        dst[at] = src[at];
+    }
+}
+cudaError_t launch_ties_copy_owned(int n_own, const int* own_ties, const double* src, double* dst, cudaStream_t st) {
+    if (n_own <= 0) return cudaSuccess;
+    k_ties_copy_owned<<<(3 * n_own + 255) / 256, 256, 0, st>>>(n_own, own_ties, src, dst);
+    return cudaGetLastError();
+}
 cudaError_t launch_ties_pack(int n_own, const int* own_ties, int64_t n_red, double* xhat, double* packed, bool unpack,
                              cudaStream_t st) {
     if (n_own <= 0) return cudaSuccess;

@@ -24,6 +24,7 @@ cudaError_t launch_border_scale(const DevProblem& P, const double* dg, double* d
                                 int n_blocks, double* gwork, cudaStream_t st, int64_t* launches);
 cudaError_t launch_ties_pack(int n_own, const int* own_ties, int64_t n_red, double* xhat, double* packed, bool unpack,
                              cudaStream_t st);
+cudaError_t launch_ties_copy_owned(int n_own, const int* own_ties, const double* src, double* dst, cudaStream_t st);
 cudaError_t launch_keep_own_rows(const DevProblem& P, double* vec, cudaStream_t st);
 cudaError_t launch_keep_own_ties(int64_t n_tie, const unsigned char* tie_mine, double* xyz3, cudaStream_t st);
 cudaError_t launch_clear_blocks(const DevProblem& P, const int2* blocks, int n_blocks, cudaStream_t st);

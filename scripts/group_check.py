@@ -57,6 +57,14 @@ def main():
         owned_ok = owned_ok and int(n_own.item()) == prob.numtie
         h.set_xhat_owned(xh)
         owned_ok = owned_ok and bool(np.array_equal(h.get_xhat(), xh))
+        # the same through a page-locked buffer (the device addresses it directly: no staging, no host gather)
+        pin = torch.full((h.u,), float("nan"), dtype=torch.float64).pin_memory()
+        xp = pin.numpy()
+        h.get_xhat_owned(xp)
+        owned_ok = owned_ok and bool(np.array_equal(xp[got], xh[got])) and bool(np.all(np.isnan(xp[~got])))
+        xp[:] = xh
+        h.set_xhat_owned(xp)
+        owned_ok = owned_ok and bool(np.array_equal(h.get_xhat(), xh))
         flag_own = torch.tensor([1.0 if owned_ok else 0.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(flag_own, op=dist.ReduceOp.MIN)
         owned_ok = flag_own.item() > 0
