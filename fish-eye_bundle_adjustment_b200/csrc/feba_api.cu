@@ -753,6 +753,15 @@ static int create_impl(const feba_problem* pr, int rank, int world, const void* 
     CU(h, dev_alloc(h, &h->dcam, (size_t)P.n_pad));
     CU(h, dev_alloc(h, &h->dcam_unscaled, (size_t)P.n_pad));
     CU(h, dev_alloc(h, &P.dpts, (size_t)pr->n_tie * 3));
+    P.pt_rec = nullptr;
+    {
+        // per-point record of the point pass for the record-based back-substitution (k_backsub_rec); the
+        // multi-camera point pass keeps per-camera Fc blocks: there the Jacobians are recomputed (k_backsub)
+        const char* e = std::getenv("FEBA_BACKSUB_REC");
+        const bool multi_cam = pr->n_cam > 1 && P.uc > 0;
+        if (pr->n_tie > 0 && !multi_cam && !(e && e[0] == '0'))
+            CU(h, dev_alloc(h, &P.pt_rec, (size_t)pr->n_tie * (size_t)(9 + 3 * (P.NK + 5))));
+    }
     CU(h, dev_alloc(h, &h->work, 64));
     CU(h, dev_alloc(h, &h->ywork, (size_t)P.n_pad));
     CU(h, dev_alloc(h, &h->dvec, (size_t)P.n_pad));

@@ -204,6 +204,18 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
                 }
                 if (lane < NC) gcacc -= sm.Fc[lane][0] * ut[0] + sm.Fc[lane][1] * ut[1] + sm.Fc[lane][2] * ut[2];
             }
+            if (P.pt_rec) {
+                // what k_backsub_rec needs of this point besides the per-observation records
+                constexpr int PR = 9 + 3 * NC;
+                double* pr = P.pt_rec + (size_t)PR * P.pt_tie[pt];
+                if (lane < 9) {
+                    const double v = lane == 0 ? i00 : lane == 1 ? i10 : lane == 2 ? i11 : lane == 3 ? i20 : lane == 4 ? i21
+                                   : lane == 5 ? i22 : lane == 6 ? ut[0] : lane == 7 ? ut[1] : ut[2];
+                    pr[lane] = v;
+                }
+                if (HAS_CAM)
+                    for (int e = lane; e < 3 * NC; e += G) pr[9 + e] = (&sm.Fc[0][0])[e];
+            }
         }
         // ---------------- pass 2: per-observation records, staged through shared memory (the
         // pass-1 row buffers are dead by now) and written as 16-byte units, contiguous per record,

@@ -54,6 +54,8 @@ struct DevProblem {
     const double* dcam;           // scaled increment of the camera part (length n_pad)
     const double* dcam_unscaled;  // un-scaled increment (main.m:458-482)
     double* dpts;                 // increment of the tie points, n_tie x 3
+    double* pt_rec;               // per tie point {L^-1 (6), L^-1 u_p (3), Fc (NC x 3)} of the point pass, stride
+                                  // 9 + 3 NC; null: the back-substitution recomputes the Jacobians
     double* partial;              // per-warp partial sums (deterministic final reduction)
     // assembly schedule and per-observation records (feba_assemble.cu)
     double* rec1;                 // n_obs x kRec1

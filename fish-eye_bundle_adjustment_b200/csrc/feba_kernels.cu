@@ -490,6 +490,75 @@ __global__ void __launch_bounds__(128) k_backsub(DevProblem P) {
     if (lane == 0) P.partial[gw] = dsum;
 }
 
+// K4 from the records of the point pass of the same iteration (single camera or no camera unknowns): with
+// V = L L', Z_a = P Jt_a L^-T (rec1), ut = L^-1 u_p and Fc = Wc L^-T (pt_rec),
+//   d_p = -L^-T ( ut + Fc' d_cam + sum_a Z_a' Je_a d_e(i_a) ):
+// no Jacobian is evaluated again; one 144-byte record gather per observation.
+template <int NK, bool HAS_CAM, int G>
+__global__ void __launch_bounds__(128) k_backsub_rec(DevProblem P) {
+    constexpr int NC = NK + 5;
+    constexpr int PR = 9 + 3 * NC;
+    const int lane = threadIdx.x & (G - 1);
+    const int nwarp = gridDim.x * (blockDim.x / G);
+    const int gw = blockIdx.x * (blockDim.x / G) + threadIdx.x / G;
+    const unsigned gmask = G == 32 ? 0xffffffffu : (0xffffu << (16 * ((threadIdx.x & 31) >> 4)));
+    double dsum = 0.0;
+    for (int seg = gw; seg < P.n_seg; seg += nwarp) {
+        const int pt = P.seg_pt[seg];
+        const int tie = P.pt_tie[pt];
+        if (tie < 0) continue;
+        const int beg = P.seg_start[seg], end = P.seg_start[seg + 1];
+        double s[3] = {0.0, 0.0, 0.0};
+        for (int o = beg + lane; o < end; o += G) {
+            const size_t pos = P.ipos ? (size_t)P.ipos[o] : (size_t)o;
+            const int row = P.img_row[P.oimg[o]];
+            const double2* q2 = reinterpret_cast<const double2*>(P.rec1 + (size_t)kRec1 * pos);
+            double r[kRec1];
+#pragma unroll
+            for (int k = 0; k < kRec1 / 2; ++k) { const double2 v = q2[k]; r[2 * k] = v.x; r[2 * k + 1] = v.y; }
+            double q[2] = {0.0, 0.0};
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                if (P.ecol[i] >= 0) {
+                    const double d = P.dcam[row + P.ecol[i]];
+                    q[0] += r[i] * d;
+                    q[1] += r[6 + i] * d;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) s[k] += r[12 + k] * q[0] + r[15 + k] * q[1];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int w = G / 2; w > 0; w >>= 1) s[k] += __shfl_xor_sync(gmask, s[k], w);
+        const double* pr = P.pt_rec + (size_t)PR * tie;
+        if (HAS_CAM) {
+#pragma unroll
+            for (int j = 0; j < NC; ++j) {
+                if (P.ccol[j] >= 0) {
+                    const double d = P.dcam[P.off_cam + P.ccol[j]];          // single camera
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) s[k] += pr[9 + 3 * j + k] * d;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s[k] += pr[6 + k];
+        const double i00 = pr[0], i10 = pr[1], i11 = pr[2], i20 = pr[3], i21 = pr[4], i22 = pr[5];
+        const double d[3] = {-(i00 * s[0] + i10 * s[1] + i20 * s[2]), -(i11 * s[1] + i21 * s[2]), -(i22 * s[2])};
+        if (lane < 3) {
+            const double dv = lane == 0 ? d[0] : (lane == 1 ? d[1] : d[2]);
+            const double xv = P.xyz[3 * pt + lane];
+            P.xyz_prev[3 * pt + lane] = xv;
+            P.xyz[3 * pt + lane] = xv + dv;                      // main.m:484
+            P.dpts[3 * tie + lane] = dv;
+        }
+        dsum += fabs(d[0]) + fabs(d[1]) + fabs(d[2]);            // main.m:487 (sumabs)
+    }
+    if (lane == 0) P.partial[gw] = dsum;
+}
+
 // Fixed-order sum of per-warp / per-block partials (deterministic).
 __global__ void k_sum_partials(const double* __restrict__ partial, int n, int stride, int offset,
                                double* __restrict__ out) {
@@ -954,6 +1023,14 @@ cudaError_t launch_backsub(const DevProblem& P, int sm_count, cudaStream_t st) {
     const bool hc = P.uc > 0;
     const int G = backsub_lanes(P);
     const int grid = backsub_warps(P, sm_count) / (128 / G);
+    if (P.pt_rec) {
+        if (G == 16) {
+            FEBA_NK_DISPATCH(P.NK, hc, (k_backsub_rec<NK_, HC_, 16><<<grid, 128, 0, st>>>(P)));
+        } else {
+            FEBA_NK_DISPATCH(P.NK, hc, (k_backsub_rec<NK_, HC_, 32><<<grid, 128, 0, st>>>(P)));
+        }
+        return cudaGetLastError();
+    }
     if (G == 16) {
         FEBA_NK_DISPATCH(P.NK, hc, (k_backsub<NK_, HC_, 16><<<grid, 128, 0, st>>>(P)));
     } else {
