@@ -451,6 +451,25 @@ def test_task_graph_factorisation_matches_recursive_form(monkeypatch, form, grap
     assert np.array_equal(b["xhat"], c["xhat"])
 
 
+@pytest.mark.parametrize("mode", ["free", "mixed"])
+def test_back_substitution_from_records_matches_recomputed_jacobians(monkeypatch, mode):
+    """The tie-point increments come from the point pass's records (k_backsub_rec: L^-1, L^-1 u_p, Fc per point,
+    Je and Z per observation); FEBA_BACKSUB_REC=0 keeps the round-1 kernel that evaluates the Jacobians again
+    (main.m:455-456 either way).  Same adjustment to rounding, same oracle parity."""
+    from oracle import cport
+    prob = synth.baseline_config(4, scale=1.0) if mode == "free" else synth.make_network(
+        24, 2500, 8, 77, mode="mixed", n_control=40)
+    err, xhat0, _ = fb.Buildxhat(prob)
+    a = fb.adjust(prob, xhat0, verbose=False)
+    monkeypatch.setenv("FEBA_BACKSUB_REC", "0")
+    b = fb.adjust(prob, xhat0, verbose=False)
+    assert a["iterations"] == b["iterations"]
+    assert group_rel(prob, a["xhat"], b["xhat"]) < 1e-11
+    assert np.max(np.abs(a["v"] - b["v"])) < 1e-9
+    ref = cport.CPort(prob).gauss_newton(xhat0)
+    assert a["iterations"] == ref["iterations"] and group_rel(prob, a["xhat"], ref["xhat"]) < 1e-9
+
+
 @pytest.mark.parametrize("variant", ["sigma_y", "y_dir_plus", "NK1", "NK8"])
 def test_setting_variants(variant):
     """Settings the reference reads that the other tests leave at their defaults: Meas_std_y (weights,
