@@ -6,7 +6,8 @@
     python scripts/ncu_extract.py launches.csv profiles/r2_ncu_traffic.json
 
 Per kernel: launches seen, mean duration, mean DRAM read + write bytes per launch.  The entry
-"assembly (k_point_pass + k_image_pass + k_pair_pass)" adds the three assembly kernels of ONE iteration: that is what
+"assembly (k_point_pass + k_image_pass + k_pair_pass)" adds the assembly kernels of ONE iteration (these three plus
+the small camera kernels k_cam_direct / k_cam_reduce when they were captured): that is what
 bench.py prints as roofline.traffic when the assembly is the dominant phase."""
 import collections
 import csv
@@ -33,7 +34,7 @@ def main(src, dst):
         wr = sum(d.get("dram__bytes_write.sum", [0])) / n
         out["kernels"][name] = {"launches": n, "ms_per_launch": sum(d["gpu__time_duration.sum"]) / n,
                                 "dram_bytes_per_launch": rd + wr, "dram_read": rd, "dram_write": wr}
-    asm = [k for k in out["kernels"] if k.startswith(("k_point_pass", "k_image_pass", "k_pair_pass"))]
+    asm = [k for k in out["kernels"] if k.startswith(("k_point_pass", "k_image_pass", "k_pair_pass", "k_cam_direct", "k_cam_reduce"))]
     if asm:
         out["kernels"]["assembly (k_point_pass + k_image_pass + k_pair_pass)"] = {
             "launches": 1, "ms_per_launch": sum(out["kernels"][k]["ms_per_launch"] for k in asm),
