@@ -218,11 +218,18 @@ def run_reference(args, rank):
     if rank != 0:
         return
     prob, desc = make_workload(args.workload, args.scale)
+    # every repetition is the same full iteration (10+ s on configs[3]): one untimed repetition warms the pages, and the
+    # timed repetitions stop after --cpu-budget seconds (at least two) so that --steps 20 --warmup 5 still ends within
+    # a few minutes; the line says how many were measured
     times, parts = [], None
-    for i in range(args.warmup + args.steps):
+    t, parts = cpu_iteration_seconds(prob, args.cpu_fraction) if args.warmup > 0 else (0.0, None)
+    spent = 0.0
+    for i in range(max(args.steps, 1)):
+        if i >= 2 and spent + (spent / i) > args.cpu_budget:
+            break
         t, parts = cpu_iteration_seconds(prob, args.cpu_fraction)
-        if i >= args.warmup:
-            times.append(t)
+        times.append(t)
+        spent += t
     sec = float(np.mean(times))
     val = prob.n_obs / sec
     line = {"impl": "reference", "metric": "observations/sec per Gauss-Newton iteration", "value": val,
@@ -233,7 +240,7 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": val, "unit": "obs/s", "cores": parts["threads"], "kind": "port",
                              "sample": cpu_sample_text(prob, parts)},
             "e2e": {"value": val, "unit": "obs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "measured_steps": len(times), "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
@@ -690,6 +697,8 @@ def main():
     ap.add_argument("--cpu-fraction", type=float, default=1.0,
                     help="--impl reference: fraction of the points the linear stages are timed on per step (1 = the "
                          "full workload, measured)")
+    ap.add_argument("--cpu-budget", type=float, default=150.0,
+                    help="--impl reference: stop timing further full iterations once this many seconds are spent (>= 2 are timed)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-iterations", type=int, default=12,
                     help="cap on the iterations of the CPU port's whole adjustment (cpu_baseline + parity at N=1)")
