@@ -761,6 +761,9 @@ static int create_impl(const feba_problem* pr, int rank, int world, const void* 
         const bool multi_cam = pr->n_cam > 1 && P.uc > 0;
         if (pr->n_tie > 0 && !multi_cam && !(e && e[0] == '0'))
             CU(h, dev_alloc(h, &P.pt_rec, (size_t)pr->n_tie * (size_t)(9 + 3 * (P.NK + 5))));
+        // camera block and right-hand side from the records (k_cam_rec) instead of a Jacobian pass (k_cam_direct)
+        const char* c = std::getenv("FEBA_CAM_REC");
+        P.cam_rec = (P.uc > 0 && !multi_cam && !(c && c[0] == '0')) ? 1 : 0;
     }
     CU(h, dev_alloc(h, &h->work, 64));
     CU(h, dev_alloc(h, &h->ywork, (size_t)P.n_pad));

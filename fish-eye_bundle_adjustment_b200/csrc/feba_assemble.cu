@@ -196,13 +196,15 @@ __global__ void __launch_bounds__(128) k_point_pass(DevProblem P) {
                     sm.Fc[lane][2] = w0 * i20 + w1 * i21 + w2 * i22;
                 }
                 __syncwarp(gmask);
+                if (!P.cam_rec) {          // else k_cam_rec forms the whole camera block from the records
 #pragma unroll
-                for (int t = 0; t < DPL; ++t) {
-                    if (lane + G * t < ND)
-                        dacc[t] -= sm.Fc[dI[t]][0] * sm.Fc[dJ[t]][0] + sm.Fc[dI[t]][1] * sm.Fc[dJ[t]][1] +
-                                   sm.Fc[dI[t]][2] * sm.Fc[dJ[t]][2];
+                    for (int t = 0; t < DPL; ++t) {
+                        if (lane + G * t < ND)
+                            dacc[t] -= sm.Fc[dI[t]][0] * sm.Fc[dJ[t]][0] + sm.Fc[dI[t]][1] * sm.Fc[dJ[t]][1] +
+                                       sm.Fc[dI[t]][2] * sm.Fc[dJ[t]][2];
+                    }
+                    if (lane < NC) gcacc -= sm.Fc[lane][0] * ut[0] + sm.Fc[lane][1] * ut[1] + sm.Fc[lane][2] * ut[2];
                 }
-                if (lane < NC) gcacc -= sm.Fc[lane][0] * ut[0] + sm.Fc[lane][1] * ut[1] + sm.Fc[lane][2] * ut[2];
             }
             if (P.pt_rec) {
                 // what k_backsub_rec needs of this point besides the per-observation records
@@ -605,6 +607,54 @@ __global__ void __launch_bounds__(256) k_cam_direct(DevProblem P, const int* __r
 #pragma unroll
             for (int j = 0; j <= i; ++j) acc[e++] += t0 * J.Jc[0][j] + t1 * J.Jc[1][j];
             acc[ND + i] += t0 * J.w[0] + t1 * J.w[1];
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], s);
+        if (lane == 0) red[warp][k] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < NE) {
+        double tot = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) tot += red[w][threadIdx.x];
+        P.cam_part[(size_t)kCamPart * (row0 + blockIdx.x) + threadIdx.x] = tot;
+    }
+}
+
+// Camera block and camera right-hand side of a single-camera problem from the records alone.  With
+// H_a = P Jc_a - Z_a Fc' and r_a = P w_a - Z_a ut (rec2), sum_a Jc_a' Z_a = Fc and sum_a Z_a' P^-1 Z_a = I per point give
+//   sum_a H_a' P^-1 H_a = sum_a Jc_a' P Jc_a - sum_p Fc Fc'      (the Schur-complemented camera block)
+//   sum_a H_a' P^-1 r_a = sum_a Jc_a' P w_a  - sum_p Fc ut       (its right-hand side)
+// (control points: Z = 0).  One streaming read of rec2 (176 B per observation for NK = 5), no Jacobian evaluation,
+// and a sum of positive semidefinite terms instead of a difference of two large ones.  Same partial-buffer rows
+// and fixed-order reduction as k_cam_direct.
+template <int NK>
+__global__ void __launch_bounds__(256) k_cam_rec(DevProblem P, int row0) {
+    constexpr int NC = NK + 5;
+    constexpr int ND = NC * (NC + 1) / 2;
+    constexpr int NE = ND + NC;
+    constexpr int R2 = 2 + 2 * NC;
+    __shared__ double red[8][NE];
+    double acc[NE];
+#pragma unroll
+    for (int k = 0; k < NE; ++k) acc[k] = 0.0;
+    const double ipx = 1.0 / P.px, ipy = 1.0 / P.py;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < P.n_obs; q += (int64_t)gridDim.x * blockDim.x) {
+        const double2* p2 = reinterpret_cast<const double2*>(P.rec2 + (size_t)R2 * q);
+        double r[R2];
+#pragma unroll
+        for (int k = 0; k < R2 / 2; ++k) { const double2 v = p2[k]; r[2 * k] = v.x; r[2 * k + 1] = v.y; }
+        int e = 0;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const double t0 = r[2 + 2 * i] * ipx, t1 = r[3 + 2 * i] * ipy;
+#pragma unroll
+            for (int j = 0; j <= i; ++j) acc[e++] += t0 * r[2 + 2 * j] + t1 * r[3 + 2 * j];
+            acc[ND + i] += t0 * r[0] + t1 * r[1];
         }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1282,6 +1332,21 @@ static cudaError_t launch_cam_direct_t(const DevProblem& P, const int* opt, int 
     return cudaGetLastError();
 }
 static cudaError_t launch_cam_direct(const DevProblem& P, const int* opt, int sm_count, cudaStream_t st) {
+    if (P.cam_rec) {
+        const int row0 = assemble_warps(P, sm_count);
+        switch (P.NK) {
+            case 1: k_cam_rec<1><<<sm_count, 256, 0, st>>>(P, row0); break;
+            case 2: k_cam_rec<2><<<sm_count, 256, 0, st>>>(P, row0); break;
+            case 3: k_cam_rec<3><<<sm_count, 256, 0, st>>>(P, row0); break;
+            case 4: k_cam_rec<4><<<sm_count, 256, 0, st>>>(P, row0); break;
+            case 5: k_cam_rec<5><<<sm_count, 256, 0, st>>>(P, row0); break;
+            case 6: k_cam_rec<6><<<sm_count, 256, 0, st>>>(P, row0); break;
+            case 7: k_cam_rec<7><<<sm_count, 256, 0, st>>>(P, row0); break;
+            case 8: k_cam_rec<8><<<sm_count, 256, 0, st>>>(P, row0); break;
+            default: return cudaErrorInvalidValue;
+        }
+        return cudaGetLastError();
+    }
     switch (P.NK) {
         case 1: return launch_cam_direct_t<1>(P, opt, sm_count, st);
         case 2: return launch_cam_direct_t<2>(P, opt, sm_count, st);

@@ -66,6 +66,7 @@ struct DevProblem {
     const int4* blocks;           // (image a, image b <= a, first pair, pairs)
     int n_blocks;
     double* cam_part;             // per-warp camera-camera partial sums
+    int cam_rec;                  // 1: camera block and right-hand side from the records (k_cam_rec), the point pass adds nothing
     double* Gt;                   // inner-constraint rows, compact: (6 n_img) x 8 row-major (col 7 unused)
     // sparse-datum form (feba_sparse.h, FEBA_SPARSE=1): flags of the datum images, or null (dense M = S + G G')
     int aug_rows;                 // rows of the augmented block in use: kAugRows, or kSparseAugRows
