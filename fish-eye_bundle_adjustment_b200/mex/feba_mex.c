@@ -13,6 +13,13 @@
  *     [S, err] = feba_mex('pack', pho, ext, cnt, int, tie, NK, allgcp);   native problem build (feba_pack.h):
  *                the numeric arrays of S straight from the five text files, instead of main.m:196-384
  *                (tie = '' when there is no .tie file); add the settings fields and pass S to 'create'
+ *   BatchRun sweep (BatchRun.m:57-65: many independent blocks), all blocks advanced by ONE graph launch per step:
+ *     b = feba_mex('batch_create', hs);          hs: uint64 vector of handles (one per block)
+ *         feba_mex('batch_iterate', b);          one Gauss-Newton step of every block, asynchronous
+ *     deltasum = feba_mex('sync', h);            per block: wait + main.m:487 of the step just issued
+ *         feba_mex('batch_destroy', b);          (handles stay valid; drop converged blocks by making a new batch)
+ *     feba_mex('iterate_async', h) / 'sync' do the same for one handle
+ *     [info, flop] = feba_mex('plan_info', h);   row order / pattern chosen for the reduced system (feba_plan_info)
  * Recoverable errors are NOT raised with mexErrMsgIdAndTxt: like the reference's 0/1 `error` flags
  * (main.m:417-421) the gateway returns the status as the LAST output and prints feba_last_error.
  * The handle travels as a uint64 scalar; all arrays stay owned by MATLAB.
@@ -152,6 +159,35 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         if (nlhs > 1) plhs[1] = mxCreateDoubleScalar(0.0);
         return;
     }
+    if (!strcmp(cmd, "batch_create")) {
+        if (nrhs < 2 || !mxIsClass(prhs[1], "uint64") || mxGetNumberOfElements(prhs[1]) < 1)
+            mexErrMsgIdAndTxt("feba:batch", "batch_create needs a uint64 vector of handles");
+        const size_t n = mxGetNumberOfElements(prhs[1]);
+        const uint64_t* raw = (const uint64_t*)mxGetData(prhs[1]);
+        feba_handle** hs = (feba_handle**)mxMalloc(sizeof(feba_handle*) * n);
+        for (size_t i = 0; i < n; ++i) hs[i] = (feba_handle*)(uintptr_t)raw[i];
+        feba_batch* b = NULL;
+        const int rc = feba_batch_create(hs, (int32_t)n, &b);
+        mxFree(hs);
+        plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
+        *(uint64_t*)mxGetData(plhs[0]) = (uint64_t)(uintptr_t)b;
+        if (rc != 0) mexPrintf("feba: batch_create failed (%d): blocks must be idle handles of one device\n", rc);
+        if (nlhs > 1) plhs[1] = mxCreateDoubleScalar((double)(rc != 0));
+        return;
+    }
+    if (!strcmp(cmd, "batch_iterate") || !strcmp(cmd, "batch_destroy")) {
+        if (nrhs < 2 || !mxIsClass(prhs[1], "uint64") || mxGetNumberOfElements(prhs[1]) != 1)
+            mexErrMsgIdAndTxt("feba:batch", "%s needs the batch handle", cmd);
+        feba_batch* b = (feba_batch*)(uintptr_t)(*(uint64_t*)mxGetData(prhs[1]));
+        if (cmd[6] == 'd') {
+            feba_batch_destroy(b);
+        } else {
+            const int rc = feba_batch_iterate_async(b);
+            if (rc != 0) mexPrintf("feba: batch_iterate failed (%d)\n", rc);
+            if (nlhs > 0) plhs[0] = mxCreateDoubleScalar((double)(rc != 0));
+        }
+        return;
+    }
     if (nrhs < 2) mexErrMsgIdAndTxt("feba:cmd", "%s needs a handle", cmd);
     feba_handle* h = get_handle(prhs[1]);
     int64_t u = 0, uc = 0;
@@ -171,6 +207,25 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         const int rc = feba_iterate(h, &deltasum);
         plhs[0] = mxCreateDoubleScalar(deltasum);                          /* main.m:487 */
         status_out(nlhs, plhs, 1, rc, h);
+    } else if (!strcmp(cmd, "iterate_async")) {
+        status_out(nlhs, plhs, 0, feba_iterate_async(h), h);
+    } else if (!strcmp(cmd, "sync")) {
+        double deltasum = 0.0;
+        const int rc = feba_sync(h, &deltasum);
+        plhs[0] = mxCreateDoubleScalar(deltasum);                          /* main.m:487 */
+        status_out(nlhs, plhs, 1, rc, h);
+    } else if (!strcmp(cmd, "plan_info")) {
+        int32_t info[8];
+        double flop[2];
+        const int rc = feba_plan_info(h, info, flop);
+        plhs[0] = mxCreateDoubleMatrix(1, 8, mxREAL);
+        for (int i = 0; i < 8; ++i) mxGetPr(plhs[0])[i] = rc == 0 ? (double)info[i] : 0.0;
+        if (nlhs > 1) {
+            plhs[1] = mxCreateDoubleMatrix(1, 2, mxREAL);
+            mxGetPr(plhs[1])[0] = rc == 0 ? flop[0] : 0.0;
+            mxGetPr(plhs[1])[1] = rc == 0 ? flop[1] : 0.0;
+        }
+        status_out(nlhs, plhs, 2, rc, h);
     } else if (!strcmp(cmd, "solve")) {
         int32_t it = 0;
         const int cap = 4096;
