@@ -16,7 +16,9 @@
 //     S[i_a, i_a]   += Je_a' (P - C_aa) Je_a             image pass
 //     g[i_a]        += Je_a' r_a,   r_a = P w_a - Z_a ut
 //     S[cam, i_a]   += H_a Je_a,    H_a = Jc_a' P - Fc Z_a'
-//     S[cam, cam]   += sum_a Jc_a' P Jc_a - Fc Fc',  g[cam] += sum_a Jc_a' P w_a - Fc ut   point pass
+//     S[cam, cam]   += sum_a Jc_a' P Jc_a - Fc Fc',  g[cam] += sum_a Jc_a' P w_a - Fc ut
+//                    = sum_a H_a P^-1 H_a'            = sum_a H_a P^-1 r_a      (sum_a Jc_a'Z_a = Fc, sum_a Z_a'P^-1 Z_a = I)
+//                    single camera: k_cam_rec from the records; several cameras: in the multi-camera point pass
 // Control points (not estimated) contribute the same terms with Z = 0, Fc = 0.
 // The point pass stores, per observation, rec1 = {Je (2x6), Z (2x3)} and rec2 = {r (2), H (NC x 2)} in
 // IMAGE-MAJOR order (an image's records are contiguous: the image pass streams them, the pair pass
