@@ -34,8 +34,7 @@ LIB = os.path.join(ROOT, "tests", "_build", "libfeba_model_host.so")
 _pd, _pi, _pb = C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_ubyte)
 
 
-@pytest.fixture(scope="module")
-def host():
+def load_host():
     newest = max(os.path.getmtime(p) for p in [SRC] + HDRS)
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
@@ -51,6 +50,11 @@ def host():
     lib.feba_host_plan_arrays.argtypes = [C.c_void_p, _pi, _pi, _pi, _pb, _pi, _pi, _pi, _pi, _pi]
     lib.feba_host_plan_point_owner.argtypes = [C.c_void_p, C.c_int, _pi, _pi, _pi]
     return lib
+
+
+@pytest.fixture(scope="module")
+def host():
+    return load_host()
 
 
 def sorted_by_point(prob):
@@ -175,35 +179,43 @@ def reduced_of(prob, x0, pts_mask=None):
     return S, g
 
 
-def solve_like_the_device(host, plan, parts, Gc, world):
-    """parts: per rank (S_r, g_r) in xhat order.  Returns delta_c (xhat order, scaled system undone)."""
-    n = len(parts[0][1])
-    n_pad, NT = plan.n_pad, plan.NT
-    ro = plan.row_of
-    blk_owner = np.repeat(plan.tile_owner, np.diff(plan.tile_b0))
-    row_owner = np.repeat(blk_owner, 64)
-    init_here = lambda r: (row_owner == r) | ((row_owner < 0) & (r == 0)) if world > 1 else np.ones(n_pad, bool)
-    # conditioned G (any non-singular C gives the same bordered solution): unit column norms
-    Gn = Gc / np.linalg.norm(Gc, axis=0)[None, :]
-    G = np.zeros((n_pad, 7))
-    G[ro] = Gn
-    E = np.zeros((n_pad, 7))
-    for im in plan.datum:
-        r0 = plan.img_row[im]
-        E[r0:r0 + 6] = G[r0:r0 + 6]
-    pad = plan.row_ext < 0
-    A = []
-    for r in range(world):
-        S_r, g_r = parts[r]
+class RankSolve:
+    """The solve half of ONE rank of a group as feba_iterate runs it (csrc/feba_api.cu::enqueue_solve), in three
+    phases separated by the three exchanges: diag() -> [sum of diag(S)] -> eliminate() -> [sum of the shared top
+    part] -> finish() -> [sum of the solution rows].  world = 1: the same code without exchanges."""
+
+    def __init__(self, host, plan, S_r, g_r, Gc, rank, world):
+        self.host, self.plan, self.rank, self.world = host, plan, rank, world
+        n_pad = plan.n_pad
+        self.ro = ro = plan.row_of
+        self.blk_owner = np.repeat(plan.tile_owner, np.diff(plan.tile_b0))
+        row_owner = np.repeat(self.blk_owner, 64)
+        self.mine = ((row_owner == rank) | ((row_owner < 0) & (rank == 0))) if world > 1 else np.ones(n_pad, bool)
+        # conditioned G (any non-singular C gives the same bordered solution): unit column norms
+        Gn = Gc / np.linalg.norm(Gc, axis=0)[None, :]
+        self.G = np.zeros((n_pad, 7))
+        self.G[ro] = Gn
+        self.E = np.zeros((n_pad, 7))
+        for im in plan.datum:
+            r0 = plan.img_row[im]
+            self.E[r0:r0 + 6] = self.G[r0:r0 + 6]
+        self.pad = plan.row_ext < 0
         a = np.zeros((n_pad + 64, n_pad + 64))
         a[np.ix_(ro, ro)] = S_r
         a[n_pad, ro] = g_r
-        A.append(a)
-    # exchange 1: diag(S)
-    dg = sum(np.diag(a)[:n_pad] for a in A)
-    d = 1.0 / np.sqrt(np.where(pad, 1.0, dg + np.sum(E * E, axis=1)))
-    for r in range(world):
-        a, mine = A[r], init_here(r)
+        self.a = a
+        self.top = plan.top_tile0 if world > 1 else plan.NT
+        self.t0 = 64 * plan.tile_b0[self.top] if self.top < plan.NT else n_pad
+
+    def diag(self):
+        """exchange 1 sends this: the diagonal of the rank's partial S"""
+        return np.diag(self.a)[:self.plan.n_pad].copy()
+
+    def eliminate(self, dg):
+        """border + scaling with the summed diagonal, elimination of the own subtrees; exchange 2 sends the result:
+        the rank's contribution to the shared top part (lower trapezoid incl. the augmented rows)"""
+        a, E, G, mine, pad, n_pad = self.a, self.E, self.G, self.mine, self.pad, self.plan.n_pad
+        self.d = d = 1.0 / np.sqrt(np.where(pad, 1.0, dg + np.sum(E * E, axis=1)))
         a[:n_pad, :n_pad] += (E * mine[:, None]) @ E.T                    # datum term where the ROW is initialised here
         a[np.nonzero(pad & mine)[0], np.nonzero(pad & mine)[0]] = 1.0
         a[:n_pad, :n_pad] *= np.outer(d, d)
@@ -211,36 +223,46 @@ def solve_like_the_device(host, plan, parts, Gc, world):
         a[n_pad + 1:n_pad + 8, :n_pad] = (G * d[:, None] * mine[:, None]).T
         a[n_pad + 8:n_pad + 15, :n_pad] = (E * d[:, None] * mine[:, None]).T
         a[:] = np.tril(a)
-    top = plan.top_tile0 if world > 1 else NT
-    for r in range(world):
-        masked_tiles_cholesky(A[r], plan, plan.nz, range(0, top), r if world > 1 else None)
-    if world > 1:
-        t0 = 64 * plan.tile_b0[top] if top < NT else n_pad
-        tot = sum(a[t0:, t0:] for a in A)
-        for a in A:
-            a[t0:, t0:] = tot
-        for r in range(world):
-            masked_tiles_cholesky(A[r], plan, plan.nz, range(top, NT), r)
-    sols = []
-    for r in range(world):
-        a = A[r]
+        masked_tiles_cholesky(a, self.plan, self.plan.nz, range(0, self.top), self.rank if self.world > 1 else None)
+        return a[self.t0:, self.t0:].copy()
+
+    def finish(self, top_sum):
+        """factorisation of the summed top (replicated), 14x14 border, backward substitution of the top and the own
+        subtrees; exchange 3 sends the result: the rows of the solution this rank is responsible for"""
+        a, plan, n_pad = self.a, self.plan, self.plan.n_pad
+        if self.world > 1:
+            a[self.t0:, self.t0:] = top_sum
+            masked_tiles_cholesky(a, plan, plan.nz, range(self.top, plan.NT), self.rank)
         Tm = a[n_pad:n_pad + 15, n_pad:n_pad + 15]
         Tm = np.tril(Tm) + np.tril(Tm, -1).T
         coef = np.zeros(14)
-        assert host.feba_host_sparse_border(np.ascontiguousarray(Tm).ctypes.data_as(_pd), coef.ctypes.data_as(_pd)) == 0
+        assert self.host.feba_host_sparse_border(np.ascontiguousarray(Tm).ctypes.data_as(_pd), coef.ctypes.data_as(_pd)) == 0
         y = a[n_pad, :n_pad] + coef @ a[n_pad + 1:n_pad + 15, :n_pad]
         x = np.zeros(n_pad)
-        nb = n_pad // 64
-        for k in range(nb - 1, -1, -1):                                   # k_backstep, owner filter
-            if world > 1 and blk_owner[k] >= 0 and blk_owner[k] != r:
+        for k in range(n_pad // 64 - 1, -1, -1):                          # k_backstep, owner filter
+            if self.world > 1 and self.blk_owner[k] >= 0 and self.blk_owner[k] != self.rank:
                 continue
             ks = slice(64 * k, 64 * k + 64)
             x[ks] = sla.solve_triangular(np.tril(a[ks, ks]), y[ks], lower=True, trans="T")
             y[:64 * k] -= a[ks, :64 * k].T @ x[ks]
-        x[~init_here(r)] = 0.0
-        sols.append(x)
+        x[~self.mine] = 0.0
+        return x
+
+    def delta(self, sol_sum):
+        return (-sol_sum * self.d)[self.ro]
+
+
+def solve_like_the_device(host, plan, parts, Gc, world):
+    """parts: per rank (S_r, g_r) in xhat order.  Returns delta_c (xhat order, scaled system undone).  All ranks in
+    one process, the exchanges are plain sums (tests/test_group_gloo.py runs the same phases in separate processes
+    with torch.distributed all_reduce in between)."""
+    ranks = [RankSolve(host, plan, parts[r][0], parts[r][1], Gc, r, world) for r in range(world)]
+    dg = sum(rk.diag() for rk in ranks)                                   # exchange 1
+    tops = [rk.eliminate(dg) for rk in ranks]
+    top_sum = sum(tops) if world > 1 else None                            # exchange 2
+    sols = [rk.finish(top_sum) for rk in ranks]
     sol = sum(sols)                                                       # exchange 3: every row exactly once
-    return (-sol * d)[ro], A
+    return ranks[0].delta(sol), [rk.a for rk in ranks]
 
 
 def truth_step(S, g, Gc):
